@@ -1,0 +1,219 @@
+/*
+ * bann.h -- C ABI of the B200-native rs-bann hot path (libbann_b200.so).
+ *
+ * The reference (medical-genomics-group/rs-bann) has no FFI boundary today: the seam is a set
+ * of Rust traits over the third-party `arrayfire` crate.  This header places the replacement
+ * boundary at exactly those traits.  Each entry point cites the
+ * reference interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every call returns int32 status: 0 = ok, < 0 = error; bann_last_error() (thread local)
+ *     describes the last error.  The library never aborts the process.
+ *   - all pointers are HOST pointers owned by the caller unless the name ends in `_dev`.
+ *   - matrices are column-major, weights are in x out, as in the reference (ArrayFire).
+ *   - parameter vectors use BranchParams::param_vec order (net/params.rs:700-715): all weights
+ *     layer by layer (column-major), then all biases.  Precision vectors use
+ *     BranchPrecisions::param_vec order (net/params.rs:272-289): weight precisions per layer,
+ *     bias precisions per layer, error precision.
+ *   - handles are opaque, not thread safe per handle.
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device (sm_100a).
+ */
+#ifndef BANN_H_
+#define BANN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bann_ctx bann_ctx;
+typedef struct bann_genotypes bann_genotypes;
+typedef struct bann_net bann_net;
+
+/* net/model_type.rs:6-13 */
+enum { BANN_STD_NORMAL = 0, BANN_RIDGE_BASE = 1, BANN_RIDGE_ARD = 2, BANN_LASSO_BASE = 3, BANN_LASSO_ARD = 4 };
+/* net/activation_functions.rs:6-12 */
+enum { BANN_TANH = 0, BANN_RELU = 1, BANN_LEAKY_RELU = 2, BANN_SILU = 3, BANN_IDENTITY = 4 };
+/* net/mcmc_cfg.rs:265-270 */
+enum { BANN_STEP_UNIFORM = 0, BANN_STEP_RANDOM = 1, BANN_STEP_STD_SCALED = 2, BANN_STEP_IZMAILOV = 3 };
+/* net/branch/branch_sampler.rs:1310-1314 (HMCStepResult) */
+enum { BANN_HMC_REJECTED_EARLY = 0, BANN_HMC_REJECTED = 1, BANN_HMC_ACCEPTED = 2 };
+
+#define BANN_MAX_LAYERS 8
+
+/* One branch's architecture: layer_widths = hidden..., summary, 1
+ * (net/branch/branch_cfg_builder.rs:285-297, net/branch/branch_cfg.rs:8-16). */
+typedef struct {
+    uint32_t num_layers;                  /* d + 2 */
+    uint32_t widths[BANN_MAX_LAYERS];     /* widths[num_layers-1] must be 1 */
+} bann_branch_layout;
+
+/* net/mcmc_cfg.rs:181-204 -- the fields the hot path reads. */
+typedef struct {
+    float    hmc_step_size_factor;        /* default 1.0 */
+    float    hmc_max_hamiltonian_error;   /* default 10.0 */
+    uint32_t hmc_integration_length;      /* default 100 */
+    int32_t  hmc_step_size_mode;          /* BANN_STEP_* , default Izmailov */
+    int32_t  fixed_param_precisions;      /* skip sample_param_precisions (net.rs:273) */
+} bann_mcmc_cfg;
+
+/* Injected randomness for parity runs.  NULL members fall back to the built-in
+ * counter-based Philox4x32-10 stream keyed by (seed, visit counter, branch). */
+typedef struct {
+    const float* momenta;        /* P_b N(0,1) draws, param_vec order (branch_sampler.rs:594-609) */
+    const float* accept_uniform; /* 1 value in [0,1)            (branch_sampler.rs:546-548) */
+    const float* step_uniforms;  /* P_b U(0,1) draws for BANN_STEP_RANDOM (branch_sampler.rs:654-681) */
+    const float* std_gammas;     /* standard-gamma variates in consumption order of one visit:
+                                    error precision; per layer l<last: weight precision(s), bias
+                                    precision; output weight precision (net.rs:272-275) */
+    uint32_t     num_std_gammas;
+} bann_rng_inject;
+
+typedef struct {
+    int32_t  status;             /* BANN_HMC_* */
+    float    log_density;        /* at the final state (valid when accepted) */
+    float    neg_h_init;
+    float    neg_h_final;
+    uint32_t steps_done;
+    int32_t  u_turn_step;        /* first step with (theta-theta0).p < 0, or -1 */
+} bann_hmc_result;
+
+/* Optional per-step trajectory (net/branch/trajectory.rs:4-11); arrays sized by the caller:
+ * params/ldg: L * P_b floats, hamiltonian: L + 1 floats. */
+typedef struct {
+    float* params;
+    float* ldg;
+    float* hamiltonian;
+} bann_trajectory;
+
+/* net/train_stats.rs:23-32 + net/log_posterior_density.rs:62-67 */
+typedef struct {
+    uint64_t num_samples;
+    uint64_t num_accepted;
+    uint64_t num_early_rejected;
+    float    mse_train;
+    float    lpd;
+    float    output_bias;
+    float    error_precision;
+    float    output_layer_precision;
+} bann_sweep_stats;
+
+const char* bann_last_error(void);
+/* 1 if a CUDA device is usable, 0 otherwise (no compute is attempted). */
+int bann_cuda_available(void);
+
+/* ---- lifetime.  One context per process/GPU.  `stream` may be NULL (own stream) or a
+ * cudaStream_t (e.g. torch's current stream).  rank/world describe the row shard this
+ * process holds; cross-rank sums are the caller's all-reduce over the buffers exposed by
+ * bann_allreduce_buffer() (torch.distributed / NCCL plumbing). */
+int  bann_ctx_create(int device, void* stream, int rank, int world, bann_ctx** out);
+void bann_ctx_destroy(bann_ctx*);
+int  bann_ctx_sync(bann_ctx*);
+
+/* ---- genotypes: replaces BedVM + MarkerGrouping + GroupedGenotypes::x_group_af
+ * (io/bed.rs:123-133,193-245,325-355; group/grouping.rs:7-15; data/genotypes.rs:7-48).
+ * bed_payload: PLINK variant-major 2-bit payload WITHOUT the 3-byte signature, m * ceil(n/4)
+ * bytes, for the n rows this rank holds.  col_means/col_stds: length m, or NULL to compute
+ * them on the device exactly as io/bed.rs:231-238 does (sequential f32, population std).
+ * branch_offsets[B+1] / col_ids[branch_offsets[B]]: CSR of each branch's marker columns
+ * (arbitrary order, may overlap).  n_total: rows over all ranks (statistics / N in formulas). */
+int  bann_genotypes_create(bann_ctx*, const uint8_t* bed_payload, uint64_t n, uint64_t n_total, uint64_t m,
+                           const float* col_means, const float* col_stds, uint64_t num_branches,
+                           const uint64_t* branch_offsets, const uint64_t* col_ids, bann_genotypes** out);
+void bann_genotypes_destroy(bann_genotypes*);
+int  bann_genotypes_col_stats(bann_genotypes*, float* col_means, float* col_stds);
+/* per-column counts of decoded values 0,1,2 over the local rows: out[3*m] (for global stats). */
+int  bann_genotypes_col_counts(bann_genotypes*, uint64_t* out);
+int  bann_genotypes_set_col_stats(bann_genotypes*, const float* col_means, const float* col_stds);
+/* test hook: decode branch b to f32 [n x m_b] column-major, raw 0/1/2 or standardised. */
+int  bann_genotypes_decode_branch(bann_genotypes*, uint64_t b, int standardized, float* out);
+
+/* ---- model state: replaces Vec<BranchCfg> + from_cfg/to_cfg round trips
+ * (net/net.rs:76-85, net/branch/branch_struct.rs:12-29, net/branch/branch_sampler.rs:155-171).
+ * hyper = dense(shape,scale), summary(shape,scale), output(shape,scale) (net/params.rs:135-142). */
+int  bann_net_create(bann_ctx*, bann_genotypes*, int model_type, int activation,
+                     const bann_branch_layout* layouts /* one per branch */, const float hyper[6], bann_net** out);
+void bann_net_destroy(bann_net*);
+int  bann_net_branch_sizes(bann_net*, uint64_t b, uint64_t* num_params, uint64_t* num_precisions);
+int  bann_net_set_branch(bann_net*, uint64_t b, const float* param_vec, const float* precision_vec);
+int  bann_net_get_branch(bann_net*, uint64_t b, float* param_vec, float* precision_vec);
+/* bulk variants over all branches, concatenated in branch order */
+int  bann_net_set_all_params(bann_net*, const float* param_vecs, const float* precision_vecs_or_null);
+int  bann_net_get_all_params(bann_net*, float* param_vecs, float* precision_vecs_or_null);
+/* GlobalParams + OutputBias (net/params.rs:13-56, net/net.rs:29-36):
+ * g[0]=error_precision g[1]=output_layer_precision g[2]=output-weight reg_sum (all branches)
+ * g[3]=output-weight num_params g[4]=output bias */
+int  bann_net_set_globals(bann_net*, const float g[5]);
+int  bann_net_get_globals(bann_net*, float g[5]);
+int  bann_net_set_targets(bann_net*, const float* y /* n local rows */);
+int  bann_net_get_residual(bann_net*, float* r /* n local rows */);
+int  bann_net_set_residual(bann_net*, const float* r /* n local rows */);
+/* initialize_stats (net/net.rs:158-171): residual = y - bias - sum_b predict_b, LPD terms. */
+int  bann_net_init_residual(bann_net*);
+
+/* ---- hot path */
+/* backpropagate + log_density_gradient for branch b (branch_sampler.rs:813-875,380-391).
+ * target NULL -> the net's targets y.  Outputs (any may be NULL): rss, log-density gradient in
+ * param_vec order, raw d_rss (1/2 dRSS/dtheta, Q4), yhat (n). */
+int  bann_branch_fwd_bwd(bann_net*, uint64_t b, const float* target, float* rss, float* ldg, float* d_rss,
+                         float* yhat);
+/* log_density(params, precisions, rss) (branch_sampler.rs:72-78; std_normal_branch.rs:147-158) */
+int  bann_branch_log_density(bann_net*, uint64_t b, float rss, float* out);
+/* per-parameter step sizes of the chosen mode (a10), param_vec order */
+int  bann_branch_step_sizes(bann_net*, uint64_t b, const bann_mcmc_cfg*, const float* step_uniforms, float* out);
+/* hmc_step(x_b, target, cfg) (branch_sampler.rs:1192-1299).  target NULL -> net targets.
+ * yhat_out (n, may be NULL) receives the prediction at the final state. */
+int  bann_hmc_step(bann_net*, uint64_t b, const float* target, const bann_mcmc_cfg*, const bann_rng_inject*,
+                   bann_hmc_result* out, bann_trajectory* traj, float* yhat_out);
+/* sample_error_precision + sample_param_precisions against the current residual
+ * (branch_sampler.rs:173-202 and the per-prior sample_prior_precisions). */
+int  bann_gibbs_branch(bann_net*, uint64_t b, const bann_mcmc_cfg*, const bann_rng_inject*);
+/* one iteration of the inner loop of Net::train (net/net.rs:258-334): globals -> cfg, Gibbs,
+ * prev_pred, HMC against residual + prev_pred, residual / LPD / globals / output-bias update. */
+int  bann_visit_branch(bann_net*, uint64_t b, const bann_mcmc_cfg*, const bann_rng_inject*, bann_hmc_result* out);
+/* a full pass over `branch_order` (sequential-exact schedule, group_size must be 1 in this
+ * release) with the built-in RNG keyed by seed; asynchronous, one sync at the end. */
+int  bann_sweep(bann_net*, const bann_mcmc_cfg*, const uint64_t* branch_order, uint64_t num, uint32_t group_size,
+                uint64_t seed, bann_sweep_stats* out);
+/* Net::predict (net/net.rs:545-559) on the training genotypes (NULL) or another store. */
+int  bann_predict(bann_net*, bann_genotypes* test_or_null, float* yhat);
+int  bann_net_stats(bann_net*, bann_sweep_stats* out);
+
+/* ---- full-network (grouped, all branches concurrently) operations */
+/* Net::gradient (net/net.rs:520-527): for every branch log_density_gradient(x_b, y).
+ * HOST buffers: params in (sum P_b, may be NULL = keep device state), y in (n, may be NULL),
+ * grads out (sum P_b), rss out (B).  This is the host-facing full-network fwd+grad call. */
+int  bann_net_gradient(bann_net*, const float* param_vecs, const float* y, float* grads, float* rss);
+/* Grouped leapfrog over ALL branches against per-branch targets (schedule G = B).
+ * begin: theta0 <- theta, step sizes, momenta (Philox, seed), targets t_b = y (shared) or
+ * residual + own prediction; then each step = B branch-leapfrogs.  Device resident, async. */
+int  bann_grouped_begin(bann_net*, const bann_mcmc_cfg*, uint64_t seed, int per_branch_targets);
+/* num_steps full-network leapfrog steps; finalize != 0: the last one ends the trajectory (no
+ * further position update) so that bann_grouped_finish can accept / reject. */
+int  bann_grouped_leapfrog(bann_net*, const bann_mcmc_cfg*, uint32_t num_steps, int finalize);
+/* split form for multi-GPU: phase A = fwd/bwd + chunk reduction into the all-reduce buffer,
+ * (caller all-reduces), phase B = gradient, momentum/position update, Hamiltonian check. */
+int  bann_grouped_phase_a(bann_net*);
+int  bann_grouped_phase_b(bann_net*, const bann_mcmc_cfg*, int is_init, int is_last);
+int  bann_grouped_finish(bann_net*, uint64_t seed, uint64_t* num_accepted, uint64_t* num_early_rejected);
+/* per-branch Hamiltonians / status after the last step (B each, may be NULL) */
+int  bann_grouped_state(bann_net*, float* neg_h_init, float* neg_h_cur, int32_t* status);
+
+/* device buffer (float) that must be sum-all-reduced across ranks between phase A and B and
+ * after residual updates; NULL/0 when nothing is pending.  Exposed so that the host side
+ * (torch.distributed over NCCL) can run the collective on the same stream. */
+int  bann_allreduce_buffer(bann_net*, void** dev_ptr, uint64_t* num_floats);
+
+/* test hook: route every K1 launch through the shape-agnostic kernel (cross-checks the tuned one) */
+int  bann_net_force_generic(bann_net*, int on);
+
+/* counters for bench.py: kernels launched by this library since the last reset */
+uint64_t bann_launch_count(int reset);
+/* algorithmic bytes of one full-network leapfrog step (SURVEY 8d formula) */
+int  bann_net_algorithmic_bytes(bann_net*, uint64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BANN_H_ */

@@ -1,0 +1,396 @@
+"""Host-side mirror of the reference's interface for the HMC/Gibbs hot path, above the C ABI.
+
+Names follow the reference: `Net.train / predict / gradient` (net/net.rs:201,545,520),
+`hmc_step`, `sample_error_precision + sample_param_precisions` (-> `gibbs_branch`),
+`BranchCfg` param/precision vectors (net/params.rs:272-289,700-715), `MCMCCfg`
+(net/mcmc_cfg.rs:181-204), `HMCStepResult` (net/branch/branch_sampler.rs:1310-1314).
+All compute happens in libbann_b200.so on the GPU; this layer only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (ACT_NAMES, HMC_ACCEPTED, HMC_REJECTED, HMC_REJECTED_EARLY, MODEL_NAMES, STEP_NAMES, BannError,
+                   check, lib)
+
+_fp = C.POINTER(C.c_float)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(_fp) if a is not None else None
+
+
+@dataclass
+class MCMCCfg:
+    """net/mcmc_cfg.rs:181-230 (fields read by the hot path; same defaults)."""
+    hmc_step_size_factor: float = 1.0
+    hmc_max_hamiltonian_error: float = 10.0
+    hmc_integration_length: int = 100
+    hmc_step_size_mode: str = "izmailov"
+    fixed_param_precisions: bool = False
+
+    def c(self) -> _lib.McmcCfg:
+        return _lib.McmcCfg(self.hmc_step_size_factor, self.hmc_max_hamiltonian_error, self.hmc_integration_length,
+                            STEP_NAMES[self.hmc_step_size_mode], int(self.fixed_param_precisions))
+
+
+@dataclass
+class HMCStepResult:
+    status: int
+    log_density: float
+    neg_h_init: float
+    neg_h_final: float
+    steps_done: int
+    u_turn_step: int
+    y_pred: Optional[np.ndarray] = None
+    trajectory: Optional[dict] = None
+
+    @property
+    def accepted(self):
+        return self.status == HMC_ACCEPTED
+
+
+def cuda_available() -> bool:
+    return bool(lib.bann_cuda_available())
+
+
+class Context:
+    """One per process / GPU. `stream`: a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device: int = 0, stream: int = 0, rank: int = 0, world: int = 1):
+        h = C.c_void_p()
+        check(lib.bann_ctx_create(device, C.c_void_p(stream) if stream else None, rank, world, C.byref(h)))
+        self.h, self.rank, self.world, self.device = h, rank, world, device
+
+    def sync(self):
+        check(lib.bann_ctx_sync(self.h))
+
+    def close(self):
+        if self.h:
+            lib.bann_ctx_destroy(self.h)
+            self.h = None
+
+
+class Genotypes:
+    """Device-resident packed genotype store = BedVM + MarkerGrouping (CompressedGenotypes,
+    data/genotypes.rs:14-48).  `payload`: PLINK variant-major bytes without signature for the
+    rows this rank holds; `groups`: list of marker-index lists (may overlap)."""
+
+    def __init__(self, ctx: Context, payload, n: int, m: int, groups: Sequence[Sequence[int]],
+                 col_means=None, col_stds=None, n_total: Optional[int] = None):
+        self.ctx, self.n, self.m = ctx, int(n), int(m)
+        self.groups = [list(map(int, g)) for g in groups]
+        payload = np.ascontiguousarray(np.frombuffer(bytes(payload), dtype=np.uint8)
+                                       if not isinstance(payload, np.ndarray) else payload, dtype=np.uint8)
+        assert payload.size == m * ((n + 3) // 4), "payload size does not match n, m"
+        offs = np.zeros(len(self.groups) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(g) for g in self.groups])
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=np.uint64) for g in self.groups]))
+        mu = _f32(col_means) if col_means is not None else None
+        sd = _f32(col_stds) if col_stds is not None else None
+        h = C.c_void_p()
+        check(lib.bann_genotypes_create(ctx.h, payload.ctypes.data_as(C.c_void_p), n, n_total or n, m, _ptr(mu), _ptr(sd),
+                                        len(self.groups), offs.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        ids.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(h)))
+        self.h = h
+
+    @property
+    def num_groups(self):
+        return len(self.groups)
+
+    def num_markers_per_group(self):
+        return [len(g) for g in self.groups]
+
+    def col_stats(self):
+        mu = np.empty(self.m, dtype=np.float32)
+        sd = np.empty(self.m, dtype=np.float32)
+        check(lib.bann_genotypes_col_stats(self.h, _ptr(mu), _ptr(sd)))
+        return mu, sd
+
+    def col_counts(self):
+        out = np.empty(3 * self.m, dtype=np.uint64)
+        check(lib.bann_genotypes_col_counts(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out.reshape(self.m, 3)
+
+    def set_col_stats(self, mu, sd):
+        mu, sd = _f32(mu), _f32(sd)
+        check(lib.bann_genotypes_set_col_stats(self.h, _ptr(mu), _ptr(sd)))
+
+    def x_group(self, b: int, standardized: bool = True) -> np.ndarray:
+        """GroupedGenotypes::x_group_af (data/genotypes.rs:44-48): [n, m_b] f32 (test hook)."""
+        out = np.empty(self.n * len(self.groups[b]), dtype=np.float32)
+        check(lib.bann_genotypes_decode_branch(self.h, b, int(standardized), _ptr(out)))
+        return out.reshape((self.n, len(self.groups[b])), order="F")
+
+    def close(self):
+        if self.h:
+            lib.bann_genotypes_destroy(self.h)
+            self.h = None
+
+
+class Net:
+    """Device-resident Net<B> (net/net.rs:74-85). Branch state stays on the GPU between visits."""
+
+    def __init__(self, ctx: Context, gen: Genotypes, model_type: str, layer_widths: Sequence[Sequence[int]],
+                 hyper=(0.001, 1000.0, 0.001, 1000.0, 0.001, 1000.0), activation: str = "tanh"):
+        self.ctx, self.gen = ctx, gen
+        self.model_type, self.activation = model_type, activation
+        self.layer_widths = [list(map(int, w)) for w in layer_widths]
+        assert len(self.layer_widths) == gen.num_groups
+        lay = (_lib.BranchLayout * len(self.layer_widths))()
+        for i, w in enumerate(self.layer_widths):
+            lay[i].num_layers = len(w)
+            for k, v in enumerate(w):
+                lay[i].widths[k] = v
+        hy = _f32(hyper)
+        h = C.c_void_p()
+        check(lib.bann_net_create(ctx.h, gen.h, MODEL_NAMES[model_type], ACT_NAMES[activation], lay, _ptr(hy),
+                                  C.byref(h)))
+        self.h = h
+        self.num_branches = len(self.layer_widths)
+        self._sizes = []
+        for b in range(self.num_branches):
+            p, q = C.c_uint64(), C.c_uint64()
+            check(lib.bann_net_branch_sizes(h, b, C.byref(p), C.byref(q)))
+            self._sizes.append((p.value, q.value))
+
+    # ---- state
+    def num_branch_params(self, b):
+        return self._sizes[b][0]
+
+    def num_branch_precisions(self, b):
+        return self._sizes[b][1]
+
+    def num_params(self):
+        return sum(p for p, _ in self._sizes)
+
+    def set_branch(self, b, param_vec=None, precision_vec=None):
+        pv = _f32(param_vec) if param_vec is not None else None
+        qv = _f32(precision_vec) if precision_vec is not None else None
+        if pv is not None:
+            assert pv.size == self._sizes[b][0]
+        if qv is not None:
+            assert qv.size == self._sizes[b][1]
+        check(lib.bann_net_set_branch(self.h, b, _ptr(pv), _ptr(qv)))
+
+    def get_branch(self, b):
+        pv = np.empty(self._sizes[b][0], dtype=np.float32)
+        qv = np.empty(self._sizes[b][1], dtype=np.float32)
+        check(lib.bann_net_get_branch(self.h, b, _ptr(pv), _ptr(qv)))
+        return pv, qv
+
+    def set_all_params(self, param_vecs, precision_vecs=None):
+        pv = _f32(param_vecs)
+        assert pv.size == self.num_params()
+        qv = _f32(precision_vecs) if precision_vecs is not None else None
+        check(lib.bann_net_set_all_params(self.h, _ptr(pv), _ptr(qv)))
+
+    def get_all_params(self):
+        pv = np.empty(self.num_params(), dtype=np.float32)
+        qv = np.empty(sum(q for _, q in self._sizes), dtype=np.float32)
+        check(lib.bann_net_get_all_params(self.h, _ptr(pv), _ptr(qv)))
+        return pv, qv
+
+    def set_globals(self, error_precision, output_layer_precision, ow_reg_sum, ow_num_params, output_bias=0.0):
+        g = _f32([error_precision, output_layer_precision, ow_reg_sum, ow_num_params, output_bias])
+        check(lib.bann_net_set_globals(self.h, _ptr(g)))
+
+    def get_globals(self):
+        g = np.empty(5, dtype=np.float32)
+        check(lib.bann_net_get_globals(self.h, _ptr(g)))
+        return dict(error_precision=float(g[0]), output_layer_precision=float(g[1]), ow_reg_sum=float(g[2]),
+                    ow_num_params=float(g[3]), output_bias=float(g[4]))
+
+    def set_targets(self, y):
+        y = _f32(y)
+        assert y.size == self.gen.n
+        check(lib.bann_net_set_targets(self.h, _ptr(y)))
+
+    def residual(self):
+        r = np.empty(self.gen.n, dtype=np.float32)
+        check(lib.bann_net_get_residual(self.h, _ptr(r)))
+        return r
+
+    def set_residual(self, r):
+        r = _f32(r)
+        check(lib.bann_net_set_residual(self.h, _ptr(r)))
+
+    def init_residual(self):
+        """initialize_stats, net/net.rs:158-171."""
+        check(lib.bann_net_init_residual(self.h))
+
+    # ---- hot path, one branch
+    def branch_fwd_bwd(self, b, target=None, want_yhat=True):
+        """backpropagate + log_density_gradient (branch_sampler.rs:813-875,380-391)."""
+        P = self._sizes[b][0]
+        t = _f32(target) if target is not None else None
+        rss = np.empty(1, dtype=np.float32)
+        ldg = np.empty(P, dtype=np.float32)
+        drss = np.empty(P, dtype=np.float32)
+        yh = np.empty(self.gen.n, dtype=np.float32) if want_yhat else None
+        check(lib.bann_branch_fwd_bwd(self.h, b, _ptr(t), _ptr(rss), _ptr(ldg), _ptr(drss), _ptr(yh)))
+        return dict(rss=float(rss[0]), ldg=ldg, d_rss=drss, yhat=yh)
+
+    def branch_log_density(self, b, rss):
+        out = np.empty(1, dtype=np.float32)
+        check(lib.bann_branch_log_density(self.h, b, float(rss), _ptr(out)))
+        return float(out[0])
+
+    def branch_step_sizes(self, b, cfg: MCMCCfg, step_uniforms=None):
+        out = np.empty(self._sizes[b][0], dtype=np.float32)
+        su = _f32(step_uniforms) if step_uniforms is not None else None
+        c = cfg.c()
+        check(lib.bann_branch_step_sizes(self.h, b, C.byref(c), _ptr(su), _ptr(out)))
+        return out
+
+    @staticmethod
+    def _inject(momenta=None, u=None, step_uniforms=None, std_gammas=None):
+        keep = []
+        inj = _lib.RngInject()
+        if momenta is not None:
+            a = _f32(momenta); keep.append(a); inj.momenta = _ptr(a)
+        if u is not None:
+            a = _f32([u]); keep.append(a); inj.accept_uniform = _ptr(a)
+        if step_uniforms is not None:
+            a = _f32(step_uniforms); keep.append(a); inj.step_uniforms = _ptr(a)
+        if std_gammas is not None:
+            a = _f32(std_gammas); keep.append(a); inj.std_gammas = _ptr(a); inj.num_std_gammas = a.size
+        return inj, keep
+
+    def hmc_step(self, b, cfg: MCMCCfg, target=None, momenta=None, u=None, step_uniforms=None, trajectory=False,
+                 want_yhat=True) -> HMCStepResult:
+        """BranchSampler::hmc_step (branch_sampler.rs:1192-1299)."""
+        P, L = self._sizes[b][0], cfg.hmc_integration_length
+        inj, keep = self._inject(momenta, u, step_uniforms)
+        t = _f32(target) if target is not None else None
+        res = _lib.HmcResult()
+        traj = _lib.Trajectory()
+        tp = tl = th = None
+        if trajectory:
+            tp = np.zeros(L * P, dtype=np.float32); tl = np.zeros(L * P, dtype=np.float32)
+            th = np.zeros(L + 1, dtype=np.float32)
+            traj.params, traj.ldg, traj.hamiltonian = _ptr(tp), _ptr(tl), _ptr(th)
+        yh = np.empty(self.gen.n, dtype=np.float32) if want_yhat else None
+        c = cfg.c()
+        check(lib.bann_hmc_step(self.h, b, _ptr(t), C.byref(c), C.byref(inj), C.byref(res),
+                                C.byref(traj) if trajectory else None, _ptr(yh)))
+        out = HMCStepResult(res.status, res.log_density, res.neg_h_init, res.neg_h_final, res.steps_done,
+                            res.u_turn_step, yh)
+        if trajectory:
+            out.trajectory = dict(params=tp.reshape(L, P), ldg=tl.reshape(L, P), hamiltonian=th)
+        return out
+
+    def gibbs_branch(self, b, cfg: MCMCCfg, std_gammas=None):
+        """sample_error_precision + sample_param_precisions (branch_sampler.rs:173-202)."""
+        inj, keep = self._inject(std_gammas=std_gammas)
+        c = cfg.c()
+        check(lib.bann_gibbs_branch(self.h, b, C.byref(c), C.byref(inj) if std_gammas is not None else None))
+
+    def visit_branch(self, b, cfg: MCMCCfg, momenta=None, u=None, step_uniforms=None, std_gammas=None) -> HMCStepResult:
+        """One iteration of the inner loop of Net::train (net/net.rs:258-334)."""
+        inj, keep = self._inject(momenta, u, step_uniforms, std_gammas)
+        res = _lib.HmcResult()
+        c = cfg.c()
+        any_inj = any(v is not None for v in (momenta, u, step_uniforms, std_gammas))
+        check(lib.bann_visit_branch(self.h, b, C.byref(c), C.byref(inj) if any_inj else None, C.byref(res)))
+        return HMCStepResult(res.status, res.log_density, res.neg_h_init, res.neg_h_final, res.steps_done,
+                             res.u_turn_step)
+
+    def sweep(self, cfg: MCMCCfg, order, seed: int = 0):
+        order = np.ascontiguousarray(order, dtype=np.uint64)
+        st = _lib.SweepStats()
+        c = cfg.c()
+        check(lib.bann_sweep(self.h, C.byref(c), order.ctypes.data_as(C.POINTER(C.c_uint64)), order.size, 1, seed,
+                             C.byref(st)))
+        return self._stats(st)
+
+    @staticmethod
+    def _stats(st):
+        return dict(num_samples=st.num_samples, num_accepted=st.num_accepted, num_early_rejected=st.num_early_rejected,
+                    mse_train=st.mse_train, lpd=st.lpd, output_bias=st.output_bias, error_precision=st.error_precision,
+                    output_layer_precision=st.output_layer_precision)
+
+    def stats(self):
+        st = _lib.SweepStats()
+        check(lib.bann_net_stats(self.h, C.byref(st)))
+        return self._stats(st)
+
+    def train(self, cfg: MCMCCfg, chain_length: int, seed: int = 0, orders=None):
+        """Net::train (net/net.rs:201-358), sequential-exact schedule, built-in RNG."""
+        self.init_residual()
+        hist = [self.stats()]
+        rng = np.random.default_rng(seed)
+        for it in range(chain_length):
+            order = orders[it] if orders is not None else rng.permutation(self.num_branches)
+            hist.append(self.sweep(cfg, order, seed=seed + 1 + it))
+        return hist
+
+    def predict(self, test: Optional[Genotypes] = None) -> np.ndarray:
+        """Net::predict (net/net.rs:545-559)."""
+        g = test or self.gen
+        out = np.empty(g.n, dtype=np.float32)
+        check(lib.bann_predict(self.h, test.h if test is not None else None, _ptr(out)))
+        return out
+
+    # ---- full network (grouped) operations
+    def gradient(self, param_vecs=None, y=None):
+        """Net::gradient (net/net.rs:520-527) through HOST buffers: returns (grads, rss per branch)."""
+        pv = _f32(param_vecs) if param_vecs is not None else None
+        yy = _f32(y) if y is not None else None
+        grads = np.empty(self.num_params(), dtype=np.float32)
+        rss = np.empty(self.num_branches, dtype=np.float32)
+        check(lib.bann_net_gradient(self.h, _ptr(pv), _ptr(yy), _ptr(grads), _ptr(rss)))
+        return grads, rss
+
+    def grouped_begin(self, cfg: MCMCCfg, seed: int = 0, per_branch_targets: bool = False):
+        c = cfg.c()
+        check(lib.bann_grouped_begin(self.h, C.byref(c), seed, int(per_branch_targets)))
+
+    def grouped_leapfrog(self, cfg: MCMCCfg, num_steps: int, finalize: bool = False):
+        c = cfg.c()
+        check(lib.bann_grouped_leapfrog(self.h, C.byref(c), num_steps, int(finalize)))
+
+    def grouped_phase_a(self):
+        check(lib.bann_grouped_phase_a(self.h))
+
+    def grouped_phase_b(self, cfg: MCMCCfg, is_init=False, is_last=False):
+        c = cfg.c()
+        check(lib.bann_grouped_phase_b(self.h, C.byref(c), int(is_init), int(is_last)))
+
+    def grouped_finish(self, seed: int = 0):
+        a, e = C.c_uint64(), C.c_uint64()
+        check(lib.bann_grouped_finish(self.h, seed, C.byref(a), C.byref(e)))
+        return a.value, e.value
+
+    def grouped_state(self):
+        B = self.num_branches
+        hi = np.empty(B, dtype=np.float32); hc = np.empty(B, dtype=np.float32); st = np.empty(B, dtype=np.int32)
+        check(lib.bann_grouped_state(self.h, _ptr(hi), _ptr(hc), st.ctypes.data_as(C.POINTER(C.c_int32))))
+        return hi, hc, st
+
+    def allreduce_buffer(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(lib.bann_allreduce_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def force_generic(self, on=True):
+        check(lib.bann_net_force_generic(self.h, int(on)))
+
+    def algorithmic_bytes(self) -> int:
+        v = C.c_uint64()
+        check(lib.bann_net_algorithmic_bytes(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            lib.bann_net_destroy(self.h)
+            self.h = None

@@ -1,0 +1,355 @@
+// Device-resident 2-bit genotype store.
+//
+// Replaces BedVM + MarkerGrouping + GroupedGenotypes::x_group_af of the reference
+// (io/bed.rs:123-133,193-245,325-355; group/grouping.rs:7-15; data/genotypes.rs:44-48).
+// The reference LUT-decodes a branch's columns to f32 on the host and uploads N x m_b floats at
+// every branch visit.  Here the packed payload is uploaded once and re-tiled into a
+// branch-major, row-tile-major layout so that the bytes one CTA needs for one (branch, 128-row
+// tile) are one contiguous block:
+//
+//   tile(b, t) = [32 row-quads][m_pad4 bytes];  byte(q, j) holds the four individuals
+//   t*128 + 4q .. +3 (LSB first, as in PLINK) of the branch's j-th marker.
+//
+// Codes are re-encoded from PLINK's {00->2, 01->missing(0), 10->1, 11->0}
+// (io/bed_lookup_tables.rs:4) to the genotype value itself {00->0, 01->1, 10->2}; rows beyond
+// n and marker padding hold 0.  Standardisation (bed.rs:354) is folded into the first layer by
+// the kernels; bann_genotypes_decode_branch reproduces (g - mean)/std bit-exactly for tests.
+#include "store.cuh"
+
+namespace bann {
+
+thread_local std::string g_last_error;
+unsigned long long g_launch_count = 0;
+void set_error(const std::string& s) { g_last_error = s; }
+
+// ------------------------------------------------------------------ kernels
+__device__ __forceinline__ uint8_t plink_to_value_codes(uint8_t b) {
+    // per 2-bit field (hi,lo): 00->10, 01->00, 10->01, 11->00
+    uint8_t H = (b >> 1) & 0x55, L = b & 0x55;
+    uint8_t ghi = (uint8_t)(~H & ~L) & 0x55;
+    uint8_t glo = (uint8_t)(H & ~L) & 0x55;
+    return (uint8_t)((ghi << 1) | glo);
+}
+
+// Sequential f32 column statistics, exactly as io/bed.rs:231-238: mean = sum(v)/n,
+// std = sqrt(sum((v-mean)^2)/n), both sums accumulated left to right in f32.
+__global__ void k_col_stats(const uint8_t* __restrict__ payload, uint64_t n, uint64_t m, uint64_t bpc,
+                            float* __restrict__ means, float* __restrict__ stds) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint8_t* col = payload + j * bpc;
+    const float lut[4] = {2.f, 0.f, 1.f, 0.f};
+    float s = 0.f;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint8_t b = col[i >> 2];
+        s = __fadd_rn(s, lut[(b >> (2 * (i & 3))) & 3]);
+    }
+    float mean = __fdiv_rn(s, (float)n);
+    float ss = 0.f;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint8_t b = col[i >> 2];
+        float d = __fsub_rn(lut[(b >> (2 * (i & 3))) & 3], mean);
+        ss = __fadd_rn(ss, __fmul_rn(d, d));
+    }
+    means[j] = mean;
+    stds[j] = __fsqrt_rn(__fdiv_rn(ss, (float)n));
+}
+
+__global__ void k_col_counts(const uint8_t* __restrict__ payload, uint64_t n, uint64_t m, uint64_t bpc,
+                             unsigned long long* __restrict__ out) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint8_t* col = payload + j * bpc;
+    unsigned long long c[3] = {0, 0, 0};
+    const int val[4] = {2, 0, 1, 0};
+    for (uint64_t i = 0; i < n; ++i) c[val[(col[i >> 2] >> (2 * (i & 3))) & 3]]++;
+    out[3 * j] = c[0]; out[3 * j + 1] = c[1]; out[3 * j + 2] = c[2];
+}
+
+// One block per (branch, tile): gather the branch's columns, re-encode, transpose to [q][j].
+__global__ void k_build_tiles(const uint8_t* __restrict__ payload, uint64_t n, uint64_t bpc,
+                              const uint64_t* __restrict__ tile_branch_start,  // prefix of tiles per branch
+                              const BranchDesc* __restrict__ descs, const uint64_t* __restrict__ col_ids,
+                              uint32_t num_branches, uint32_t ntiles, uint8_t* __restrict__ store) {
+    extern __shared__ uint8_t sm[];
+    uint64_t gt = blockIdx.x;  // global tile index = b * ntiles + t
+    uint32_t b = (uint32_t)(gt / ntiles), t = (uint32_t)(gt % ntiles);
+    const BranchDesc& d = descs[b];
+    const uint64_t* cols = col_ids + d.col_off;
+    uint32_t mp = d.m_pad4;
+    uint32_t total = mp * kTileQuads;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        uint32_t j = idx / kTileQuads, q = idx % kTileQuads;
+        uint8_t v = 0;
+        uint64_t src = (uint64_t)t * kTileQuads + q;  // byte within the column
+        if (j < d.m && src < bpc) {
+            v = plink_to_value_codes(payload[cols[j] * bpc + src]);
+            uint64_t row0 = src * 4;
+            if (row0 + 4 > n) {  // mask the individuals beyond n (PLINK pads with 00 == value 2)
+                uint32_t valid = (uint32_t)(n - row0);
+                v &= (uint8_t)((1u << (2 * valid)) - 1u);
+            }
+        }
+        sm[q * mp + j] = v;
+    }
+    __syncthreads();
+    uint8_t* dst = store + d.tile_off + (uint64_t)t * total;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) dst[idx] = sm[idx];
+}
+
+// test hook: decode branch b -> f32 [n x m_b] column-major
+__global__ void k_decode_branch(const uint8_t* __restrict__ store, BranchDesc d, uint64_t n,
+                                const float* __restrict__ mu, const float* __restrict__ sd, int standardized,
+                                float* __restrict__ out) {
+    uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * d.m) return;
+    uint64_t i = idx % n, j = idx / n;
+    uint64_t t = i / kTileRows;
+    uint32_t r = (uint32_t)(i % kTileRows);
+    uint8_t byte = store[d.tile_off + t * (uint64_t)(kTileQuads * d.m_pad4) + (r >> 2) * d.m_pad4 + j];
+    float g = (float)((byte >> (2 * (r & 3))) & 3);
+    if (standardized) g = __fdiv_rn(__fsub_rn(g, mu[d.col_off + j]), sd[d.col_off + j]);  // bed.rs:354
+    out[idx] = g;
+}
+
+__global__ void k_gather_stats(const float* __restrict__ means, const float* __restrict__ stds,
+                               const uint64_t* __restrict__ col_ids, uint64_t total, float* __restrict__ mu,
+                               float* __restrict__ sd) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    mu[i] = means[col_ids[i]];
+    sd[i] = stds[col_ids[i]];
+}
+
+}  // namespace bann
+
+using namespace bann;
+
+extern "C" {
+
+const char* bann_last_error(void) { return g_last_error.c_str(); }
+
+int bann_cuda_available(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n > 0 ? 1 : 0;
+}
+
+uint64_t bann_launch_count(int reset) {
+    uint64_t v = g_launch_count;
+    if (reset) g_launch_count = 0;
+    return v;
+}
+
+int bann_ctx_create(int device, void* stream, int rank, int world, bann_ctx** out) {
+    if (!out) BANN_FAIL("out is NULL");
+    if (!bann_cuda_available()) BANN_FAIL("no CUDA device: libbann_b200 has no CPU fallback");
+    if (world < 1 || rank < 0 || rank >= world) BANN_FAIL("bad rank/world");
+    BANN_CUDA(cudaSetDevice(device));
+    bann_ctx* c = new bann_ctx();
+    c->device = device;
+    c->rank = rank;
+    c->world = world;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->owns_stream = false;
+    } else {
+        BANN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->owns_stream = true;
+    }
+    cudaDeviceProp prop;
+    BANN_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    *out = c;
+    return 0;
+}
+
+void bann_ctx_destroy(bann_ctx* c) {
+    if (!c) return;
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int bann_ctx_sync(bann_ctx* c) {
+    if (!c) BANN_FAIL("ctx is NULL");
+    BANN_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bann_genotypes_create(bann_ctx* ctx, const uint8_t* bed_payload, uint64_t n, uint64_t n_total, uint64_t m,
+                          const float* col_means, const float* col_stds, uint64_t num_branches,
+                          const uint64_t* branch_offsets, const uint64_t* col_ids, bann_genotypes** out) {
+    if (!ctx || !bed_payload || !branch_offsets || !col_ids || !out) BANN_FAIL("NULL argument");
+    if (n == 0 || m == 0 || num_branches == 0) BANN_FAIL("empty genotype store");
+    if ((col_means == nullptr) != (col_stds == nullptr)) BANN_FAIL("col_means and col_stds must both be given or both NULL");
+    if (!col_means && ctx->world > 1)
+        BANN_FAIL("column statistics must be global: pass col_means/col_stds when rows are sharded");
+    BANN_CUDA(cudaSetDevice(ctx->device));
+    uint64_t total_cols = branch_offsets[num_branches];
+    for (uint64_t b = 0; b < num_branches; ++b) {
+        if (branch_offsets[b + 1] <= branch_offsets[b]) BANN_FAIL("branch with no markers / offsets not increasing");
+    }
+    for (uint64_t k = 0; k < total_cols; ++k)
+        if (col_ids[k] >= m) BANN_FAIL("column id out of range");
+
+    bann_genotypes* g = new bann_genotypes();
+    g->ctx = ctx;
+    g->n = n;
+    g->n_total = n_total ? n_total : n;
+    g->m = m;
+    g->num_branches = num_branches;
+    g->ntiles = (uint32_t)((n + kTileRows - 1) / kTileRows);
+    g->total_cols = total_cols;
+    uint64_t bpc = (n + 3) / 4;
+    cudaStream_t st = ctx->stream;
+
+    // branch geometry
+    g->m_b.resize(num_branches);
+    g->m_pad4.resize(num_branches);
+    g->tile_off.resize(num_branches);
+    g->col_off.resize(num_branches);
+    uint64_t off = 0;
+    uint32_t max_mp = 0;
+    for (uint64_t b = 0; b < num_branches; ++b) {
+        uint32_t mb = (uint32_t)(branch_offsets[b + 1] - branch_offsets[b]);
+        uint32_t mp = (mb + 3) & ~3u;
+        g->m_b[b] = mb;
+        g->m_pad4[b] = mp;
+        g->tile_off[b] = off;
+        g->col_off[b] = branch_offsets[b];
+        off += (uint64_t)g->ntiles * kTileQuads * mp;
+        off = (off + 15) & ~15ull;  // keep every branch 16-byte aligned
+        if (mp > max_mp) max_mp = mp;
+    }
+    g->store_bytes = off;
+    g->packed_bytes = 0;
+    for (uint64_t b = 0; b < num_branches; ++b) g->packed_bytes += (uint64_t)g->m_b[b] * bpc;
+
+    uint8_t* d_payload = nullptr;
+    uint64_t* d_cols = nullptr;
+    BranchDesc* d_descs = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_payload);
+        cudaFree(d_descs);
+    };
+    BANN_CUDA(cudaMalloc(&d_payload, m * bpc));
+    BANN_CUDA(cudaMemcpyAsync(d_payload, bed_payload, m * bpc, cudaMemcpyHostToDevice, st));
+    BANN_CUDA(cudaMalloc(&d_cols, total_cols * sizeof(uint64_t)));
+    BANN_CUDA(cudaMemcpyAsync(d_cols, col_ids, total_cols * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    g->d_col_ids = d_cols;
+    BANN_CUDA(cudaMalloc(&g->d_means, m * sizeof(float)));
+    BANN_CUDA(cudaMalloc(&g->d_stds, m * sizeof(float)));
+    BANN_CUDA(cudaMalloc(&g->d_mu, total_cols * sizeof(float)));
+    BANN_CUDA(cudaMalloc(&g->d_sd, total_cols * sizeof(float)));
+    BANN_CUDA(cudaMalloc(&g->d_store, g->store_bytes));
+    BANN_CUDA(cudaMemsetAsync(g->d_store, 0, g->store_bytes, st));
+
+    if (col_means) {
+        BANN_CUDA(cudaMemcpyAsync(g->d_means, col_means, m * sizeof(float), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaMemcpyAsync(g->d_stds, col_stds, m * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        k_col_stats<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_payload, n, m, bpc, g->d_means, g->d_stds);
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaGetLastError());
+    }
+    BANN_CUDA(cudaMalloc(&g->d_counts, 3 * m * sizeof(unsigned long long)));
+    k_col_counts<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_payload, n, m, bpc, g->d_counts);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+
+    // minimal descs for the tile builder
+    std::vector<BranchDesc> descs(num_branches);
+    for (uint64_t b = 0; b < num_branches; ++b) {
+        memset(&descs[b], 0, sizeof(BranchDesc));
+        descs[b].m = g->m_b[b];
+        descs[b].m_pad4 = g->m_pad4[b];
+        descs[b].tile_off = g->tile_off[b];
+        descs[b].col_off = g->col_off[b];
+    }
+    BANN_CUDA(cudaMalloc(&d_descs, num_branches * sizeof(BranchDesc)));
+    BANN_CUDA(cudaMemcpyAsync(d_descs, descs.data(), num_branches * sizeof(BranchDesc), cudaMemcpyHostToDevice, st));
+    size_t smem = (size_t)max_mp * kTileQuads;
+    if (smem > 200 * 1024) { cleanup(); BANN_FAIL("branch with more than 6400 markers is not supported by the tile builder"); }
+    if (smem > 48 * 1024) BANN_CUDA(cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t nblocks = num_branches * (uint64_t)g->ntiles;
+    if (nblocks > 0x7fffffffull) { cleanup(); BANN_FAIL("too many tiles for one launch"); }
+    k_build_tiles<<<(unsigned)nblocks, 256, smem, st>>>(d_payload, n, bpc, nullptr, d_descs, d_cols,
+                                                      (uint32_t)num_branches, g->ntiles, g->d_store);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    k_gather_stats<<<(unsigned)((total_cols + 255) / 256), 256, 0, st>>>(g->d_means, g->d_stds, d_cols, total_cols,
+                                                                         g->d_mu, g->d_sd);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    BANN_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+    *out = g;
+    return 0;
+}
+
+void bann_genotypes_destroy(bann_genotypes* g) {
+    if (!g) return;
+    cudaFree(g->d_store);
+    cudaFree(g->d_means);
+    cudaFree(g->d_stds);
+    cudaFree(g->d_mu);
+    cudaFree(g->d_sd);
+    cudaFree(g->d_col_ids);
+    cudaFree(g->d_counts);
+    delete g;
+}
+
+int bann_genotypes_col_stats(bann_genotypes* g, float* col_means, float* col_stds) {
+    if (!g || !col_means || !col_stds) BANN_FAIL("NULL argument");
+    BANN_CUDA(cudaMemcpyAsync(col_means, g->d_means, g->m * sizeof(float), cudaMemcpyDeviceToHost, g->ctx->stream));
+    BANN_CUDA(cudaMemcpyAsync(col_stds, g->d_stds, g->m * sizeof(float), cudaMemcpyDeviceToHost, g->ctx->stream));
+    BANN_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    return 0;
+}
+
+int bann_genotypes_col_counts(bann_genotypes* g, uint64_t* out) {
+    if (!g || !out) BANN_FAIL("NULL argument");
+    BANN_CUDA(cudaMemcpyAsync(out, g->d_counts, 3 * g->m * sizeof(uint64_t), cudaMemcpyDeviceToHost, g->ctx->stream));
+    BANN_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    return 0;
+}
+
+int bann_genotypes_set_col_stats(bann_genotypes* g, const float* col_means, const float* col_stds) {
+    if (!g || !col_means || !col_stds) BANN_FAIL("NULL argument");
+    cudaStream_t st = g->ctx->stream;
+    BANN_CUDA(cudaMemcpyAsync(g->d_means, col_means, g->m * sizeof(float), cudaMemcpyHostToDevice, st));
+    BANN_CUDA(cudaMemcpyAsync(g->d_stds, col_stds, g->m * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_gather_stats<<<(unsigned)((g->total_cols + 255) / 256), 256, 0, st>>>(g->d_means, g->d_stds, g->d_col_ids,
+                                                                            g->total_cols, g->d_mu, g->d_sd);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_genotypes_decode_branch(bann_genotypes* g, uint64_t b, int standardized, float* out) {
+    if (!g || !out) BANN_FAIL("NULL argument");
+    if (b >= g->num_branches) BANN_FAIL("branch index out of range");
+    BranchDesc d;
+    memset(&d, 0, sizeof(d));
+    d.m = g->m_b[b];
+    d.m_pad4 = g->m_pad4[b];
+    d.tile_off = g->tile_off[b];
+    d.col_off = g->col_off[b];
+    uint64_t total = g->n * d.m;
+    float* dout = nullptr;
+    BANN_CUDA(cudaMalloc(&dout, total * sizeof(float)));
+    k_decode_branch<<<(unsigned)((total + 255) / 256), 256, 0, g->ctx->stream>>>(g->d_store, d, g->n, g->d_mu, g->d_sd,
+                                                                                 standardized, dout);
+    BANN_LAUNCHED();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, total * sizeof(float), cudaMemcpyDeviceToHost, g->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(dout);
+    BANN_CUDA(e);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1191 @@
+// Host orchestration behind the C ABI: device-resident Net state, branch visits, grouped
+// full-network leapfrog.  Mirrors Net<B>::train / predict / gradient (net/net.rs) and
+// BranchSampler::hmc_step (net/branch/branch_sampler.rs:1192-1299); see include/bann.h.
+#include <algorithm>
+#include <cmath>
+
+#include "chain.cuh"
+#include "k1_small.cuh"
+#include "store.cuh"
+
+using namespace bann;
+
+struct bann_net {
+    bann_ctx* ctx = nullptr;
+    bann_genotypes* gen = nullptr;
+    int model = 0, act = 0;
+    Hyper6 hyper;
+    uint64_t B = 0;
+    uint32_t n = 0;
+    float n_total = 0.f;
+    std::vector<BranchDesc> descs;
+    BranchDesc* d_descs = nullptr;
+    uint64_t total_params = 0, total_prec = 0;
+    uint32_t maxP = 0, pstride = 0;
+    size_t max_generic_smem = 0;
+    float *d_theta = nullptr, *d_theta0 = nullptr, *d_mom = nullptr, *d_grad = nullptr, *d_eps = nullptr;
+    float* d_prec = nullptr;
+    BranchState* d_states = nullptr;
+    NetGlobals* d_G = nullptr;
+    float *d_y = nullptr, *d_r = nullptr, *d_t = nullptr, *d_prev = nullptr, *d_ynew = nullptr;
+    float* d_part = nullptr;
+    size_t part_cap = 0;
+    float* d_gsum = nullptr;
+    size_t gsum_cap = 0;
+    float* d_rpart = nullptr;
+    uint32_t rblk = 0;
+    float* d_ow_others = nullptr;
+    float* d_bias2 = nullptr;
+    float* d_lpd_local = nullptr;
+    int* d_errflag = nullptr;
+    uint32_t* d_list_all = nullptr;
+    float* d_inj = nullptr;   // scratch for injected randomness: momenta[maxP] uniforms[maxP] u[1] gammas[...]
+    size_t inj_gamma_cap = 0;
+    float* d_T = nullptr;     // grouped per-branch targets [B][n]
+    int grouped_per_branch = 0;
+    uint64_t grouped_seed = 0;
+    float* d_traj = nullptr;
+    size_t traj_cap = 0;
+    float* d_scratchB = nullptr;  // [3*B] gather buffer
+    uint64_t visit_seq = 0;
+    int force_generic = 0;
+    float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient
+};
+
+static int ensure_cap(float** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    BANN_CUDA(cudaMalloc(p, need * sizeof(float)));
+    *cap = need;
+    return 0;
+}
+
+// ------------------------------------------------------------------ K1 launch
+struct K1Launch {
+    const uint32_t* list = nullptr;  // device
+    uint32_t nlist = 0;
+    const BranchState* states = nullptr;
+    int target_mode = TGT_SHARED;
+    const float* tgt = nullptr;
+    const float* resid = nullptr;
+    float* tgt_out = nullptr;
+    float* prev_out = nullptr;
+    int out_per_entry = 0;
+    float* yhat_out = nullptr;
+    int yhat_accumulate = 0;
+    int fwd_only = 0;
+    // alternative store (predict on test data)
+    const bann_genotypes* store = nullptr;
+    const BranchDesc* descs_dev = nullptr;
+    int single_branch = -1;  // host index of the only branch in the list (for kernel selection), -1: all
+};
+
+static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
+    const bann_genotypes* g = L.store ? L.store : net->gen;
+    cudaStream_t st = net->ctx->stream;
+    uint32_t ntiles = g->ntiles;
+    // chunking: enough CTAs to fill the machine, never more chunks than tiles
+    uint32_t want = (uint32_t)std::max<uint64_t>(1, ((uint64_t)net->ctx->num_sms * 4 + L.nlist - 1) / L.nlist);
+    uint32_t nchunk = std::min(want, ntiles);
+    uint32_t tpc = (ntiles + nchunk - 1) / nchunk;
+    nchunk = (ntiles + tpc - 1) / tpc;
+    if (L.fwd_only) {  // no partials: one CTA per few tiles
+        tpc = std::max<uint32_t>(1, tpc);
+    }
+    float* part = nullptr;
+    if (!L.fwd_only) {
+        BANN_CHECK(ensure_cap(&net->d_gsum, &net->gsum_cap, (size_t)L.nlist * net->pstride));
+        if (nchunk == 1) part = net->d_gsum;
+        else {
+            BANN_CHECK(ensure_cap(&net->d_part, &net->part_cap, (size_t)L.nlist * nchunk * net->pstride));
+            part = net->d_part;
+        }
+    }
+    K1Args a;
+    a.store = g->d_store;
+    a.descs = L.descs_dev ? L.descs_dev : net->d_descs;
+    a.theta = net->d_theta;
+    a.mu = g->d_mu;
+    a.sd = g->d_sd;
+    a.list = L.list;
+    a.states = L.states;
+    a.n = (uint32_t)g->n;
+    a.ntiles = ntiles;
+    a.tiles_per_chunk = tpc;
+    a.nchunk = nchunk;
+    a.target_mode = L.target_mode;
+    a.tgt = L.tgt;
+    a.resid = L.resid;
+    a.tgt_out = L.tgt_out;
+    a.prev_out = L.prev_out;
+    a.out_per_entry = L.out_per_entry;
+    a.yhat_out = L.yhat_out;
+    a.yhat_accumulate = L.yhat_accumulate;
+    a.fwd_only = L.fwd_only;
+    a.part = part;
+    a.pstride = net->pstride;
+    a.act = net->act;
+
+    bool launched = false;
+    if (!net->force_generic) {
+        int r = launch_k1_small(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
+                                &nchunk, L.fwd_only ? nullptr : &part, net);
+        if (r != 0) return r;
+    }
+    if (!launched) {
+        dim3 grid(nchunk, L.nlist);
+        k1_generic<<<grid, 128, net->max_generic_smem, st>>>(a);
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaGetLastError());
+    }
+    if (reduce && !L.fwd_only && part != net->d_gsum) {
+        dim3 grid((net->pstride + 255) / 256, L.nlist);
+        k_reduce_partials<<<grid, 256, 0, st>>>(part, net->d_gsum, nchunk, net->pstride, L.list, a.descs, L.states);
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// hooks used by k1_small.cuh to size its partial buffers
+float* bann_net_partials(bann_net* net, size_t need) {
+    if (ensure_cap(&net->d_part, &net->part_cap, need) != 0) return nullptr;
+    return net->d_part;
+}
+float* bann_net_gsum(bann_net* net) { return net->d_gsum; }
+uint32_t bann_net_pstride(bann_net* net) { return net->pstride; }
+
+// gradient under the prior without touching the HMC state (log_density_gradient, a8)
+__global__ void __launch_bounds__(256) k_grad_only(const BranchDesc* descs, const uint32_t* list, const float* theta,
+                                                   const float* prec, const float* gsum, uint32_t pstride, int model,
+                                                   float* grad) {
+    const uint32_t li = blockIdx.x;
+    const uint32_t b = list ? list[li] : li;
+    const BranchDesc& d = descs[b];
+    const float* th = theta + d.param_off;
+    const float* pr = prec + d.prec_off;
+    const float* gs = gsum + (size_t)li * pstride;
+    const float lam_e = pr[d.ep_off];
+    const bool lasso = (model == BANN_LASSO_BASE || model == BANN_LASSO_ARD);
+    for (uint32_t k = threadIdx.x; k < d.P; k += 256) {
+        int l; uint32_t row, col; bool isb;
+        locate_param(d, k, l, row, col, isb);
+        const float w = th[k];
+        float g;
+        if (isb) g = -(lam_e * gs[k]);
+        else {
+            const float lam = param_prior_precision(d, pr, model, l, row, false);
+            if (model == BANN_STD_NORMAL) g = -(lam_e * gs[k] + w);
+            else if (lasso) g = -(lam_e * gs[k] + lam * ((w > 0.f) ? 1.f : (w < 0.f ? -1.f : 0.f)));
+            else g = -(lam_e * gs[k] + lam * w);
+        }
+        grad[d.param_off + k] = g;
+    }
+}
+
+// log_density(params, precisions, rss) (branch_sampler.rs:72-78)
+__global__ void __launch_bounds__(256) k_log_density(const BranchDesc* descs, uint32_t b, const float* theta,
+                                                     const float* prec, int model, float rss, float* out) {
+    __shared__ float red[8];
+    const BranchDesc& d = descs[b];
+    const float* th = theta + d.param_off;
+    const float* pr = prec + d.prec_off;
+    const bool lasso = (model == BANN_LASSO_BASE || model == BANN_LASSO_ARD);
+    float prior = 0.f;
+    for (uint32_t k = threadIdx.x; k < d.P; k += 256) {
+        int l; uint32_t row, col; bool isb;
+        locate_param(d, k, l, row, col, isb);
+        const float w = th[k];
+        if (isb) {
+            if (model == BANN_STD_NORMAL) prior -= 0.5f * w * w;
+        } else {
+            const float lam = param_prior_precision(d, pr, model, l, row, false);
+            if (model == BANN_STD_NORMAL) prior -= 0.5f * w * w;
+            else if (lasso) prior -= lam * fabsf(w);
+            else prior -= 0.5f * lam * w * w;
+        }
+    }
+    prior = block_sum<256>(prior, red);
+    if (threadIdx.x == 0) *out = prior + (-1.0f * pr[d.ep_off] * (rss / 2.0f));
+}
+
+__global__ void k_gather_states(const BranchState* st, uint32_t B, float* h_init, float* h_cur, int* status) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    h_init[b] = st[b].neg_h_init;
+    h_cur[b] = st[b].neg_h_cur;
+    status[b] = st[b].status;
+}
+
+__global__ void k_count_status(const BranchState* st, uint32_t B, unsigned long long* out /*[2]*/) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (st[b].status == ST_ACCEPTED) atomicAdd(&out[0], 1ull);
+    if (st[b].status == ST_REJECTED_EARLY) atomicAdd(&out[1], 1ull);
+}
+
+__global__ void k_gather_rss(const float* gsum, uint32_t pstride, const BranchDesc* descs, uint32_t B, float* out) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) out[b] = gsum[(size_t)b * pstride + descs[b].P];
+}
+
+// ------------------------------------------------------------------ HMC driver
+struct HmcRun {
+    const uint32_t* list;   // device
+    uint32_t nlist;
+    int single_branch;
+    int first_mode;         // target mode of the first evaluation
+    const float* tgt;       // shared target (d_t / d_y) or per-entry base
+    int later_mode;
+    const float* inj_mom = nullptr;
+    const float* inj_su = nullptr;
+    const float* inj_u = nullptr;
+    uint64_t seed = 0;
+    uint64_t stream_base = 0;
+    float* traj_params = nullptr;
+    float* traj_ldg = nullptr;
+    float* traj_h = nullptr;
+};
+
+static int hmc_init_and_first_eval(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, int keep_momenta) {
+    cudaStream_t st = net->ctx->stream;
+    const bool ard = (net->model == BANN_RIDGE_ARD || net->model == BANN_LASSO_ARD);
+    if (cfg->hmc_step_size_mode == BANN_STEP_STD_SCALED && ard)
+        BANN_FAIL("StdScaled step sizes are not implemented for ARD priors (reference returns empty vectors, ridge_ard.rs:56-68)");
+    if (cfg->hmc_step_size_mode < 0 || cfg->hmc_step_size_mode > 3) BANN_FAIL("bad step size mode");
+    InitArgs ia;
+    ia.descs = net->d_descs;
+    ia.list = R.list;
+    ia.states = net->d_states;
+    ia.theta = net->d_theta;
+    ia.theta0 = net->d_theta0;
+    ia.mom = net->d_mom;
+    ia.eps = net->d_eps;
+    ia.prec = net->d_prec;
+    ia.model = net->model;
+    ia.step_mode = cfg->hmc_step_size_mode;
+    ia.factor = cfg->hmc_step_size_factor;
+    ia.L = (float)cfg->hmc_integration_length;
+    ia.inj_momenta = R.inj_mom;
+    ia.inj_step_uniforms = R.inj_su;
+    ia.seed = R.seed;
+    ia.stream_base = R.stream_base;
+    ia.keep_momenta = keep_momenta;
+    k_hmc_init<<<R.nlist, 256, 0, st>>>(ia);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static K2Args make_k2(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, int mode_init, int is_last) {
+    K2Args a;
+    a.descs = net->d_descs;
+    a.list = R.list;
+    a.states = net->d_states;
+    a.theta = net->d_theta;
+    a.theta0 = net->d_theta0;
+    a.mom = net->d_mom;
+    a.grad = net->d_grad;
+    a.eps = net->d_eps;
+    a.prec = net->d_prec;
+    a.gsum = net->d_gsum;
+    a.pstride = net->pstride;
+    a.model = net->model;
+    a.max_h_err = cfg->hmc_max_hamiltonian_error;
+    a.mode_init = mode_init;
+    a.is_last = is_last;
+    a.traj_params = R.traj_params;
+    a.traj_ldg = R.traj_ldg;
+    a.traj_h = R.traj_h;
+    return a;
+}
+
+// full HMC transition for the listed branches (sequential-exact when nlist == 1)
+static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, float* ynew_out, float* tgt_out,
+                   float* prev_out, const float* resid) {
+    cudaStream_t st = net->ctx->stream;
+    BANN_CHECK(hmc_init_and_first_eval(net, cfg, R, 0));
+    const uint32_t Lsteps = cfg->hmc_integration_length;
+    K1Launch k;
+    k.list = R.list;
+    k.nlist = R.nlist;
+    k.single_branch = R.single_branch;
+    k.states = net->d_states;
+    k.target_mode = R.first_mode;
+    k.tgt = R.tgt;
+    k.resid = resid;
+    k.tgt_out = tgt_out;
+    k.prev_out = prev_out;
+    if (Lsteps == 0) k.yhat_out = ynew_out;
+    BANN_CHECK(launch_k1(net, k, true));
+    K2Args a = make_k2(net, cfg, R, 1, Lsteps == 0);
+    k2_step<<<R.nlist, 256, 0, st>>>(a);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    k.target_mode = R.later_mode;
+    k.tgt = (R.first_mode == TGT_RESID_PLUS_PRED) ? tgt_out : R.tgt;
+    k.resid = nullptr;
+    k.tgt_out = nullptr;
+    k.prev_out = nullptr;
+    for (uint32_t s = 1; s <= Lsteps; ++s) {
+        k.yhat_out = (s == Lsteps) ? ynew_out : nullptr;
+        BANN_CHECK(launch_k1(net, k, true));
+        a.mode_init = 0;
+        a.is_last = (s == Lsteps);
+        k2_step<<<R.nlist, 256, 0, st>>>(a);
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaGetLastError());
+    }
+    k_accept<<<R.nlist, 256, 0, st>>>(net->d_descs, R.list, net->d_states, net->d_theta, net->d_theta0, R.inj_u, R.seed,
+                                      R.stream_base);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int stage_inject(bann_net* net, const bann_rng_inject* inj, uint32_t P, HmcRun* R, const float** d_gam,
+                        uint32_t* n_gam) {
+    cudaStream_t st = net->ctx->stream;
+    if (d_gam) { *d_gam = nullptr; *n_gam = 0; }
+    if (!inj) return 0;
+    float* base = net->d_inj;
+    if (inj->momenta && R) {
+        BANN_CUDA(cudaMemcpyAsync(base, inj->momenta, P * sizeof(float), cudaMemcpyHostToDevice, st));
+        R->inj_mom = base;
+    }
+    if (inj->step_uniforms && R) {
+        BANN_CUDA(cudaMemcpyAsync(base + net->maxP, inj->step_uniforms, P * sizeof(float), cudaMemcpyHostToDevice, st));
+        R->inj_su = base + net->maxP;
+    }
+    if (inj->accept_uniform && R) {
+        BANN_CUDA(cudaMemcpyAsync(base + 2 * (size_t)net->maxP, inj->accept_uniform, sizeof(float), cudaMemcpyHostToDevice, st));
+        R->inj_u = base + 2 * (size_t)net->maxP;
+    }
+    if (inj->std_gammas && d_gam) {
+        if (inj->num_std_gammas > net->inj_gamma_cap) BANN_FAIL("too many injected gamma variates");
+        float* gp = base + 2 * (size_t)net->maxP + 4;
+        BANN_CUDA(cudaMemcpyAsync(gp, inj->std_gammas, inj->num_std_gammas * sizeof(float), cudaMemcpyHostToDevice, st));
+        *d_gam = gp;
+        *n_gam = inj->num_std_gammas;
+    }
+    return 0;
+}
+
+static int launch_gibbs(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, int do_draws, const float* d_gam,
+                        uint32_t n_gam, uint64_t seed, uint64_t stream) {
+    GibbsArgs g;
+    g.descs = net->d_descs;
+    g.b = b;
+    g.theta = net->d_theta;
+    g.prec = net->d_prec;
+    g.G = net->d_G;
+    g.ow_others = net->d_ow_others;
+    g.hyper = net->hyper;
+    g.model = net->model;
+    g.n_total = net->n_total;
+    g.fixed_param_precisions = cfg ? cfg->fixed_param_precisions : 0;
+    g.do_draws = do_draws;
+    g.inj = d_gam;
+    g.n_inj = n_gam;
+    g.seed = seed;
+    g.stream = stream;
+    k_gibbs<<<1, 256, 0, net->ctx->stream>>>(g);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int check_error_flag(bann_net* net) {
+    int flag = 0;
+    BANN_CUDA(cudaMemcpyAsync(&flag, net->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, net->ctx->stream));
+    BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    if (flag) BANN_FAIL("Invalid output weight summary statistic (negative or NaN), params.rs:49-54");
+    return 0;
+}
+
+// one iteration of the inner loop of Net::train, fully asynchronous
+static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj, uint64_t seed) {
+    cudaStream_t st = net->ctx->stream;
+    if (net->ctx->world > 1) BANN_FAIL("sequential-exact visits are single-GPU in this release (use the grouped phases)");
+    HmcRun R;
+    R.list = net->d_list_all + b;
+    R.nlist = 1;
+    R.single_branch = (int)b;
+    R.first_mode = TGT_RESID_PLUS_PRED;
+    R.later_mode = TGT_SHARED;
+    R.tgt = nullptr;
+    R.seed = seed;
+    R.stream_base = net->visit_seq * net->B;
+    const float* d_gam = nullptr;
+    uint32_t n_gam = 0;
+    BANN_CHECK(stage_inject(net, inj, net->descs[b].P, &R, &d_gam, &n_gam));
+    BANN_CHECK(launch_gibbs(net, b, cfg, 1, d_gam, n_gam, seed, net->visit_seq * net->B + b));   // net.rs:261-277
+    BANN_CHECK(run_hmc(net, cfg, R, net->d_ynew, net->d_t, net->d_prev, net->d_r));               // net.rs:279-290
+    k_resid_after_hmc<<<net->rblk, 256, 0, st>>>(net->d_r, net->d_t, net->d_ynew, net->d_prev, net->n,
+                                                 net->d_states + b, net->d_G, net->d_rpart);      // net.rs:292-300
+    BANN_LAUNCHED();
+    FinishArgs f;
+    f.descs = net->d_descs;
+    f.b = b;
+    f.theta = net->d_theta;
+    f.prec = net->d_prec;
+    f.G = net->d_G;
+    f.st = net->d_states + b;
+    f.ow_others = net->d_ow_others;
+    f.lpd_local = net->d_lpd_local;
+    f.hyper = net->hyper;
+    f.model = net->model;
+    f.n_total = net->n_total;
+    f.part = net->d_rpart;
+    f.nblk = net->rblk;
+    f.bias_old_new = net->d_bias2;
+    f.update_bias = 1;
+    f.error_flag = net->d_errflag;
+    k_visit_finish<<<1, 256, 0, st>>>(f);                                                          // net.rs:296,303-305,320-330
+    BANN_LAUNCHED();
+    k_resid_apply_bias<<<net->rblk, 256, 0, st>>>(net->d_r, net->n, net->d_bias2, net->d_rpart);   // net.rs:321,332
+    BANN_LAUNCHED();
+    k_resid_reduce<<<1, 32, 0, st>>>(net->d_rpart, net->rblk, net->d_G);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    net->visit_seq += 1;
+    return 0;
+}
+
+static int read_hmc_result(bann_net* net, uint32_t b, bann_hmc_result* out) {
+    BranchState s;
+    BANN_CUDA(cudaMemcpyAsync(&s, net->d_states + b, sizeof(s), cudaMemcpyDeviceToHost, net->ctx->stream));
+    BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    out->status = s.status;
+    out->log_density = s.log_density;
+    out->neg_h_init = s.neg_h_init;
+    out->neg_h_final = s.neg_h_cur;
+    out->steps_done = (uint32_t)s.steps_done;
+    out->u_turn_step = s.u_turn_step;
+    return 0;
+}
+
+static int refresh_resid_stats(bann_net* net) {
+    cudaStream_t st = net->ctx->stream;
+    k_resid_stats<<<net->rblk, 256, 0, st>>>(net->d_r, net->n, net->d_rpart);
+    BANN_LAUNCHED();
+    k_resid_reduce<<<1, 32, 0, st>>>(net->d_rpart, net->rblk, net->d_G);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int activation,
+                    const bann_branch_layout* layouts, const float hyper[6], bann_net** out) {
+    if (!ctx || !gen || !layouts || !hyper || !out) BANN_FAIL("NULL argument");
+    if (model_type < 0 || model_type > 4) BANN_FAIL("unknown model type");
+    if (activation < 0 || activation > 4) BANN_FAIL("unknown activation function");
+    BANN_CUDA(cudaSetDevice(ctx->device));
+    bann_net* net = new bann_net();
+    net->ctx = ctx;
+    net->gen = gen;
+    net->model = model_type;
+    net->act = activation;
+    for (int i = 0; i < 6; ++i) net->hyper.v[i] = hyper[i];
+    net->B = gen->num_branches;
+    net->n = (uint32_t)gen->n;
+    net->n_total = (float)gen->n_total;
+    const bool ard = (model_type == BANN_RIDGE_ARD || model_type == BANN_LASSO_ARD);
+    net->descs.resize(net->B);
+    uint64_t poff = 0, qoff = 0;
+    uint32_t max_gam = 4;
+    for (uint64_t b = 0; b < net->B; ++b) {
+        const bann_branch_layout& L = layouts[b];
+        if (L.num_layers < 2 || L.num_layers > BANN_MAX_LAYERS) { delete net; BANN_FAIL("num_layers must be in [2, 8]"); }
+        if (L.widths[L.num_layers - 1] != 1) { delete net; BANN_FAIL("output layer width must be 1"); }
+        BranchDesc& d = net->descs[b];
+        memset(&d, 0, sizeof(d));
+        d.m = gen->m_b[b];
+        d.m_pad4 = gen->m_pad4[b];
+        d.nl = L.num_layers;
+        d.tile_off = gen->tile_off[b];
+        d.col_off = gen->col_off[b];
+        uint32_t prev = d.m, off = 0, aoff = 0, gam = 1;
+        for (uint32_t l = 0; l < d.nl; ++l) {
+            if (L.widths[l] == 0) { delete net; BANN_FAIL("layer width 0"); }
+            d.widths[l] = L.widths[l];
+            d.in_dim[l] = prev;
+            d.w_off[l] = off;
+            off += prev * L.widths[l];
+            if (l + 1 < d.nl) { d.a_off[l] = aoff; aoff += L.widths[l]; }
+            prev = L.widths[l];
+        }
+        d.sumw = aoff;
+        for (uint32_t l = 0; l + 1 < d.nl; ++l) { d.b_off[l] = off; off += d.widths[l]; }
+        d.P = off;
+        uint32_t q = 0;
+        for (uint32_t l = 0; l < d.nl; ++l) {
+            d.wp_off[l] = q;
+            d.wp_len[l] = (ard && l + 1 < d.nl) ? d.in_dim[l] : 1;
+            q += d.wp_len[l];
+            if (l + 1 < d.nl) gam += d.wp_len[l] + 1;
+        }
+        for (uint32_t l = 0; l + 1 < d.nl; ++l) d.bp_off[l] = q++;
+        d.ep_off = q++;
+        d.nprec = q;
+        d.param_off = poff;
+        d.prec_off = qoff;
+        poff += (d.P + 3) & ~3u;
+        qoff += d.nprec;
+        net->maxP = std::max(net->maxP, d.P);
+        max_gam = std::max(max_gam, gam + 1);
+        size_t sm = k1_generic_smem(d);
+        net->max_generic_smem = std::max(net->max_generic_smem, sm);
+    }
+    if (net->max_generic_smem > 227 * 1024) { delete net; BANN_FAIL("branch too large for the generic kernel's shared memory"); }
+    net->total_params = poff;
+    net->total_prec = qoff;
+    net->pstride = (net->maxP + 1 + 3) & ~3u;
+    BANN_CHECK(ensure_cap(&net->d_gsum, &net->gsum_cap, (size_t)net->B * net->pstride));   // all-reduce buffer, fixed address
+    cudaStream_t st = ctx->stream;
+    size_t pb = poff * sizeof(float);
+    BANN_CUDA(cudaMalloc(&net->d_descs, net->B * sizeof(BranchDesc)));
+    BANN_CUDA(cudaMemcpyAsync(net->d_descs, net->descs.data(), net->B * sizeof(BranchDesc), cudaMemcpyHostToDevice, st));
+    BANN_CUDA(cudaMalloc(&net->d_theta, pb));
+    BANN_CUDA(cudaMalloc(&net->d_theta0, pb));
+    BANN_CUDA(cudaMalloc(&net->d_mom, pb));
+    BANN_CUDA(cudaMalloc(&net->d_grad, pb));
+    BANN_CUDA(cudaMalloc(&net->d_eps, pb));
+    BANN_CUDA(cudaMemsetAsync(net->d_theta, 0, pb, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_theta0, 0, pb, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_mom, 0, pb, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_grad, 0, pb, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_eps, 0, pb, st));
+    BANN_CUDA(cudaMalloc(&net->d_prec, qoff * sizeof(float)));
+    {
+        std::vector<float> ones(qoff, 1.0f);
+        BANN_CUDA(cudaMemcpyAsync(net->d_prec, ones.data(), qoff * sizeof(float), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaStreamSynchronize(st));
+    }
+    BANN_CUDA(cudaMalloc(&net->d_states, net->B * sizeof(BranchState)));
+    BANN_CUDA(cudaMemsetAsync(net->d_states, 0xff, net->B * sizeof(BranchState), st));   // status = -1 (idle)
+    BANN_CUDA(cudaMalloc(&net->d_G, sizeof(NetGlobals)));
+    NetGlobals G;
+    memset(&G, 0, sizeof(G));
+    G.error_precision = 2.0f;            // architectures.rs:229-235
+    G.output_layer_precision = 0.05f;    // architectures.rs:16
+    G.lpd_rss = -INFINITY;               // log_posterior_density.rs:19-25
+    G.lpd_out_w = -INFINITY;
+    BANN_CUDA(cudaMemcpyAsync(net->d_G, &G, sizeof(G), cudaMemcpyHostToDevice, st));
+    size_t nb = (size_t)net->n * sizeof(float);
+    BANN_CUDA(cudaMalloc(&net->d_y, nb));
+    BANN_CUDA(cudaMalloc(&net->d_r, nb));
+    BANN_CUDA(cudaMalloc(&net->d_t, nb));
+    BANN_CUDA(cudaMalloc(&net->d_prev, nb));
+    BANN_CUDA(cudaMalloc(&net->d_ynew, nb));
+    BANN_CUDA(cudaMemsetAsync(net->d_y, 0, nb, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_r, 0, nb, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_t, 0, nb, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_prev, 0, nb, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_ynew, 0, nb, st));
+    net->rblk = std::min<uint32_t>((net->n + 255) / 256, (uint32_t)ctx->num_sms * 4);
+    BANN_CUDA(cudaMalloc(&net->d_rpart, 2 * (size_t)net->rblk * sizeof(float)));
+    BANN_CUDA(cudaMalloc(&net->d_ow_others, sizeof(float)));
+    BANN_CUDA(cudaMemsetAsync(net->d_ow_others, 0, sizeof(float), st));
+    BANN_CUDA(cudaMalloc(&net->d_bias2, 2 * sizeof(float)));
+    BANN_CUDA(cudaMalloc(&net->d_lpd_local, net->B * sizeof(float)));
+    {
+        std::vector<float> ninf(net->B, -INFINITY);
+        BANN_CUDA(cudaMemcpyAsync(net->d_lpd_local, ninf.data(), net->B * sizeof(float), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaStreamSynchronize(st));
+    }
+    BANN_CUDA(cudaMalloc(&net->d_errflag, sizeof(int)));
+    BANN_CUDA(cudaMemsetAsync(net->d_errflag, 0, sizeof(int), st));
+    {
+        std::vector<uint32_t> ids(net->B);
+        for (uint64_t b = 0; b < net->B; ++b) ids[b] = (uint32_t)b;
+        BANN_CUDA(cudaMalloc(&net->d_list_all, net->B * sizeof(uint32_t)));
+        BANN_CUDA(cudaMemcpyAsync(net->d_list_all, ids.data(), net->B * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaStreamSynchronize(st));
+    }
+    net->inj_gamma_cap = max_gam;
+    BANN_CUDA(cudaMalloc(&net->d_inj, (2 * (size_t)net->maxP + 4 + max_gam) * sizeof(float)));
+    BANN_CUDA(cudaMalloc(&net->d_scratchB, 3 * net->B * sizeof(float) + 16));
+    BANN_CUDA(cudaFuncSetAttribute(k1_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)net->max_generic_smem));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    *out = net;
+    return 0;
+}
+
+void bann_net_destroy(bann_net* net) {
+    if (!net) return;
+    cudaFree(net->d_descs); cudaFree(net->d_theta); cudaFree(net->d_theta0); cudaFree(net->d_mom);
+    cudaFree(net->d_grad); cudaFree(net->d_eps); cudaFree(net->d_prec); cudaFree(net->d_states);
+    cudaFree(net->d_G); cudaFree(net->d_y); cudaFree(net->d_r); cudaFree(net->d_t); cudaFree(net->d_prev);
+    cudaFree(net->d_ynew); cudaFree(net->d_part); cudaFree(net->d_gsum); cudaFree(net->d_rpart);
+    cudaFree(net->d_ow_others); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
+    cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj);
+    cudaFree(net->d_scratchB);
+    if (net->h_pin_a) cudaFreeHost(net->h_pin_a);
+    if (net->h_pin_b) cudaFreeHost(net->h_pin_b);
+    delete net;
+}
+
+int bann_net_branch_sizes(bann_net* net, uint64_t b, uint64_t* num_params, uint64_t* num_precisions) {
+    if (!net) BANN_FAIL("NULL net");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    if (num_params) *num_params = net->descs[b].P;
+    if (num_precisions) *num_precisions = net->descs[b].nprec;
+    return 0;
+}
+
+int bann_net_set_branch(bann_net* net, uint64_t b, const float* param_vec, const float* precision_vec) {
+    if (!net) BANN_FAIL("NULL net");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    const BranchDesc& d = net->descs[b];
+    cudaStream_t st = net->ctx->stream;
+    if (param_vec) BANN_CUDA(cudaMemcpyAsync(net->d_theta + d.param_off, param_vec, d.P * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (precision_vec) BANN_CUDA(cudaMemcpyAsync(net->d_prec + d.prec_off, precision_vec, d.nprec * sizeof(float), cudaMemcpyHostToDevice, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_net_get_branch(bann_net* net, uint64_t b, float* param_vec, float* precision_vec) {
+    if (!net) BANN_FAIL("NULL net");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    const BranchDesc& d = net->descs[b];
+    cudaStream_t st = net->ctx->stream;
+    if (param_vec) BANN_CUDA(cudaMemcpyAsync(param_vec, net->d_theta + d.param_off, d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (precision_vec) BANN_CUDA(cudaMemcpyAsync(precision_vec, net->d_prec + d.prec_off, d.nprec * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int copy_all(bann_net* net, float* dev, float* host_out, const float* host_in) {
+    // branches are stored with 4-float aligned offsets; the host view is densely concatenated
+    cudaStream_t st = net->ctx->stream;
+    std::vector<float> tmp(net->total_params);
+    if (host_in) {
+        size_t k = 0;
+        for (uint64_t b = 0; b < net->B; ++b) {
+            const BranchDesc& d = net->descs[b];
+            memcpy(&tmp[d.param_off], host_in + k, d.P * sizeof(float));
+            k += d.P;
+        }
+        BANN_CUDA(cudaMemcpyAsync(dev, tmp.data(), net->total_params * sizeof(float), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaStreamSynchronize(st));
+    } else {
+        BANN_CUDA(cudaMemcpyAsync(tmp.data(), dev, net->total_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+        BANN_CUDA(cudaStreamSynchronize(st));
+        size_t k = 0;
+        for (uint64_t b = 0; b < net->B; ++b) {
+            const BranchDesc& d = net->descs[b];
+            memcpy(host_out + k, &tmp[d.param_off], d.P * sizeof(float));
+            k += d.P;
+        }
+    }
+    return 0;
+}
+
+int bann_net_set_all_params(bann_net* net, const float* param_vecs, const float* precision_vecs) {
+    if (!net || !param_vecs) BANN_FAIL("NULL argument");
+    BANN_CHECK(copy_all(net, net->d_theta, nullptr, param_vecs));
+    if (precision_vecs) {
+        BANN_CUDA(cudaMemcpyAsync(net->d_prec, precision_vecs, net->total_prec * sizeof(float), cudaMemcpyHostToDevice, net->ctx->stream));
+        BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    }
+    return 0;
+}
+
+int bann_net_get_all_params(bann_net* net, float* param_vecs, float* precision_vecs) {
+    if (!net || !param_vecs) BANN_FAIL("NULL argument");
+    BANN_CHECK(copy_all(net, net->d_theta, param_vecs, nullptr));
+    if (precision_vecs) {
+        BANN_CUDA(cudaMemcpyAsync(precision_vecs, net->d_prec, net->total_prec * sizeof(float), cudaMemcpyDeviceToHost, net->ctx->stream));
+        BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    }
+    return 0;
+}
+
+int bann_net_set_globals(bann_net* net, const float g[5]) {
+    if (!net || !g) BANN_FAIL("NULL argument");
+    NetGlobals G;
+    cudaStream_t st = net->ctx->stream;
+    BANN_CUDA(cudaMemcpyAsync(&G, net->d_G, sizeof(G), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    G.error_precision = g[0];
+    G.output_layer_precision = g[1];
+    G.ow_reg_sum = g[2];
+    G.ow_num_params = g[3];
+    G.output_bias = g[4];
+    BANN_CUDA(cudaMemcpyAsync(net->d_G, &G, sizeof(G), cudaMemcpyHostToDevice, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_net_get_globals(bann_net* net, float g[5]) {
+    if (!net || !g) BANN_FAIL("NULL argument");
+    NetGlobals G;
+    BANN_CUDA(cudaMemcpyAsync(&G, net->d_G, sizeof(G), cudaMemcpyDeviceToHost, net->ctx->stream));
+    BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    g[0] = G.error_precision; g[1] = G.output_layer_precision; g[2] = G.ow_reg_sum; g[3] = G.ow_num_params;
+    g[4] = G.output_bias;
+    return 0;
+}
+
+int bann_net_set_targets(bann_net* net, const float* y) {
+    if (!net || !y) BANN_FAIL("NULL argument");
+    cudaStream_t st = net->ctx->stream;
+    BANN_CUDA(cudaMemcpyAsync(net->d_y, y, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, st));
+    BANN_CUDA(cudaMemcpyAsync(net->d_r, net->d_y, (size_t)net->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    BANN_CHECK(refresh_resid_stats(net));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_net_get_residual(bann_net* net, float* r) {
+    if (!net || !r) BANN_FAIL("NULL argument");
+    BANN_CUDA(cudaMemcpyAsync(r, net->d_r, (size_t)net->n * sizeof(float), cudaMemcpyDeviceToHost, net->ctx->stream));
+    BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    return 0;
+}
+
+int bann_net_set_residual(bann_net* net, const float* r) {
+    if (!net || !r) BANN_FAIL("NULL argument");
+    BANN_CUDA(cudaMemcpyAsync(net->d_r, r, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, net->ctx->stream));
+    BANN_CHECK(refresh_resid_stats(net));
+    BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    return 0;
+}
+
+int bann_net_init_residual(bann_net* net) {
+    if (!net) BANN_FAIL("NULL net");
+    if (net->ctx->world > 1) BANN_FAIL("bann_net_init_residual is single-GPU in this release");
+    cudaStream_t st = net->ctx->stream;
+    k_init_residual<<<(net->n + 255) / 256, 256, 0, st>>>(net->d_r, net->d_y, net->n, net->d_G);
+    BANN_LAUNCHED();
+    for (uint64_t b = 0; b < net->B; ++b) {
+        BANN_CHECK(launch_gibbs(net, (uint32_t)b, nullptr, 0, nullptr, 0, 0, 0));   // update_global_params + from_cfg
+        K1Launch k;
+        k.list = net->d_list_all + b;
+        k.nlist = 1;
+        k.single_branch = (int)b;
+        k.fwd_only = 1;
+        k.yhat_out = net->d_r;
+        k.yhat_accumulate = -1;                                                      // net.rs:166
+        BANN_CHECK(launch_k1(net, k, false));
+        k_resid_stats<<<net->rblk, 256, 0, st>>>(net->d_r, net->n, net->d_rpart);
+        BANN_LAUNCHED();
+        FinishArgs f;
+        f.descs = net->d_descs; f.b = (uint32_t)b; f.theta = net->d_theta; f.prec = net->d_prec; f.G = net->d_G;
+        f.st = nullptr; f.ow_others = net->d_ow_others; f.lpd_local = net->d_lpd_local; f.hyper = net->hyper;
+        f.model = net->model; f.n_total = net->n_total; f.part = net->d_rpart; f.nblk = net->rblk;
+        f.bias_old_new = net->d_bias2; f.update_bias = 0; f.error_flag = net->d_errflag;
+        k_visit_finish<<<1, 256, 0, st>>>(f);                                         // net.rs:167
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaGetLastError());
+    }
+    BANN_CHECK(refresh_resid_stats(net));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_branch_fwd_bwd(bann_net* net, uint64_t b, const float* target, float* rss, float* ldg, float* d_rss,
+                        float* yhat) {
+    if (!net) BANN_FAIL("NULL net");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    if (net->ctx->world > 1) BANN_FAIL("bann_branch_fwd_bwd is single-GPU in this release");
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[b];
+    const float* tgt = net->d_y;
+    if (target) {
+        BANN_CUDA(cudaMemcpyAsync(net->d_t, target, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, st));
+        tgt = net->d_t;
+    }
+    K1Launch k;
+    k.list = net->d_list_all + b;
+    k.nlist = 1;
+    k.single_branch = (int)b;
+    k.target_mode = TGT_SHARED;
+    k.tgt = tgt;
+    k.yhat_out = yhat ? net->d_ynew : nullptr;
+    BANN_CHECK(launch_k1(net, k, true));
+    if (ldg) {
+        k_grad_only<<<1, 256, 0, st>>>(net->d_descs, net->d_list_all + b, net->d_theta, net->d_prec, net->d_gsum,
+                                       net->pstride, net->model, net->d_grad);
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaGetLastError());
+        BANN_CUDA(cudaMemcpyAsync(ldg, net->d_grad + d.param_off, d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (d_rss) BANN_CUDA(cudaMemcpyAsync(d_rss, net->d_gsum, d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (rss) BANN_CUDA(cudaMemcpyAsync(rss, net->d_gsum + d.P, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (yhat) BANN_CUDA(cudaMemcpyAsync(yhat, net->d_ynew, (size_t)net->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_branch_log_density(bann_net* net, uint64_t b, float rss, float* out) {
+    if (!net || !out) BANN_FAIL("NULL argument");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    cudaStream_t st = net->ctx->stream;
+    k_log_density<<<1, 256, 0, st>>>(net->d_descs, (uint32_t)b, net->d_theta, net->d_prec, net->model, rss, net->d_scratchB);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    BANN_CUDA(cudaMemcpyAsync(out, net->d_scratchB, sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_branch_step_sizes(bann_net* net, uint64_t b, const bann_mcmc_cfg* cfg, const float* step_uniforms, float* out) {
+    if (!net || !cfg || !out) BANN_FAIL("NULL argument");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[b];
+    // k_hmc_init also overwrites theta0 / momenta / state of the branch: harmless outside a transition
+    HmcRun R;
+    R.list = net->d_list_all + b;
+    R.nlist = 1;
+    R.single_branch = (int)b;
+    R.first_mode = TGT_SHARED;
+    R.later_mode = TGT_SHARED;
+    R.tgt = net->d_y;
+    bann_rng_inject inj;
+    memset(&inj, 0, sizeof(inj));
+    inj.step_uniforms = step_uniforms;
+    BANN_CHECK(stage_inject(net, &inj, d.P, &R, nullptr, nullptr));
+    BANN_CHECK(hmc_init_and_first_eval(net, cfg, R, 0));
+    BANN_CUDA(cudaMemcpyAsync(out, net->d_eps + d.param_off, d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaMemsetAsync(net->d_states + b, 0xff, sizeof(BranchState), st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_hmc_step(bann_net* net, uint64_t b, const float* target, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj,
+                  bann_hmc_result* out, bann_trajectory* traj, float* yhat_out) {
+    if (!net || !cfg) BANN_FAIL("NULL argument");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    if (net->ctx->world > 1) BANN_FAIL("bann_hmc_step is single-GPU in this release (use the grouped phases)");
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[b];
+    const float* tgt = net->d_y;
+    if (target) {
+        BANN_CUDA(cudaMemcpyAsync(net->d_t, target, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, st));
+        tgt = net->d_t;
+    }
+    HmcRun R;
+    R.list = net->d_list_all + b;
+    R.nlist = 1;
+    R.single_branch = (int)b;
+    R.first_mode = TGT_SHARED;
+    R.later_mode = TGT_SHARED;
+    R.tgt = tgt;
+    R.seed = 0x243f6a8885a308d3ull;
+    R.stream_base = net->visit_seq * net->B;
+    BANN_CHECK(stage_inject(net, inj, d.P, &R, nullptr, nullptr));
+    const uint32_t Ls = cfg->hmc_integration_length;
+    if (traj && (traj->params || traj->ldg || traj->hamiltonian)) {
+        size_t need = 2 * (size_t)Ls * d.P + Ls + 1;
+        BANN_CHECK(ensure_cap(&net->d_traj, &net->traj_cap, need));
+        BANN_CUDA(cudaMemsetAsync(net->d_traj, 0, need * sizeof(float), st));
+        R.traj_params = net->d_traj;
+        R.traj_ldg = net->d_traj + (size_t)Ls * d.P;
+        R.traj_h = net->d_traj + 2 * (size_t)Ls * d.P;
+    }
+    BANN_CHECK(run_hmc(net, cfg, R, net->d_ynew, nullptr, nullptr, nullptr));
+    net->visit_seq += 1;
+    if (traj && R.traj_params) {
+        if (traj->params) BANN_CUDA(cudaMemcpyAsync(traj->params, R.traj_params, (size_t)Ls * d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (traj->ldg) BANN_CUDA(cudaMemcpyAsync(traj->ldg, R.traj_ldg, (size_t)Ls * d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (traj->hamiltonian) BANN_CUDA(cudaMemcpyAsync(traj->hamiltonian, R.traj_h, (Ls + 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (yhat_out) BANN_CUDA(cudaMemcpyAsync(yhat_out, net->d_ynew, (size_t)net->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_gibbs_branch(bann_net* net, uint64_t b, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj) {
+    if (!net) BANN_FAIL("NULL net");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    const float* d_gam = nullptr;
+    uint32_t n_gam = 0;
+    BANN_CHECK(stage_inject(net, inj, net->descs[b].P, nullptr, &d_gam, &n_gam));
+    BANN_CHECK(launch_gibbs(net, (uint32_t)b, cfg, 1, d_gam, n_gam, 0x13198a2e03707344ull, net->visit_seq * net->B + b));
+    net->visit_seq += 1;
+    BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    return 0;
+}
+
+int bann_visit_branch(bann_net* net, uint64_t b, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj,
+                      bann_hmc_result* out) {
+    if (!net || !cfg) BANN_FAIL("NULL argument");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    BANN_CHECK(visit_async(net, (uint32_t)b, cfg, inj, 0x452821e638d01377ull));
+    if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
+    BANN_CHECK(check_error_flag(net));
+    return 0;
+}
+
+int bann_net_stats(bann_net* net, bann_sweep_stats* out) {
+    if (!net || !out) BANN_FAIL("NULL argument");
+    cudaStream_t st = net->ctx->stream;
+    NetGlobals G;
+    std::vector<float> loc(net->B);
+    BANN_CUDA(cudaMemcpyAsync(&G, net->d_G, sizeof(G), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaMemcpyAsync(loc.data(), net->d_lpd_local, net->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    float acc = 0.f;   // log_posterior_density.rs:62-67: sequential f32 sum of the local terms
+    for (uint64_t b = 0; b < net->B; ++b) acc += loc[b];
+    out->num_samples = G.num_samples;
+    out->num_accepted = G.num_accepted;
+    out->num_early_rejected = G.num_early_rejected;
+    out->mse_train = G.resid_ss / net->n_total;   // net.rs:604-606
+    out->lpd = (G.lpd_rss + G.lpd_out_w) + acc;
+    out->output_bias = G.output_bias;
+    out->error_precision = G.error_precision;
+    out->output_layer_precision = G.output_layer_precision;
+    return 0;
+}
+
+int bann_sweep(bann_net* net, const bann_mcmc_cfg* cfg, const uint64_t* branch_order, uint64_t num, uint32_t group_size,
+               uint64_t seed, bann_sweep_stats* out) {
+    if (!net || !cfg || !branch_order) BANN_FAIL("NULL argument");
+    if (group_size != 1) BANN_FAIL("bann_sweep supports group_size 1 (sequential-exact); use bann_grouped_* for G = B");
+    for (uint64_t i = 0; i < num; ++i) {
+        if (branch_order[i] >= net->B) BANN_FAIL("branch index out of range");
+        BANN_CHECK(visit_async(net, (uint32_t)branch_order[i], cfg, nullptr, seed));
+    }
+    BANN_CHECK(check_error_flag(net));
+    if (out) BANN_CHECK(bann_net_stats(net, out));
+    return 0;
+}
+
+int bann_predict(bann_net* net, bann_genotypes* test, float* yhat) {
+    if (!net || !yhat) BANN_FAIL("NULL argument");
+    cudaStream_t st = net->ctx->stream;
+    bann_genotypes* g = test ? test : net->gen;
+    if (g->num_branches != net->B) BANN_FAIL("test genotypes have a different number of branches");
+    std::vector<BranchDesc> descs = net->descs;
+    for (uint64_t b = 0; b < net->B; ++b) {
+        if (g->m_b[b] != net->descs[b].m) BANN_FAIL("test genotypes: branch marker count mismatch");
+        descs[b].tile_off = g->tile_off[b];
+        descs[b].col_off = g->col_off[b];
+    }
+    BranchDesc* d_descs = nullptr;
+    float* d_out = nullptr;
+    BANN_CUDA(cudaMalloc(&d_descs, net->B * sizeof(BranchDesc)));
+    BANN_CUDA(cudaMalloc(&d_out, g->n * sizeof(float)));
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(d_descs, descs.data(), net->B * sizeof(BranchDesc), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = -2; break; }
+        NetGlobals G;
+        if (cudaMemcpyAsync(&G, net->d_G, sizeof(G), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = -2; break; }
+        cudaStreamSynchronize(st);
+        std::vector<float> init(g->n, G.output_bias);   // net.rs:547-552
+        if (cudaMemcpyAsync(d_out, init.data(), g->n * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = -2; break; }
+        cudaStreamSynchronize(st);
+        for (uint64_t b = 0; b < net->B && rc == 0; ++b) {   // net.rs:554-557, branch order preserved
+            K1Launch k;
+            k.list = net->d_list_all + b;
+            k.nlist = 1;
+            k.single_branch = (int)b;
+            k.fwd_only = 1;
+            k.yhat_out = d_out;
+            k.yhat_accumulate = 1;
+            k.store = g;
+            k.descs_dev = d_descs;
+            rc = launch_k1(net, k, false);
+        }
+        if (rc) break;
+        if (cudaMemcpyAsync(yhat, d_out, g->n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = -2; break; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -2; break; }
+    } while (0);
+    cudaFree(d_descs);
+    cudaFree(d_out);
+    if (rc == -2) BANN_FAIL("CUDA error in bann_predict");
+    return rc;
+}
+
+// ------------------------------------------------------------------ full-network (grouped) operations
+int bann_net_gradient(bann_net* net, const float* param_vecs, const float* y, float* grads, float* rss) {
+    if (!net) BANN_FAIL("NULL net");
+    if (net->ctx->world > 1) BANN_FAIL("bann_net_gradient is single-GPU in this release (use the grouped phases)");
+    cudaStream_t st = net->ctx->stream;
+    // pinned staging so that the copies are true async DMA (the e2e form of the benchmark)
+    if (!net->h_pin_a) {
+        BANN_CUDA(cudaMallocHost(&net->h_pin_a, net->total_params * sizeof(float)));
+        BANN_CUDA(cudaMallocHost(&net->h_pin_b, (net->total_params + net->B) * sizeof(float)));
+    }
+    if (param_vecs) {
+        size_t k = 0;
+        for (uint64_t b = 0; b < net->B; ++b) {
+            const BranchDesc& d = net->descs[b];
+            memcpy(net->h_pin_a + d.param_off, param_vecs + k, d.P * sizeof(float));
+            k += d.P;
+        }
+        BANN_CUDA(cudaMemcpyAsync(net->d_theta, net->h_pin_a, net->total_params * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    const float* tgt = net->d_y;
+    if (y) {
+        BANN_CUDA(cudaMemcpyAsync(net->d_t, y, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, st));
+        tgt = net->d_t;
+    }
+    K1Launch k;
+    k.list = nullptr;
+    k.nlist = (uint32_t)net->B;
+    k.target_mode = TGT_SHARED;
+    k.tgt = tgt;
+    BANN_CHECK(launch_k1(net, k, true));
+    k_grad_only<<<(unsigned)net->B, 256, 0, st>>>(net->d_descs, nullptr, net->d_theta, net->d_prec, net->d_gsum,
+                                                  net->pstride, net->model, net->d_grad);
+    BANN_LAUNCHED();
+    k_gather_rss<<<((unsigned)net->B + 255) / 256, 256, 0, st>>>(net->d_gsum, net->pstride, net->d_descs, (uint32_t)net->B,
+                                                                 net->d_scratchB);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    if (grads) BANN_CUDA(cudaMemcpyAsync(net->h_pin_b, net->d_grad, net->total_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (rss) BANN_CUDA(cudaMemcpyAsync(net->h_pin_b + net->total_params, net->d_scratchB, net->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    if (grads) {
+        size_t kk = 0;
+        for (uint64_t b = 0; b < net->B; ++b) {
+            const BranchDesc& d = net->descs[b];
+            memcpy(grads + kk, net->h_pin_b + d.param_off, d.P * sizeof(float));
+            kk += d.P;
+        }
+    }
+    if (rss) memcpy(rss, net->h_pin_b + net->total_params, net->B * sizeof(float));
+    return 0;
+}
+
+static HmcRun grouped_run(bann_net* net) {
+    HmcRun R;
+    R.list = nullptr;
+    R.nlist = (uint32_t)net->B;
+    R.single_branch = -1;
+    R.first_mode = net->grouped_per_branch ? TGT_RESID_PLUS_PRED : TGT_SHARED;
+    R.later_mode = net->grouped_per_branch ? TGT_PER_ENTRY : TGT_SHARED;
+    R.tgt = net->grouped_per_branch ? net->d_T : net->d_y;
+    R.seed = net->grouped_seed;
+    R.stream_base = net->visit_seq * net->B;
+    return R;
+}
+
+static int grouped_k1(bann_net* net, int first) {
+    HmcRun R = grouped_run(net);
+    K1Launch k;
+    k.list = nullptr;
+    k.nlist = (uint32_t)net->B;
+    k.states = net->d_states;
+    if (first && net->grouped_per_branch) {
+        k.target_mode = TGT_RESID_PLUS_PRED;
+        k.resid = net->d_r;
+        k.tgt_out = net->d_T;
+        k.out_per_entry = 1;
+    } else {
+        k.target_mode = R.later_mode;
+        k.tgt = R.tgt;
+    }
+    return launch_k1(net, k, true);
+}
+
+int bann_grouped_begin(bann_net* net, const bann_mcmc_cfg* cfg, uint64_t seed, int per_branch_targets) {
+    if (!net || !cfg) BANN_FAIL("NULL argument");
+    net->grouped_per_branch = per_branch_targets ? 1 : 0;
+    net->grouped_seed = seed;
+    if (per_branch_targets && !net->d_T) BANN_CUDA(cudaMalloc(&net->d_T, (size_t)net->B * net->n * sizeof(float)));
+    HmcRun R = grouped_run(net);
+    BANN_CHECK(hmc_init_and_first_eval(net, cfg, R, 0));
+    BANN_CHECK(grouped_k1(net, 1));
+    if (net->ctx->world > 1) return 0;   // caller all-reduces, then bann_grouped_phase_b(is_init = 1)
+    K2Args a = make_k2(net, cfg, R, 1, 0);
+    k2_step<<<R.nlist, 256, 0, net->ctx->stream>>>(a);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bann_grouped_phase_a(bann_net* net) {
+    if (!net) BANN_FAIL("NULL net");
+    return grouped_k1(net, 0);
+}
+
+int bann_grouped_phase_b(bann_net* net, const bann_mcmc_cfg* cfg, int is_init, int is_last) {
+    if (!net || !cfg) BANN_FAIL("NULL argument");
+    HmcRun R = grouped_run(net);
+    K2Args a = make_k2(net, cfg, R, is_init, is_last);
+    k2_step<<<R.nlist, 256, 0, net->ctx->stream>>>(a);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bann_grouped_leapfrog(bann_net* net, const bann_mcmc_cfg* cfg, uint32_t num_steps, int finalize) {
+    if (!net || !cfg) BANN_FAIL("NULL argument");
+    if (net->ctx->world > 1) BANN_FAIL("multi-GPU runs drive bann_grouped_phase_a / _b with an all-reduce in between");
+    for (uint32_t s = 0; s < num_steps; ++s) {
+        BANN_CHECK(grouped_k1(net, 0));
+        BANN_CHECK(bann_grouped_phase_b(net, cfg, 0, (finalize && s + 1 == num_steps) ? 1 : 0));
+    }
+    return 0;
+}
+
+int bann_grouped_finish(bann_net* net, uint64_t seed, uint64_t* num_accepted, uint64_t* num_early_rejected) {
+    if (!net) BANN_FAIL("NULL net");
+    cudaStream_t st = net->ctx->stream;
+    k_accept<<<(unsigned)net->B, 256, 0, st>>>(net->d_descs, nullptr, net->d_states, net->d_theta, net->d_theta0, nullptr,
+                                               seed, net->visit_seq * net->B);
+    BANN_LAUNCHED();
+    unsigned long long* cnt = (unsigned long long*)net->d_scratchB;
+    BANN_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), st));
+    k_count_status<<<((unsigned)net->B + 255) / 256, 256, 0, st>>>(net->d_states, (uint32_t)net->B, cnt);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    unsigned long long h[2];
+    BANN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    if (num_accepted) *num_accepted = h[0];
+    if (num_early_rejected) *num_early_rejected = h[1];
+    net->visit_seq += 1;
+    return 0;
+}
+
+int bann_grouped_state(bann_net* net, float* neg_h_init, float* neg_h_cur, int32_t* status) {
+    if (!net) BANN_FAIL("NULL net");
+    cudaStream_t st = net->ctx->stream;
+    float* hi = net->d_scratchB;
+    float* hc = hi + net->B;
+    int* ss = (int*)(hc + net->B);
+    k_gather_states<<<((unsigned)net->B + 255) / 256, 256, 0, st>>>(net->d_states, (uint32_t)net->B, hi, hc, ss);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    if (neg_h_init) BANN_CUDA(cudaMemcpyAsync(neg_h_init, hi, net->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (neg_h_cur) BANN_CUDA(cudaMemcpyAsync(neg_h_cur, hc, net->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (status) BANN_CUDA(cudaMemcpyAsync(status, ss, net->B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_allreduce_buffer(bann_net* net, void** dev_ptr, uint64_t* num_floats) {
+    if (!net || !dev_ptr || !num_floats) BANN_FAIL("NULL argument");
+    BANN_CHECK(ensure_cap(&net->d_gsum, &net->gsum_cap, (size_t)net->B * net->pstride));
+    *dev_ptr = net->d_gsum;
+    *num_floats = (uint64_t)net->B * net->pstride;
+    return 0;
+}
+
+int bann_net_algorithmic_bytes(bann_net* net, uint64_t* bytes) {
+    if (!net || !bytes) BANN_FAIL("NULL argument");
+    // sum_b m_b*ceil(N/4) + 4*N*B + 12*sum_b P_b   (N = rows this rank holds)
+    uint64_t sumP = 0;
+    for (uint64_t b = 0; b < net->B; ++b) sumP += net->descs[b].P;
+    *bytes = net->gen->packed_bytes + 4ull * net->n * net->B + 12ull * sumP;
+    return 0;
+}
+
+int bann_net_force_generic(bann_net* net, int on) {
+    if (!net) BANN_FAIL("NULL net");
+    net->force_generic = on;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Host-side handle definitions shared by genotypes.cu and net.cu.
+#pragma once
+
+#include <string.h>
+
+#include "common.cuh"
+
+struct bann_ctx {
+    int device = 0;
+    int rank = 0;
+    int world = 1;
+    int num_sms = 148;
+    int cc_major = 10;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+};
+
+struct bann_genotypes {
+    bann_ctx* ctx = nullptr;
+    uint64_t n = 0;        // local rows
+    uint64_t n_total = 0;  // rows over all ranks
+    uint64_t m = 0;
+    uint64_t num_branches = 0;
+    uint32_t ntiles = 0;
+    uint64_t total_cols = 0;
+    uint64_t store_bytes = 0;
+    uint64_t packed_bytes = 0;  // sum_b m_b * ceil(n/4): the algorithmic genotype bytes of one pass
+    std::vector<uint32_t> m_b, m_pad4;
+    std::vector<uint64_t> tile_off, col_off;
+    uint8_t* d_store = nullptr;
+    float* d_means = nullptr;
+    float* d_stds = nullptr;
+    float* d_mu = nullptr;  // per-branch gathered means (sum m_b)
+    float* d_sd = nullptr;
+    uint64_t* d_col_ids = nullptr;
+    unsigned long long* d_counts = nullptr;
+};
