@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- full-network HMC leapfrog steps / second (BASELINE.json metric).
+
+One "step" = one full-network leapfrog step = B branch-leapfrogs (momentum half step, position
+step, fused forward+backward of every branch over all N rows against its own target vector, prior
+gradient, second half step, Hamiltonian), schedule G = B (all branches advance concurrently,
+SURVEY H1).  Rows are sharded over ranks; the per-step [gW | gb | rss] sums are all-reduced (NCCL).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# BASELINE.json configs.  widths = hidden..., summary, 1
+WORKLOADS = {
+    "cfg1": dict(desc="configs[0] tiny: 1k individuals x 10 branches x 100 markers, widths [2,2,1], StdNormal",
+                 n=1000, B=10, per=100, widths=[2, 2, 1], model="std_normal"),
+    "cfg2": dict(desc="configs[1]: 10k individuals x 1000 branches x 500 markers, widths [5,5,1], RidgeARD",
+                 n=10000, B=1000, per=500, widths=[5, 5, 1], model="ridge_ard"),
+    "cfg3": dict(desc="configs[2] biobank: 100k individuals x 10000 branches x 50 markers (500k markers), "
+                      "widths [5,5,1], RidgeARD", n=100000, B=10000, per=50, widths=[5, 5, 1], model="ridge_ard"),
+    "cfg3s": dict(desc="configs[2] at 1/10 of the branches (smoke size)", n=100000, B=1000, per=50, widths=[5, 5, 1],
+                  model="ridge_ard"),
+}
+METRIC = "full_network_hmc_leapfrog_steps_per_sec"
+UNIT = "steps/s"
+# ncu --set full capture of the dominant kernel (profiles/): dram bytes per launch, filled in once measured
+NCU_TRAFFIC_BYTES = {}
+
+
+def default_params(wl, seed=42):
+    """Reference default init (branch_cfg_builder.rs:180-186,308-328): W ~ N(0, 1/m_b), b = 0, ML ARD
+    precisions out_l / sum_c W[r,c]^2, output precision placeholder, error precision 2.0.  Bias
+    precisions: the ML value for zero biases is +inf (step size 0, Q7); a chain resamples them at
+    the first Gibbs visit, the bench uses 1.0 so that every parameter moves."""
+    rng = np.random.default_rng(seed)
+    B, m, widths, model = wl["B"], wl["per"], wl["widths"], wl["model"]
+    ins = [m] + widths[:-1]
+    ard = model.endswith("ard")
+    Ws = [rng.normal(0.0, np.sqrt(1.0 / m), size=(B, o, i)).astype(np.float32) for i, o in zip(ins, widths)]  # [B][col][row]
+    nb = sum(widths[:-1])
+    pv = np.concatenate([w.reshape(B, -1) for w in Ws] + [np.zeros((B, nb), dtype=np.float32)], axis=1)
+    precs = []
+    for l, w in enumerate(Ws):
+        if ard and l < len(widths) - 1:
+            precs.append((np.float32(widths[l]) / np.sum(w * w, axis=1)).astype(np.float32))       # per input row
+        elif model == "std_normal" or l == len(widths) - 1:
+            precs.append(np.ones((B, 1), dtype=np.float32))
+        else:
+            precs.append((np.float32(w[0].size) / np.sum(w * w, axis=(1, 2)))[:, None].astype(np.float32))
+    precs.append(np.ones((B, len(widths) - 1), dtype=np.float32))          # bias precisions
+    precs.append(np.full((B, 1), 2.0, dtype=np.float32))                  # error precision
+    qv = np.concatenate(precs, axis=1)
+    return np.ascontiguousarray(pv.reshape(-1)), np.ascontiguousarray(qv.reshape(-1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.stop_flag, self.idx = [], False, gpu_index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 8 for k in range(4) if r[4 + k].lower() == "active"})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def cpu_reference_rate(wl, seconds=10.0, max_branches=64, leapfrogs=2, threads_note=True):
+    """Times the oracle's C restatement of the reference's op sequence (host decode + dense f32 +
+    2 forwards and 1 backward per leapfrog) on a bounded sample: all N rows, a few branches."""
+    from oracle import bed as obed
+    from oracle.cport import CPort
+    cp = CPort()
+    n, m, widths, B = wl["n"], wl["per"], wl["widths"], wl["B"]
+    rng = np.random.default_rng(1)
+    ncols = m * 4
+    g = rng.binomial(2, rng.uniform(0.01, 0.5, size=ncols)[None, :], size=(n, ncols)).astype(np.uint8)
+    payload = obed.pack_columns(g)
+    gm = g.astype(np.float32)
+    mu = gm.mean(axis=0).astype(np.float32)
+    sd = np.maximum(gm.std(axis=0), 1e-3).astype(np.float32)
+    y = rng.normal(size=n).astype(np.float32)
+    ins = [m] + widths[:-1]
+    P = sum(i * o for i, o in zip(ins, widths)) + sum(widths[:-1])
+    L_ref = 100.0                       # decode happens once per visit of L = 100 leapfrogs (mcmc_cfg.rs:38)
+    t_decode, t_leap, nbr = 0.0, 0.0, 0
+    t_start = time.perf_counter()
+    while nbr < max_branches and (time.perf_counter() - t_start < seconds or nbr < 2):
+        cols = np.arange((nbr % 4) * m, (nbr % 4 + 1) * m)
+        theta = rng.normal(0, np.sqrt(1.0 / m), size=P).astype(np.float32)
+        mom = rng.normal(size=P).astype(np.float32)
+        eps = np.full(P, 1e-3, dtype=np.float32)
+        lam = np.ones(P, dtype=np.float32)
+        t0 = time.perf_counter()
+        X = cp.decode_std(payload, n, cols, mu, sd)
+        t1 = time.perf_counter()
+        cp.leapfrog(X, y, n, m, widths, "tanh", False, wl["model"] == "std_normal", theta, mom, eps, lam, 2.0, leapfrogs)
+        t2 = time.perf_counter()
+        if nbr > 0:                       # first branch = warm-up (thread pool, page faults)
+            t_decode += t1 - t0
+            t_leap += (t2 - t1) / (leapfrogs + 0.5)   # + initial gradient evaluation (half a leapfrog)
+        nbr += 1
+    k = max(nbr - 1, 1)
+    per_branch_leapfrog = t_leap / k + (t_decode / k) / L_ref
+    steps_per_s = 1.0 / (per_branch_leapfrog * B)
+    sample = (f"{k} branches x {leapfrogs} leapfrogs over all {n} rows (m_b={m}, widths {widths}); host decode per visit "
+              f"amortised over L=100; extrapolated to B={B} branches")
+    return dict(value=steps_per_s, unit=UNIT, cores=cp.threads, kind="port", sample=sample), per_branch_leapfrog
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(args.steps, 1)
+    per = []
+    base = None
+    for s in range(args.warmup + steps):
+        base, t = cpu_reference_rate(wl, seconds=2.0, max_branches=8)
+        if s >= args.warmup:
+            per.append(t)
+    t_bl = statistics.mean(per)
+    value = 1.0 / (t_bl * wl["B"])
+    base["value"] = value
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=args.warmup,
+                ms_per_step=t_bl * wl["B"] * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=f"{args.workload}: {wl['desc']}", schedule="sequential branch visits (reference order)",
+                            note="CPU restatement of the reference's op sequence (oracle C port), not the reference binary: "
+                                 "rs-bann needs cargo + ArrayFire, neither is in this image"),
+                cpu_baseline=base, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generic", action="store_true", help="force the shape-agnostic kernel (debug)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+
+    import rs_bann_b200 as rb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = rb.Context(local, stream=stream, rank=rank, world=world)
+
+    N, B, per, widths = wl["n"], wl["B"], wl["per"], wl["widths"]
+    M = B * per
+    # row shards on 128-row tile boundaries
+    tiles = (N + 127) // 128
+    tpr = (tiles + world - 1) // world
+    r0, r1 = min(N, rank * tpr * 128), min(N, (rank + 1) * tpr * 128)
+    n_local = r1 - r0
+    gen = rb.Genotypes.random(ctx, n_local, M, None, seed=42, row_offset=r0, n_total=N, uniform_groups=(B, per))
+    counts = torch.from_numpy(gen.col_counts().astype(np.int64)).to(dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    mu, sd = rb.stats_from_counts(counts.cpu().numpy(), N)      # global column statistics
+    gen.set_col_stats(mu, sd)
+    net = rb.Net(ctx, gen, wl["model"], [widths] * B)
+    pv, qv = default_params(wl)
+    net.set_all_params(pv, qv)
+    y = np.random.default_rng(42).normal(size=N).astype(np.float32)
+    y_local = np.ascontiguousarray(y[r0:r1])
+    net.set_targets(y_local)
+    if args.generic:
+        net.force_generic(True)
+    ptr, nfl = net.allreduce_buffer()
+
+    class _Dev:
+        __cuda_array_interface__ = {"shape": (nfl,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    gbuf = torch.as_tensor(_Dev(), device=dev) if world > 1 else None
+
+    def allreduce():
+        if world > 1:
+            dist.all_reduce(gbuf)
+
+    cfg = rb.MCMCCfg(hmc_step_size_factor=0.1, hmc_integration_length=100, hmc_max_hamiltonian_error=1e30)
+    net.grouped_begin(cfg, seed=42, per_branch_targets=True)      # t_b = r + yhat_b (net.rs:279-280), momenta, H_init
+    if world > 1:
+        allreduce()
+        net.grouped_phase_b(cfg, is_init=True)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        net.grouped_phase_a()          # K1: fused fwd+bwd of every branch (+ chunk reduction)
+        if ev:
+            ev[1].record()
+        allreduce()
+        net.grouped_phase_b(cfg)       # K2: gradient, half steps, position step, Hamiltonian
+        if ev:
+            ev[2].record()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    rb.launch_count(reset=True)
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        step(evs[s])
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = rb.launch_count()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = evs[0][0].elapsed_time(end)
+    k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    tm = torch.tensor([total_ms, k1_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, k1_ms = float(tm[0]), float(tm[1])
+    hi, hc, st = net.grouped_state()
+    active = int(np.sum(st == 3))
+    assert active == B, f"{B - active} branches stopped during the timed region: number invalid"
+    assert np.all(np.isfinite(hc)), "non-finite Hamiltonian"
+    alg_bytes = net.algorithmic_bytes()                  # this rank's rows
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+    value = args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-facing call (Net::gradient = full-network fwd+grad), HOST buffers
+    grads = np.empty(net.num_params(), dtype=np.float32)
+    rss = np.empty(B, dtype=np.float32)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        net.gradient(pv, y_local, allreduce=allreduce if world > 1 else None, out=(grads, rss))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        net.gradient(pv, y_local, allreduce=allreduce if world > 1 else None, out=(grads, rss))
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps / float(te[0])
+    h2d = world * 4 * pv.size + 4 * N
+    d2h = world * 4 * (pv.size + B)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f32", data="synthetic",
+                    config=dict(workload=f"{args.workload}: {wl['desc']}", schedule="grouped G=B (all branches per launch)",
+                                individuals=N, branches=B, markers_per_branch=per, widths=widths, prior=wl["model"],
+                                rows_per_gpu=n_local, parallelism=f"row-sharded x{world}, all-reduce of [gW|gb|rss]",
+                                l2="working set (packed genotypes + per-branch targets) >> 126 MB L2, no flush needed",
+                                init="reference default init, seed 42; bias precisions 1.0",
+                                branch_leapfrogs_per_step=B, active_branches=active),
+                    k1_ms=k1_ms, wall_s=t_wall, gpu_launches=int(launches) * world,
+                    roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                                  traffic=NCU_TRAFFIC_BYTES.get(args.workload), peak_source=peak_src,
+                                  algorithmic_bytes_per_launch=alg_bytes, kernel="k1 fused fwd+bwd (phase A)",
+                                  kernel_ms=k1_ms),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             call="Net.gradient / bann_net_gradient (host params + targets in, gradients + rss out)"),
+                    clocks=clocks)
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"], _ = cpu_reference_rate(wl, seconds=12.0)
+            except Exception as ex:   # the oracle is test infrastructure; never let it break the GPU number
+                line["cpu_baseline"] = dict(error=str(ex))
+        print(json.dumps(line))
+    net.close()
+    gen.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

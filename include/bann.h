@@ -121,6 +121,13 @@ int  bann_ctx_sync(bann_ctx*);
 int  bann_genotypes_create(bann_ctx*, const uint8_t* bed_payload, uint64_t n, uint64_t n_total, uint64_t m,
                            const float* col_means, const float* col_stds, uint64_t num_branches,
                            const uint64_t* branch_offsets, const uint64_t* col_ids, bann_genotypes** out);
+/* Synthetic store generated on the device, in the spirit of BedVM::random (io/bed.rs:136-188):
+ * maf_j ~ U(maf_lo, maf_hi), g_ij ~ Binomial(2, maf_j); counter-based RNG keyed by column and
+ * GLOBAL row (row_offset + i), so the data are independent of the row sharding.  With world > 1
+ * the column statistics must then be set from all-reduced bann_genotypes_col_counts. */
+int  bann_genotypes_random(bann_ctx*, uint64_t n, uint64_t row_offset, uint64_t n_total, uint64_t m, uint64_t seed,
+                           float maf_lo, float maf_hi, uint64_t num_branches, const uint64_t* branch_offsets,
+                           const uint64_t* col_ids, bann_genotypes** out);
 void bann_genotypes_destroy(bann_genotypes*);
 int  bann_genotypes_col_stats(bann_genotypes*, float* col_means, float* col_stds);
 /* per-column counts of decoded values 0,1,2 over the local rows: out[3*m] (for global stats). */
@@ -185,6 +192,10 @@ int  bann_net_stats(bann_net*, bann_sweep_stats* out);
  * HOST buffers: params in (sum P_b, may be NULL = keep device state), y in (n, may be NULL),
  * grads out (sum P_b), rss out (B).  This is the host-facing full-network fwd+grad call. */
 int  bann_net_gradient(bann_net*, const float* param_vecs, const float* y, float* grads, float* rss);
+/* the same in two halves for row-sharded runs: begin (H2D, fused fwd+bwd, raw sums into the
+ * all-reduce buffer) -- caller all-reduces -- end (gradient under the prior, D2H). */
+int  bann_net_gradient_begin(bann_net*, const float* param_vecs, const float* y);
+int  bann_net_gradient_end(bann_net*, float* grads, float* rss);
 /* Grouped leapfrog over ALL branches against per-branch targets (schedule G = B).
  * begin: theta0 <- theta, step sizes, momenta (Philox, seed), targets t_b = y (shared) or
  * residual + own prediction; then each step = B branch-leapfrogs.  Device resident, async. */

@@ -76,16 +76,33 @@ static void make_shape(shape_t* s, uint32_t m, const uint32_t* widths, uint32_t 
     s->P = off;
 }
 
-/* forward for one row; a[l][c], dh[l][c] for activated layers; returns yhat */
-static inline float fwd_row(const shape_t* s, int act, const float* th, const float* X, uint64_t n, uint64_t i,
-                            float a[MAXL][MAXW], float dh[MAXL][MAXW]) {
+#define BLK 256
+
+/* first-layer pre-activations for a block of rows: Z[c][ii] = b0[c] + sum_j X[i0+ii, j] W0[j, c]
+ * (column-major X: the inner loop runs over contiguous rows and vectorises) */
+static inline void first_layer_block(const shape_t* s, const float* th, const float* X, uint64_t n, uint64_t i0,
+                                     uint32_t nb, float Z[MAXW][BLK]) {
+    for (uint32_t c = 0; c < s->w[0]; ++c) {
+        float b = th[s->boff[0] + c];
+        for (uint32_t ii = 0; ii < nb; ++ii) Z[c][ii] = b;
+    }
+    for (uint32_t j = 0; j < s->m; ++j) {
+        const float* xj = X + (uint64_t)j * n + i0;
+        for (uint32_t c = 0; c < s->w[0]; ++c) {
+            float w = th[s->woff[0] + (uint64_t)c * s->m + j];
+            float* z = Z[c];
+            for (uint32_t ii = 0; ii < nb; ++ii) z[ii] += xj[ii] * w;
+        }
+    }
+}
+
+/* remaining layers for one row given its first-layer pre-activations; returns yhat */
+static inline float tail_row(const shape_t* s, int act, const float* th, const float* z0, float a[MAXL][MAXW],
+                             float dh[MAXL][MAXW]) {
     const uint32_t nl = s->nl;
     for (uint32_t c = 0; c < s->w[0]; ++c) {
-        float z = th[s->boff[0] + c];
-        const float* W = th + s->woff[0] + (uint64_t)c * s->m;
-        for (uint32_t j = 0; j < s->m; ++j) z += X[(uint64_t)j * n + i] * W[j];
-        float h = act_h(act, z);
-        a[0][c] = h; dh[0][c] = act_dh(act, z, h);
+        float h = act_h(act, z0[c]);
+        a[0][c] = h; dh[0][c] = act_dh(act, z0[c], h);
     }
     for (uint32_t l = 1; l + 1 < nl; ++l)
         for (uint32_t c = 0; c < s->w[l]; ++c) {
@@ -105,13 +122,21 @@ float bann_cpu_rss(const float* X, const float* y, uint64_t n, uint32_t m, const
                    const float* theta, float* yhat) {
     shape_t s; make_shape(&s, m, widths, nl);
     double rss = 0.0;
+    int64_t nblk = (int64_t)((n + BLK - 1) / BLK);
 #pragma omp parallel for schedule(static) reduction(+ : rss)
-    for (int64_t i = 0; i < (int64_t)n; ++i) {
-        float a[MAXL][MAXW], dh[MAXL][MAXW];
-        float yh = fwd_row(&s, act, theta, X, n, (uint64_t)i, a, dh);
-        if (yhat) yhat[i] = yh;
-        float e = yh - y[i];
-        rss += (double)(e * e);
+    for (int64_t bi = 0; bi < nblk; ++bi) {
+        float Z[MAXW][BLK];
+        uint64_t i0 = (uint64_t)bi * BLK;
+        uint32_t nb = (uint32_t)((n - i0 < BLK) ? (n - i0) : BLK);
+        first_layer_block(&s, theta, X, n, i0, nb, Z);
+        for (uint32_t ii = 0; ii < nb; ++ii) {
+            float a[MAXL][MAXW], dh[MAXL][MAXW], z0[MAXW];
+            for (uint32_t c = 0; c < s.w[0]; ++c) z0[c] = Z[c][ii];
+            float yh = tail_row(&s, act, theta, z0, a, dh);
+            if (yhat) yhat[i0 + ii] = yh;
+            float e = yh - y[i0 + ii];
+            rss += (double)(e * e);
+        }
     }
     return (float)rss;
 }
@@ -123,6 +148,7 @@ float bann_cpu_backprop(const float* X, const float* y, uint64_t n, uint32_t m, 
     const uint32_t P = s.P;
     int nt = bann_cpu_num_threads();
     double* acc = (double*)calloc((size_t)nt * (P + 1), sizeof(double));
+    int64_t nblk = (int64_t)((n + BLK - 1) / BLK);
 #pragma omp parallel
     {
 #ifdef _OPENMP
@@ -131,29 +157,42 @@ float bann_cpu_backprop(const float* X, const float* y, uint64_t n, uint32_t m, 
         int tidx = 0;
 #endif
         double* g = acc + (size_t)tidx * (P + 1);
+        float Z[MAXW][BLK];   /* pre-activations, then delta_0 */
 #pragma omp for schedule(static)
-        for (int64_t i = 0; i < (int64_t)n; ++i) {
-            float a[MAXL][MAXW], dh[MAXL][MAXW], delta[MAXW], nd[MAXW];
-            float yh = fwd_row(&s, act, theta, X, n, (uint64_t)i, a, dh);
-            float e = yh - y[i];
-            g[P] += (double)(e * e);
-            const uint32_t L = nl - 2;
-            const float* Wo = theta + s.woff[nl - 1];
-            for (uint32_t k = 0; k < s.w[L]; ++k) { g[s.woff[nl - 1] + k] += a[L][k] * e; delta[k] = dh[L][k] * (e * Wo[k]); }
-            for (uint32_t l = L; l >= 1; --l) {
-                for (uint32_t k = 0; k < s.in[l]; ++k) nd[k] = 0.f;
-                for (uint32_t c = 0; c < s.w[l]; ++c) {
-                    g[s.boff[l] + c] += delta[c];
-                    const float* W = theta + s.woff[l] + c * s.in[l];
-                    for (uint32_t k = 0; k < s.in[l]; ++k) { g[s.woff[l] + c * s.in[l] + k] += a[l - 1][k] * delta[c]; nd[k] += delta[c] * W[k]; }
+        for (int64_t bi = 0; bi < nblk; ++bi) {
+            uint64_t i0 = (uint64_t)bi * BLK;
+            uint32_t nb = (uint32_t)((n - i0 < BLK) ? (n - i0) : BLK);
+            first_layer_block(&s, theta, X, n, i0, nb, Z);
+            for (uint32_t ii = 0; ii < nb; ++ii) {
+                float a[MAXL][MAXW], dh[MAXL][MAXW], delta[MAXW], nd[MAXW], z0[MAXW];
+                for (uint32_t c = 0; c < s.w[0]; ++c) z0[c] = Z[c][ii];
+                float yh = tail_row(&s, act, theta, z0, a, dh);
+                float e = yh - y[i0 + ii];
+                g[P] += (double)(e * e);
+                const uint32_t L = nl - 2;
+                const float* Wo = theta + s.woff[nl - 1];
+                for (uint32_t k = 0; k < s.w[L]; ++k) { g[s.woff[nl - 1] + k] += a[L][k] * e; delta[k] = dh[L][k] * (e * Wo[k]); }
+                for (uint32_t l = L; l >= 1; --l) {
+                    for (uint32_t k = 0; k < s.in[l]; ++k) nd[k] = 0.f;
+                    for (uint32_t c = 0; c < s.w[l]; ++c) {
+                        g[s.boff[l] + c] += delta[c];
+                        const float* W = theta + s.woff[l] + c * s.in[l];
+                        for (uint32_t k = 0; k < s.in[l]; ++k) { g[s.woff[l] + c * s.in[l] + k] += a[l - 1][k] * delta[c]; nd[k] += delta[c] * W[k]; }
+                    }
+                    for (uint32_t k = 0; k < s.in[l]; ++k) delta[k] = dh[l - 1][k] * nd[k];
                 }
-                for (uint32_t k = 0; k < s.in[l]; ++k) delta[k] = dh[l - 1][k] * nd[k];
+                for (uint32_t c = 0; c < s.w[0]; ++c) { g[s.boff[0] + c] += delta[c]; Z[c][ii] = delta[c]; }
             }
-            for (uint32_t c = 0; c < s.w[0]; ++c) {
-                g[s.boff[0] + c] += delta[c];
-                double* gw = g + s.woff[0] + (uint64_t)c * m;
-                float dc = delta[c];
-                for (uint32_t j = 0; j < m; ++j) gw[j] += X[(uint64_t)j * n + i] * dc;
+            /* gW0[j, c] += sum_ii X[i0+ii, j] * delta_0[ii, c]  (contiguous over rows) */
+            for (uint32_t j = 0; j < m; ++j) {
+                const float* xj = X + (uint64_t)j * n + i0;
+                for (uint32_t c = 0; c < s.w[0]; ++c) {
+                    const float* dz = Z[c];
+                    float t = 0.f;
+#pragma omp simd reduction(+ : t)
+                    for (uint32_t ii = 0; ii < nb; ++ii) t += xj[ii] * dz[ii];
+                    g[s.woff[0] + (uint64_t)c * m + j] += t;
+                }
             }
         }
     }

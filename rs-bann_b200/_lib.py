@@ -66,6 +66,8 @@ PROTOTYPES = {
     "bann_ctx_sync": (C.c_int, [_vp]),
     "bann_genotypes_create": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _fp, _fp, _u64, C.POINTER(_u64),
                                          C.POINTER(_u64), C.POINTER(_vp)]),
+    "bann_genotypes_random": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _u64, C.c_float, C.c_float, _u64, C.POINTER(_u64),
+                                         C.POINTER(_u64), C.POINTER(_vp)]),
     "bann_genotypes_destroy": (None, [_vp]),
     "bann_genotypes_col_stats": (C.c_int, [_vp, _fp, _fp]),
     "bann_genotypes_col_counts": (C.c_int, [_vp, C.POINTER(_u64)]),
@@ -96,6 +98,8 @@ PROTOTYPES = {
     "bann_predict": (C.c_int, [_vp, _vp, _fp]),
     "bann_net_stats": (C.c_int, [_vp, C.POINTER(SweepStats)]),
     "bann_net_gradient": (C.c_int, [_vp, _fp, _fp, _fp, _fp]),
+    "bann_net_gradient_begin": (C.c_int, [_vp, _fp, _fp]),
+    "bann_net_gradient_end": (C.c_int, [_vp, _fp, _fp]),
     "bann_grouped_begin": (C.c_int, [_vp, C.POINTER(McmcCfg), _u64, C.c_int]),
     "bann_grouped_leapfrog": (C.c_int, [_vp, C.POINTER(McmcCfg), C.c_uint32, C.c_int]),
     "bann_grouped_phase_a": (C.c_int, [_vp]),

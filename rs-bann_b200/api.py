@@ -80,6 +80,31 @@ class Context:
             self.h = None
 
 
+class _UniformGroups:
+    """UniformGrouping (group/uniform.rs:11-24) without materialising the index lists."""
+
+    def __init__(self, nb, per):
+        self.nb, self.per = nb, per
+
+    def __len__(self):
+        return self.nb
+
+    def __getitem__(self, b):
+        return range(b * self.per, (b + 1) * self.per)
+
+
+def stats_from_counts(counts: np.ndarray, n_total: int):
+    """Column mean / population std from per-value counts (global over all row shards).
+    mean = (n1 + 2 n2) / N is exact; the std sum is evaluated in f64 (the reference's sequential f32
+    sum, io/bed.rs:231-238, is order dependent and cannot be reproduced from shard partials)."""
+    c = counts.astype(np.float64)
+    nf = float(n_total)
+    mean = ((c[:, 1] + 2.0 * c[:, 2]) / nf).astype(np.float32)
+    m64 = mean.astype(np.float64)
+    ss = c[:, 0] * (0 - m64) ** 2 + c[:, 1] * (1 - m64) ** 2 + c[:, 2] * (2 - m64) ** 2
+    return mean, np.sqrt(ss / nf).astype(np.float32)
+
+
 class Genotypes:
     """Device-resident packed genotype store = BedVM + MarkerGrouping (CompressedGenotypes,
     data/genotypes.rs:14-48).  `payload`: PLINK variant-major bytes without signature for the
@@ -102,6 +127,30 @@ class Genotypes:
                                         len(self.groups), offs.ctypes.data_as(C.POINTER(C.c_uint64)),
                                         ids.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(h)))
         self.h = h
+
+    @classmethod
+    def random(cls, ctx: Context, n: int, m: int, groups, seed: int = 42, row_offset: int = 0,
+               n_total: Optional[int] = None, maf_lo: float = 0.01, maf_hi: float = 0.5, uniform_groups=None):
+        """Device-generated synthetic store in the spirit of BedVM::random (io/bed.rs:136-188).
+        `uniform_groups=(B, per)` avoids materialising Python lists for very large groupings."""
+        self = cls.__new__(cls)
+        self.ctx, self.n, self.m = ctx, int(n), int(m)
+        if uniform_groups is not None:
+            nb, per = uniform_groups
+            offs = (np.arange(nb + 1, dtype=np.uint64) * np.uint64(per))
+            ids = np.arange(nb * per, dtype=np.uint64)
+            self.groups = _UniformGroups(nb, per)
+        else:
+            self.groups = [list(map(int, g)) for g in groups]
+            offs = np.zeros(len(self.groups) + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(g) for g in self.groups])
+            ids = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=np.uint64) for g in self.groups]))
+        h = C.c_void_p()
+        check(lib.bann_genotypes_random(ctx.h, n, row_offset, n_total or n, m, seed, maf_lo, maf_hi, len(self.groups),
+                                        offs.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        ids.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(h)))
+        self.h = h
+        return self
 
     @property
     def num_groups(self):
@@ -342,13 +391,17 @@ class Net:
         return out
 
     # ---- full network (grouped) operations
-    def gradient(self, param_vecs=None, y=None):
-        """Net::gradient (net/net.rs:520-527) through HOST buffers: returns (grads, rss per branch)."""
+    def gradient(self, param_vecs=None, y=None, allreduce=None, out=None):
+        """Net::gradient (net/net.rs:520-527) through HOST buffers: returns (grads, rss per branch).
+        `allreduce`: callable run between the two halves when rows are sharded over ranks."""
         pv = _f32(param_vecs) if param_vecs is not None else None
         yy = _f32(y) if y is not None else None
-        grads = np.empty(self.num_params(), dtype=np.float32)
-        rss = np.empty(self.num_branches, dtype=np.float32)
-        check(lib.bann_net_gradient(self.h, _ptr(pv), _ptr(yy), _ptr(grads), _ptr(rss)))
+        grads, rss = out if out is not None else (np.empty(self.num_params(), dtype=np.float32),
+                                                  np.empty(self.num_branches, dtype=np.float32))
+        check(lib.bann_net_gradient_begin(self.h, _ptr(pv), _ptr(yy)))
+        if allreduce is not None:
+            allreduce()
+        check(lib.bann_net_gradient_end(self.h, _ptr(grads), _ptr(rss)))
         return grads, rss
 
     def grouped_begin(self, cfg: MCMCCfg, seed: int = 0, per_branch_targets: bool = False):

@@ -112,6 +112,31 @@ __global__ void k_decode_branch(const uint8_t* __restrict__ store, BranchDesc d,
     out[idx] = g;
 }
 
+// Synthetic genotypes in the spirit of BedVM::random (io/bed.rs:136-188): maf_j ~ U(lo, hi),
+// g_ij ~ Binomial(2, maf_j), written as PLINK codes.  Counter-based (Philox keyed by column and
+// GLOBAL row), so the data do not depend on how rows are sharded over GPUs.
+__global__ void k_random_payload(uint8_t* __restrict__ payload, uint64_t n, uint64_t row_offset, uint64_t m,
+                                 uint64_t bpc, uint64_t seed, float maf_lo, float maf_hi) {
+    uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (idx >= m * bpc) return;
+    const uint64_t j = idx / bpc, q = idx % bpc;
+    Philox pm(seed ^ 0x6a09e667f3bcc908ull, j, 0);
+    uint32_t r[4];
+    pm.next(r);
+    const float maf = maf_lo + (maf_hi - maf_lo) * u01_half_open(r[0]);
+    const float p2 = maf * maf, p1 = p2 + 2.f * maf * (1.f - maf);
+    Philox pg(seed, j, (row_offset >> 2) + q);
+    pg.next(r);
+    uint8_t byte = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (4 * q + k >= n) break;
+        const float u = u01_half_open(r[k]);
+        const uint8_t code = (u < p2) ? 0x0 : (u < p1 ? 0x2 : 0x3);   // value 2 -> 00, 1 -> 10, 0 -> 11 (bed.rs:16)
+        byte |= (uint8_t)(code << (2 * k));
+    }
+    payload[idx] = byte;
+}
+
 __global__ void k_gather_stats(const float* __restrict__ means, const float* __restrict__ stds,
                                const uint64_t* __restrict__ col_ids, uint64_t total, float* __restrict__ mu,
                                float* __restrict__ sd) {
@@ -178,22 +203,11 @@ int bann_ctx_sync(bann_ctx* c) {
     return 0;
 }
 
-int bann_genotypes_create(bann_ctx* ctx, const uint8_t* bed_payload, uint64_t n, uint64_t n_total, uint64_t m,
-                          const float* col_means, const float* col_stds, uint64_t num_branches,
-                          const uint64_t* branch_offsets, const uint64_t* col_ids, bann_genotypes** out) {
-    if (!ctx || !bed_payload || !branch_offsets || !col_ids || !out) BANN_FAIL("NULL argument");
-    if (n == 0 || m == 0 || num_branches == 0) BANN_FAIL("empty genotype store");
-    if ((col_means == nullptr) != (col_stds == nullptr)) BANN_FAIL("col_means and col_stds must both be given or both NULL");
-    if (!col_means && ctx->world > 1)
-        BANN_FAIL("column statistics must be global: pass col_means/col_stds when rows are sharded");
-    BANN_CUDA(cudaSetDevice(ctx->device));
+static int build_from_device_payload(bann_ctx* ctx, uint8_t* d_payload /* consumed */, uint64_t n, uint64_t n_total,
+                                     uint64_t m, const float* col_means, const float* col_stds, int device_stats,
+                                     uint64_t num_branches, const uint64_t* branch_offsets, const uint64_t* col_ids,
+                                     bann_genotypes** out) {
     uint64_t total_cols = branch_offsets[num_branches];
-    for (uint64_t b = 0; b < num_branches; ++b) {
-        if (branch_offsets[b + 1] <= branch_offsets[b]) BANN_FAIL("branch with no markers / offsets not increasing");
-    }
-    for (uint64_t k = 0; k < total_cols; ++k)
-        if (col_ids[k] >= m) BANN_FAIL("column id out of range");
-
     bann_genotypes* g = new bann_genotypes();
     g->ctx = ctx;
     g->n = n;
@@ -227,15 +241,8 @@ int bann_genotypes_create(bann_ctx* ctx, const uint8_t* bed_payload, uint64_t n,
     g->packed_bytes = 0;
     for (uint64_t b = 0; b < num_branches; ++b) g->packed_bytes += (uint64_t)g->m_b[b] * bpc;
 
-    uint8_t* d_payload = nullptr;
     uint64_t* d_cols = nullptr;
     BranchDesc* d_descs = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_payload);
-        cudaFree(d_descs);
-    };
-    BANN_CUDA(cudaMalloc(&d_payload, m * bpc));
-    BANN_CUDA(cudaMemcpyAsync(d_payload, bed_payload, m * bpc, cudaMemcpyHostToDevice, st));
     BANN_CUDA(cudaMalloc(&d_cols, total_cols * sizeof(uint64_t)));
     BANN_CUDA(cudaMemcpyAsync(d_cols, col_ids, total_cols * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     g->d_col_ids = d_cols;
@@ -249,10 +256,15 @@ int bann_genotypes_create(bann_ctx* ctx, const uint8_t* bed_payload, uint64_t n,
     if (col_means) {
         BANN_CUDA(cudaMemcpyAsync(g->d_means, col_means, m * sizeof(float), cudaMemcpyHostToDevice, st));
         BANN_CUDA(cudaMemcpyAsync(g->d_stds, col_stds, m * sizeof(float), cudaMemcpyHostToDevice, st));
-    } else {
+    } else if (device_stats) {
         k_col_stats<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_payload, n, m, bpc, g->d_means, g->d_stds);
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
+    } else {   // caller will provide global statistics through bann_genotypes_set_col_stats
+        std::vector<float> zeros(m, 0.f), ones(m, 1.f);
+        BANN_CUDA(cudaMemcpyAsync(g->d_means, zeros.data(), m * sizeof(float), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaMemcpyAsync(g->d_stds, ones.data(), m * sizeof(float), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaStreamSynchronize(st));
     }
     BANN_CUDA(cudaMalloc(&g->d_counts, 3 * m * sizeof(unsigned long long)));
     k_col_counts<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_payload, n, m, bpc, g->d_counts);
@@ -271,10 +283,10 @@ int bann_genotypes_create(bann_ctx* ctx, const uint8_t* bed_payload, uint64_t n,
     BANN_CUDA(cudaMalloc(&d_descs, num_branches * sizeof(BranchDesc)));
     BANN_CUDA(cudaMemcpyAsync(d_descs, descs.data(), num_branches * sizeof(BranchDesc), cudaMemcpyHostToDevice, st));
     size_t smem = (size_t)max_mp * kTileQuads;
-    if (smem > 200 * 1024) { cleanup(); BANN_FAIL("branch with more than 6400 markers is not supported by the tile builder"); }
+    if (smem > 200 * 1024) BANN_FAIL("branch with more than 6400 markers is not supported by the tile builder");
     if (smem > 48 * 1024) BANN_CUDA(cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint64_t nblocks = num_branches * (uint64_t)g->ntiles;
-    if (nblocks > 0x7fffffffull) { cleanup(); BANN_FAIL("too many tiles for one launch"); }
+    if (nblocks > 0x7fffffffull) BANN_FAIL("too many tiles for one launch");
     k_build_tiles<<<(unsigned)nblocks, 256, smem, st>>>(d_payload, n, bpc, nullptr, d_descs, d_cols,
                                                       (uint32_t)num_branches, g->ntiles, g->d_store);
     BANN_LAUNCHED();
@@ -284,9 +296,58 @@ int bann_genotypes_create(bann_ctx* ctx, const uint8_t* bed_payload, uint64_t n,
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     BANN_CUDA(cudaStreamSynchronize(st));
-    cleanup();
+    cudaFree(d_payload);
+    cudaFree(d_descs);
     *out = g;
     return 0;
+}
+
+static int check_csr(uint64_t m, uint64_t num_branches, const uint64_t* branch_offsets, const uint64_t* col_ids) {
+    for (uint64_t b = 0; b < num_branches; ++b)
+        if (branch_offsets[b + 1] <= branch_offsets[b]) BANN_FAIL("branch with no markers / offsets not increasing");
+    for (uint64_t k = 0; k < branch_offsets[num_branches]; ++k)
+        if (col_ids[k] >= m) BANN_FAIL("column id out of range");
+    return 0;
+}
+
+int bann_genotypes_create(bann_ctx* ctx, const uint8_t* bed_payload, uint64_t n, uint64_t n_total, uint64_t m,
+                          const float* col_means, const float* col_stds, uint64_t num_branches,
+                          const uint64_t* branch_offsets, const uint64_t* col_ids, bann_genotypes** out) {
+    if (!ctx || !bed_payload || !branch_offsets || !col_ids || !out) BANN_FAIL("NULL argument");
+    if (n == 0 || m == 0 || num_branches == 0) BANN_FAIL("empty genotype store");
+    if ((col_means == nullptr) != (col_stds == nullptr)) BANN_FAIL("col_means and col_stds must both be given or both NULL");
+    if (!col_means && ctx->world > 1)
+        BANN_FAIL("column statistics must be global: pass col_means/col_stds when rows are sharded");
+    BANN_CUDA(cudaSetDevice(ctx->device));
+    BANN_CHECK(check_csr(m, num_branches, branch_offsets, col_ids));
+    uint64_t bpc = (n + 3) / 4;
+    uint8_t* d_payload = nullptr;
+    BANN_CUDA(cudaMalloc(&d_payload, m * bpc));
+    BANN_CUDA(cudaMemcpyAsync(d_payload, bed_payload, m * bpc, cudaMemcpyHostToDevice, ctx->stream));
+    return build_from_device_payload(ctx, d_payload, n, n_total, m, col_means, col_stds, 1, num_branches, branch_offsets,
+                                     col_ids, out);
+}
+
+int bann_genotypes_random(bann_ctx* ctx, uint64_t n, uint64_t row_offset, uint64_t n_total, uint64_t m, uint64_t seed,
+                          float maf_lo, float maf_hi, uint64_t num_branches, const uint64_t* branch_offsets,
+                          const uint64_t* col_ids, bann_genotypes** out) {
+    if (!ctx || !branch_offsets || !col_ids || !out) BANN_FAIL("NULL argument");
+    if (n == 0 || m == 0 || num_branches == 0) BANN_FAIL("empty genotype store");
+    if (row_offset % 4 != 0) BANN_FAIL("row_offset must be a multiple of 4");
+    BANN_CUDA(cudaSetDevice(ctx->device));
+    BANN_CHECK(check_csr(m, num_branches, branch_offsets, col_ids));
+    uint64_t bpc = (n + 3) / 4;
+    uint8_t* d_payload = nullptr;
+    BANN_CUDA(cudaMalloc(&d_payload, m * bpc));
+    uint64_t total = m * bpc;
+    k_random_payload<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_payload, n, row_offset, m, bpc, seed,
+                                                                              maf_lo, maf_hi);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    // statistics: exact sequential ones when this rank holds every row, else the caller combines
+    // bann_genotypes_col_counts over ranks and calls bann_genotypes_set_col_stats
+    return build_from_device_payload(ctx, d_payload, n, n_total, m, nullptr, nullptr, ctx->world == 1 ? 1 : 0, num_branches,
+                                     branch_offsets, col_ids, out);
 }
 
 void bann_genotypes_destroy(bann_genotypes* g) {

@@ -1006,13 +1006,15 @@ int bann_predict(bann_net* net, bann_genotypes* test, float* yhat) {
 }
 
 // ------------------------------------------------------------------ full-network (grouped) operations
-int bann_net_gradient(bann_net* net, const float* param_vecs, const float* y, float* grads, float* rss) {
+// Net::gradient split in two so that a multi-GPU caller can all-reduce the raw sums in between:
+//   begin: H2D params / y, fused fwd+bwd over every branch, chunk reduction into the all-reduce buffer
+//   end  : gradient under the prior, D2H of gradients and rss
+int bann_net_gradient_begin(bann_net* net, const float* param_vecs, const float* y) {
     if (!net) BANN_FAIL("NULL net");
-    if (net->ctx->world > 1) BANN_FAIL("bann_net_gradient is single-GPU in this release (use the grouped phases)");
     cudaStream_t st = net->ctx->stream;
     // pinned staging so that the copies are true async DMA (the e2e form of the benchmark)
     if (!net->h_pin_a) {
-        BANN_CUDA(cudaMallocHost(&net->h_pin_a, net->total_params * sizeof(float)));
+        BANN_CUDA(cudaMallocHost(&net->h_pin_a, (net->total_params + net->n) * sizeof(float)));
         BANN_CUDA(cudaMallocHost(&net->h_pin_b, (net->total_params + net->B) * sizeof(float)));
     }
     if (param_vecs) {
@@ -1026,7 +1028,9 @@ int bann_net_gradient(bann_net* net, const float* param_vecs, const float* y, fl
     }
     const float* tgt = net->d_y;
     if (y) {
-        BANN_CUDA(cudaMemcpyAsync(net->d_t, y, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, st));
+        memcpy(net->h_pin_a + net->total_params, y, (size_t)net->n * sizeof(float));
+        BANN_CUDA(cudaMemcpyAsync(net->d_t, net->h_pin_a + net->total_params, (size_t)net->n * sizeof(float),
+                                  cudaMemcpyHostToDevice, st));
         tgt = net->d_t;
     }
     K1Launch k;
@@ -1034,7 +1038,13 @@ int bann_net_gradient(bann_net* net, const float* param_vecs, const float* y, fl
     k.nlist = (uint32_t)net->B;
     k.target_mode = TGT_SHARED;
     k.tgt = tgt;
-    BANN_CHECK(launch_k1(net, k, true));
+    return launch_k1(net, k, true);
+}
+
+int bann_net_gradient_end(bann_net* net, float* grads, float* rss) {
+    if (!net) BANN_FAIL("NULL net");
+    cudaStream_t st = net->ctx->stream;
+    if (!net->h_pin_b) BANN_FAIL("bann_net_gradient_end without bann_net_gradient_begin");
     k_grad_only<<<(unsigned)net->B, 256, 0, st>>>(net->d_descs, nullptr, net->d_theta, net->d_prec, net->d_gsum,
                                                   net->pstride, net->model, net->d_grad);
     BANN_LAUNCHED();
@@ -1055,6 +1065,13 @@ int bann_net_gradient(bann_net* net, const float* param_vecs, const float* y, fl
     }
     if (rss) memcpy(rss, net->h_pin_b + net->total_params, net->B * sizeof(float));
     return 0;
+}
+
+int bann_net_gradient(bann_net* net, const float* param_vecs, const float* y, float* grads, float* rss) {
+    if (!net) BANN_FAIL("NULL net");
+    if (net->ctx->world > 1) BANN_FAIL("with sharded rows call bann_net_gradient_begin, all-reduce, bann_net_gradient_end");
+    BANN_CHECK(bann_net_gradient_begin(net, param_vecs, y));
+    return bann_net_gradient_end(net, grads, rss);
 }
 
 static HmcRun grouped_run(bann_net* net) {

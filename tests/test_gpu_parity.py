@@ -518,14 +518,13 @@ def test_net_gradient_matches_per_branch(rb, ctx):
 
 
 def test_grouped_leapfrog_conserves_energy_and_matches_kernels(rb, ctx):
-    P = Problem(rb, ctx, "ridge_ard", 1200, [50] * 6, 5, 5, seed=6)
-    try:
-        cfg = rb.MCMCCfg(hmc_step_size_factor=0.05, hmc_integration_length=20, hmc_step_size_mode="izmailov")
-        out = {}
-        for generic in (True, False):
+    cfg = rb.MCMCCfg(hmc_step_size_factor=0.05, hmc_integration_length=20, hmc_step_size_mode="izmailov")
+    out = {}
+    for generic in (True, False):
+        # fresh net per kernel: the built-in Philox stream is keyed by (seed, visit counter, branch)
+        P = Problem(rb, ctx, "ridge_ard", 1200, [50] * 6, 5, 5, seed=6)
+        try:
             P.net.force_generic(generic)
-            for b, c in enumerate(P.cfgs):
-                P.net.set_branch(b, c.param_vec(), c.precision_vec())
             P.net.grouped_begin(cfg, seed=7, per_branch_targets=False)
             P.net.grouped_leapfrog(cfg, 20, finalize=True)
             hi, hc, st = P.net.grouped_state()
@@ -534,10 +533,31 @@ def test_grouped_leapfrog_conserves_energy_and_matches_kernels(rb, ctx):
             acc, early = P.net.grouped_finish(seed=7)
             assert early == 0 and acc >= 4
             out[generic] = (hi.copy(), hc.copy(), P.net.get_all_params()[0])
-        assert np.allclose(out[True][0], out[False][0], rtol=1e-5)
-        assert np.allclose(out[True][1], out[False][1], rtol=1e-4)
-    finally:
-        P.close()
+        finally:
+            P.close()
+    assert np.allclose(out[True][0], out[False][0], rtol=1e-5)
+    assert np.allclose(out[True][1], out[False][1], rtol=1e-4)
+    assert np.allclose(out[True][2], out[False][2], rtol=1e-3, atol=1e-4)
+
+
+def test_synthetic_store_is_independent_of_row_sharding(rb, ctx):
+    n, m, groups = 1000, 60, obed.uniform_grouping(3, 20)
+    full = rb.Genotypes.random(ctx, n, m, groups, seed=5)
+    lo = rb.Genotypes.random(ctx, 512, m, groups, seed=5, row_offset=0, n_total=n)
+    hi = rb.Genotypes.random(ctx, n - 512, m, groups, seed=5, row_offset=512, n_total=n)
+    for b in range(3):
+        x = full.x_group(b, standardized=False)
+        assert set(np.unique(x)) <= {0.0, 1.0, 2.0}
+        assert np.array_equal(x[:512], lo.x_group(b, False)) and np.array_equal(x[512:], hi.x_group(b, False))
+    cnt = lo.col_counts() + hi.col_counts()
+    assert np.array_equal(cnt, full.col_counts())
+    mu, sd = rb.stats_from_counts(cnt, n)
+    fmu, fsd = full.col_stats()          # sequential f32 statistics of the full store
+    assert np.array_equal(mu, fmu) and np.allclose(sd, fsd, rtol=2e-6)
+    # allele frequencies look like U(0.01, 0.5) draws
+    assert 0.05 < fmu.mean() / 2 < 0.45
+    for g in (full, lo, hi):
+        g.close()
 
 
 def test_grouped_per_branch_targets_equal_residual_plus_prediction(rb, ctx):
