@@ -66,9 +66,11 @@ def cuda_available() -> bool:
 class Context:
     """One per process / GPU. `stream`: a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
 
-    def __init__(self, device: int = 0, stream: int = 0, rank: int = 0, world: int = 1):
+    def __init__(self, device: int = 0, stream: Optional[int] = None, rank: int = 0, world: int = 1):
         h = C.c_void_p()
-        check(lib.bann_ctx_create(device, C.c_void_p(stream) if stream else None, rank, world, C.byref(h)))
+        if stream is not None and stream == 0:
+            stream = 1          # torch's default stream is handle 0 == the legacy default stream: cudaStreamLegacy
+        check(lib.bann_ctx_create(device, C.c_void_p(stream) if stream is not None else None, rank, world, C.byref(h)))
         self.h, self.rank, self.world, self.device = h, rank, world, device
 
     def sync(self):
@@ -99,7 +101,7 @@ def stats_from_counts(counts: np.ndarray, n_total: int):
     sum, io/bed.rs:231-238, is order dependent and cannot be reproduced from shard partials)."""
     c = counts.astype(np.float64)
     nf = float(n_total)
-    mean = ((c[:, 1] + 2.0 * c[:, 2]) / nf).astype(np.float32)
+    mean = ((c[:, 1] + 2.0 * c[:, 2]).astype(np.float32) / np.float32(n_total)).astype(np.float32)  # f32 division as bed.rs:233
     m64 = mean.astype(np.float64)
     ss = c[:, 0] * (0 - m64) ** 2 + c[:, 1] * (1 - m64) ** 2 + c[:, 2] * (2 - m64) ** 2
     return mean, np.sqrt(ss / nf).astype(np.float32)

@@ -553,7 +553,7 @@ def test_synthetic_store_is_independent_of_row_sharding(rb, ctx):
     assert np.array_equal(cnt, full.col_counts())
     mu, sd = rb.stats_from_counts(cnt, n)
     fmu, fsd = full.col_stats()          # sequential f32 statistics of the full store
-    assert np.array_equal(mu, fmu) and np.allclose(sd, fsd, rtol=2e-6)
+    assert np.array_equal(mu, fmu) and np.allclose(sd, fsd, rtol=2e-5)
     # allele frequencies look like U(0.01, 0.5) draws
     assert 0.05 < fmu.mean() / 2 < 0.45
     for g in (full, lo, hi):
