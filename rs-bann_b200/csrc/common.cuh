@@ -23,7 +23,7 @@ enum : int { ST_IDLE = -1, ST_RUNNING = 3, ST_REJECTED_EARLY = BANN_HMC_REJECTED
 // One branch: architecture + offsets into the arenas.  param_vec order (params.rs:700-715).
 struct BranchDesc {
     uint32_t m;                 // markers in the branch
-    uint32_t m_pad4;            // m rounded up to a multiple of 4 (bytes per row-quad in a tile)
+    uint32_t m_pad4;            // bytes per row-quad in a tile: m rounded up to whole 32-bit words, odd word count
     uint32_t nl;                // layers incl. output
     uint32_t P;                 // parameters
     uint32_t nprec;             // precisions (weight precs, bias precs, error prec)

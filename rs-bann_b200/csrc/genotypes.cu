@@ -7,7 +7,7 @@
 // branch-major, row-tile-major layout so that the bytes one CTA needs for one (branch, 128-row
 // tile) are one contiguous block:
 //
-//   tile(b, t) = [32 row-quads][m_pad4 bytes];  byte(q, j) holds the four individuals
+//   tile(b, t) = [32 row-quads][m_pad4 bytes] (m_pad4 = 4 * odd);  byte(q, j) holds the four individuals
 //   t*128 + 4q .. +3 (LSB first, as in PLINK) of the branch's j-th marker.
 //
 // Codes are re-encoded from PLINK's {00->2, 01->missing(0), 10->1, 11->0}
@@ -228,7 +228,7 @@ static int build_from_device_payload(bann_ctx* ctx, uint8_t* d_payload /* consum
     uint32_t max_mp = 0;
     for (uint64_t b = 0; b < num_branches; ++b) {
         uint32_t mb = (uint32_t)(branch_offsets[b + 1] - branch_offsets[b]);
-        uint32_t mp = (mb + 3) & ~3u;
+        uint32_t mp = 4u * (((mb + 3) / 4) | 1u);   // bytes per row-quad: whole words, ODD word count (bank-conflict free)
         g->m_b[b] = mb;
         g->m_pad4[b] = mp;
         g->tile_off[b] = off;

@@ -1,15 +1,21 @@
 // Tuned K1 for narrow branches: fused forward + backward, FP32 FFMA, one warp per 128-row tile.
 //
 // Template <H, S, D, NP>: D hidden layers of width H, summary width S (compile time, fully
-// unrolled), up to 32*NP markers per branch.  Layout of the work inside a warp:
+// unrolled, tanh), up to 32*NP markers per branch.  Work layout inside a warp:
+//   load     : the tile (32 row-quads x 4*wpr bytes, wpr odd by construction of the store) is
+//              copied HBM -> shared memory with 16-byte cp.async, double buffered, so the next
+//              tile streams in while the current one is being computed.
 //   forward  : lane = row-quad q (4 individuals = one packed byte per marker); the first-layer
 //              pre-activations of its 4 rows live in registers; markers stream from shared memory
-//              four at a time (one 32-bit word), W' = W0/sd rows are broadcast float4 loads.
+//              four at a time (one 32-bit word, conflict free because wpr is odd); W' rows are
+//              broadcast float4 loads.  Decode is LOP3 + I2FP: float(word & (3 << s)) = g * 2^s,
+//              the power of two is folded into the staged weights / undone exactly afterwards.
 //   tail     : the lane runs the remaining tiny layers + backward deltas for its 4 rows; the
 //              cross-row sums of every layer >= 1 (gW_l, gb_l, rss) accumulate in per-lane
 //              registers over ALL tiles of the CTA and are reduced once at the end.
-//   backward : lane = marker (pass p: marker 32p + lane); delta_0 of the tile is broadcast from
-//              shared memory; sum_i g_ij delta_0[i,c] accumulates in registers over all tiles.
+//   backward : lane = marker (pass p: marker 32p + lane); delta_0 of the tile is staged
+//              transposed ([unit][row], conflict-free float4 stores, broadcast float4 loads);
+//              sum_i g_ij delta_0[i,c] accumulates in registers over all tiles.
 // The packed tile is read from HBM once and used for both directions.  Standardisation is folded
 // into the first layer (W' = W/sd, b' = b - sum mu W') and unfolded on the gradient.
 // Partial sums leave the CTA in a fixed order (deterministic, no float atomics).
@@ -22,6 +28,29 @@ float* bann_net_gsum(bann_net* net);
 uint32_t bann_net_pstride(bann_net* net);
 
 namespace bann {
+
+// tanh with ~3 ulp error, branch free: odd Taylor polynomial below 0.25, 1 - 2/(e^{2|x|}+1) above.
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float ax = fabsf(x);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    const float big = copysignf(fmaf(-2.f, r, 1.f), x);
+    const float x2 = x * x;
+    float p = fmaf(x2, 0.021869488536155203f, -0.05396825396825397f);
+    p = fmaf(x2, p, 0.13333333333333333f);
+    p = fmaf(x2, p, -0.3333333333333333f);
+    const float small = fmaf(p * x2, x, x);
+    return ax < 0.25f ? small : big;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 template <int H, int S, int D>
 struct TailShape {
@@ -44,31 +73,30 @@ struct TailShape {
         return o;
     }
     __host__ __device__ static constexpr int n_tail() { return b_off(NLA - 1) + width(NLA - 1); }
+    static constexpr int NTACC = 1 + S + W0 + (NLA > 1 ? (NLA - 1) * (MW * MW + MW) : 0);
 };
 
 template <int H, int S, int D, int NP, int NW>
-__global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
+__global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a, int nstage) {
     using T = TailShape<H, S, D>;
-    constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, MW = T::MW;
+    constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, MW = T::MW, NTACC = T::NTACC;
     extern __shared__ __align__(16) uint8_t smraw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
     const uint32_t b = a.list ? a.list[li] : li;
     if (a.states && a.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = a.descs[b];
-    const uint32_t m = d.m, mp = d.m_pad4, wpr = mp >> 2;     // words per row-quad in global memory
-    const uint32_t tsw = wpr | 1u;                            // odd word stride in shared memory
+    const uint32_t m = d.m, mp = d.m_pad4, wpr = mp >> 2;     // words per row-quad (odd)
+    const uint32_t tile_words = kTileQuads * wpr;             // multiple of 4
     // ---- shared memory carve-up
-    float* Wp = reinterpret_cast<float*>(smraw);              // [mp][W0P]   W' = W0 / sd (zero rows beyond m)
+    float* Wp = reinterpret_cast<float*>(smraw);              // [mp][W0P]   W' = W0/sd * 2^-(8*(j%4)), zero rows beyond m
     float* b0p = Wp + (size_t)mp * W0P;                       // [W0P]
     float* sp = b0p + W0P;                                    // tail parameters [n_tail]
-    float* red = sp + ((T::n_tail() + 3) & ~3);               // cross-warp reduction scratch [NW][...]
-    constexpr int NTACC = 1 + S + W0 + (NLA > 1 ? (NLA - 1) * (MW * MW + MW) : 0);
-    float* wbase = red + NW * (NTACC > NP * W0 ? NTACC : NP * W0) + 4;
-    const uint32_t per_warp_words = ((32 * tsw + 3) & ~3u) + 128 * W0P;
-    uint32_t* tilew = reinterpret_cast<uint32_t*>(wbase) + (size_t)warp * per_warp_words;
-    float* dbuf = reinterpret_cast<float*>(tilew + ((32 * tsw + 3) & ~3u));   // [128][W0P] delta_0
-    const uint8_t* tileb = reinterpret_cast<const uint8_t*>(tilew);
+    float* red = sp + ((T::n_tail() + 3) & ~3);               // cross-warp reduction scratch
+    float* wbase = red + NW * (NTACC > 32 * W0 ? NTACC : 32 * W0) + 4;
+    const uint32_t per_warp_words = (uint32_t)nstage * tile_words + W0 * 128;
+    uint32_t* wtile = reinterpret_cast<uint32_t*>(wbase) + (size_t)warp * per_warp_words;
+    float* dT = reinterpret_cast<float*>(wtile + (size_t)nstage * tile_words);   // [W0][128] delta_0 (transposed)
 
     const float* th = a.theta + d.param_off;
     const float* mu = a.mu + d.col_off;
@@ -76,14 +104,16 @@ __global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
     // ---- stage parameters
     for (uint32_t k = tid; k < mp * W0P; k += NW * 32) {
         const uint32_t j = k / W0P, c = k % W0P;
-        Wp[k] = (j < m && c < W0) ? __fdiv_rn(th[c * m + j], sd[j]) : 0.f;
+        float v = 0.f;
+        if (j < m && c < W0) v = __fdiv_rn(th[c * m + j], sd[j]) * exp2f(-8.f * (float)(j & 3u));   // exact scaling
+        Wp[k] = v;
     }
     for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += NW * 32) sp[k] = th[m * W0 + k];
     __syncthreads();
     if (tid < W0P) {
         float acc = 0.f;
         if (tid < W0) {
-            for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], Wp[j * W0P + tid], acc);
+            for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], Wp[j * W0P + tid] * exp2f(8.f * (float)(j & 3u)), acc);
             acc = sp[T::b_off(0) + tid] - acc;
         }
         b0p[tid] = acc;
@@ -112,33 +142,58 @@ __global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
         }
 
     const size_t eoff = a.out_per_entry ? (size_t)li * a.n : 0;
+    const size_t toff = (a.target_mode == TGT_PER_ENTRY) ? (size_t)li * a.n : 0;
+    const bool vec_ok = (a.n & 3u) == 0;
     const uint32_t t_begin = chunk * a.tiles_per_chunk;
     const uint32_t t_end = min(a.ntiles, t_begin + a.tiles_per_chunk);
-    for (uint32_t t = t_begin + warp; t < t_end; t += NW) {
-        // ---- load the packed tile (coalesced 16-byte reads, re-strided to an odd word stride)
+    const uint8_t* gbase = a.store + d.tile_off;
+    const uint32_t nvec = tile_words >> 2;
+
+    auto issue_load = [&](uint32_t t, uint32_t stage) {
+        const uint4* src = reinterpret_cast<const uint4*>(gbase + (size_t)t * tile_words * 4);
+        uint4* dst = reinterpret_cast<uint4*>(wtile + (size_t)stage * tile_words);
+        for (uint32_t v = lane; v < nvec; v += 32) cp_async16(dst + v, src + v);
+        cp_async_commit();
+    };
+
+    uint32_t t = t_begin + warp;
+    uint32_t stage = 0;
+    if (t < t_end) issue_load(t, 0);
+    for (; t < t_end; t += NW) {
+        // ---- prefetch the next tile, wait for the current one
+        const uint32_t tn = t + NW;
+        if (nstage == 2) {
+            if (tn < t_end) { issue_load(tn, stage ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const uint32_t* tilew = wtile + (size_t)stage * tile_words;
+        const uint8_t* tileb = reinterpret_cast<const uint8_t*>(tilew);
+        // targets of the lane's 4 rows (issued early, consumed in the tail)
+        const uint32_t row0 = t * kTileRows + lane * 4;
+        float tg4[4] = {0.f, 0.f, 0.f, 0.f};
         {
-            const uint4* src = reinterpret_cast<const uint4*>(a.store + d.tile_off + (size_t)t * (kTileQuads * mp));
-            const uint32_t nvec = (kTileQuads * wpr) >> 2;    // 32*wpr words is a multiple of 4
-            __syncwarp();
-            for (uint32_t v = lane; v < nvec; v += 32) {
-                const uint4 x = __ldg(src + v);
-                const uint32_t w0i = v * 4;
-                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+            const float* src = (a.target_mode == TGT_RESID_PLUS_PRED) ? a.resid : (a.tgt ? a.tgt + toff : nullptr);
+            if (src) {
+                if (vec_ok && row0 + 3 < a.n) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + row0));
+                    tg4[0] = v.x; tg4[1] = v.y; tg4[2] = v.z; tg4[3] = v.w;
+                } else {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t wi = w0i + u;
-                    tilew[(wi / wpr) * tsw + (wi % wpr)] = xs[u];
+                    for (int r = 0; r < 4; ++r)
+                        if (row0 + r < a.n) tg4[r] = src[row0 + r];
                 }
             }
-            __syncwarp();
         }
-        // ---- forward, first layer: lane = row-quad
+        // ---- forward, first layer: lane = row-quad; z[r][c] accumulates 4^r * (x W')
         float z[4][W0];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c < W0; ++c) z[r][c] = b0p[c];
-        const uint32_t* myrow = tilew + lane * tsw;
+            for (int c = 0; c < W0; ++c) z[r][c] = 0.f;
+        const uint32_t* myrow = tilew + lane * wpr;
         for (uint32_t jw = 0; jw < wpr; ++jw) {
             const uint32_t word = myrow[jw];
 #pragma unroll
@@ -152,24 +207,21 @@ __global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const float gf = (float)((word >> (8 * k + 2 * r)) & 3u);
+                    const float gf = (float)(word & (3u << (8 * k + 2 * r)));   // g * 2^(8k+2r), exact
 #pragma unroll
                     for (int c = 0; c < W0; ++c) z[r][c] = fmaf(gf, w[c], z[r][c]);
                 }
             }
         }
         // ---- tail: remaining layers, error, backward deltas, for the lane's 4 rows
+        float yh4[4], dl0[4][W0];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint32_t row = t * kTileRows + lane * 4 + r;
-            const bool valid = row < a.n;
-            float act[NLA][MW], dh[NLA][MW];
+            const bool valid = row0 + r < a.n;
+            const float unscale = 1.f / (float)(1 << (2 * r));
+            float act[NLA][MW];
 #pragma unroll
-            for (int c = 0; c < W0; ++c) {
-                const float h = act_h(a.act, z[r][c]);
-                act[0][c] = h;
-                dh[0][c] = act_dh(a.act, z[r][c], h);
-            }
+            for (int c = 0; c < W0; ++c) act[0][c] = fast_tanh(fmaf(z[r][c], unscale, b0p[c]));
 #pragma unroll
             for (int l = 1; l < NLA; ++l) {
 #pragma unroll
@@ -179,38 +231,23 @@ __global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
 #pragma unroll
                         for (int i = 0; i < MW; ++i)
                             if (i < T::in_w(l)) zz = fmaf(act[l - 1][i], sp[T::w_off(l) + c * T::in_w(l) + i], zz);
-                        const float h = act_h(a.act, zz);
-                        act[l][c] = h;
-                        dh[l][c] = act_dh(a.act, zz, h);
+                        act[l][c] = fast_tanh(zz);
                     }
                 }
             }
             float yh = 0.f;
 #pragma unroll
             for (int i = 0; i < S; ++i) yh = fmaf(act[NLA - 1][i], sp[T::w_off(NLA) + i], yh);
-            float tg = 0.f;
-            if (valid) {
-                if (a.target_mode == TGT_RESID_PLUS_PRED) {
-                    tg = a.resid[row] + yh;
-                    if (a.tgt_out) a.tgt_out[eoff + row] = tg;
-                    if (a.prev_out) a.prev_out[eoff + row] = yh;
-                } else if (a.tgt) {
-                    tg = a.tgt[(a.target_mode == TGT_PER_ENTRY ? (size_t)li * a.n : 0) + row];
-                }
-                if (a.yhat_out) {
-                    if (a.yhat_accumulate > 0) a.yhat_out[eoff + row] += yh;
-                    else if (a.yhat_accumulate < 0) a.yhat_out[eoff + row] -= yh;
-                    else a.yhat_out[eoff + row] = yh;
-                }
-            }
-            if (a.fwd_only) continue;
-            const float e = valid ? yh - tg : 0.f;
+            yh4[r] = yh;
+            float tg = tg4[r];
+            if (a.target_mode == TGT_RESID_PLUS_PRED) { tg = tg + yh; tg4[r] = tg; }   // net.rs:280
+            const float e = valid ? yh - tg : 0.f;                                      // branch_sampler.rs:821
             rss = fmaf(e, e, rss);
             float delta[MW];
 #pragma unroll
             for (int i = 0; i < S; ++i) {
                 gWo[i] = fmaf(act[NLA - 1][i], e, gWo[i]);
-                delta[i] = dh[NLA - 1][i] * (e * sp[T::w_off(NLA) + i]);
+                delta[i] = (1.f - act[NLA - 1][i] * act[NLA - 1][i]) * (e * sp[T::w_off(NLA) + i]);
             }
 #pragma unroll
             for (int l = NLA - 1; l >= 1; --l) {
@@ -231,50 +268,75 @@ __global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
                 }
 #pragma unroll
                 for (int i = 0; i < MW; ++i)
-                    if (i < T::in_w(l)) delta[i] = dh[l - 1][i] * nd[i];
+                    if (i < T::in_w(l)) delta[i] = (1.f - act[l - 1][i] * act[l - 1][i]) * nd[i];
             }
-            float* drow = dbuf + (lane * 4 + r) * W0P;
 #pragma unroll
             for (int c = 0; c < W0; ++c) {
                 gb0[c] += delta[c];
-                drow[c] = delta[c];
+                dl0[r][c] = delta[c] * unscale;      // backward decodes g * 4^r from the byte
             }
         }
-        if (a.fwd_only) continue;
-        __syncwarp();
-        // ---- backward, first layer: lane = marker
-        for (uint32_t q = 0; q < kTileQuads; ++q) {
-            float dl[4][W0P];
+        // ---- per-row outputs (vector stores when the row block is complete)
+        {
+            const bool full = vec_ok && row0 + 3 < a.n;
+            auto put4 = [&](float* dst, const float v[4], int accumulate) {
+                if (!dst) return;
+                float* p = dst + eoff + row0;
+                if (full && accumulate == 0) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+                else {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float4* dr = reinterpret_cast<const float4*>(dbuf + (q * 4 + r) * W0P);
-#pragma unroll
-                for (int v = 0; v < W0P / 4; ++v) {
-                    const float4 f = dr[v];
-                    dl[r][4 * v] = f.x; dl[r][4 * v + 1] = f.y; dl[r][4 * v + 2] = f.z; dl[r][4 * v + 3] = f.w;
+                    for (int r = 0; r < 4; ++r)
+                        if (row0 + r < a.n) {
+                            if (accumulate > 0) p[r] += v[r];
+                            else if (accumulate < 0) p[r] -= v[r];
+                            else p[r] = v[r];
+                        }
                 }
+            };
+            if (a.target_mode == TGT_RESID_PLUS_PRED) {
+                put4(a.tgt_out, tg4, 0);
+                put4(a.prev_out, yh4, 0);      // net.rs:279
             }
+            put4(a.yhat_out, yh4, a.yhat_accumulate);
+        }
+        if (!a.fwd_only) {
+            // ---- stage delta_0 transposed: dT[c][row], one conflict-free float4 per unit
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                if (32u * p < m) {
-                    const uint32_t j = 32 * p + lane;
-                    const uint32_t byte = (j < mp) ? tileb[q * tsw * 4 + j] : 0u;
+            for (int c = 0; c < W0; ++c)
+                *reinterpret_cast<float4*>(dT + c * 128 + lane * 4) = make_float4(dl0[0][c], dl0[1][c], dl0[2][c], dl0[3][c]);
+            __syncwarp();
+            // ---- backward, first layer: lane = marker
+            for (uint32_t q = 0; q < kTileQuads; ++q) {
+                float dl[W0][4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float gf = (float)((byte >> (2 * r)) & 3u);
+                for (int c = 0; c < W0; ++c) {
+                    const float4 f = *reinterpret_cast<const float4*>(dT + c * 128 + q * 4);
+                    dl[c][0] = f.x; dl[c][1] = f.y; dl[c][2] = f.z; dl[c][3] = f.w;
+                }
 #pragma unroll
-                        for (int c = 0; c < W0; ++c) acc0[p][c] = fmaf(gf, dl[r][c], acc0[p][c]);
+                for (int p = 0; p < NP; ++p) {
+                    if (32u * p < m) {
+                        const uint32_t j = 32 * p + lane;
+                        const uint32_t byte = (j < mp) ? tileb[q * mp + j] : 0u;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const float gf = (float)(byte & (3u << (2 * r)));      // g * 4^r
+#pragma unroll
+                            for (int c = 0; c < W0; ++c) acc0[p][c] = fmaf(gf, dl[c][r], acc0[p][c]);
+                        }
                     }
                 }
             }
         }
+        __syncwarp();
+        stage ^= (nstage == 2) ? 1u : 0u;
+        if (nstage == 1 && tn < t_end) issue_load(tn, 0);
     }
     if (a.fwd_only || !a.part) return;
 
     // ---- CTA epilogue: fixed-order reduction over lanes and warps, unfold the standardisation
     float* pp = a.part + ((size_t)li * a.nchunk + chunk) * a.pstride;
     const uint32_t P = d.P;
-    // (1) per-lane tail accumulators -> warp sums (xor tree) -> red[warp][...]
     {
         float* rw = red + warp * NTACC;
         int idx = 0;
@@ -305,7 +367,6 @@ __global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < NW; ++w) s += red[w * NTACC + tid];
-        // scatter to param_vec order
         int idx = tid;
         if (idx == 0) pp[P] = s;
         else if (idx < 1 + S) pp[m * W0 + T::w_off(NLA) + (idx - 1)] = s;                       // output weights
@@ -325,7 +386,7 @@ __global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
         }
     }
     __syncthreads();
-    // (2) first-layer weight gradient: sum over warps, then (S_jc - mu_j * gb0_c) / sd_j
+    // first-layer weight gradient: sum over warps, then (S_jc - mu_j * gb0_c) / sd_j
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         if (32u * p < m) {
@@ -347,21 +408,19 @@ __global__ void __launch_bounds__(NW * 32) k1_small(K1Args a) {
 }
 
 template <int H, int S, int D, int NP, int NW>
-size_t k1_small_smem(uint32_t mp) {
+size_t k1_small_smem(uint32_t mp, int nstage) {
     using T = TailShape<H, S, D>;
-    constexpr int NTACC = 1 + S + T::W0 + (T::NLA > 1 ? (T::NLA - 1) * (T::MW * T::MW + T::MW) : 0);
-    const uint32_t tsw = (mp >> 2) | 1u;
     size_t fl = (size_t)mp * T::W0P + T::W0P + ((T::n_tail() + 3) & ~3);
-    size_t redn = (size_t)NW * (NTACC > 32 * T::W0 ? NTACC : 32 * T::W0) + 4;
-    size_t perw = ((32 * tsw + 3) & ~3u) + 128 * T::W0P;
+    size_t redn = (size_t)NW * (T::NTACC > 32 * T::W0 ? T::NTACC : 32 * T::W0) + 4;
+    size_t perw = (size_t)nstage * kTileQuads * (mp >> 2) + (size_t)T::W0 * 128;
     return (fl + redn + (size_t)NW * perw) * 4 + 16;
 }
 
-struct SmallKey { int H, S, D; };
-
 template <int H, int S, int D, int NP, int NW>
 int launch_one_small(K1Args& a, uint32_t nlist, uint32_t mp, cudaStream_t st) {
-    size_t smem = k1_small_smem<H, S, D, NP, NW>(mp);
+    int nstage = 2;
+    size_t smem = k1_small_smem<H, S, D, NP, NW>(mp, 2);
+    if (smem > 100 * 1024) { nstage = 1; smem = k1_small_smem<H, S, D, NP, NW>(mp, 1); }
     auto kern = k1_small<H, S, D, NP, NW>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -369,18 +428,18 @@ int launch_one_small(K1Args& a, uint32_t nlist, uint32_t mp, cudaStream_t st) {
         configured = smem;
     }
     dim3 grid(a.nchunk, nlist);
-    kern<<<grid, NW * 32, smem, st>>>(a);
+    kern<<<grid, NW * 32, smem, st>>>(a, nstage);
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
 }
 
 // picks an instantiation for a homogeneous launch (all listed branches share the architecture and
-// fit the marker bound); otherwise leaves *launched = false and the generic kernel runs.
+// fit the marker bound, activation tanh); otherwise leaves *launched = false and the generic kernel runs.
 inline int launch_k1_small(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
                            cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
-    // architecture of the launch: single branch, or all branches (must be homogeneous)
+    if (a.act != BANN_TANH) return 0;
     const BranchDesc& d0 = descs[single_branch >= 0 ? single_branch : 0];
     uint32_t max_m = d0.m, max_mp = d0.m_pad4;
     if (single_branch < 0) {
@@ -397,7 +456,7 @@ inline int launch_k1_small(const std::vector<BranchDesc>& descs, int single_bran
     const int H = D > 0 ? (int)d0.widths[0] : S;
     for (int l = 0; l < D; ++l)
         if ((int)d0.widths[l] != H) return 0;
-    // the small kernel wants fewer, fatter chunks: every CTA keeps NW warps busy on its own tiles
+    // fewer, fatter chunks than the generic kernel: every CTA keeps NW warps busy on its own tiles
     constexpr int NW = 8;
     uint32_t ntiles = a.ntiles;
     uint32_t want = (uint32_t)std::max<uint64_t>(1, ((uint64_t)num_sms * 2 + nlist - 1) / nlist);
@@ -406,7 +465,7 @@ inline int launch_k1_small(const std::vector<BranchDesc>& descs, int single_bran
     nchunk = (ntiles + tpc - 1) / tpc;
 #define BANN_TRY(HH, SS, DD, NPP)                                                                         \
     if (!*launched && H == HH && S == SS && D == DD && max_m <= 32u * NPP &&                              \
-        k1_small_smem<HH, SS, DD, NPP, NW>(max_mp) <= 200 * 1024) {                                       \
+        k1_small_smem<HH, SS, DD, NPP, NW>(max_mp, 1) <= 200 * 1024) {                                    \
         a.nchunk = nchunk;                                                                                \
         a.tiles_per_chunk = tpc;                                                                          \
         if (part_io) {                                                                                    \
