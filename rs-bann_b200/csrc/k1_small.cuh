@@ -44,6 +44,16 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return ax < 0.25f ? small : big;
 }
 
+// packed FP32 FMA (Blackwell FFMA2): {d0,d1} += {a0,a1} * {b0,b1} in one issue slot
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rc));
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
@@ -58,6 +68,7 @@ struct TailShape {
     static constexpr int W0 = D > 0 ? H : S;          // width of the layer fed by the genotypes
     static constexpr int MW = H > S ? H : S;
     static constexpr int W0P = (W0 + 3) & ~3;         // padded to float4
+    static constexpr int W2P = (2 * W0 + 3) & ~3;     // staged first-layer row: every weight duplicated {w,w} for FFMA2
     __host__ __device__ static constexpr int width(int l) { return l < D ? H : S; }   // l < NLA
     __host__ __device__ static constexpr int in_w(int l) { return width(l - 1); }     // 1 <= l <= NLA (NLA: output)
     // offsets inside the "tail" parameter block = theta[m*W0 .. P): weights of layers 1..NLA, then all biases
@@ -79,7 +90,8 @@ struct TailShape {
 template <int H, int S, int D, int NP, int NW>
 __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a, int nstage) {
     using T = TailShape<H, S, D>;
-    constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, MW = T::MW, NTACC = T::NTACC;
+    constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, W2P = T::W2P, MW = T::MW, NTACC = T::NTACC;
+    constexpr bool PK = NP <= 4;   // packed backward accumulators (2 per marker-unit) only when registers allow
     extern __shared__ __align__(16) uint8_t smraw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
@@ -89,8 +101,8 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
     const uint32_t m = d.m, mp = d.m_pad4, wpr = mp >> 2;     // words per row-quad (odd)
     const uint32_t tile_words = kTileQuads * wpr;             // multiple of 4
     // ---- shared memory carve-up
-    float* Wp = reinterpret_cast<float*>(smraw);              // [mp][W0P]   W' = W0/sd * 2^-(8*(j%4)), zero rows beyond m
-    float* b0p = Wp + (size_t)mp * W0P;                       // [W0P]
+    float* Wp = reinterpret_cast<float*>(smraw);              // [mp][W2P]   {w,w} pairs, w = W0/sd * 2^-(8*(j%4)); zero rows beyond m
+    float* b0p = Wp + (size_t)mp * W2P;                       // [W0P]
     float* sp = b0p + W0P;                                    // tail parameters [n_tail]
     float* red = sp + ((T::n_tail() + 3) & ~3);               // cross-warp reduction scratch
     float* wbase = red + NW * (NTACC > 32 * W0 ? NTACC : 32 * W0) + 4;
@@ -102,8 +114,8 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
     const float* mu = a.mu + d.col_off;
     const float* sd = a.sd + d.col_off;
     // ---- stage parameters
-    for (uint32_t k = tid; k < mp * W0P; k += NW * 32) {
-        const uint32_t j = k / W0P, c = k % W0P;
+    for (uint32_t k = tid; k < mp * W2P; k += NW * 32) {
+        const uint32_t j = k / W2P, c = (k % W2P) >> 1;
         float v = 0.f;
         if (j < m && c < W0) v = __fdiv_rn(th[c * m + j], sd[j]) * exp2f(-8.f * (float)(j & 3u));   // exact scaling
         Wp[k] = v;
@@ -113,7 +125,7 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
     if (tid < W0P) {
         float acc = 0.f;
         if (tid < W0) {
-            for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], Wp[j * W0P + tid] * exp2f(8.f * (float)(j & 3u)), acc);
+            for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], Wp[j * W2P + 2 * tid] * exp2f(8.f * (float)(j & 3u)), acc);
             acc = sp[T::b_off(0) + tid] - acc;
         }
         b0p[tid] = acc;
@@ -121,11 +133,13 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
     __syncthreads();
 
     // ---- persistent per-lane accumulators
-    float acc0[NP][W0];                  // backward first layer: lane = marker
+    float acc0[NP][W0][PK ? 2 : 1];      // backward first layer: lane = marker (packed: even / odd rows)
 #pragma unroll
     for (int p = 0; p < NP; ++p)
 #pragma unroll
-        for (int c = 0; c < W0; ++c) acc0[p][c] = 0.f;
+        for (int c = 0; c < W0; ++c)
+#pragma unroll
+            for (int e = 0; e < (PK ? 2 : 1); ++e) acc0[p][c][e] = 0.f;
     float gb0[W0], gWo[S], rss = 0.f;
     float gWt[NLA > 1 ? NLA - 1 : 1][MW][MW], gbt[NLA > 1 ? NLA - 1 : 1][MW];
 #pragma unroll
@@ -198,18 +212,20 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
             const uint32_t word = myrow[jw];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float w[W0P];
-                const float4* wr = reinterpret_cast<const float4*>(Wp + (size_t)(4 * jw + k) * W0P);
+                float w[W2P];
+                const float4* wr = reinterpret_cast<const float4*>(Wp + (size_t)(4 * jw + k) * W2P);
 #pragma unroll
-                for (int v = 0; v < W0P / 4; ++v) {
+                for (int v = 0; v < W2P / 4; ++v) {
                     const float4 f = wr[v];
                     w[4 * v] = f.x; w[4 * v + 1] = f.y; w[4 * v + 2] = f.z; w[4 * v + 3] = f.w;
                 }
+                float gf[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float gf = (float)(word & (3u << (8 * k + 2 * r)));   // g * 2^(8k+2r), exact
+                for (int r = 0; r < 4; ++r) gf[r] = (float)(word & (3u << (8 * k + 2 * r)));   // g * 2^(8k+2r), exact
 #pragma unroll
-                    for (int c = 0; c < W0; ++c) z[r][c] = fmaf(gf, w[c], z[r][c]);
+                for (int c = 0; c < W0; ++c) {
+                    ffma2(z[0][c], z[1][c], gf[0], gf[1], w[2 * c], w[2 * c + 1]);
+                    ffma2(z[2][c], z[3][c], gf[2], gf[3], w[2 * c], w[2 * c + 1]);
                 }
             }
         }
@@ -315,14 +331,21 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
                 }
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
-                    if (32u * p < m) {
-                        const uint32_t j = 32 * p + lane;
-                        const uint32_t byte = (j < mp) ? tileb[q * mp + j] : 0u;
+                    if (p + 1 < NP || 32u * p < m) {   // only the last pass can be empty (dispatch picks the smallest NP)
+                        // lanes beyond the row read neighbouring bytes of the CTA's own shared memory; their sums are dropped
+                        const uint32_t byte = tileb[q * mp + 32 * p + lane];
+                        float gf[4];
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const float gf = (float)(byte & (3u << (2 * r)));      // g * 4^r
+                        for (int r = 0; r < 4; ++r) gf[r] = (float)(byte & (3u << (2 * r)));      // g * 4^r
 #pragma unroll
-                            for (int c = 0; c < W0; ++c) acc0[p][c] = fmaf(gf, dl[c][r], acc0[p][c]);
+                        for (int c = 0; c < W0; ++c) {
+                            if constexpr (PK) {
+                                ffma2(acc0[p][c][0], acc0[p][c][1], gf[0], gf[1], dl[c][0], dl[c][1]);
+                                ffma2(acc0[p][c][0], acc0[p][c][1], gf[2], gf[3], dl[c][2], dl[c][3]);
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) acc0[p][c][0] = fmaf(gf[r], dl[c][r], acc0[p][c][0]);
+                            }
                         }
                     }
                 }
@@ -392,7 +415,7 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
         if (32u * p < m) {
             __syncthreads();
 #pragma unroll
-            for (int c = 0; c < W0; ++c) red[(warp * W0 + c) * 32 + lane] = acc0[p][c];
+            for (int c = 0; c < W0; ++c) red[(warp * W0 + c) * 32 + lane] = PK ? acc0[p][c][0] + acc0[p][c][PK ? 1 : 0] : acc0[p][c][0];
             __syncthreads();
             for (uint32_t k = tid; k < 32 * W0; k += NW * 32) {
                 const uint32_t c = k / 32, ln = k % 32, j = 32 * p + ln;
@@ -410,7 +433,7 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
 template <int H, int S, int D, int NP, int NW>
 size_t k1_small_smem(uint32_t mp, int nstage) {
     using T = TailShape<H, S, D>;
-    size_t fl = (size_t)mp * T::W0P + T::W0P + ((T::n_tail() + 3) & ~3);
+    size_t fl = (size_t)mp * T::W2P + T::W0P + ((T::n_tail() + 3) & ~3);
     size_t redn = (size_t)NW * (T::NTACC > 32 * T::W0 ? T::NTACC : 32 * T::W0) + 4;
     size_t perw = (size_t)nstage * kTileQuads * (mp >> 2) + (size_t)T::W0 * 128;
     return (fl + redn + (size_t)NW * perw) * 4 + 16;
