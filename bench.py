@@ -39,7 +39,7 @@ WORKLOADS = {
 METRIC = "full_network_hmc_leapfrog_steps_per_sec"
 UNIT = "steps/s"
 # ncu --set full capture of the dominant kernel (profiles/): dram bytes per launch, filled in once measured
-NCU_TRAFFIC_BYTES = {}
+NCU_TRAFFIC_BYTES = {"cfg3s": 1.7125e9}   # profiles/r1_k1_ncu_summary.md: dram read 1.7054 GB + write 7.1 MB per launch
 
 
 def default_params(wl, seed=42):
@@ -207,16 +207,15 @@ def main():
 
     N, B, per, widths = wl["n"], wl["B"], wl["per"], wl["widths"]
     M = B * per
-    # row shards on 128-row tile boundaries
-    tiles = (N + 127) // 128
-    tpr = (tiles + world - 1) // world
-    r0, r1 = min(N, rank * tpr * 128), min(N, (rank + 1) * tpr * 128)
+    r0, r1 = rb.row_shard(N, rank, world)          # row shards on 128-row tile boundaries
     n_local = r1 - r0
     gen = rb.Genotypes.random(ctx, n_local, M, None, seed=42, row_offset=r0, n_total=N, uniform_groups=(B, per))
-    counts = torch.from_numpy(gen.col_counts().astype(np.int64)).to(dev)
-    if world > 1:
-        dist.all_reduce(counts)
-    mu, sd = rb.stats_from_counts(counts.cpu().numpy(), N)      # global column statistics
+    def allreduce_counts(c):
+        t = torch.from_numpy(c).to(dev)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    mu, sd = rb.global_col_stats(gen.col_counts(), N, allreduce_counts if world > 1 else None)
     gen.set_col_stats(mu, sd)
     net = rb.Net(ctx, gen, wl["model"], [widths] * B)
     pv, qv = default_params(wl)

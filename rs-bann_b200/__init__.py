@@ -9,3 +9,4 @@ from .api import Context, Genotypes, HMCStepResult, MCMCCfg, Net, cuda_available
 
 def launch_count(reset: bool = False) -> int:
     return int(lib.bann_launch_count(int(reset)))
+from .dist import global_col_stats, row_shard, shard_payload  # noqa: E402

@@ -1,0 +1,40 @@
+"""Host-side logic of the row-sharded (multi-GPU) path: one process per GPU, torch.distributed
+for the plumbing.  Individuals (rows) are sharded on 128-row tile boundaries; parameters,
+momenta and precisions are replicated; the only data-path collectives are
+  * an all-reduce(sum) of the per-column genotype counts at load (global column statistics),
+  * an all-reduce(sum) of the per-step [gW | gb | rss] sums between K1 and K2.
+Every replica then applies the identical update (same Philox keys), so nothing is broadcast."""
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+TILE_ROWS = 128
+
+
+def row_shard(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """[r0, r1) of this rank: whole 128-row tiles, remainder to the last non-empty rank."""
+    tiles = (n_total + TILE_ROWS - 1) // TILE_ROWS
+    tpr = (tiles + world - 1) // world
+    r0 = min(n_total, rank * tpr * TILE_ROWS)
+    r1 = min(n_total, (rank + 1) * tpr * TILE_ROWS)
+    return r0, r1
+
+
+def shard_payload(payload: np.ndarray, n_total: int, m: int, r0: int, r1: int) -> np.ndarray:
+    """Rows [r0, r1) of a PLINK variant-major payload (r0 must be a multiple of 4)."""
+    assert r0 % 4 == 0
+    bpc = (n_total + 3) // 4
+    cols = np.asarray(payload, dtype=np.uint8).reshape(m, bpc)
+    out = cols[:, r0 // 4:(r1 + 3) // 4].copy()
+    if (r1 - r0) % 4:
+        out[:, -1] &= np.uint8((1 << (2 * ((r1 - r0) % 4))) - 1)   # pad fields of the local last byte -> code 00
+    return np.ascontiguousarray(out).reshape(-1)
+
+
+def global_col_stats(local_counts: np.ndarray, n_total: int, allreduce_sum: Optional[Callable] = None):
+    """Column mean / population std over ALL rows from per-shard value counts."""
+    from .api import stats_from_counts
+    counts = np.ascontiguousarray(local_counts, dtype=np.int64)
+    if allreduce_sum is not None:
+        counts = allreduce_sum(counts)
+    return stats_from_counts(counts, n_total)
