@@ -73,6 +73,8 @@ PROTOTYPES = {
     "bann_genotypes_col_counts": (C.c_int, [_vp, C.POINTER(_u64)]),
     "bann_genotypes_set_col_stats": (C.c_int, [_vp, _fp, _fp]),
     "bann_genotypes_decode_branch": (C.c_int, [_vp, _u64, C.c_int, _fp]),
+    "bann_genotypes_decode_branch_tc": (C.c_int, [_vp, _u64, C.c_int, _fp]),
+    "bann_genotypes_has_tc_store": (C.c_int, [_vp]),
     "bann_net_create": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(BranchLayout), _fp, C.POINTER(_vp)]),
     "bann_net_destroy": (None, [_vp]),
     "bann_net_branch_sizes": (C.c_int, [_vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
@@ -108,6 +110,7 @@ PROTOTYPES = {
     "bann_grouped_state": (C.c_int, [_vp, _fp, _fp, C.POINTER(C.c_int32)]),
     "bann_allreduce_buffer": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
     "bann_net_force_generic": (C.c_int, [_vp, C.c_int]),
+    "bann_net_select_k1": (C.c_int, [_vp, C.c_int]),
     "bann_launch_count": (_u64, [C.c_int]),
     "bann_net_algorithmic_bytes": (C.c_int, [_vp, C.POINTER(_u64)]),
 }

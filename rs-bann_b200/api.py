@@ -182,6 +182,15 @@ class Genotypes:
         check(lib.bann_genotypes_decode_branch(self.h, b, int(standardized), _ptr(out)))
         return out.reshape((self.n, len(self.groups[b])), order="F")
 
+    def x_group_tc(self, b: int, standardized: bool = True) -> np.ndarray:
+        """The same matrix decoded from the tensor-core store (test hook)."""
+        out = np.empty(self.n * len(self.groups[b]), dtype=np.float32)
+        check(lib.bann_genotypes_decode_branch_tc(self.h, b, int(standardized), _ptr(out)))
+        return out.reshape((self.n, len(self.groups[b])), order="F")
+
+    def has_tc_store(self) -> bool:
+        return bool(lib.bann_genotypes_has_tc_store(self.h))
+
     def close(self):
         if self.h:
             lib.bann_genotypes_destroy(self.h)
@@ -439,6 +448,12 @@ class Net:
 
     def force_generic(self, on=True):
         check(lib.bann_net_force_generic(self.h, int(on)))
+
+    K1_AUTO, K1_TENSOR, K1_FFMA, K1_GENERIC = 0, 1, 2, 3
+
+    def select_k1(self, which: int):
+        """Which fused forward+backward kernel may run: auto / tensor-core / FFMA / shape-agnostic."""
+        check(lib.bann_net_select_k1(self.h, int(which)))
 
     def algorithmic_bytes(self) -> int:
         v = C.c_uint64()

@@ -41,6 +41,9 @@ struct BranchDesc {
     uint64_t prec_off;          // offset (floats) into the precision arena
     uint64_t tile_off;          // byte offset of the branch's first tile in the store
     uint64_t col_off;           // offset into the per-branch gathered mu / sd arrays
+    uint64_t tc_off;            // byte offset of the branch in the tensor-core store (k1_tc.cuh)
+    uint32_t nc;                // 8-marker chunks per row in the tensor-core store: ceil(m / 8)
+    uint32_t pad_;
 };
 
 // GlobalParams + OutputBias + LPD + TrainingStats, device resident (net/params.rs:13-56,

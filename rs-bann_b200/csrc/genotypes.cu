@@ -97,6 +97,59 @@ __global__ void k_build_tiles(const uint8_t* __restrict__ payload, uint64_t n, u
     for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) dst[idx] = sm[idx];
 }
 
+// Tensor-core store (k1_tc.cuh).  One block per (branch, 256-row super-tile), thread t = row pair
+// (256 s + t, 256 s + 128 + t).  Word i of the thread holds the pair's i-th 8-marker chunk: genotype value
+// codes (00->0, 01->1, 10->2; PLINK missing and padding -> 0) of marker 8i + 2p     at bits [2p+1 : 2p]      (row A)
+//                                                              marker 8i + 2p + 1 at bits [16+2p+1 : 16+2p]  (row A)
+// and the same two markers of row B 8 bits higher (p = 0..3).  `x & (0x00030003 << 2p)` is then the pair of
+// bf16 subnormals g * 4^p * 2^-133 of row A, `(x >> 8) & ...` that of row B.
+__device__ __forceinline__ uint32_t plink_value_code(const uint8_t* __restrict__ payload, uint64_t col, uint64_t bpc,
+                                                     uint64_t row) {
+    const uint32_t c = (payload[col * bpc + (row >> 2)] >> (2 * (row & 3))) & 3u;
+    return c == 0 ? 2u : (c == 2 ? 1u : 0u);   // io/bed_lookup_tables.rs:4
+}
+__global__ void __launch_bounds__(128) k_build_tc(const uint8_t* __restrict__ payload, uint64_t n, uint64_t bpc,
+                                                  const BranchDesc* __restrict__ descs,
+                                                  const uint64_t* __restrict__ col_ids, uint32_t nst,
+                                                  uint32_t* __restrict__ store_tc) {
+    const uint32_t b = blockIdx.x / nst, s = blockIdx.x % nst, t = threadIdx.x;
+    const BranchDesc& d = descs[b];
+    const uint64_t* cols = col_ids + d.col_off;
+    const uint64_t rowA = (uint64_t)s * 256 + t, rowB = rowA + 128;
+    uint32_t* dst = store_tc + (d.tc_off >> 2) + (size_t)s * d.nc * 128 + t;
+    for (uint32_t i = 0; i < d.nc; ++i) {
+        uint32_t w = 0;
+        for (uint32_t p = 0; p < 4; ++p)
+            for (uint32_t hi = 0; hi < 2; ++hi) {
+                const uint32_t j = 8 * i + 2 * p + hi;
+                if (j >= d.m) continue;
+                const uint32_t sh = 16 * hi + 2 * p;
+                if (rowA < n) w |= plink_value_code(payload, cols[j], bpc, rowA) << sh;
+                if (rowB < n) w |= plink_value_code(payload, cols[j], bpc, rowB) << (sh + 8);
+            }
+        dst[(size_t)i * 128] = w;
+    }
+}
+
+// test hook: decode branch b from the tensor-core store exactly as k1_tc expands it
+__global__ void k_decode_branch_tc(const uint32_t* __restrict__ store_tc, BranchDesc d, uint64_t n,
+                                   const float* __restrict__ mu, const float* __restrict__ sd, int standardized,
+                                   float* __restrict__ out) {
+    uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * d.m) return;
+    const uint64_t i = idx % n, j = idx / n;
+    const uint64_t s = i / 256;
+    const uint32_t r = (uint32_t)(i % 256), t = r & 127u, rowB = r >> 7;
+    uint32_t x = store_tc[(d.tc_off >> 2) + (size_t)s * d.nc * 128 + (size_t)(j >> 3) * 128 + t];
+    if (rowB) x >>= 8;
+    const uint32_t p = (uint32_t)((j & 7u) >> 1);
+    const uint32_t pair = x & (0x00030003u << (2 * p));               // two bf16 bit patterns
+    const uint32_t bits = (j & 1u) ? (pair >> 16) : (pair & 0xFFFFu);
+    float g = (float)(bits >> (2 * p));                               // the subnormal's integer significand / 4^p
+    if (standardized) g = __fdiv_rn(__fsub_rn(g, mu[d.col_off + j]), sd[d.col_off + j]);  // bed.rs:354
+    out[idx] = g;
+}
+
 // test hook: decode branch b -> f32 [n x m_b] column-major
 __global__ void k_decode_branch(const uint8_t* __restrict__ store, BranchDesc d, uint64_t n,
                                 const float* __restrict__ mu, const float* __restrict__ sd, int standardized,
@@ -238,6 +291,18 @@ static int build_from_device_payload(bann_ctx* ctx, uint8_t* d_payload /* consum
         if (mp > max_mp) max_mp = mp;
     }
     g->store_bytes = off;
+    // tensor-core store geometry (all-or-nothing: every branch must fit the M = 64 accumulator)
+    g->nst = (uint32_t)((n + 255) / 256);
+    g->tc_off.assign(num_branches, 0);
+    bool tc_ok = true;
+    for (uint64_t b = 0; b < num_branches; ++b) tc_ok = tc_ok && g->m_b[b] <= 64;
+    g->tc_bytes = 0;
+    if (tc_ok) {
+        for (uint64_t b = 0; b < num_branches; ++b) {
+            g->tc_off[b] = g->tc_bytes;
+            g->tc_bytes += (uint64_t)g->nst * ((g->m_b[b] + 7) / 8) * 128 * 4;
+        }
+    }
     g->packed_bytes = 0;
     for (uint64_t b = 0; b < num_branches; ++b) g->packed_bytes += (uint64_t)g->m_b[b] * bpc;
 
@@ -279,6 +344,8 @@ static int build_from_device_payload(bann_ctx* ctx, uint8_t* d_payload /* consum
         descs[b].m_pad4 = g->m_pad4[b];
         descs[b].tile_off = g->tile_off[b];
         descs[b].col_off = g->col_off[b];
+        descs[b].tc_off = g->tc_off[b];
+        descs[b].nc = (g->m_b[b] + 7) / 8;
     }
     BANN_CUDA(cudaMalloc(&d_descs, num_branches * sizeof(BranchDesc)));
     BANN_CUDA(cudaMemcpyAsync(d_descs, descs.data(), num_branches * sizeof(BranchDesc), cudaMemcpyHostToDevice, st));
@@ -291,6 +358,14 @@ static int build_from_device_payload(bann_ctx* ctx, uint8_t* d_payload /* consum
                                                       (uint32_t)num_branches, g->ntiles, g->d_store);
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
+    if (g->tc_bytes) {
+        uint64_t nb_tc = num_branches * (uint64_t)g->nst;
+        if (nb_tc > 0x7fffffffull) BANN_FAIL("too many super-tiles for one launch");
+        BANN_CUDA(cudaMalloc(&g->d_store_tc, g->tc_bytes));
+        k_build_tc<<<(unsigned)nb_tc, 128, 0, st>>>(d_payload, n, bpc, d_descs, d_cols, g->nst, g->d_store_tc);
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaGetLastError());
+    }
     k_gather_stats<<<(unsigned)((total_cols + 255) / 256), 256, 0, st>>>(g->d_means, g->d_stds, d_cols, total_cols,
                                                                          g->d_mu, g->d_sd);
     BANN_LAUNCHED();
@@ -353,6 +428,7 @@ int bann_genotypes_random(bann_ctx* ctx, uint64_t n, uint64_t row_offset, uint64
 void bann_genotypes_destroy(bann_genotypes* g) {
     if (!g) return;
     cudaFree(g->d_store);
+    cudaFree(g->d_store_tc);
     cudaFree(g->d_means);
     cudaFree(g->d_stds);
     cudaFree(g->d_mu);
@@ -412,5 +488,31 @@ int bann_genotypes_decode_branch(bann_genotypes* g, uint64_t b, int standardized
     BANN_CUDA(e);
     return 0;
 }
+
+int bann_genotypes_decode_branch_tc(bann_genotypes* g, uint64_t b, int standardized, float* out) {
+    if (!g || !out) BANN_FAIL("NULL argument");
+    if (b >= g->num_branches) BANN_FAIL("branch index out of range");
+    if (!g->d_store_tc) BANN_FAIL("no tensor-core store (a branch has more than 64 markers)");
+    BranchDesc d;
+    memset(&d, 0, sizeof(d));
+    d.m = g->m_b[b];
+    d.col_off = g->col_off[b];
+    d.tc_off = g->tc_off[b];
+    d.nc = (d.m + 7) / 8;
+    uint64_t total = g->n * d.m;
+    float* dout = nullptr;
+    BANN_CUDA(cudaMalloc(&dout, total * sizeof(float)));
+    k_decode_branch_tc<<<(unsigned)((total + 255) / 256), 256, 0, g->ctx->stream>>>(g->d_store_tc, d, g->n, g->d_mu, g->d_sd,
+                                                                                    standardized, dout);
+    BANN_LAUNCHED();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, total * sizeof(float), cudaMemcpyDeviceToHost, g->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(dout);
+    BANN_CUDA(e);
+    return 0;
+}
+
+int bann_genotypes_has_tc_store(bann_genotypes* g) { return g && g->d_store_tc ? 1 : 0; }
 
 }  // extern "C"

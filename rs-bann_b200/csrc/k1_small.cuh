@@ -513,7 +513,7 @@ inline int launch_k1_small(const std::vector<BranchDesc>& descs, int single_bran
     BANN_TRY(4, 3, 1, 2)
     BANN_TRY(4, 3, 2, 2)
     BANN_TRY(5, 3, 2, 4)
-    BANN_TRY(4, 2, 0, 2)
+    BANN_TRY(2, 2, 0, 2)
 #undef BANN_TRY
     return 0;
 }

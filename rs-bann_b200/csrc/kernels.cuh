@@ -80,6 +80,10 @@ struct K1Args {
     float* part;               // [entry][chunk][pstride]; d_rss in param_vec order, rss at [P]
     uint32_t pstride;
     int act;
+    // tensor-core path (k1_tc.cuh)
+    const uint32_t* store_tc;  // NULL: no tensor-core store
+    uint32_t nst;              // 256-row super-tiles
+    uint32_t st_per_chunk;
 };
 
 __device__ __forceinline__ void locate_param(const BranchDesc& d, uint32_t k, int& layer, uint32_t& row,

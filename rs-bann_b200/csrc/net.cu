@@ -6,6 +6,7 @@
 
 #include "chain.cuh"
 #include "k1_small.cuh"
+#include "k1_tc.cuh"
 #include "store.cuh"
 
 using namespace bann;
@@ -48,7 +49,7 @@ struct bann_net {
     size_t traj_cap = 0;
     float* d_scratchB = nullptr;  // [3*B] gather buffer
     uint64_t visit_seq = 0;
-    int force_generic = 0;
+    int k1_mode = BANN_K1_AUTO;   // which K1 kernel launch_k1 may pick (bann_net_select_k1)
     float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient
 };
 
@@ -127,9 +128,19 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
     a.part = part;
     a.pstride = net->pstride;
     a.act = net->act;
+    a.store_tc = g->d_store_tc;
+    a.nst = g->nst;
+    a.st_per_chunk = 0;
 
     bool launched = false;
-    if (!net->force_generic) {
+    if (net->k1_mode == BANN_K1_AUTO || net->k1_mode == BANN_K1_TENSOR) {
+        int r = launch_k1_tc(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
+                             &nchunk, L.fwd_only ? nullptr : &part, net);
+        if (r != 0) return r;
+        if (!launched && net->k1_mode == BANN_K1_TENSOR)
+            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (tanh, <= 64 markers, 3 * width <= 16)");
+    }
+    if (!launched && net->k1_mode != BANN_K1_GENERIC) {
         int r = launch_k1_small(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
                                 &nchunk, L.fwd_only ? nullptr : &part, net);
         if (r != 0) return r;
@@ -509,6 +520,8 @@ int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int acti
         d.nl = L.num_layers;
         d.tile_off = gen->tile_off[b];
         d.col_off = gen->col_off[b];
+        d.tc_off = gen->tc_off[b];
+        d.nc = (d.m + 7) / 8;
         uint32_t prev = d.m, off = 0, aoff = 0, gam = 1;
         for (uint32_t l = 0; l < d.nl; ++l) {
             if (L.widths[l] == 0) { delete net; BANN_FAIL("layer width 0"); }
@@ -969,6 +982,7 @@ int bann_predict(bann_net* net, bann_genotypes* test, float* yhat) {
         if (g->m_b[b] != net->descs[b].m) BANN_FAIL("test genotypes: branch marker count mismatch");
         descs[b].tile_off = g->tile_off[b];
         descs[b].col_off = g->col_off[b];
+        descs[b].tc_off = g->tc_off[b];
     }
     BranchDesc* d_descs = nullptr;
     float* d_out = nullptr;
@@ -1201,7 +1215,14 @@ int bann_net_algorithmic_bytes(bann_net* net, uint64_t* bytes) {
 
 int bann_net_force_generic(bann_net* net, int on) {
     if (!net) BANN_FAIL("NULL net");
-    net->force_generic = on;
+    net->k1_mode = on ? BANN_K1_GENERIC : BANN_K1_AUTO;
+    return 0;
+}
+
+int bann_net_select_k1(bann_net* net, int which) {
+    if (!net) BANN_FAIL("NULL net");
+    if (which < BANN_K1_AUTO || which > BANN_K1_GENERIC) BANN_FAIL("unknown K1 selector");
+    net->k1_mode = which;
     return 0;
 }
 

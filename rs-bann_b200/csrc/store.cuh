@@ -28,6 +28,12 @@ struct bann_genotypes {
     std::vector<uint32_t> m_b, m_pad4;
     std::vector<uint64_t> tile_off, col_off;
     uint8_t* d_store = nullptr;
+    // tensor-core store (only when every branch has <= 64 markers): per branch, per 256-row super-tile,
+    // [ceil(m/8) chunks][128 row pairs] 32-bit words, see k_build_tc
+    uint32_t* d_store_tc = nullptr;
+    uint32_t nst = 0;            // super-tiles of 256 rows
+    uint64_t tc_bytes = 0;
+    std::vector<uint64_t> tc_off;
     float* d_means = nullptr;
     float* d_stds = nullptr;
     float* d_mu = nullptr;  // per-branch gathered means (sum m_b)

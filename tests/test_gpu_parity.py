@@ -182,8 +182,8 @@ def test_fwd_bwd_parity(rb, ctx, model, shape):
     n, gs, h, s, d = shape
     P = Problem(rb, ctx, model, n, gs, h, s, depth=d, seed=(sum(map(ord, model)) + n) % 1000, overlap=len(gs) > 1)
     try:
-        for generic in (True, False):
-            P.net.force_generic(generic)
+        for k1 in (P.net.K1_GENERIC, P.net.K1_FFMA, P.net.K1_AUTO):   # AUTO = tensor-core kernel where eligible
+            P.net.select_k1(k1)
             for b in range(len(gs)):
                 tgt = P.y if b % 2 == 0 else (P.y * 0.5 + 0.1).astype(np.float32)
                 got = P.net.branch_fwd_bwd(b, target=None if b % 2 == 0 else tgt)
@@ -194,6 +194,66 @@ def test_fwd_bwd_parity(rb, ctx, model, shape):
                 within(got["ldg"], t64["ldg"], t32["ldg"])
                 within(P.net.branch_log_density(b, t32["rss"]), Branch(P.cfgs[b], np.float64).log_density(t32["rss"]),
                        Branch(P.cfgs[b], np.float32).log_density(np.float32(t32["rss"])))
+    finally:
+        P.close()
+
+
+# shapes the tensor-core kernel (k1_tc.cuh) must take: <= 64 markers per branch, 3 * first width <= 16
+TC_SHAPES = [  # n, group sizes, hidden, summary, depth
+    (7, [5], 5, 5, 1),
+    (255, [1, 8, 9], 5, 5, 1),
+    (256, [50, 64], 5, 5, 1),
+    (257, [16, 17], 2, 2, 1),
+    (1030, [50, 50, 50, 33], 5, 5, 1),     # several super-tiles, ragged tail, overlapping groups
+    (700, [40, 24], 4, 3, 1),
+    (515, [64, 7], 4, 3, 2),
+    (300, [20, 64], 5, 3, 2),
+    (150, [12, 7], 4, 2, 0),
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tensor_core_store_decode_bit_exact(rb, ctx, shape):
+    n, gs, h, s, d = shape
+    P = Problem(rb, ctx, "ridge_ard", n, gs, h, s, depth=d, seed=n, overlap=len(gs) > 1)
+    try:
+        assert P.gen.has_tc_store()
+        for b, cols in enumerate(P.groups):
+            assert np.array_equal(P.gen.x_group_tc(b, False), obed.decode_columns(P.payload, n, cols))
+            assert np.array_equal(P.gen.x_group_tc(b, True), P.x(b, np.float32))
+    finally:
+        P.close()
+
+
+@pytest.mark.parametrize("model", ["ridge_ard", "std_normal", "lasso_base"])
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tensor_core_fwd_bwd_parity(rb, ctx, model, shape):
+    """k1_tc (tcgen05, bf16-subnormal genotypes x 3-piece bf16 weights / deltas) against the oracle and the FFMA kernel."""
+    n, gs, h, s, d = shape
+    P = Problem(rb, ctx, model, n, gs, h, s, depth=d, seed=(sum(map(ord, model)) + 7 * n) % 1000, overlap=len(gs) > 1)
+    try:
+        for b in range(len(gs)):
+            tgt = P.y if b % 2 == 0 else (P.y * 0.5 + 0.1).astype(np.float32)
+            P.net.select_k1(P.net.K1_TENSOR)          # fails loudly if the launch is not eligible
+            got = P.net.branch_fwd_bwd(b, target=None if b % 2 == 0 else tgt)
+            P.net.select_k1(P.net.K1_FFMA)
+            ffma = P.net.branch_fwd_bwd(b, target=None if b % 2 == 0 else tgt)
+            t64, t32 = oracle_fwd_bwd(P, b, tgt, np.float64), oracle_fwd_bwd(P, b, tgt, np.float32)
+            for key in ("yhat", "rss", "d_rss", "ldg"):
+                within(got[key], t64[key], t32[key])
+                sc = np.max(np.abs(t64[key]))
+                assert np.max(np.abs(np.asarray(got[key], dtype=np.float64) - ffma[key])) <= 4e-5 * sc + 1e-30, key
+    finally:
+        P.close()
+
+
+def test_tensor_core_kernel_refuses_ineligible_launch(rb, ctx):
+    P = Problem(rb, ctx, "ridge_ard", 300, [100], 5, 5, seed=3)        # 100 markers: no tensor-core store
+    try:
+        assert not P.gen.has_tc_store()
+        P.net.select_k1(P.net.K1_TENSOR)
+        with pytest.raises(RuntimeError):
+            P.net.branch_fwd_bwd(0)
     finally:
         P.close()
 
@@ -520,11 +580,11 @@ def test_net_gradient_matches_per_branch(rb, ctx):
 def test_grouped_leapfrog_conserves_energy_and_matches_kernels(rb, ctx):
     cfg = rb.MCMCCfg(hmc_step_size_factor=0.05, hmc_integration_length=20, hmc_step_size_mode="izmailov")
     out = {}
-    for generic in (True, False):
+    for generic in (3, 2, 0):                            # K1_GENERIC, K1_FFMA, K1_AUTO (tensor-core kernel here)
         # fresh net per kernel: the built-in Philox stream is keyed by (seed, visit counter, branch)
         P = Problem(rb, ctx, "ridge_ard", 1200, [50] * 6, 5, 5, seed=6)
         try:
-            P.net.force_generic(generic)
+            P.net.select_k1(generic)
             P.net.grouped_begin(cfg, seed=7, per_branch_targets=False)
             P.net.grouped_leapfrog(cfg, 20, finalize=True)
             hi, hc, st = P.net.grouped_state()
@@ -535,9 +595,10 @@ def test_grouped_leapfrog_conserves_energy_and_matches_kernels(rb, ctx):
             out[generic] = (hi.copy(), hc.copy(), P.net.get_all_params()[0])
         finally:
             P.close()
-    assert np.allclose(out[True][0], out[False][0], rtol=1e-5)
-    assert np.allclose(out[True][1], out[False][1], rtol=1e-4)
-    assert np.allclose(out[True][2], out[False][2], rtol=1e-3, atol=1e-4)
+    for other in (2, 0):
+        assert np.allclose(out[3][0], out[other][0], rtol=1e-5)
+        assert np.allclose(out[3][1], out[other][1], rtol=1e-4)
+        assert np.allclose(out[3][2], out[other][2], rtol=1e-3, atol=1e-4)
 
 
 def test_synthetic_store_is_independent_of_row_sharding(rb, ctx):
