@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--generic", action="store_true", help="force the shape-agnostic kernel (debug)")
+    ap.add_argument("--k1", default="auto", choices=["auto", "tensor", "ffma", "generic"],
+                    help="which fused forward+backward kernel may run (auto: tensor-core where eligible)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -225,6 +227,10 @@ def main():
     net.set_targets(y_local)
     if args.generic:
         net.force_generic(True)
+    elif args.k1 != "auto":
+        net.select_k1(dict(tensor=net.K1_TENSOR, ffma=net.K1_FFMA, generic=net.K1_GENERIC)[args.k1])
+    k1_name = ("k1_tc (tcgen05 tensor-core fused fwd+bwd, phase A)" if args.k1 in ("auto", "tensor") and gen.has_tc_store()
+               and not args.generic else "k1 fused fwd+bwd (phase A)")
     ptr, nfl = net.allreduce_buffer()
 
     class _Dev:
@@ -329,7 +335,7 @@ def main():
                     k1_ms=k1_ms, wall_s=t_wall, gpu_launches=int(launches) * world,
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                                   traffic=NCU_TRAFFIC_BYTES.get(args.workload), peak_source=peak_src,
-                                  algorithmic_bytes_per_launch=alg_bytes, kernel="k1 fused fwd+bwd (phase A)",
+                                  algorithmic_bytes_per_launch=alg_bytes, kernel=k1_name,
                                   kernel_ms=k1_ms),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              call="Net.gradient / bann_net_gradient (host params + targets in, gradients + rss out)"),
