@@ -18,9 +18,12 @@
 // bits), side by side in the N dimension, so products are exact and only the f32 accumulation rounds.
 // Pieces are pre-scaled by 2^100 (exact) so that subnormal * piece stays a normal f32.
 //
-// Per CTA (128 threads, one branch, a range of super-tiles): expand -> MMA fwd (2 x M128 N16 K16*ks)
-// -> tcgen05.ld -> per-row tail -> delta pieces to shared memory -> MMA bwd (M64 N16 K16 x 16,
-// accumulating in tensor memory over ALL super-tiles of the CTA) -> one read of the gradient at the end.
+// Per CTA (128 threads, one branch, a range of super-tiles), software pipelined over two operand buffers:
+//   wait fwd(i) -> tcgen05.ld z0 -> tail part 1 (layers, tanh, error; both rows of a thread as packed f32x2)
+//   -> wait bwd(i-1) -> expand(i+1) -> issue MMA fwd(i+1) (2 x M128 N16 K16*ks)  [runs under part 2]
+//   -> tail part 2 (deltas, cross-row sums) -> delta pieces to shared memory
+//   -> issue MMA bwd(i) (M64 N16 K16 x 16, accumulating in tensor memory over ALL super-tiles of the CTA)
+//   [runs under part 1 of the next super-tile] -> one read of the first-layer gradient at the end.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -34,11 +37,32 @@ constexpr int kTcRows = 256;          // rows per super-tile: thread t owns rows
 constexpr uint32_t kTcChunkStride = kTcRows * 16;   // bytes between 8-marker chunks of the expanded tile
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
 __device__ __forceinline__ float pow2f(int e) { return __int_as_float((127 + e) << 23); }
+
+// ---- packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): lane .x = row t, lane .y = row 128 + t
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 mk2(float x, float y) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ f2 dup2(float x) { return mk2(x, x); }
+__device__ __forceinline__ float lo2(f2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); return x; }
+__device__ __forceinline__ float hi2(f2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); return y; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 ld2(const float2* p) { f2 r; r.v = *reinterpret_cast<const unsigned long long*>(p); return r; }
+
+// tanh of a pair: 1 - 2 / (2^(2x log2 e) + 1); saturates correctly (ex2 -> inf / 0), absolute error ~1.5e-7
+__device__ __forceinline__ f2 tanh2(f2 x) {
+    const f2 t = mul2(x, dup2(2.8853900817779268f));
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(lo2(t)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(hi2(t)));
+    const f2 s = add2(mk2(e0, e1), dup2(1.f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(lo2(s)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(hi2(s)));
+    return fma2(mk2(r0, r1), dup2(-2.f), dup2(1.f));
+}
+// 1 - a^2 (activation_functions.rs:33-45 for tanh, evaluated from the activation)
+__device__ __forceinline__ f2 dtanh2(f2 a) { return fma2(a, mul2(a, dup2(-1.f)), dup2(1.f)); }
 
 template <int H, int S, int D>
 struct TcShape {
@@ -47,33 +71,45 @@ struct TcShape {
     static constexpr int NN = 16;                       // accumulator columns: 3 pieces x W0 units, padded
     static_assert(3 * W0 <= NN, "first-layer width too large for one N = 16 accumulator");
     static constexpr int TMEM_COLS = 64;                // 2 x NN forward (row halves) + NN backward
-    static constexpr size_t SA = 8 * kTcChunkStride;    // expanded genotypes, 8 chunks x 256 rows x 16 B
     static constexpr size_t SD = (NN / 8) * kTcChunkStride;   // delta pieces  [n-chunk][row] x 16 B
     static constexpr size_t SW = 8 * NN * 16;           // weight pieces [k-chunk][n] x 16 B
     static constexpr int NRED = 4 * (T::NTACC > 64 ? T::NTACC : 64);
-    static constexpr size_t SMEM = SA + SD + SW + (size_t)(((T::n_tail() + 3) & ~3) + T::W0P + NRED + 8) * 4 + 64 + 128;
+    // two expanded-genotype buffers of ncb chunks each.  The operand reads overrun a buffer: the last forward
+    // K-step of an odd ncb reads chunk ncb (x zero weights) and the M = 64 backward operand always reads 8
+    // chunks (rows >= m of the result are never used), so the region behind the second buffer must exist.
+    __host__ __device__ static constexpr uint32_t slots(uint32_t ncb) {
+        return (2 * ncb + (ncb & 1u)) > (ncb + 8) ? (2 * ncb + (ncb & 1u)) : (ncb + 8);
+    }
+    static size_t smem(uint32_t ncb) {
+        return (size_t)slots(ncb) * kTcChunkStride + SD + SW +
+               (size_t)(2 * ((T::n_tail() + 3) & ~3) + 2 * T::W0P + NRED + 8) * 4 + 64 + 128;
+    }
 };
 
-template <int H, int S, int D>
-__global__ void __launch_bounds__(128, 4) k1_tc(K1Args a) {
+// LEAN: gradient / leapfrog launches (targets given, no per-row outputs, backward always) -- the hot configuration
+template <int H, int S, int D, bool LEAN>
+__global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
     constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, MW = T::MW, NTACC = T::NTACC, NN = C::NN;
     extern __shared__ __align__(16) uint8_t smraw[];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
     const uint32_t b = a.list ? a.list[li] : li;
     if (a.states && a.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = a.descs[b];
-    const uint32_t m = d.m, NC = d.nc, NKS = (NC + 1) >> 1;
+    const uint32_t m = d.m, NC = d.nc, NKS = (NC + 1) >> 1, NCB = a.ncb;
+    // the warp that issues the MMAs rotates over CTAs so that the issue work spreads over the four SM sub-partitions
+    const uint32_t issuer = (blockIdx.x + blockIdx.y) & 3u;
     // ---- shared memory carve-up
-    uint8_t* sA = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 127) & ~(uintptr_t)127);   // whole core matrices
-    uint8_t* sD = sA + C::SA;
-    uint8_t* sW = sD + C::SD;
-    float* sp = reinterpret_cast<float*>(sW + C::SW);          // tail parameters [n_tail]
-    float* b0p = sp + ((T::n_tail() + 3) & ~3);                // [W0P] first-layer bias with the means folded in
-    float* red = b0p + W0P;                                    // [NRED] reduction scratch
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);   // [0] forward done, [1] backward done
+    uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // whole core matrices (keeps the shared address space)
+    const uint32_t sa_bytes = NCB * kTcChunkStride;                        // one expanded-genotype buffer
+    uint8_t* sW = sA + (size_t)C::slots(NCB) * kTcChunkStride;
+    uint8_t* sD = sW + C::SW;
+    float2* wp2 = reinterpret_cast<float2*>(sD + C::SD);                   // tail parameters, duplicated {w, w}
+    float2* b0p2 = wp2 + ((T::n_tail() + 3) & ~3);                         // [W0P] first-layer bias with the means folded in
+    float* red = reinterpret_cast<float*>(b0p2 + W0P);                     // [NRED] reduction scratch
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);           // [0] forward done, [1] backward done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
 
     const float* th = a.theta + d.param_off;
@@ -81,14 +117,20 @@ __global__ void __launch_bounds__(128, 4) k1_tc(K1Args a) {
     const float* sd = a.sd + d.col_off;
 
     // ---- one-time setup: zero operand buffers, barriers, tensor memory
-    for (uint32_t k = tid; k < (C::SA + C::SD + C::SW) / 16; k += 128) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
+    {
+        const uint32_t nz = (uint32_t)((sD + C::SD - sA) / 16);
+        for (uint32_t k = tid; k < nz; k += 128) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
+    }
     if (tid == 0) {
         umma::mbar_init(&mbar[0], 1);
         umma::mbar_init(&mbar[1], 1);
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, C::TMEM_COLS);
-    for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += 128) sp[k] = th[m * W0 + k];
+    for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += 128) {
+        const float w = th[m * W0 + k];
+        wp2[k] = make_float2(w, w);
+    }
     __syncthreads();
     // ---- stage W' = W0 / sd (f32, in the delta buffer for the bias fold) and its three bf16 pieces
     float* wtmp = reinterpret_cast<float*>(sD);                // [m][W0], transient
@@ -108,9 +150,9 @@ __global__ void __launch_bounds__(128, 4) k1_tc(K1Args a) {
         float acc = 0.f;
         if (tid < W0) {
             for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], wtmp[j * W0 + tid], acc);
-            acc = sp[T::b_off(0) + tid] - acc;
+            acc = wp2[T::b_off(0) + tid].x - acc;
         }
-        b0p[tid] = acc;
+        b0p2[tid] = make_float2(acc, acc);
     }
     __syncthreads();
     for (uint32_t k = tid; k < m * W0; k += 128) wtmp[k] = 0.f;   // the pad columns of the delta operand must stay zero
@@ -124,28 +166,31 @@ __global__ void __launch_bounds__(128, 4) k1_tc(K1Args a) {
     constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
     constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
 
-    // ---- persistent per-thread accumulators (cross-row sums of the layers >= 1)
-    float gb0[W0], gWo[S], rss = 0.f;
-    float gWt[NLA > 1 ? NLA - 1 : 1][MW][MW], gbt[NLA > 1 ? NLA - 1 : 1][MW];
+    // ---- persistent per-thread accumulators (cross-row sums of the layers >= 1), one lane per row of the pair
+    const f2 zero2 = dup2(0.f);
+    f2 gb0[W0], gWo[S], rss = zero2;
+    f2 gWt[NLA > 1 ? NLA - 1 : 1][MW][MW], gbt[NLA > 1 ? NLA - 1 : 1][MW];
 #pragma unroll
-    for (int c = 0; c < W0; ++c) gb0[c] = 0.f;
+    for (int c = 0; c < W0; ++c) gb0[c] = zero2;
 #pragma unroll
-    for (int c = 0; c < S; ++c) gWo[c] = 0.f;
+    for (int c = 0; c < S; ++c) gWo[c] = zero2;
 #pragma unroll
     for (int l = 0; l < (NLA > 1 ? NLA - 1 : 1); ++l)
 #pragma unroll
         for (int i = 0; i < MW; ++i) {
-            gbt[l][i] = 0.f;
+            gbt[l][i] = zero2;
 #pragma unroll
-            for (int c = 0; c < MW; ++c) gWt[l][i][c] = 0.f;
+            for (int c = 0; c < MW; ++c) gWt[l][i][c] = zero2;
         }
 
     const size_t eoff = a.out_per_entry ? (size_t)li * a.n : 0;
     const size_t toff = (a.target_mode == TGT_PER_ENTRY) ? (size_t)li * a.n : 0;
     const uint32_t t_begin = chunk * a.st_per_chunk;
     const uint32_t t_end = min(a.nst, t_begin + a.st_per_chunk);
+    const uint32_t nit = t_end > t_begin ? t_end - t_begin : 0;
     const uint32_t* gbase = a.store_tc + (d.tc_off >> 2) + tid;
-    const float* tsrc = (a.target_mode == TGT_RESID_PLUS_PRED) ? a.resid : (a.tgt ? a.tgt + toff : nullptr);
+    const float* tsrc = (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) ? a.resid : (a.tgt ? a.tgt + toff : nullptr);
+    const bool bwd = LEAN || !a.fwd_only;
 
     uint32_t wreg[8];
     auto load_words = [&](uint32_t st) {
@@ -154,116 +199,87 @@ __global__ void __launch_bounds__(128, 4) k1_tc(K1Args a) {
         for (int i = 0; i < 8; ++i)
             if ((uint32_t)i < NC) wreg[i] = __ldg(src + i * 128);
     };
-    if (t_begin < t_end) load_words(t_begin);
-    uint32_t it = 0;
-    for (uint32_t st = t_begin; st < t_end; ++st, ++it) {
-        // the previous backward contraction still reads both operand buffers
-        if (it > 0 && !a.fwd_only) umma::mbar_wait(&mbar[1], (it - 1) & 1u);
-        // ---- expand: one AND per two operand elements, 16-byte conflict-free stores
-        {
-            uint8_t* rowA = sA + tid * 16;
+    // expand: one AND per two operand elements, 16-byte conflict-free stores (row t and row 128 + t)
+    auto expand = [&](uint32_t buf) {
+        uint8_t* rowA = sA + buf * sa_bytes + tid * 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if ((uint32_t)i < NC) {
-                    const uint32_t x = wreg[i], y = x >> 8;
-                    *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) =
-                        make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
-                    *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride + 128 * 16) =
-                        make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
-                }
-        }
-        if (st + 1 < t_end) load_words(st + 1);
-        const uint32_t rowA_g = st * kTcRows + tid, rowB_g = rowA_g + 128;
-        float tg2[2] = {0.f, 0.f};
-        if (tsrc) {
-            if (rowA_g < a.n) tg2[0] = __ldg(tsrc + rowA_g);
-            if (rowB_g < a.n) tg2[1] = __ldg(tsrc + rowB_g);
-        }
-        umma::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
+        for (int i = 0; i < 8; ++i)
+            if ((uint32_t)i < NC) {
+                const uint32_t x = wreg[i], y = x >> 8;
+                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) =
+                    make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
+                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride + 128 * 16) =
+                    make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
+            }
+    };
+    // forward contraction of the super-tile in buffer `buf`: z0 pieces -> tensor memory columns [0, 2 NN)
+    // (whole issuer warp enters; one elected lane issues)
+    const uint64_t dA_f = umma::make_desc(sA_u, kTcChunkStride, 128), dW_f = umma::make_desc(sW_u, NN * 16, 128);
+    const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
+    auto issue_fwd = [&](uint32_t buf) {
+        umma::fence_after_sync();
+        const uint64_t base = dA_f + ((buf * sa_bytes) >> 4);
+        if (umma::elect_one()) {
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h)
-                for (uint32_t ks = 0; ks < NKS; ++ks) {
-                    const uint64_t ad = umma::make_desc(sA_u + h * 2048u + ks * 2u * kTcChunkStride, kTcChunkStride, 128);
-                    const uint64_t bd = umma::make_desc(sW_u + ks * 2u * (NN * 16), NN * 16, 128);
-                    umma::mma_f16(tmem + h * NN, ad, bd, idesc_f, ks > 0);
-                }
+#pragma unroll
+                for (uint32_t ks = 0; ks < 4; ++ks)
+                    if (ks < NKS)
+                        umma::mma_f16(tmem + h * NN, base + ((h * 2048u + ks * 2u * kTcChunkStride) >> 4),
+                                      dW_f + ((ks * 2u * (NN * 16)) >> 4), idesc_f, ks > 0);
             umma::commit(&mbar[0]);
         }
+        __syncwarp();
+    };
+
+    if (nit > 0) {
+        load_words(t_begin);
+        expand(0);
+        if (nit > 1) load_words(t_begin + 1);
+        umma::fence_async_smem();
+        __syncthreads();
+        if (warp == issuer) issue_fwd(0);
+    }
+    for (uint32_t it = 0; it < nit; ++it) {
+        const uint32_t st = t_begin + it, buf = it & 1u;
+        const uint32_t rowA_g = st * kTcRows + tid, rowB_g = rowA_g + 128;
+        const bool vA = rowA_g < a.n, vB = rowB_g < a.n;
+        f2 tg = zero2;
+        if (tsrc) tg = mk2(vA ? __ldg(tsrc + rowA_g) : 0.f, vB ? __ldg(tsrc + rowB_g) : 0.f);
+        // ---- z0 of this super-tile (its forward contraction was issued one stage ago)
         umma::mbar_wait(&mbar[0], it & 1u);
         umma::fence_after_sync();
-        float acc[2][16];
-        umma::tmem_ld16x2(tlane, tlane + NN, acc[0], acc[1]);
+        float accA[16], accB[16];
+        umma::tmem_ld16x2(tlane, tlane + NN, accA, accB);
+        umma::fence_before_sync();      // these reads precede the next forward MMA (ordered by the barrier below)
 
-        // ---- tail: remaining layers, error, backward deltas, one row per half
-        float yh2[2], dl0[2][W0];
+        // ---- tail, part 1: remaining layers and the error, both rows of the pair in packed FP32
+        f2 act[NLA][MW];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const bool valid = (h ? rowB_g : rowA_g) < a.n;
-            float act[NLA][MW];
+        for (int c = 0; c < W0; ++c) {
+            const f2 z = mk2(accA[c] + (accA[W0 + c] + accA[2 * W0 + c]), accB[c] + (accB[W0 + c] + accB[2 * W0 + c]));
+            act[0][c] = tanh2(fma2(z, dup2(8589934592.f /* 2^33 */), ld2(b0p2 + c)));
+        }
 #pragma unroll
-            for (int c = 0; c < W0; ++c) {
-                const float z = acc[h][c] + (acc[h][W0 + c] + acc[h][2 * W0 + c]);
-                act[0][c] = fast_tanh(fmaf(z, 8589934592.f /* 2^33 */, b0p[c]));
-            }
+        for (int l = 1; l < NLA; ++l) {
 #pragma unroll
-            for (int l = 1; l < NLA; ++l) {
+            for (int c = 0; c < MW; ++c) {
+                if (c < T::width(l)) {
+                    f2 zz = ld2(wp2 + T::b_off(l) + c);
 #pragma unroll
-                for (int c = 0; c < MW; ++c) {
-                    if (c < T::width(l)) {
-                        float zz = sp[T::b_off(l) + c];
-#pragma unroll
-                        for (int i = 0; i < MW; ++i)
-                            if (i < T::in_w(l)) zz = fmaf(act[l - 1][i], sp[T::w_off(l) + c * T::in_w(l) + i], zz);
-                        act[l][c] = fast_tanh(zz);
-                    }
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) zz = fma2(act[l - 1][i], ld2(wp2 + T::w_off(l) + c * T::in_w(l) + i), zz);
+                    act[l][c] = tanh2(zz);
                 }
-            }
-            float yh = 0.f;
-#pragma unroll
-            for (int i = 0; i < S; ++i) yh = fmaf(act[NLA - 1][i], sp[T::w_off(NLA) + i], yh);
-            yh2[h] = yh;
-            float tg = tg2[h];
-            if (a.target_mode == TGT_RESID_PLUS_PRED) { tg = tg + yh; tg2[h] = tg; }   // net.rs:280
-            const float e = valid ? yh - tg : 0.f;                                      // branch_sampler.rs:821
-            rss = fmaf(e, e, rss);
-            float delta[MW];
-#pragma unroll
-            for (int i = 0; i < S; ++i) {
-                gWo[i] = fmaf(act[NLA - 1][i], e, gWo[i]);
-                delta[i] = (1.f - act[NLA - 1][i] * act[NLA - 1][i]) * (e * sp[T::w_off(NLA) + i]);
-            }
-#pragma unroll
-            for (int l = NLA - 1; l >= 1; --l) {
-                float nd[MW];
-#pragma unroll
-                for (int i = 0; i < MW; ++i) nd[i] = 0.f;
-#pragma unroll
-                for (int c = 0; c < MW; ++c) {
-                    if (c < T::width(l)) {
-                        gbt[l - 1][c] += delta[c];
-#pragma unroll
-                        for (int i = 0; i < MW; ++i)
-                            if (i < T::in_w(l)) {
-                                gWt[l - 1][i][c] = fmaf(act[l - 1][i], delta[c], gWt[l - 1][i][c]);
-                                nd[i] = fmaf(delta[c], sp[T::w_off(l) + c * T::in_w(l) + i], nd[i]);
-                            }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < MW; ++i)
-                    if (i < T::in_w(l)) delta[i] = (1.f - act[l - 1][i] * act[l - 1][i]) * nd[i];
-            }
-#pragma unroll
-            for (int c = 0; c < W0; ++c) {
-                gb0[c] += delta[c];
-                dl0[h][c] = delta[c];
             }
         }
+        f2 yh = zero2;
+#pragma unroll
+        for (int i = 0; i < S; ++i) yh = fma2(act[NLA - 1][i], ld2(wp2 + T::w_off(NLA) + i), yh);
+        if (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) tg = add2(tg, yh);            // net.rs:280
+        const f2 e = mul2(fma2(tg, dup2(-1.f), yh), mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f));  // branch_sampler.rs:821
         // ---- per-row outputs
-        {
+        if (!LEAN) {
             auto put = [&](float* dst, uint32_t row, float v, int accumulate) {
                 if (!dst || row >= a.n) return;
                 float* p = dst + eoff + row;
@@ -272,68 +288,115 @@ __global__ void __launch_bounds__(128, 4) k1_tc(K1Args a) {
                 else *p = v;
             };
             if (a.target_mode == TGT_RESID_PLUS_PRED) {
-                put(a.tgt_out, rowA_g, tg2[0], 0); put(a.tgt_out, rowB_g, tg2[1], 0);
-                put(a.prev_out, rowA_g, yh2[0], 0); put(a.prev_out, rowB_g, yh2[1], 0);   // net.rs:279
+                put(a.tgt_out, rowA_g, lo2(tg), 0); put(a.tgt_out, rowB_g, hi2(tg), 0);
+                put(a.prev_out, rowA_g, lo2(yh), 0); put(a.prev_out, rowB_g, hi2(yh), 0);   // net.rs:279
             }
-            put(a.yhat_out, rowA_g, yh2[0], a.yhat_accumulate);
-            put(a.yhat_out, rowB_g, yh2[1], a.yhat_accumulate);
+            put(a.yhat_out, rowA_g, lo2(yh), a.yhat_accumulate);
+            put(a.yhat_out, rowB_g, hi2(yh), a.yhat_accumulate);
         }
-        umma::fence_before_sync();      // the accumulator reads above precede the next forward MMA
-        if (!a.fwd_only) {
-            // ---- delta_0 -> three bf16 pieces per unit (n = piece * W0 + unit), MN-major B operand
+        // ---- stage the next super-tile and start its forward contraction; it runs under part 2 of this tail
+        if (bwd && it > 0) umma::mbar_wait(&mbar[1], (it - 1) & 1u);   // backward of the previous super-tile read buffer buf^1 and sD
+        if (it + 1 < nit) {
+            expand(buf ^ 1u);
+            if (it + 2 < nit) load_words(st + 2);
+        }
+        umma::fence_async_smem();
+        __syncthreads();
+        if (warp == issuer && it + 1 < nit) issue_fwd(buf ^ 1u);
+        if (!bwd) continue;
+
+        // ---- tail, part 2: backward deltas and the cross-row sums of the layers >= 1
+        rss = fma2(e, e, rss);
+        f2 delta[MW];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float pv[NN];
+        for (int i = 0; i < S; ++i) {
+            gWo[i] = fma2(act[NLA - 1][i], e, gWo[i]);
+            delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e, ld2(wp2 + T::w_off(NLA) + i)));
+        }
 #pragma unroll
-                for (int n = 0; n < NN; ++n) pv[n] = 0.f;
+        for (int l = NLA - 1; l >= 1; --l) {
+            f2 nd[MW];
 #pragma unroll
-                for (int c = 0; c < W0; ++c) {
-                    const float v = dl0[h][c] * 1.2676506002282294e30f;   // 2^100, exact
-                    const float p0 = bf16_round(v), r1 = v - p0, p1 = bf16_round(r1), p2 = bf16_round(r1 - p1);
-                    pv[c] = p0; pv[W0 + c] = p1; pv[2 * W0 + c] = p2;
+            for (int i = 0; i < MW; ++i) nd[i] = zero2;
+#pragma unroll
+            for (int c = 0; c < MW; ++c) {
+                if (c < T::width(l)) {
+                    gbt[l - 1][c] = add2(gbt[l - 1][c], delta[c]);
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) {
+                            gWt[l - 1][i][c] = fma2(act[l - 1][i], delta[c], gWt[l - 1][i][c]);
+                            nd[i] = fma2(delta[c], ld2(wp2 + T::w_off(l) + c * T::in_w(l) + i), nd[i]);
+                        }
                 }
-                uint8_t* dst = sD + (h * 128 + tid) * 16;
-#pragma unroll
-                for (int q = 0; q < NN / 8; ++q)
-                    *reinterpret_cast<uint4*>(dst + q * kTcChunkStride) =
-                        make_uint4(pack_bf16(pv[8 * q], pv[8 * q + 1]), pack_bf16(pv[8 * q + 2], pv[8 * q + 3]),
-                                   pack_bf16(pv[8 * q + 4], pv[8 * q + 5]), pack_bf16(pv[8 * q + 6], pv[8 * q + 7]));
             }
-            umma::fence_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                umma::fence_after_sync();
 #pragma unroll
-                for (uint32_t ks = 0; ks < kTcRows / 16; ++ks) {
-                    const uint64_t ad = umma::make_desc(sA_u + ks * 256u, 128, kTcChunkStride);
-                    const uint64_t bd = umma::make_desc(sD_u + ks * 256u, 128, kTcChunkStride);
-                    umma::mma_f16(tmem + 2 * NN, ad, bd, idesc_b, (it | ks) != 0);
+            for (int i = 0; i < MW; ++i)
+                if (i < T::in_w(l)) delta[i] = mul2(dtanh2(act[l - 1][i]), nd[i]);
+        }
+        // ---- delta_0 -> three bf16 pieces per unit by truncation (exact: 3 x 8 significand bits = f32),
+        //      n = piece * W0 + unit, MN-major B operand: one 16-byte chunk per 8 n
+        {
+            uint32_t pa[NN], pb[NN];      // f32 bit patterns whose upper halves are the bf16 pieces (row A / row B)
+#pragma unroll
+            for (int n = 0; n < NN; ++n) { pa[n] = 0u; pb[n] = 0u; }
+#pragma unroll
+            for (int c = 0; c < W0; ++c) {
+                gb0[c] = add2(gb0[c], delta[c]);
+                f2 v = mul2(delta[c], dup2(1.2676506002282294e30f));   // 2^100, exact
+#pragma unroll
+                for (int piece = 0; piece < 3; ++piece) {
+                    const uint32_t ua = __float_as_uint(lo2(v)) & 0xFFFF0000u, ub = __float_as_uint(hi2(v)) & 0xFFFF0000u;
+                    pa[piece * W0 + c] = ua; pb[piece * W0 + c] = ub;
+                    if (piece < 2) v = add2(v, mk2(-__uint_as_float(ua), -__uint_as_float(ub)));
                 }
+            }
+            uint8_t* dst = sD + tid * 16;
+#pragma unroll
+            for (int q = 0; q < NN / 8; ++q) {
+                uint4 wa, wb;
+                wa.x = __byte_perm(pa[8 * q], pa[8 * q + 1], 0x7632); wa.y = __byte_perm(pa[8 * q + 2], pa[8 * q + 3], 0x7632);
+                wa.z = __byte_perm(pa[8 * q + 4], pa[8 * q + 5], 0x7632); wa.w = __byte_perm(pa[8 * q + 6], pa[8 * q + 7], 0x7632);
+                wb.x = __byte_perm(pb[8 * q], pb[8 * q + 1], 0x7632); wb.y = __byte_perm(pb[8 * q + 2], pb[8 * q + 3], 0x7632);
+                wb.z = __byte_perm(pb[8 * q + 4], pb[8 * q + 5], 0x7632); wb.w = __byte_perm(pb[8 * q + 6], pb[8 * q + 7], 0x7632);
+                *reinterpret_cast<uint4*>(dst + q * kTcChunkStride) = wa;
+                *reinterpret_cast<uint4*>(dst + q * kTcChunkStride + 128 * 16) = wb;
+            }
+        }
+        umma::fence_async_smem();
+        __syncthreads();
+        if (warp == issuer) {
+            umma::fence_after_sync();
+            const uint64_t base = dA_b + ((buf * sa_bytes) >> 4);
+            if (umma::elect_one()) {
+#pragma unroll
+                for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
+                    umma::mma_f16(tmem + 2 * NN, base + ks * 16u, dD_b + ks * 16u, idesc_b, (it | ks) != 0);
                 umma::commit(&mbar[1]);
             }
-        } else {
-            __syncthreads();
+            __syncwarp();
         }
     }
-    const bool has_bwd = !a.fwd_only && a.part && it > 0;
+    const bool has_bwd = bwd && a.part && nit > 0;
     float sacc[16];
     if (has_bwd) {
-        umma::mbar_wait(&mbar[1], (it - 1) & 1u);
+        umma::mbar_wait(&mbar[1], (nit - 1) & 1u);
         umma::fence_after_sync();
         umma::tmem_ld16(tlane + 2 * NN, sacc);
     }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, C::TMEM_COLS);
-    if (a.fwd_only || !a.part) return;
+    if (!bwd || !a.part) return;
 
-    // ---- CTA epilogue: fixed-order reduction over lanes and warps, unfold the standardisation
+    // ---- CTA epilogue: fixed-order reduction over row pairs, lanes and warps; unfold the standardisation
     float* pp = a.part + ((size_t)li * a.nchunk + chunk) * a.pstride;
     const uint32_t P = d.P;
     {
         float* rw = red + warp * NTACC;
         int idx = 0;
-        auto put = [&](float v) {
+        auto put = [&](f2 v2) {
+            float v = lo2(v2) + hi2(v2);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) rw[idx] = v;
@@ -387,7 +450,7 @@ __global__ void __launch_bounds__(128, 4) k1_tc(K1Args a) {
             const float unscale = pow2f(33 - 2 * (int)((j & 7u) >> 1));
 #pragma unroll
             for (int c = 0; c < W0; ++c) {
-                const float s = (it > 0 ? (sacc[c] + (sacc[W0 + c] + sacc[2 * W0 + c])) : 0.f) * unscale;
+                const float s = (nit > 0 ? (sacc[c] + (sacc[W0 + c] + sacc[2 * W0 + c])) : 0.f) * unscale;
                 pp[c * m + j] = __fdiv_rn(s - mu[j] * s_gb0[c], sd[j]);
             }
         }
@@ -397,14 +460,17 @@ __global__ void __launch_bounds__(128, 4) k1_tc(K1Args a) {
 template <int H, int S, int D>
 int launch_one_tc(K1Args& a, uint32_t nlist, cudaStream_t st) {
     using C = TcShape<H, S, D>;
-    auto kern = k1_tc<H, S, D>;
     static bool configured = false;
     if (!configured) {
-        BANN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
         configured = true;
     }
+    const size_t smem = C::smem(a.ncb);
     dim3 grid(a.nchunk, nlist);
-    kern<<<grid, 128, C::SMEM, st>>>(a);
+    const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
+    if (lean) k1_tc<H, S, D, true><<<grid, 128, smem, st>>>(a);
+    else k1_tc<H, S, D, false><<<grid, 128, smem, st>>>(a);
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
@@ -427,6 +493,7 @@ inline int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch,
         }
     }
     if (max_m > (uint32_t)kTcMaxMarkers) return 0;
+    a.ncb = (max_m + 7) / 8;
     const int D = (int)d0.nl - 2;
     const int S = (int)d0.widths[d0.nl - 2];
     const int H = D > 0 ? (int)d0.widths[0] : S;

@@ -84,6 +84,7 @@ struct K1Args {
     const uint32_t* store_tc;  // NULL: no tensor-core store
     uint32_t nst;              // 256-row super-tiles
     uint32_t st_per_chunk;
+    uint32_t ncb;              // 8-marker chunks per expanded-genotype buffer (max over the listed branches)
 };
 
 __device__ __forceinline__ void locate_param(const BranchDesc& d, uint32_t k, int& layer, uint32_t& row,
