@@ -74,20 +74,20 @@ struct TcShape {
     static constexpr size_t SD = (NN / 8) * kTcChunkStride;   // delta pieces  [n-chunk][row] x 16 B
     static constexpr size_t SW = 8 * NN * 16;           // weight pieces [k-chunk][n] x 16 B
     static constexpr int NRED = 4 * (T::NTACC > 64 ? T::NTACC : 64);
-    // two expanded-genotype buffers of ncb chunks each.  The operand reads overrun a buffer: the last forward
-    // K-step of an odd ncb reads chunk ncb (x zero weights) and the M = 64 backward operand always reads 8
-    // chunks (rows >= m of the result are never used), so the region behind the second buffer must exist.
-    __host__ __device__ static constexpr uint32_t slots(uint32_t ncb) {
-        return (2 * ncb + (ncb & 1u)) > (ncb + 8) ? (2 * ncb + (ncb & 1u)) : (ncb + 8);
-    }
+    // Layout: [expanded genotypes: 2 buffers x ncb chunks][weight pieces][packed words of the next tile][delta pieces][misc].
+    // The operand reads overrun a buffer on purpose: the last forward K-step of an odd ncb reads chunk ncb (times
+    // zero weights; what lies there -- the other buffer, weight pieces, packed words -- is always finite) and the
+    // M = 64 backward operand always reads 8 chunks (result rows >= m are never used), so ncb + 8 chunks must exist.
+    static constexpr size_t MISC = (size_t)(2 * ((T::n_tail() + 3) & ~3) + 2 * T::W0P + NRED + 16) * 4 + 64;
     static size_t smem(uint32_t ncb) {
-        return (size_t)slots(ncb) * kTcChunkStride + SD + SW +
-               (size_t)(2 * ((T::n_tail() + 3) & ~3) + 2 * T::W0P + NRED + 8) * 4 + 64 + 128;
+        const size_t used = (size_t)2 * ncb * kTcChunkStride + SW + (size_t)ncb * 512 + SD + MISC;
+        const size_t need = (size_t)(ncb + 8) * kTcChunkStride;
+        return (used > need ? used : need) + 128;
     }
 };
 
 // LEAN: gradient / leapfrog launches (targets given, no per-row outputs, backward always) -- the hot configuration
-template <int H, int S, int D, bool LEAN>
+template <int H, int S, int D, bool LEAN, int NCT>
 __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
@@ -98,19 +98,22 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     const uint32_t b = a.list ? a.list[li] : li;
     if (a.states && a.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = a.descs[b];
-    const uint32_t m = d.m, NC = d.nc, NKS = (NC + 1) >> 1, NCB = a.ncb;
+    const uint32_t m = d.m, NC = NCT ? (uint32_t)NCT : d.nc, NKS = (NC + 1) >> 1, NCB = a.ncb;
     // the warp that issues the MMAs rotates over CTAs so that the issue work spreads over the four SM sub-partitions
     const uint32_t issuer = (blockIdx.x + blockIdx.y) & 3u;
     // ---- shared memory carve-up
     uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // whole core matrices (keeps the shared address space)
     const uint32_t sa_bytes = NCB * kTcChunkStride;                        // one expanded-genotype buffer
-    uint8_t* sW = sA + (size_t)C::slots(NCB) * kTcChunkStride;
-    uint8_t* sD = sW + C::SW;
+    uint8_t* sW = sA + (size_t)2 * sa_bytes;
+    uint32_t* sG = reinterpret_cast<uint32_t*>(sW + C::SW);               // [NC][128] packed words of the next super-tile (bulk copy target)
+    uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + (size_t)NCB * 512;
     float2* wp2 = reinterpret_cast<float2*>(sD + C::SD);                   // tail parameters, duplicated {w, w}
     float2* b0p2 = wp2 + ((T::n_tail() + 3) & ~3);                         // [W0P] first-layer bias with the means folded in
     float* red = reinterpret_cast<float*>(b0p2 + W0P);                     // [NRED] reduction scratch
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);           // [0] forward done, [1] backward done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    // [0] forward MMAs done, [1] backward MMAs done (tcgen05.commit); [2] next tile expanded, [3] delta pieces written
+    // (128 arrivals each); [4] packed words landed (bulk copy transaction bytes)
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 6);
 
     const float* th = a.theta + d.param_off;
     const float* mu = a.mu + d.col_off;
@@ -124,6 +127,9 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     if (tid == 0) {
         umma::mbar_init(&mbar[0], 1);
         umma::mbar_init(&mbar[1], 1);
+        umma::mbar_init(&mbar[2], 128);
+        umma::mbar_init(&mbar[3], 128);
+        umma::mbar_init(&mbar[4], 1);
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -188,16 +194,14 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     const uint32_t t_begin = chunk * a.st_per_chunk;
     const uint32_t t_end = min(a.nst, t_begin + a.st_per_chunk);
     const uint32_t nit = t_end > t_begin ? t_end - t_begin : 0;
-    const uint32_t* gbase = a.store_tc + (d.tc_off >> 2) + tid;
     const float* tsrc = (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) ? a.resid : (a.tgt ? a.tgt + toff : nullptr);
     const bool bwd = LEAN || !a.fwd_only;
 
-    uint32_t wreg[8];
-    auto load_words = [&](uint32_t st) {
-        const uint32_t* src = gbase + (size_t)st * NC * 128;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if ((uint32_t)i < NC) wreg[i] = __ldg(src + i * 128);
+    // packed words of super-tile `st` -> shared memory, one bulk copy (the branch's super-tiles are contiguous: [st][NC][128] u32)
+    const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
+    auto issue_load = [&](uint32_t st) {        // whole issuer warp enters
+        if (umma::elect_one()) umma::bulk_load(sG, gwords + (size_t)st * NC * 128, NC * 512u, &mbar[4]);
+        __syncwarp();
     };
     // expand: one AND per two operand elements, 16-byte conflict-free stores (row t and row 128 + t)
     auto expand = [&](uint32_t buf) {
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             if ((uint32_t)i < NC) {
-                const uint32_t x = wreg[i], y = x >> 8;
+                const uint32_t x = sG[i * 128 + tid], y = x >> 8;
                 *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) =
                     make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
                 *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride + 128 * 16) =
@@ -232,20 +236,29 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         __syncwarp();
     };
 
+    auto load_targets = [&](uint32_t st) -> f2 {
+        const uint32_t rA = st * kTcRows + tid, rB = rA + 128;
+        if (!tsrc || st >= t_end) return zero2;
+        return mk2(rA < a.n ? __ldg(tsrc + rA) : 0.f, rB < a.n ? __ldg(tsrc + rB) : 0.f);
+    };
+    f2 tg_next = load_targets(t_begin);
     if (nit > 0) {
-        load_words(t_begin);
+        if (warp == issuer) issue_load(t_begin);
+        umma::mbar_wait(&mbar[4], 0);
         expand(0);
-        if (nit > 1) load_words(t_begin + 1);
         umma::fence_async_smem();
         __syncthreads();
-        if (warp == issuer) issue_fwd(0);
+        if (warp == issuer) {
+            issue_fwd(0);
+            if (nit > 1) issue_load(t_begin + 1);
+        }
     }
     for (uint32_t it = 0; it < nit; ++it) {
         const uint32_t st = t_begin + it, buf = it & 1u;
         const uint32_t rowA_g = st * kTcRows + tid, rowB_g = rowA_g + 128;
         const bool vA = rowA_g < a.n, vB = rowB_g < a.n;
-        f2 tg = zero2;
-        if (tsrc) tg = mk2(vA ? __ldg(tsrc + rowA_g) : 0.f, vB ? __ldg(tsrc + rowB_g) : 0.f);
+        f2 tg = tg_next;                 // loaded one super-tile ahead: nothing in this iteration waits on HBM
+        tg_next = load_targets(st + 1);
         // ---- z0 of this super-tile (its forward contraction was issued one stage ago)
         umma::mbar_wait(&mbar[0], it & 1u);
         umma::fence_after_sync();
@@ -297,12 +310,17 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         // ---- stage the next super-tile and start its forward contraction; it runs under part 2 of this tail
         if (bwd && it > 0) umma::mbar_wait(&mbar[1], (it - 1) & 1u);   // backward of the previous super-tile read buffer buf^1 and sD
         if (it + 1 < nit) {
+            umma::mbar_wait(&mbar[4], (it + 1) & 1u);    // words of super-tile it + 1 (requested one stage ago)
             expand(buf ^ 1u);
-            if (it + 2 < nit) load_words(st + 2);
         }
+        // no CTA-wide barrier: every thread arrives and moves on, only the issuer warp waits for all 128 arrivals
         umma::fence_async_smem();
-        __syncthreads();
-        if (warp == issuer && it + 1 < nit) issue_fwd(buf ^ 1u);
+        umma::mbar_arrive(&mbar[2]);
+        if (warp == issuer) {
+            umma::mbar_wait(&mbar[2], it & 1u);
+            if (it + 1 < nit) issue_fwd(buf ^ 1u);
+            if (it + 2 < nit) issue_load(st + 2);        // every thread has read the staged words by now
+        }
         if (!bwd) continue;
 
         // ---- tail, part 2: backward deltas and the cross-row sums of the layers >= 1
@@ -364,8 +382,9 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
             }
         }
         umma::fence_async_smem();
-        __syncthreads();
+        umma::mbar_arrive(&mbar[3]);
         if (warp == issuer) {
+            umma::mbar_wait(&mbar[3], it & 1u);
             umma::fence_after_sync();
             const uint64_t base = dA_b + ((buf * sa_bytes) >> 4);
             if (umma::elect_one()) {
@@ -462,15 +481,17 @@ int launch_one_tc(K1Args& a, uint32_t nlist, cudaStream_t st) {
     using C = TcShape<H, S, D>;
     static bool configured = false;
     if (!configured) {
-        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
-        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
         configured = true;
     }
     const size_t smem = C::smem(a.ncb);
     dim3 grid(a.nchunk, nlist);
     const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
-    if (lean) k1_tc<H, S, D, true><<<grid, 128, smem, st>>>(a);
-    else k1_tc<H, S, D, false><<<grid, 128, smem, st>>>(a);
+    if (lean && a.nc_uniform == 7) k1_tc<H, S, D, true, 7><<<grid, 128, smem, st>>>(a);   // 49..56 markers in every listed branch
+    else if (lean) k1_tc<H, S, D, true, 0><<<grid, 128, smem, st>>>(a);
+    else k1_tc<H, S, D, false, 0><<<grid, 128, smem, st>>>(a);
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
@@ -494,6 +515,10 @@ inline int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch,
     }
     if (max_m > (uint32_t)kTcMaxMarkers) return 0;
     a.ncb = (max_m + 7) / 8;
+    a.nc_uniform = a.ncb;
+    if (single_branch < 0)
+        for (const BranchDesc& d : descs)
+            if (d.nc != a.ncb) a.nc_uniform = 0;
     const int D = (int)d0.nl - 2;
     const int S = (int)d0.widths[d0.nl - 2];
     const int H = D > 0 ? (int)d0.widths[0] : S;

@@ -85,6 +85,7 @@ struct K1Args {
     uint32_t nst;              // 256-row super-tiles
     uint32_t st_per_chunk;
     uint32_t ncb;              // 8-marker chunks per expanded-genotype buffer (max over the listed branches)
+    uint32_t nc_uniform;       // chunks per row when every listed branch has the same count, else 0
 };
 
 __device__ __forceinline__ void locate_param(const BranchDesc& d, uint32_t k, int& layer, uint32_t& row,

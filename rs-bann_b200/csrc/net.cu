@@ -132,6 +132,7 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
     a.nst = g->nst;
     a.st_per_chunk = 0;
     a.ncb = 8;
+    a.nc_uniform = 0;
 
     bool launched = false;
     if (net->k1_mode == BANN_K1_AUTO || net->k1_mode == BANN_K1_TENSOR) {

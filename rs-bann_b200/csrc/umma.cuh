@@ -85,6 +85,18 @@ __device__ __forceinline__ void commit(uint64_t* mbar) {
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
 }
+// non-blocking arrival (release at CTA scope): the arriving thread's earlier writes / fences are ordered before a later wait
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+// bulk asynchronous copy global -> shared (TMA engine, 1-D): `bytes` (multiple of 16, both sides 16-byte aligned)
+// land in shared memory and complete on the mbarrier, which must expect them (arrive.expect_tx by the same thread)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     asm volatile(
