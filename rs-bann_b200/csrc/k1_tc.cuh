@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     const BranchDesc& d = a.descs[b];
     const uint32_t m = d.m, NC = NCT ? (uint32_t)NCT : d.nc, NKS = (NC + 1) >> 1, NCB = a.ncb;
     // the warp that issues the MMAs rotates over CTAs so that the issue work spreads over the four SM sub-partitions
-    const uint32_t issuer = (blockIdx.x + blockIdx.y) & 3u;
+    const uint32_t issuer = a.issuer_warp < 4 ? a.issuer_warp : ((blockIdx.x + blockIdx.y) & 3u);
     // ---- shared memory carve-up
     uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // whole core matrices (keeps the shared address space)
     const uint32_t sa_bytes = NCB * kTcChunkStride;                        // one expanded-genotype buffer

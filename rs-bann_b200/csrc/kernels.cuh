@@ -85,6 +85,7 @@ struct K1Args {
     uint32_t nst;              // 256-row super-tiles
     uint32_t st_per_chunk;
     uint32_t ncb;              // 8-marker chunks per expanded-genotype buffer (max over the listed branches)
+    uint32_t issuer_warp;      // warp that issues the MMAs (>= 4: rotate over CTAs)
     uint32_t nc_uniform;       // chunks per row when every listed branch has the same count, else 0
 };
 
