@@ -189,6 +189,10 @@ int  bann_sweep(bann_net*, const bann_mcmc_cfg*, const uint64_t* branch_order, u
 /* Net::predict (net/net.rs:545-559) on the training genotypes (NULL) or another store. */
 int  bann_predict(bann_net*, bann_genotypes* test_or_null, float* yhat);
 int  bann_net_stats(bann_net*, bann_sweep_stats* out);
+/* the three groups of terms of LogPosteriorDensity (net/log_posterior_density.rs:9-16), as serialised in a model file;
+ * wrt_local_params: one value per branch */
+int  bann_net_lpd_terms(bann_net*, float* wrt_rss_and_error_precision, float* wrt_output_weights_and_precision,
+                        float* wrt_local_params);
 
 /* ---- full-network (grouped, all branches concurrently) operations */
 /* Net::gradient (net/net.rs:520-527): for every branch log_density_gradient(x_b, y).

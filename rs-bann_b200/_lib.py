@@ -110,6 +110,7 @@ PROTOTYPES = {
     "bann_grouped_state": (C.c_int, [_vp, _fp, _fp, C.POINTER(C.c_int32)]),
     "bann_allreduce_buffer": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
     "bann_net_force_generic": (C.c_int, [_vp, C.c_int]),
+    "bann_net_lpd_terms": (C.c_int, [_vp, _fp, _fp, _fp]),
     "bann_net_select_k1": (C.c_int, [_vp, C.c_int]),
     "bann_launch_count": (_u64, [C.c_int]),
     "bann_net_algorithmic_bytes": (C.c_int, [_vp, C.POINTER(_u64)]),

@@ -384,6 +384,13 @@ class Net:
         check(lib.bann_net_stats(self.h, C.byref(st)))
         return self._stats(st)
 
+    def lpd_terms(self):
+        """LogPosteriorDensity fields (net/log_posterior_density.rs:9-16): (rss term, output-weight term, per-branch terms)."""
+        a, b = np.empty(1, dtype=np.float32), np.empty(1, dtype=np.float32)
+        loc = np.empty(self.num_branches, dtype=np.float32)
+        check(lib.bann_net_lpd_terms(self.h, _ptr(a), _ptr(b), _ptr(loc)))
+        return float(a[0]), float(b[0]), loc
+
     def train(self, cfg: MCMCCfg, chain_length: int, seed: int = 0, orders=None):
         """Net::train (net/net.rs:201-358), sequential-exact schedule, built-in RNG."""
         self.init_residual()

@@ -962,6 +962,19 @@ int bann_net_stats(bann_net* net, bann_sweep_stats* out) {
     return 0;
 }
 
+int bann_net_lpd_terms(bann_net* net, float* wrt_rss_and_error_precision, float* wrt_output_weights_and_precision,
+                       float* wrt_local_params) {
+    if (!net || !wrt_rss_and_error_precision || !wrt_output_weights_and_precision || !wrt_local_params) BANN_FAIL("NULL argument");
+    cudaStream_t st = net->ctx->stream;
+    NetGlobals G;
+    BANN_CUDA(cudaMemcpyAsync(&G, net->d_G, sizeof(G), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaMemcpyAsync(wrt_local_params, net->d_lpd_local, net->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    *wrt_rss_and_error_precision = G.lpd_rss;
+    *wrt_output_weights_and_precision = G.lpd_out_w;
+    return 0;
+}
+
 int bann_sweep(bann_net* net, const bann_mcmc_cfg* cfg, const uint64_t* branch_order, uint64_t num, uint32_t group_size,
                uint64_t seed, bann_sweep_stats* out) {
     if (!net || !cfg || !branch_order) BANN_FAIL("NULL argument");

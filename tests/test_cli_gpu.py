@@ -1,0 +1,81 @@
+"""End-to-end run of the kept command surface on the GPU: simulate-xy -> train-new -> predict -> train (resume),
+checking every output file of the reference and that the chain learns (posterior predictive R^2)."""
+import glob
+import io
+import json
+import os
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import rs_bann_b200 as rb
+    if not rb.cuda_available():
+        pytest.skip("no CUDA device")
+    return rb
+
+
+def run(argv):
+    from rs_bann_b200.cli import main
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        main(argv)
+    return buf.getvalue()
+
+
+def test_simulate_train_predict_resume(rb, tmp_path):
+    from rs_bann_b200 import files
+    from rs_bann_b200.cli import r2
+    sim = run(["simulate-xy", "-o", str(tmp_path), "--seed", "1", "ridge-base", "tanh", "20", "5", "1200", "3", "1", "0.6"]).strip()
+    for f in ("model.bin", "model.params", "args.json", "train.bed", "train.dims", "train.groups", "train.phen",
+              "test.bed", "test.phen", "train_phen_stats.json", "test_phen_stats.json"):
+        assert os.path.exists(os.path.join(sim, f)), f
+    assert os.path.basename(sim) == "RidgeBase_Tanh_b5_wh3_ws3_d1_m20_n1200_h0.6_rep1"        # rs-bann.rs:803-814,776-787
+    stats = json.load(open(os.path.join(sim, "train_phen_stats.json")))
+    assert stats["env_variance"] == pytest.approx(stats["variance"] * 0.4, rel=0.15)           # h2 = 0.6
+    truth = files.read_net(os.path.join(sim, "model.bin"))
+    assert len(truth.branch_cfgs) == 5 and truth.branch_cfgs[0].layer_widths == [3, 3, 1]
+
+    tr, te = os.path.join(sim, "train"), os.path.join(sim, "test")
+    out = run(["train-new", tr, tr + ".phen", tr + ".groups", "30", "20", "ridge-base", "tanh", "1",
+               "--fixed-hidden-layer-width", "3", "--bfile-test", te, "--p-test", te + ".phen", "-o", str(tmp_path / "fit"),
+               "--burn-in", "20", "--step-size", "0.3", "--trace", "--seed", "7", "--report-interval", "10"]).strip()
+    assert os.path.basename(out).startswith("RidgeBase_Tanh_d1_cl30_il20_Izmailov_st0.3_dpk0.001_dps1000_spk0.001_sps1000"
+                                            "_opk0.001_ops1000_fhlw3_rslw1_rep1")
+    args = json.load(open(os.path.join(out, "args.json")))
+    assert args["model_type"] == "RidgeBase" and args["branch_depth"] == 1
+    hyper = json.load(open(os.path.join(out, "hyperparams")))
+    assert len(hyper["branch_hyperparams"]) == 5 and hyper["precision_hyperparams"]["dense"] == {"shape": 0.001, "scale": 1000.0}
+    ts = json.load(open(os.path.join(out, "training_stats")))
+    assert ts["num_samples"] == 30 * 5 and len(ts["mse_train"]) == 31 and len(ts["mse_test"]) == 31 and len(ts["lpd"]) == 31
+    assert ts["num_accepted"] > 0.3 * ts["num_samples"]
+    assert ts["mse_train"][-1] < 0.9 * ts["mse_train"][0]                                      # the chain fits
+    assert sum(1 for _ in open(os.path.join(out, "trace"))) == 31                              # one line per iteration incl. 0
+    models = sorted(glob.glob(os.path.join(out, "models", "*.bin")))
+    assert [os.path.basename(m) for m in models] == sorted(f"{i}.bin" for i in range(20, 31))  # chain_ix >= burn_in
+    last = files.read_net(os.path.join(out, "models", "30.bin"))
+    assert last.num_samples == 150 and len(last.lpd_local) == 5 and np.isfinite(last.lpd_rss)
+    assert last.mse_train == pytest.approx(ts["mse_train"])
+
+    csv = run(["predict", te, te + ".groups", "-m", os.path.join(out, "models")]).strip().splitlines()
+    assert len(csv) == len(models)
+    preds = np.array([[float(v) for v in row.split(",")] for row in csv])
+    assert preds.shape == (len(models), 1200)
+    y_te = files.read_phen(te + ".phen")
+    r2_fit = r2(y_te, preds.mean(axis=0))
+    assert r2_fit > 0.15, r2_fit                                                               # h2 = 0.6 upper bound
+    # mse_test recorded during training = mse of the same model on the same data (net.rs:637-646)
+    assert np.mean((y_te - preds[-1]) ** 2) == pytest.approx(ts["mse_test"][-1], rel=1e-4)
+
+    res = run(["train", tr, tr + ".phen", tr + ".groups", "3", "10", "ridge-base", os.path.join(out, "models", "30.bin"),
+               "-o", str(tmp_path / "resume"), "--burn-in", "0", "--seed", "3"]).strip()
+    assert os.path.basename(res) == "30_cl3_il10_Izmailov_st1_dtheta0_dlambda0"                # rs-bann.rs:1152-1160
+    assert sorted(os.path.basename(m) for m in glob.glob(os.path.join(res, "models", "*.bin"))) == ["0.bin", "1.bin", "2.bin", "3.bin"]
+    first = files.read_net(os.path.join(res, "models", "0.bin"))
+    assert np.array_equal(first.branch_cfgs[2].param_vec(), last.branch_cfgs[2].param_vec())   # resumed from the saved state
+    assert first.mse_train[-1] == pytest.approx(last.mse_train[-1], rel=1e-4)
