@@ -334,7 +334,8 @@ def main():
                                 branch_leapfrogs_per_step=B, active_branches=active),
                     k1_ms=k1_ms, wall_s=t_wall, gpu_launches=int(launches) * world,
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                                  traffic=NCU_TRAFFIC_BYTES.get(args.workload), peak_source=peak_src,
+                                  traffic=(NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 and k1_name.startswith("k1_tc") else None),
+                                  peak_source=peak_src,
                                   algorithmic_bytes_per_launch=alg_bytes, kernel=k1_name,
                                   kernel_ms=k1_ms),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
