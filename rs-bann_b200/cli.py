@@ -315,6 +315,50 @@ def cmd_r2(a):
     gen.close(); ctx.close()
 
 
+def cmd_branch_r2(a):
+    """branch_r2 (rs-bann.rs:128-170, net.rs:648-656): per model a CSV row of 1 - rss_b / sum(y^2) for every branch."""
+    ctx = Context(a.device)
+    gen, y = _load_data(ctx, a.bfile, a.groups, a.phen)
+    model = _read_model_type(a.model_path)
+    yy = float(np.sum(y.astype(np.float32) ** 2, dtype=np.float32))
+    for path in _model_files(a.model_path):
+        net = net_to_device(ctx, gen, model, files.read_net(path))
+        net.set_targets(y)
+        print(",".join(repr(1.0 - float(net.branch_fwd_bwd(b, want_yhat=False)["rss"]) / yy) for b in range(net.num_branches)))
+        net.close()
+    gen.close(); ctx.close()
+
+
+def cmd_gradients(a):
+    """gradients (rs-bann.rs:226-274, net.rs:520-527): log-density gradient of every branch against y, one JSON file per
+    model under <model dir>/../gradients/.  (The reference serialises ArrayFire arrays through afserde; here each branch
+    is {"wrt_weights": [[...] per layer, column-major], "wrt_biases": [[...] per layer]}.)"""
+    ctx = Context(a.device)
+    gen, y = _load_data(ctx, a.bfile, a.groups, a.phen)
+    model = _read_model_type(a.model_path)
+    outdir = os.path.join(os.path.dirname(os.path.normpath(a.model_path)), "gradients")
+    os.makedirs(outdir, exist_ok=True)
+    for path in _model_files(a.model_path):
+        nf = files.read_net(path)
+        net = net_to_device(ctx, gen, model, nf)
+        grads, _ = net.gradient(y=y)                                              # one fused full-network launch
+        out, off = [], 0
+        for c in nf.branch_cfgs:
+            g = grads[off:off + c.num_params]
+            off += c.num_params
+            ws, bs, ix, prev = [], [], 0, c.num_markers
+            for w in c.layer_widths:
+                ws.append([float(v) for v in g[ix:ix + prev * w]]); ix += prev * w; prev = w
+            for w in c.layer_widths[:-1]:
+                bs.append([float(v) for v in g[ix:ix + w]]); ix += w
+            out.append(dict(wrt_weights=ws, wrt_biases=bs))
+        stem = os.path.splitext(os.path.basename(path))[0]
+        json.dump(out, open(os.path.join(outdir, stem + ".json"), "w"))
+        net.close()
+    gen.close(); ctx.close()
+    print(outdir)
+
+
 def cmd_simulate_xy(a):
     """simulate_xy (rs-bann.rs:793-964): random genotypes (io/bed.rs:136-188), a random net, y = net(X) + noise."""
     if not 0.0 <= a.heritability <= 1.0:
@@ -404,6 +448,12 @@ def build_parser():
     p.add_argument("bfile"); p.add_argument("phen"); p.add_argument("groups"); p.add_argument("-m", "--model-path", default="./models")
     p.add_argument("--device", type=int, default=0)
     p.set_defaults(func=cmd_r2)
+    for name, fn, hlp in (("branch-r2", cmd_branch_r2, "Use trained model to compute r2 values for each model branch."),
+                          ("gradients", cmd_gradients, "Report gradient wrt to params in trained model.")):
+        p = sub.add_parser(name, help=hlp)
+        p.add_argument("bfile"); p.add_argument("phen"); p.add_argument("groups"); p.add_argument("-m", "--model-path", default="./models")
+        p.add_argument("--device", type=int, default=0)
+        p.set_defaults(func=fn)
     p = sub.add_parser("simulate-xy", help="Simulate marker and phenotype data under a network model.")
     p.add_argument("-o", "--outdir", default="./")
     p.add_argument("model_type", type=_model_type); p.add_argument("activation_function", type=_activation)

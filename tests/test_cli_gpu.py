@@ -72,6 +72,14 @@ def test_simulate_train_predict_resume(rb, tmp_path):
     # mse_test recorded during training = mse of the same model on the same data (net.rs:637-646)
     assert np.mean((y_te - preds[-1]) ** 2) == pytest.approx(ts["mse_test"][-1], rel=1e-4)
 
+    rows = run(["branch-r2", te, te + ".phen", te + ".groups", "-m", os.path.join(out, "models")]).strip().splitlines()
+    assert len(rows) == len(models) and len(rows[0].split(",")) == 5
+    assert all(float(v) < 1.0 for v in rows[-1].split(","))
+    gdir = run(["gradients", tr, tr + ".phen", tr + ".groups", "-m", os.path.join(out, "models")]).strip()
+    gj = json.load(open(os.path.join(gdir, "30.json")))
+    assert len(gj) == 5 and [len(w) for w in gj[0]["wrt_weights"]] == [60, 9, 3] and [len(b) for b in gj[0]["wrt_biases"]] == [3, 3]
+    assert np.all(np.isfinite(np.concatenate([np.concatenate([np.array(w) for w in br["wrt_weights"]]) for br in gj])))
+
     res = run(["train", tr, tr + ".phen", tr + ".groups", "3", "10", "ridge-base", os.path.join(out, "models", "30.bin"),
                "-o", str(tmp_path / "resume"), "--burn-in", "0", "--seed", "3"]).strip()
     assert os.path.basename(res) == "30_cl3_il10_Izmailov_st1_dtheta0_dlambda0"                # rs-bann.rs:1152-1160

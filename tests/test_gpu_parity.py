@@ -577,6 +577,24 @@ def test_net_gradient_matches_per_branch(rb, ctx):
         P.close()
 
 
+@pytest.mark.parametrize("model,sizes", [("lasso_ard", [64, 57, 8, 1]), ("std_normal", [7, 56, 49])])
+def test_tensor_core_grouped_launch_heterogeneous_branches(rb, ctx, model, sizes):
+    """One tensor-core launch over branches with different chunk counts (8-chunk operand buffers when a branch has 64 markers)."""
+    P = Problem(rb, ctx, model, 1111, sizes, 5, 5, seed=11)
+    try:
+        P.net.select_k1(P.net.K1_TENSOR)
+        grads, rss = P.net.gradient()
+        k = 0
+        for b in range(len(sizes)):
+            n = P.net.num_branch_params(b)
+            t64, t32 = oracle_fwd_bwd(P, b, P.y, np.float64), oracle_fwd_bwd(P, b, P.y, np.float32)
+            within(grads[k:k + n], t64["ldg"], t32["ldg"])
+            within(rss[b], t64["rss"], t32["rss"])
+            k += n
+    finally:
+        P.close()
+
+
 def test_grouped_leapfrog_conserves_energy_and_matches_kernels(rb, ctx):
     cfg = rb.MCMCCfg(hmc_step_size_factor=0.05, hmc_integration_length=20, hmc_step_size_mode="izmailov")
     out = {}
