@@ -135,7 +135,7 @@ int  bann_genotypes_col_counts(bann_genotypes*, uint64_t* out);
 int  bann_genotypes_set_col_stats(bann_genotypes*, const float* col_means, const float* col_stds);
 /* test hook: decode branch b to f32 [n x m_b] column-major, raw 0/1/2 or standardised. */
 int  bann_genotypes_decode_branch(bann_genotypes*, uint64_t b, int standardized, float* out);
-/* the same, decoded from the tensor-core store (bf16-subnormal layout, every branch <= 64 markers) */
+/* the same, decoded from the tensor-core store (bf16-subnormal layout, every branch <= 512 markers) */
 int  bann_genotypes_decode_branch_tc(bann_genotypes*, uint64_t b, int standardized, float* out);
 int  bann_genotypes_has_tc_store(bann_genotypes*);
 
@@ -226,7 +226,7 @@ int  bann_allreduce_buffer(bann_net*, void** dev_ptr, uint64_t* num_floats);
 /* test hook: route every K1 launch through the shape-agnostic kernel (cross-checks the tuned one) */
 int  bann_net_force_generic(bann_net*, int on);
 /* test / profiling hook: which fused forward+backward kernel launches may use.  AUTO tries the tensor-core
- * kernel (tcgen05, <= 64 markers per branch), then the FFMA kernel, then the shape-agnostic one. */
+ * kernels (tcgen05; <= 64 markers per branch, or K-blocked up to 512), then the FFMA kernel, then the shape-agnostic one. */
 enum { BANN_K1_AUTO = 0, BANN_K1_TENSOR = 1, BANN_K1_FFMA = 2, BANN_K1_GENERIC = 3 };
 int  bann_net_select_k1(bann_net*, int which);
 

@@ -291,11 +291,11 @@ static int build_from_device_payload(bann_ctx* ctx, uint8_t* d_payload /* consum
         if (mp > max_mp) max_mp = mp;
     }
     g->store_bytes = off;
-    // tensor-core store geometry (all-or-nothing: every branch must fit the M = 64 accumulator)
+    // tensor-core store geometry (all-or-nothing: every branch within the 512 markers of the K-blocked tensor-core kernel)
     g->nst = (uint32_t)((n + 255) / 256);
     g->tc_off.assign(num_branches, 0);
     bool tc_ok = true;
-    for (uint64_t b = 0; b < num_branches; ++b) tc_ok = tc_ok && g->m_b[b] <= 64;
+    for (uint64_t b = 0; b < num_branches; ++b) tc_ok = tc_ok && g->m_b[b] <= 512;
     g->tc_bytes = 0;
     if (tc_ok) {
         for (uint64_t b = 0; b < num_branches; ++b) {
@@ -492,7 +492,7 @@ int bann_genotypes_decode_branch(bann_genotypes* g, uint64_t b, int standardized
 int bann_genotypes_decode_branch_tc(bann_genotypes* g, uint64_t b, int standardized, float* out) {
     if (!g || !out) BANN_FAIL("NULL argument");
     if (b >= g->num_branches) BANN_FAIL("branch index out of range");
-    if (!g->d_store_tc) BANN_FAIL("no tensor-core store (a branch has more than 64 markers)");
+    if (!g->d_store_tc) BANN_FAIL("no tensor-core store (a branch has more than 512 markers)");
     BranchDesc d;
     memset(&d, 0, sizeof(d));
     d.m = g->m_b[b];

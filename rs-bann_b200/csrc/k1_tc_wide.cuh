@@ -1,0 +1,498 @@
+// Tensor-core K1 for branches with 65 .. 512 markers (first-layer width <= 5): the k1_tc scheme, K-blocked.
+//
+// A branch is cut into blocks of 64 markers (8 chunks of 8).  Per 256-row super-tile the CTA streams the blocks through
+// two operand buffers TWICE:
+//   forward pass : expand block kb -> MMA fwd (M128 N16 K16 x 4, two row halves) accumulating z0 over all blocks in
+//                  tensor memory;
+//   tail         : exactly as in k1_tc (packed f32x2, one row pair per thread), delta_0 pieces -> shared memory;
+//   backward pass: expand block kb again -> MMA bwd (M64 N16 K16 x 16) into the block's own 16 accumulator columns,
+//                  which keep accumulating over ALL super-tiles of the CTA.
+// The packed words of a block (8 chunks x 128 row pairs x 4 B = 4 KB, contiguous in the tensor-core store) arrive by bulk
+// async copies into a 4-slot ring, requested 4 blocks ahead; the second pass re-reads them (from L2).  Every stage is
+// decoupled by mbarriers: "block expanded" (128 arrivals, one barrier per operand buffer), "buffer free" (tcgen05.commit of
+// the MMAs that read it), "words landed" (transaction bytes, one barrier per ring slot).
+// Shared memory: 2 x 32 KB operands + 16 KB ring + 8 KB delta pieces + 16 KB weight pieces -> 2 CTAs per SM;
+// tensor memory: 32 + 16 x ceil(m/64) <= 160 columns (256 allocated).
+#pragma once
+#include "k1_tc.cuh"
+
+namespace bann {
+
+constexpr int kTcwMaxMarkers = 512;
+constexpr int kTcwBlockChunks = 8;                       // chunks (of 8 markers) per block = one M = 64 backward tile
+constexpr uint32_t kTcwBlockBytes = kTcwBlockChunks * kTcChunkStride;   // 32 KB: one expanded block
+constexpr uint32_t kTcwRing = 4;                         // packed-word ring slots (4 KB each)
+
+template <int H, int S, int D>
+struct TcwShape {
+    using T = TailShape<H, S, D>;
+    using C = TcShape<H, S, D>;
+    static constexpr int NN = C::NN;
+    static constexpr int TMEM_COLS = 256;
+    static constexpr size_t SW = (size_t)(kTcwMaxMarkers / 8) * NN * 16;       // weight pieces of all 64 k-chunks
+    static constexpr size_t SMEM = 2 * (size_t)kTcwBlockBytes + kTcwRing * (size_t)kTcwBlockChunks * 512 + C::SD + SW + C::MISC + 128 + 128;
+};
+
+template <int H, int S, int D, bool LEAN>
+__global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
+    using T = TailShape<H, S, D>;
+    using C = TcShape<H, S, D>;
+    using CW = TcwShape<H, S, D>;
+    constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, MW = T::MW, NTACC = T::NTACC, NN = C::NN;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t li = blockIdx.y, chunk = blockIdx.x;
+    const uint32_t b = a.list ? a.list[li] : li;
+    if (a.states && a.states[b].status != ST_RUNNING) return;
+    const BranchDesc& d = a.descs[b];
+    const uint32_t m = d.m, NC = d.nc, NKB = (NC + kTcwBlockChunks - 1) / kTcwBlockChunks;
+    const uint32_t issuer = 0;
+    // ---- shared memory carve-up
+    uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);       // 2 operand buffers of 8 chunks
+    uint32_t* sG = reinterpret_cast<uint32_t*>(sA + 2 * kTcwBlockBytes);           // ring: [slot][chunk][128] packed words
+    uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + kTcwRing * kTcwBlockChunks * 512;
+    uint8_t* sW = sD + C::SD;                                                     // [k-chunk][n] x 16 B, all blocks
+    float2* wp2 = reinterpret_cast<float2*>(sW + CW::SW);
+    float2* b0p2 = wp2 + ((T::n_tail() + 3) & ~3);
+    float* red = reinterpret_cast<float*>(b0p2 + W0P);
+    // mbarriers: [0..1] MMAs that read operand buffer 0/1 done; [2..3] buffer 0/1 expanded (128 arrivals);
+    //            [4..7] ring slot 0..3 landed
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 8);
+
+    const float* th = a.theta + d.param_off;
+    const float* mu = a.mu + d.col_off;
+    const float* sd = a.sd + d.col_off;
+
+    // ---- one-time setup
+    {
+        const uint32_t nz = (uint32_t)((sW + CW::SW - sA) / 16);
+        for (uint32_t k = tid; k < nz; k += 128) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        umma::mbar_init(&mbar[0], 1); umma::mbar_init(&mbar[1], 1);
+        umma::mbar_init(&mbar[2], 128); umma::mbar_init(&mbar[3], 128);
+        for (int k = 0; k < (int)kTcwRing; ++k) umma::mbar_init(&mbar[4 + k], 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(tmem_slot, CW::TMEM_COLS);
+    for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += 128) {
+        const float w = th[m * W0 + k];
+        wp2[k] = make_float2(w, w);
+    }
+    __syncthreads();
+    // first-layer weights: W' = W0 / sd, its three bf16 pieces (scaled as in k1_tc), and the mean-folded bias
+    float bacc[W0];
+#pragma unroll
+    for (int c = 0; c < W0; ++c) bacc[c] = 0.f;
+    for (uint32_t j = tid; j < m; j += 128) {
+#pragma unroll
+        for (int c = 0; c < W0; ++c) {
+            const float w = __fdiv_rn(th[c * m + j], sd[j]);
+            bacc[c] = fmaf(mu[j], w, bacc[c]);
+            const float v = w * pow2f(100 - 2 * (int)((j & 7u) >> 1));
+            const float p0 = bf16_round(v), r1 = v - p0, p1 = bf16_round(r1), p2 = bf16_round(r1 - p1);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sW + (j >> 3) * (NN * 16) + (j & 7u) * 2);
+            dst[(0 * W0 + c) * 8] = __float2bfloat16_rn(p0);
+            dst[(1 * W0 + c) * 8] = __float2bfloat16_rn(p1);
+            dst[(2 * W0 + c) * 8] = __float2bfloat16_rn(p2);
+        }
+    }
+    // fixed-order block sum of the bias fold (lanes -> warps), result b0' = b0 - sum_j mu_j W'_j
+#pragma unroll
+    for (int c = 0; c < W0; ++c) {
+        float v = bacc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp * W0 + c] = v;
+    }
+    __syncthreads();
+    if (tid < W0P) {
+        float acc = 0.f;
+        if (tid < W0) acc = wp2[T::b_off(0) + tid].x - (red[tid] + red[W0 + tid] + red[2 * W0 + tid] + red[3 * W0 + tid]);
+        b0p2[tid] = make_float2(acc, acc);
+    }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((warp * 32u) << 16);
+    const uint32_t sA_u = umma::smem_u32(sA), sD_u = umma::smem_u32(sD), sW_u = umma::smem_u32(sW);
+    constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
+    constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
+    const uint64_t dA_f = umma::make_desc(sA_u, kTcChunkStride, 128), dW_f = umma::make_desc(sW_u, NN * 16, 128);
+    const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
+
+    // ---- persistent per-thread accumulators (as in k1_tc)
+    const f2 zero2 = dup2(0.f);
+    f2 gb0[W0], gWo[S], rss = zero2;
+    f2 gWt[NLA > 1 ? NLA - 1 : 1][MW][MW], gbt[NLA > 1 ? NLA - 1 : 1][MW];
+#pragma unroll
+    for (int c = 0; c < W0; ++c) gb0[c] = zero2;
+#pragma unroll
+    for (int c = 0; c < S; ++c) gWo[c] = zero2;
+#pragma unroll
+    for (int l = 0; l < (NLA > 1 ? NLA - 1 : 1); ++l)
+#pragma unroll
+        for (int i = 0; i < MW; ++i) {
+            gbt[l][i] = zero2;
+#pragma unroll
+            for (int c = 0; c < MW; ++c) gWt[l][i][c] = zero2;
+        }
+
+    const size_t eoff = a.out_per_entry ? (size_t)li * a.n : 0;
+    const size_t toff = (a.target_mode == TGT_PER_ENTRY) ? (size_t)li * a.n : 0;
+    const uint32_t t_begin = chunk * a.st_per_chunk;
+    const uint32_t t_end = min(a.nst, t_begin + a.st_per_chunk);
+    const uint32_t nit = t_end > t_begin ? t_end - t_begin : 0;
+    const float* tsrc = (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) ? a.resid : (a.tgt ? a.tgt + toff : nullptr);
+    const bool bwd = LEAN || !a.fwd_only;
+    const uint32_t npass = bwd ? 2u : 1u;                       // block passes per super-tile
+    const uint32_t bpt = npass * NKB;                           // blocks per super-tile in the stream
+    const uint32_t nblk = nit * bpt;                            // length of the block stream of this CTA
+    const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
+
+    // stream position q -> (super-tile, pass, block)
+    auto chunks_of = [&](uint32_t kb) { return min((uint32_t)kTcwBlockChunks, NC - kb * kTcwBlockChunks); };
+    auto issue_load = [&](uint32_t q) {        // whole issuer warp enters; words of stream block q -> ring slot q % 4
+        const uint32_t it = q / bpt, kb = (q % bpt) % NKB;
+        if (umma::elect_one())
+            umma::bulk_load(sG + (q % kTcwRing) * (kTcwBlockChunks * 128), gwords + ((size_t)(t_begin + it) * NC + kb * kTcwBlockChunks) * 128,
+                            chunks_of(kb) * 512u, &mbar[4 + (q % kTcwRing)]);
+        __syncwarp();
+    };
+    auto issue_mma = [&](uint32_t q) {         // whole issuer warp enters; the MMAs of stream block q
+        const uint32_t it = q / bpt, r = q % bpt, pass = r / NKB, kb = r % NKB, buf = q & 1u;
+        umma::fence_after_sync();
+        if (umma::elect_one()) {
+            if (pass == 0) {
+                const uint32_t nks = (chunks_of(kb) + 1) >> 1;
+                const uint64_t base = dA_f + ((buf * kTcwBlockBytes) >> 4), wbase = dW_f + ((kb * kTcwBlockChunks * (NN * 16)) >> 4);
+#pragma unroll
+                for (uint32_t h = 0; h < 2; ++h)
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks)
+                        if (ks < nks)
+                            umma::mma_f16(tmem + h * NN, base + ((h * 2048u + ks * 2u * kTcChunkStride) >> 4),
+                                          wbase + ((ks * 2u * (NN * 16)) >> 4), idesc_f, (kb | ks) != 0);
+            } else {
+                const uint64_t base = dA_b + ((buf * kTcwBlockBytes) >> 4);
+#pragma unroll
+                for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
+                    umma::mma_f16(tmem + (2 + kb) * NN, base + ks * 16u, dD_b + ks * 16u, idesc_b, (it | ks) != 0);
+            }
+            umma::commit(&mbar[buf]);
+        }
+        __syncwarp();
+    };
+    // expand stream block q into operand buffer q % 2 (waits: its words, and the MMAs that last read the buffer)
+    auto expand_block = [&](uint32_t q) {
+        const uint32_t kb = (q % bpt) % NKB, buf = q & 1u, nch = chunks_of(kb);
+        umma::mbar_wait(&mbar[4 + (q % kTcwRing)], (q / kTcwRing) & 1u);
+        if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);
+        const uint32_t* src = sG + (q % kTcwRing) * (kTcwBlockChunks * 128) + tid;
+        uint8_t* rowA = sA + buf * kTcwBlockBytes + tid * 16;
+#pragma unroll
+        for (int i = 0; i < kTcwBlockChunks; ++i)
+            if ((uint32_t)i < nch) {
+                const uint32_t x = src[i * 128], y = x >> 8;
+                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) =
+                    make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
+                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride + 128 * 16) =
+                    make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
+            }
+        umma::fence_async_smem();
+        umma::mbar_arrive(&mbar[2 + buf]);
+        if (warp == issuer) {
+            umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);
+            issue_mma(q);
+            if (q + kTcwRing < nblk) issue_load(q + kTcwRing);     // every thread has consumed ring slot q % 4
+        }
+    };
+
+    auto load_targets = [&](uint32_t st) -> f2 {
+        const uint32_t rA = st * kTcRows + tid, rB = rA + 128;
+        if (!tsrc || st >= t_end) return zero2;
+        return mk2(rA < a.n ? __ldg(tsrc + rA) : 0.f, rB < a.n ? __ldg(tsrc + rB) : 0.f);
+    };
+    f2 tg_next = load_targets(t_begin);
+    if (warp == issuer)
+        for (uint32_t q = 0; q < kTcwRing && q < nblk; ++q) issue_load(q);
+
+    uint32_t q = 0;
+    for (uint32_t it = 0; it < nit; ++it) {
+        const uint32_t st = t_begin + it;
+        const uint32_t rowA_g = st * kTcRows + tid, rowB_g = rowA_g + 128;
+        const bool vA = rowA_g < a.n, vB = rowB_g < a.n;
+        f2 tg = tg_next;
+        tg_next = load_targets(st + 1);
+        // ---- forward pass over the marker blocks
+        for (uint32_t kb = 0; kb < NKB; ++kb, ++q) expand_block(q);
+        // z0 is complete when the MMAs of the last forward block are (commits complete in issue order)
+        umma::mbar_wait(&mbar[(q - 1) & 1u], ((q - 1) >> 1) & 1u);
+        umma::fence_after_sync();
+        float accA[16], accB[16];
+        umma::tmem_ld16x2(tlane, tlane + NN, accA, accB);
+        umma::fence_before_sync();
+
+        // ---- tail, part 1
+        f2 act[NLA][MW];
+#pragma unroll
+        for (int c = 0; c < W0; ++c) {
+            const f2 z = mk2(accA[c] + (accA[W0 + c] + accA[2 * W0 + c]), accB[c] + (accB[W0 + c] + accB[2 * W0 + c]));
+            act[0][c] = tanh2(fma2(z, dup2(8589934592.f /* 2^33 */), ld2(b0p2 + c)));
+        }
+#pragma unroll
+        for (int l = 1; l < NLA; ++l) {
+#pragma unroll
+            for (int c = 0; c < MW; ++c) {
+                if (c < T::width(l)) {
+                    f2 zz = ld2(wp2 + T::b_off(l) + c);
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) zz = fma2(act[l - 1][i], ld2(wp2 + T::w_off(l) + c * T::in_w(l) + i), zz);
+                    act[l][c] = tanh2(zz);
+                }
+            }
+        }
+        f2 yh = zero2;
+#pragma unroll
+        for (int i = 0; i < S; ++i) yh = fma2(act[NLA - 1][i], ld2(wp2 + T::w_off(NLA) + i), yh);
+        if (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) tg = add2(tg, yh);            // net.rs:280
+        const f2 e = mul2(fma2(tg, dup2(-1.f), yh), mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f));  // branch_sampler.rs:821
+        if (!LEAN) {
+            auto put = [&](float* dst, uint32_t row, float v, int accumulate) {
+                if (!dst || row >= a.n) return;
+                float* p = dst + eoff + row;
+                if (accumulate > 0) *p += v;
+                else if (accumulate < 0) *p -= v;
+                else *p = v;
+            };
+            if (a.target_mode == TGT_RESID_PLUS_PRED) {
+                put(a.tgt_out, rowA_g, lo2(tg), 0); put(a.tgt_out, rowB_g, hi2(tg), 0);
+                put(a.prev_out, rowA_g, lo2(yh), 0); put(a.prev_out, rowB_g, hi2(yh), 0);   // net.rs:279
+            }
+            put(a.yhat_out, rowA_g, lo2(yh), a.yhat_accumulate);
+            put(a.yhat_out, rowB_g, hi2(yh), a.yhat_accumulate);
+        }
+        if (!bwd) continue;
+
+        // ---- tail, part 2
+        rss = fma2(e, e, rss);
+        f2 delta[MW];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            gWo[i] = fma2(act[NLA - 1][i], e, gWo[i]);
+            delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e, ld2(wp2 + T::w_off(NLA) + i)));
+        }
+#pragma unroll
+        for (int l = NLA - 1; l >= 1; --l) {
+            f2 nd[MW];
+#pragma unroll
+            for (int i = 0; i < MW; ++i) nd[i] = zero2;
+#pragma unroll
+            for (int c = 0; c < MW; ++c) {
+                if (c < T::width(l)) {
+                    gbt[l - 1][c] = add2(gbt[l - 1][c], delta[c]);
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) {
+                            gWt[l - 1][i][c] = fma2(act[l - 1][i], delta[c], gWt[l - 1][i][c]);
+                            nd[i] = fma2(delta[c], ld2(wp2 + T::w_off(l) + c * T::in_w(l) + i), nd[i]);
+                        }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MW; ++i)
+                if (i < T::in_w(l)) delta[i] = mul2(dtanh2(act[l - 1][i]), nd[i]);
+        }
+        // delta_0 pieces.  The delta buffer was last read by the previous super-tile's backward MMAs, all of which completed
+        // before the forward pass above could recycle their operand buffers (NKB >= 2).
+        {
+            uint32_t pa[NN], pb[NN];
+#pragma unroll
+            for (int n = 0; n < NN; ++n) { pa[n] = 0u; pb[n] = 0u; }
+#pragma unroll
+            for (int c = 0; c < W0; ++c) {
+                gb0[c] = add2(gb0[c], delta[c]);
+                f2 v = mul2(delta[c], dup2(1.2676506002282294e30f));   // 2^100, exact
+#pragma unroll
+                for (int piece = 0; piece < 3; ++piece) {
+                    const uint32_t ua = __float_as_uint(lo2(v)) & 0xFFFF0000u, ub = __float_as_uint(hi2(v)) & 0xFFFF0000u;
+                    pa[piece * W0 + c] = ua; pb[piece * W0 + c] = ub;
+                    if (piece < 2) v = add2(v, mk2(-__uint_as_float(ua), -__uint_as_float(ub)));
+                }
+            }
+            uint8_t* dst = sD + tid * 16;
+#pragma unroll
+            for (int qq = 0; qq < NN / 8; ++qq) {
+                uint4 wa, wb;
+                wa.x = __byte_perm(pa[8 * qq], pa[8 * qq + 1], 0x7632); wa.y = __byte_perm(pa[8 * qq + 2], pa[8 * qq + 3], 0x7632);
+                wa.z = __byte_perm(pa[8 * qq + 4], pa[8 * qq + 5], 0x7632); wa.w = __byte_perm(pa[8 * qq + 6], pa[8 * qq + 7], 0x7632);
+                wb.x = __byte_perm(pb[8 * qq], pb[8 * qq + 1], 0x7632); wb.y = __byte_perm(pb[8 * qq + 2], pb[8 * qq + 3], 0x7632);
+                wb.z = __byte_perm(pb[8 * qq + 4], pb[8 * qq + 5], 0x7632); wb.w = __byte_perm(pb[8 * qq + 6], pb[8 * qq + 7], 0x7632);
+                *reinterpret_cast<uint4*>(dst + qq * kTcChunkStride) = wa;
+                *reinterpret_cast<uint4*>(dst + qq * kTcChunkStride + 128 * 16) = wb;
+            }
+        }
+        // ---- backward pass over the marker blocks (the first arrival below also publishes the delta pieces)
+        for (uint32_t kb = 0; kb < NKB; ++kb, ++q) expand_block(q);
+    }
+    // ---- drain: all MMAs done (the last two stream blocks cover both operand buffers)
+    if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
+    if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
+    umma::fence_after_sync();
+    const bool has_bwd = bwd && a.part && nit > 0;
+    if (!bwd || !a.part) {
+        umma::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) umma::tmem_dealloc(tmem, CW::TMEM_COLS);
+        return;
+    }
+
+    // ---- CTA epilogue: cross-row sums of the layers >= 1 (fixed order), then the first-layer gradient per marker block
+    float* pp = a.part + ((size_t)li * a.nchunk + chunk) * a.pstride;
+    const uint32_t P = d.P;
+    {
+        float* rw = red + warp * NTACC;
+        int idx = 0;
+        auto put = [&](f2 v2) {
+            float v = lo2(v2) + hi2(v2);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) rw[idx] = v;
+            ++idx;
+        };
+        put(rss);
+#pragma unroll
+        for (int c = 0; c < S; ++c) put(gWo[c]);
+#pragma unroll
+        for (int c = 0; c < W0; ++c) put(gb0[c]);
+#pragma unroll
+        for (int l = 1; l < NLA; ++l) {
+#pragma unroll
+            for (int c = 0; c < MW; ++c) put(gbt[l - 1][c]);
+#pragma unroll
+            for (int i = 0; i < MW; ++i)
+#pragma unroll
+                for (int c = 0; c < MW; ++c) put(gWt[l - 1][i][c]);
+        }
+    }
+    __syncthreads();
+    __shared__ float s_gb0[W0];
+    if (tid < NTACC) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) s += red[w * NTACC + tid];
+        int idx = tid;
+        if (idx == 0) pp[P] = s;
+        else if (idx < 1 + S) pp[m * W0 + T::w_off(NLA) + (idx - 1)] = s;
+        else if (idx < 1 + S + W0) { pp[m * W0 + T::b_off(0) + (idx - 1 - S)] = s; s_gb0[idx - 1 - S] = s; }
+        else {
+            int k = idx - (1 + S + W0);
+            const int per = MW + MW * MW;
+            const int l = 1 + k / per;
+            k %= per;
+            if (k < MW) {
+                if (k < T::width(l)) pp[m * W0 + T::b_off(l) + k] = s;
+            } else {
+                k -= MW;
+                const int i = k / MW, c = k % MW;
+                if (i < T::in_w(l) && c < T::width(l)) pp[m * W0 + T::w_off(l) + c * T::in_w(l) + i] = s;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t kb = 0; kb < NKB; ++kb) {
+        float sacc[16];
+        if (has_bwd) umma::tmem_ld16(tlane + (2 + kb) * NN, sacc);
+        if (lane < 16) {
+            const uint32_t j = kb * 64 + warp * 16 + lane;      // M = 64 accumulator: row r in lane r % 16 of warp r / 16
+            if (j < m) {
+                const float unscale = pow2f(33 - 2 * (int)((j & 7u) >> 1));
+#pragma unroll
+                for (int c = 0; c < W0; ++c) {
+                    const float s = (has_bwd ? (sacc[c] + (sacc[W0 + c] + sacc[2 * W0 + c])) : 0.f) * unscale;
+                    pp[c * m + j] = __fdiv_rn(s - mu[j] * s_gb0[c], sd[j]);
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, CW::TMEM_COLS);
+}
+
+template <int H, int S, int D>
+int launch_one_tcw(K1Args& a, uint32_t nlist, cudaStream_t st) {
+    using CW = TcwShape<H, S, D>;
+    static bool configured = false;
+    if (!configured) {
+        BANN_CUDA(cudaFuncSetAttribute(k1_tcw<H, S, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tcw<H, S, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM));
+        configured = true;
+    }
+    dim3 grid(a.nchunk, nlist);
+    const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
+    if (lean) k1_tcw<H, S, D, true><<<grid, 128, CW::SMEM, st>>>(a);
+    else k1_tcw<H, S, D, false><<<grid, 128, CW::SMEM, st>>>(a);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// K-blocked tensor-core K1: homogeneous architecture, tanh, every listed branch with 65..512 markers (so that each has at
+// least two marker blocks), 3 * W0 <= 16, tensor-core store present.
+inline int launch_k1_tcw(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
+                         cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
+    *launched = false;
+    if (a.act != BANN_TANH || !a.store_tc) return 0;
+    const BranchDesc& d0 = descs[single_branch >= 0 ? single_branch : 0];
+    uint32_t max_m = d0.m, min_m = d0.m;
+    if (single_branch < 0) {
+        for (const BranchDesc& d : descs) {
+            if (d.nl != d0.nl) return 0;
+            for (uint32_t l = 0; l < d.nl; ++l)
+                if (d.widths[l] != d0.widths[l]) return 0;
+            max_m = std::max(max_m, d.m);
+            min_m = std::min(min_m, d.m);
+        }
+    }
+    if (max_m > (uint32_t)kTcwMaxMarkers || min_m <= (uint32_t)kTcMaxMarkers) return 0;
+    const int D = (int)d0.nl - 2;
+    const int S = (int)d0.widths[d0.nl - 2];
+    const int H = D > 0 ? (int)d0.widths[0] : S;
+    for (int l = 0; l < D; ++l)
+        if ((int)d0.widths[l] != H) return 0;
+    const uint32_t nst = a.nst;
+    uint32_t want = (uint32_t)std::max<uint64_t>(1, ((uint64_t)num_sms * 2 + nlist - 1) / nlist);
+    uint32_t nchunk = std::min<uint32_t>(want, std::max<uint32_t>(1, nst));
+    uint32_t spc = (nst + nchunk - 1) / nchunk;
+    nchunk = (nst + spc - 1) / spc;
+#define BANN_TRY_TCW(HH, SS, DD)                                                                          \
+    if (!*launched && H == HH && S == SS && D == DD) {                                                    \
+        a.nchunk = nchunk;                                                                                \
+        a.st_per_chunk = spc;                                                                             \
+        if (part_io) {                                                                                    \
+            if (nchunk == 1) *part_io = bann_net_gsum(net);                                               \
+            else {                                                                                        \
+                float* p = bann_net_partials(net, (size_t)nlist * nchunk * bann_net_pstride(net));        \
+                if (!p) return -2;                                                                        \
+                *part_io = p;                                                                             \
+            }                                                                                             \
+            a.part = *part_io;                                                                            \
+        }                                                                                                 \
+        *nchunk_io = nchunk;                                                                              \
+        int rc = launch_one_tcw<HH, SS, DD>(a, nlist, st);                                                \
+        if (rc) return rc;                                                                                \
+        *launched = true;                                                                                 \
+    }
+    BANN_TRY_TCW(5, 5, 1)
+    BANN_TRY_TCW(2, 2, 1)
+    BANN_TRY_TCW(4, 3, 1)
+#undef BANN_TRY_TCW
+    return 0;
+}
+
+}  // namespace bann

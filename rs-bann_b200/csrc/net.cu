@@ -7,6 +7,7 @@
 #include "chain.cuh"
 #include "k1_small.cuh"
 #include "k1_tc.cuh"
+#include "k1_tc_wide.cuh"
 #include "store.cuh"
 
 using namespace bann;
@@ -140,8 +141,13 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
         int r = launch_k1_tc(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
                              &nchunk, L.fwd_only ? nullptr : &part, net);
         if (r != 0) return r;
+        if (!launched) {   // 65..512 markers per branch: the K-blocked variant
+            r = launch_k1_tcw(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched, &nchunk,
+                              L.fwd_only ? nullptr : &part, net);
+            if (r != 0) return r;
+        }
         if (!launched && net->k1_mode == BANN_K1_TENSOR)
-            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (tanh, <= 64 markers, 3 * width <= 16)");
+            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (tanh, <= 512 markers, 3 * width <= 16)");
     }
     if (!launched && net->k1_mode != BANN_K1_GENERIC) {
         int r = launch_k1_small(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,

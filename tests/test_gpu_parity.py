@@ -209,6 +209,11 @@ TC_SHAPES = [  # n, group sizes, hidden, summary, depth
     (515, [64, 7], 4, 3, 2),
     (300, [20, 64], 5, 3, 2),
     (150, [12, 7], 4, 2, 0),
+    # 65..512 markers: the K-blocked variant (k1_tc_wide.cuh), 2..8 marker blocks, ragged last block
+    (300, [100], 5, 5, 1),
+    (1030, [500, 65], 5, 5, 1),
+    (515, [128, 129], 2, 2, 1),
+    (700, [512], 4, 3, 1),
 ]
 
 
@@ -248,7 +253,7 @@ def test_tensor_core_fwd_bwd_parity(rb, ctx, model, shape):
 
 
 def test_tensor_core_kernel_refuses_ineligible_launch(rb, ctx):
-    P = Problem(rb, ctx, "ridge_ard", 300, [100], 5, 5, seed=3)        # 100 markers: no tensor-core store
+    P = Problem(rb, ctx, "ridge_ard", 300, [600], 5, 5, seed=3)        # 600 markers: no tensor-core store
     try:
         assert not P.gen.has_tc_store()
         P.net.select_k1(P.net.K1_TENSOR)
@@ -577,7 +582,8 @@ def test_net_gradient_matches_per_branch(rb, ctx):
         P.close()
 
 
-@pytest.mark.parametrize("model,sizes", [("lasso_ard", [64, 57, 8, 1]), ("std_normal", [7, 56, 49])])
+@pytest.mark.parametrize("model,sizes", [("lasso_ard", [64, 57, 8, 1]), ("std_normal", [7, 56, 49]),
+                                         ("ridge_ard", [100, 200, 65, 333])])     # last: K-blocked kernel, 2..6 blocks
 def test_tensor_core_grouped_launch_heterogeneous_branches(rb, ctx, model, sizes):
     """One tensor-core launch over branches with different chunk counts (8-chunk operand buffers when a branch has 64 markers)."""
     P = Problem(rb, ctx, model, 1111, sizes, 5, 5, seed=11)
