@@ -153,52 +153,63 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
     const uint32_t nblk = nit * bpt;                            // length of the block stream of this CTA
     const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
 
-    // stream position q -> (super-tile, pass, block)
+    // The block stream: position q = (super-tile it, pass, marker block kb); buffer q % 2, ring slot q % 4.  Positions are
+    // advanced incrementally (no integer divisions in the loop).
+    struct Pos { uint32_t it, pass, kb; };
+    auto advance = [&](Pos& p) {
+        if (++p.kb == NKB) { p.kb = 0; if (++p.pass == npass) { p.pass = 0; ++p.it; } }
+    };
     auto chunks_of = [&](uint32_t kb) { return min((uint32_t)kTcwBlockChunks, NC - kb * kTcwBlockChunks); };
-    auto issue_load = [&](uint32_t q) {        // whole issuer warp enters; words of stream block q -> ring slot q % 4
-        const uint32_t it = q / bpt, kb = (q % bpt) % NKB;
+    auto issue_load = [&](uint32_t q, const Pos& p) {   // whole issuer warp enters; words of stream block q -> ring slot q % 4
         if (umma::elect_one())
-            umma::bulk_load(sG + (q % kTcwRing) * (kTcwBlockChunks * 128), gwords + ((size_t)(t_begin + it) * NC + kb * kTcwBlockChunks) * 128,
-                            chunks_of(kb) * 512u, &mbar[4 + (q % kTcwRing)]);
+            umma::bulk_load(sG + (q % kTcwRing) * (kTcwBlockChunks * 128),
+                            gwords + ((size_t)(t_begin + p.it) * NC + p.kb * kTcwBlockChunks) * 128, chunks_of(p.kb) * 512u,
+                            &mbar[4 + (q % kTcwRing)]);
         __syncwarp();
     };
-    auto issue_mma = [&](uint32_t q) {         // whole issuer warp enters; the MMAs of stream block q
-        const uint32_t it = q / bpt, r = q % bpt, pass = r / NKB, kb = r % NKB, buf = q & 1u;
+    auto issue_mma = [&](uint32_t q, const Pos& p) {    // whole issuer warp enters; the MMAs of stream block q
+        const uint32_t buf = q & 1u;
         umma::fence_after_sync();
         if (umma::elect_one()) {
-            if (pass == 0) {
-                const uint32_t nks = (chunks_of(kb) + 1) >> 1;
-                const uint64_t base = dA_f + ((buf * kTcwBlockBytes) >> 4), wbase = dW_f + ((kb * kTcwBlockChunks * (NN * 16)) >> 4);
+            if (p.pass == 0) {
+                const uint32_t nks = (chunks_of(p.kb) + 1) >> 1;
+                const uint64_t base = dA_f + ((buf * kTcwBlockBytes) >> 4), wbase = dW_f + ((p.kb * kTcwBlockChunks * (NN * 16)) >> 4);
 #pragma unroll
                 for (uint32_t h = 0; h < 2; ++h)
 #pragma unroll
                     for (uint32_t ks = 0; ks < 4; ++ks)
                         if (ks < nks)
                             umma::mma_f16(tmem + h * NN, base + ((h * 2048u + ks * 2u * kTcChunkStride) >> 4),
-                                          wbase + ((ks * 2u * (NN * 16)) >> 4), idesc_f, (kb | ks) != 0);
+                                          wbase + ((ks * 2u * (NN * 16)) >> 4), idesc_f, (p.kb | ks) != 0);
             } else {
                 const uint64_t base = dA_b + ((buf * kTcwBlockBytes) >> 4);
 #pragma unroll
                 for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
-                    umma::mma_f16(tmem + (2 + kb) * NN, base + ks * 16u, dD_b + ks * 16u, idesc_b, (it | ks) != 0);
+                    umma::mma_f16(tmem + (2 + p.kb) * NN, base + ks * 16u, dD_b + ks * 16u, idesc_b, (p.it | ks) != 0);
             }
             umma::commit(&mbar[buf]);
         }
         __syncwarp();
     };
+    Pos pos{0, 0, 0};           // position of stream block q (all threads)
+    Pos lpos{0, 0, 0};          // position of the next block whose words get requested (issuer warp)
+    uint32_t lq = 0;
     // expand stream block q into operand buffer q % 2 (waits: its words, and the MMAs that last read the buffer)
     auto expand_block = [&](uint32_t q) {
-        const uint32_t kb = (q % bpt) % NKB, buf = q & 1u, nch = chunks_of(kb);
+        const uint32_t buf = q & 1u, nch = chunks_of(pos.kb);
         umma::mbar_wait(&mbar[4 + (q % kTcwRing)], (q / kTcwRing) & 1u);
-        if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);
         const uint32_t* src = sG + (q % kTcwRing) * (kTcwBlockChunks * 128) + tid;
+        uint32_t x[kTcwBlockChunks];
+#pragma unroll
+        for (int i = 0; i < kTcwBlockChunks; ++i) x[i] = (uint32_t)i < nch ? src[i * 128] : 0u;   // all loads first
+        if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);
         uint8_t* rowA = sA + buf * kTcwBlockBytes + tid * 16;
 #pragma unroll
         for (int i = 0; i < kTcwBlockChunks; ++i)
             if ((uint32_t)i < nch) {
-                const uint32_t x = src[i * 128], y = x >> 8;
+                const uint32_t y = x[i] >> 8;
                 *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) =
-                    make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
+                    make_uint4(x[i] & 0x00030003u, x[i] & 0x000C000Cu, x[i] & 0x00300030u, x[i] & 0x00C000C0u);
                 *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride + 128 * 16) =
                     make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
             }
@@ -206,9 +217,10 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
         umma::mbar_arrive(&mbar[2 + buf]);
         if (warp == issuer) {
             umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);
-            issue_mma(q);
-            if (q + kTcwRing < nblk) issue_load(q + kTcwRing);     // every thread has consumed ring slot q % 4
+            issue_mma(q, pos);
+            if (lq < nblk) { issue_load(lq, lpos); ++lq; advance(lpos); }   // every thread has consumed ring slot q % 4
         }
+        advance(pos);
     };
 
     auto load_targets = [&](uint32_t st) -> f2 {
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
     };
     f2 tg_next = load_targets(t_begin);
     if (warp == issuer)
-        for (uint32_t q = 0; q < kTcwRing && q < nblk; ++q) issue_load(q);
+        for (; lq < kTcwRing && lq < nblk; ++lq) { issue_load(lq, lpos); advance(lpos); }
 
     uint32_t q = 0;
     for (uint32_t it = 0; it < nit; ++it) {
