@@ -161,7 +161,7 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
         BANN_CUDA(cudaGetLastError());
     }
     if (reduce && !L.fwd_only && part != net->d_gsum) {
-        dim3 grid((net->pstride + 255) / 256, L.nlist);
+        dim3 grid((net->pstride + 31) / 32, L.nlist);
         k_reduce_partials<<<grid, 256, 0, st>>>(part, net->d_gsum, nchunk, net->pstride, L.list, a.descs, L.states);
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
