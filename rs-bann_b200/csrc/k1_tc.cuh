@@ -70,7 +70,7 @@ struct TcShape {
     static constexpr int W0 = T::W0;
     static constexpr int NN = 16;                       // accumulator columns: 3 pieces x W0 units, padded
     static_assert(3 * W0 <= NN, "first-layer width too large for one N = 16 accumulator");
-    static constexpr int TMEM_COLS = 64;                // 2 x NN forward (row halves) + NN backward
+    static constexpr int TMEM_COLS = 64;                // 2 x NN forward (row halves) + 2 x NN backward (row halves)
     static constexpr size_t SD = (NN / 8) * kTcChunkStride;   // delta pieces  [n-chunk][row] x 16 B
     static constexpr size_t SW = 8 * NN * 16;           // weight pieces [k-chunk][n] x 16 B
     static constexpr int NRED = 4 * (T::NTACC > 64 ? T::NTACC : 64);
@@ -99,8 +99,10 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     if (a.states && a.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = a.descs[b];
     const uint32_t m = d.m, NC = NCT ? (uint32_t)NCT : d.nc, NKS = (NC + 1) >> 1, NCB = a.ncb;
-    // the warp that issues the MMAs rotates over CTAs so that the issue work spreads over the four SM sub-partitions
-    const uint32_t issuer = a.issuer_warp < 4 ? a.issuer_warp : ((blockIdx.x + blockIdx.y) & 3u);
+    // Issuing a tcgen05.mma costs the issuing warp ~40 clk (measured: 8 forward MMAs + bulk copy 600 clk, 16 backward MMAs
+    // 630 clk); on one warp that made it the straggler every other warp waited for (~1250 clk per super-tile).  The work is
+    // therefore split: warp 0 forward row half 0, warp 1 forward row half 1 + the bulk copy, warp 2 / 3 backward row half 0 / 1.
+    // The two backward halves accumulate in SEPARATE tensor-memory columns (each in its own fixed order) and are added at the end.
     // ---- shared memory carve-up
     uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // whole core matrices (keeps the shared address space)
     const uint32_t sa_bytes = NCB * kTcChunkStride;                        // one expanded-genotype buffer
@@ -125,8 +127,8 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         for (uint32_t k = tid; k < nz; k += 128) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        umma::mbar_init(&mbar[0], 1);
-        umma::mbar_init(&mbar[1], 1);
+        umma::mbar_init(&mbar[0], 2);        // two commits each: the MMA issue work is split over the four warps (see issue_*)
+        umma::mbar_init(&mbar[1], 2);
         umma::mbar_init(&mbar[2], 128);
         umma::mbar_init(&mbar[3], 128);
         umma::mbar_init(&mbar[4], 1);
@@ -220,18 +222,28 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     // (whole issuer warp enters; one elected lane issues)
     const uint64_t dA_f = umma::make_desc(sA_u, kTcChunkStride, 128), dW_f = umma::make_desc(sW_u, NN * 16, 128);
     const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
-    auto issue_fwd = [&](uint32_t buf) {
+    auto issue_fwd = [&](uint32_t buf, uint32_t h) {       // whole warp enters; row half h of the super-tile in buffer `buf`
         umma::fence_after_sync();
-        const uint64_t base = dA_f + ((buf * sa_bytes) >> 4);
+        const uint64_t base = dA_f + ((buf * sa_bytes + h * 2048u) >> 4);
         if (umma::elect_one()) {
 #pragma unroll
-            for (uint32_t h = 0; h < 2; ++h)
-#pragma unroll
-                for (uint32_t ks = 0; ks < 4; ++ks)
-                    if (ks < NKS)
-                        umma::mma_f16(tmem + h * NN, base + ((h * 2048u + ks * 2u * kTcChunkStride) >> 4),
-                                      dW_f + ((ks * 2u * (NN * 16)) >> 4), idesc_f, ks > 0);
+            for (uint32_t ks = 0; ks < 4; ++ks)
+                if (ks < NKS)
+                    umma::mma_f16(tmem + h * NN, base + ((ks * 2u * kTcChunkStride) >> 4), dW_f + ((ks * 2u * (NN * 16)) >> 4),
+                                  idesc_f, ks > 0);
             umma::commit(&mbar[0]);
+        }
+        __syncwarp();
+    };
+    // backward contraction, row half h (K steps 8h .. 8h + 7) into accumulator columns [(2 + h) NN, (3 + h) NN)
+    auto issue_bwd = [&](uint32_t buf, uint32_t h, uint32_t it) {
+        umma::fence_after_sync();
+        const uint64_t base = dA_b + ((buf * sa_bytes) >> 4) + h * 128u, dbase = dD_b + h * 128u;
+        if (umma::elect_one()) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < kTcRows / 32; ++ks)
+                umma::mma_f16(tmem + (2 + h) * NN, base + ks * 16u, dbase + ks * 16u, idesc_b, (it | ks) != 0);
+            umma::commit(&mbar[1]);
         }
         __syncwarp();
     };
@@ -243,15 +255,13 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     };
     f2 tg_next = load_targets(t_begin);
     if (nit > 0) {
-        if (warp == issuer) issue_load(t_begin);
+        if (warp == 1) issue_load(t_begin);
         umma::mbar_wait(&mbar[4], 0);
         expand(0);
         umma::fence_async_smem();
         __syncthreads();
-        if (warp == issuer) {
-            issue_fwd(0);
-            if (nit > 1) issue_load(t_begin + 1);
-        }
+        if (warp < 2) issue_fwd(0, warp);
+        if (warp == 1 && nit > 1) issue_load(t_begin + 1);
     }
     for (uint32_t it = 0; it < nit; ++it) {
         const uint32_t st = t_begin + it, buf = it & 1u;
@@ -316,20 +326,21 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         // no CTA-wide barrier: every thread arrives and moves on, only the issuer warp waits for all 128 arrivals
         umma::fence_async_smem();
         umma::mbar_arrive(&mbar[2]);
-        if (warp == issuer) {
+        if (warp < 2) {
             umma::mbar_wait(&mbar[2], it & 1u);
-            if (it + 1 < nit) issue_fwd(buf ^ 1u);
-            if (it + 2 < nit) issue_load(st + 2);        // every thread has read the staged words by now
+            if (it + 1 < nit) issue_fwd(buf ^ 1u, warp);
+            if (warp == 1 && it + 2 < nit) issue_load(st + 2);        // every thread has read the staged words by now
         }
         if (!bwd) continue;
 
         // ---- tail, part 2: backward deltas and the cross-row sums of the layers >= 1
-        rss = fma2(e, e, rss);
+        const f2 e2 = e;
+        rss = fma2(e2, e2, rss);
         f2 delta[MW];
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            gWo[i] = fma2(act[NLA - 1][i], e, gWo[i]);
-            delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e, ld2(wp2 + T::w_off(NLA) + i)));
+            gWo[i] = fma2(act[NLA - 1][i], e2, gWo[i]);
+            delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e2, ld2(wp2 + T::w_off(NLA) + i)));
         }
 #pragma unroll
         for (int l = NLA - 1; l >= 1; --l) {
@@ -383,17 +394,9 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         }
         umma::fence_async_smem();
         umma::mbar_arrive(&mbar[3]);
-        if (warp == issuer) {
+        if (warp >= 2) {
             umma::mbar_wait(&mbar[3], it & 1u);
-            umma::fence_after_sync();
-            const uint64_t base = dA_b + ((buf * sa_bytes) >> 4);
-            if (umma::elect_one()) {
-#pragma unroll
-                for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
-                    umma::mma_f16(tmem + 2 * NN, base + ks * 16u, dD_b + ks * 16u, idesc_b, (it | ks) != 0);
-                umma::commit(&mbar[1]);
-            }
-            __syncwarp();
+            issue_bwd(buf, warp - 2, it);
         }
     }
     const bool has_bwd = bwd && a.part && nit > 0;
@@ -401,7 +404,10 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     if (has_bwd) {
         umma::mbar_wait(&mbar[1], (nit - 1) & 1u);
         umma::fence_after_sync();
-        umma::tmem_ld16(tlane + 2 * NN, sacc);
+        float sacc1[16];
+        umma::tmem_ld16x2(tlane + 2 * NN, tlane + 3 * NN, sacc, sacc1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sacc[k] += sacc1[k];       // row half 0 + row half 1, fixed order
     }
     umma::fence_before_sync();
     __syncthreads();
