@@ -70,7 +70,7 @@ struct TcShape {
     static constexpr int W0 = T::W0;
     static constexpr int NN = 16;                       // accumulator columns: 3 pieces x W0 units, padded
     static_assert(3 * W0 <= NN, "first-layer width too large for one N = 16 accumulator");
-    static constexpr int TMEM_COLS = 64;                // 2 x NN forward (row halves) + 2 x NN backward (row halves)
+    static constexpr int TMEM_COLS = 128;               // 2 x NN forward + 2 x NN backward accumulators, 2 x 32 columns: forward A operand
     static constexpr size_t SD = (NN / 8) * kTcChunkStride;   // delta pieces  [n-chunk][row] x 16 B
     static constexpr size_t SW = 8 * NN * 16;           // weight pieces [k-chunk][n] x 16 B
     static constexpr int NRED = 4 * (T::NTACC > 64 ? T::NTACC : 64);
@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     umma::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tlane = tmem + ((warp * 32u) << 16);
+    // forward A operand in tensor memory: row half h at columns [64 + 32 h, 96 + 32 h), column 4 i + o = markers 8 i + 2 o, + 1
+    // of this thread's row.  The forward MMA then reads no shared memory for A (the kernel is shared-memory-wavefront bound).
+    const uint32_t tA = tlane + 4 * NN;
+    for (uint32_t c = 0; c < 64; c += 4) umma::tmem_st4(tA + c, 0u, 0u, 0u, 0u);
+    umma::tmem_st_wait();
     const uint32_t sA_u = umma::smem_u32(sA), sD_u = umma::smem_u32(sD), sW_u = umma::smem_u32(sW);
     constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
     constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
@@ -212,25 +217,27 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         for (int i = 0; i < 8; ++i)
             if ((uint32_t)i < NC) {
                 const uint32_t x = sG[i * 128 + tid], y = x >> 8;
-                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) =
-                    make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
-                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride + 128 * 16) =
-                    make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
+                const uint4 oa = make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
+                const uint4 ob = make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
+                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) = oa;                   // backward operand (MN-major view)
+                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride + 128 * 16) = ob;
+                umma::tmem_st4(tA + 4 * i, oa.x, oa.y, oa.z, oa.w);                          // forward operand
+                umma::tmem_st4(tA + 32 + 4 * i, ob.x, ob.y, ob.z, ob.w);
             }
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
     };
     // forward contraction of the super-tile in buffer `buf`: z0 pieces -> tensor memory columns [0, 2 NN)
     // (whole issuer warp enters; one elected lane issues)
-    const uint64_t dA_f = umma::make_desc(sA_u, kTcChunkStride, 128), dW_f = umma::make_desc(sW_u, NN * 16, 128);
+    const uint64_t dW_f = umma::make_desc(sW_u, NN * 16, 128);
     const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
-    auto issue_fwd = [&](uint32_t buf, uint32_t h) {       // whole warp enters; row half h of the super-tile in buffer `buf`
+    auto issue_fwd = [&](uint32_t h) {       // whole warp enters; row half h of the super-tile just expanded
         umma::fence_after_sync();
-        const uint64_t base = dA_f + ((buf * sa_bytes + h * 2048u) >> 4);
         if (umma::elect_one()) {
 #pragma unroll
             for (uint32_t ks = 0; ks < 4; ++ks)
                 if (ks < NKS)
-                    umma::mma_f16(tmem + h * NN, base + ((ks * 2u * kTcChunkStride) >> 4), dW_f + ((ks * 2u * (NN * 16)) >> 4),
-                                  idesc_f, ks > 0);
+                    umma::mma_f16_ts(tmem + h * NN, tmem + 4 * NN + h * 32 + ks * 8, dW_f + ((ks * 2u * (NN * 16)) >> 4), idesc_f, ks > 0);
             umma::commit(&mbar[0]);
         }
         __syncwarp();
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         expand(0);
         umma::fence_async_smem();
         __syncthreads();
-        if (warp < 2) issue_fwd(0, warp);
+        if (warp < 2) issue_fwd(warp);
         if (warp == 1 && nit > 1) issue_load(t_begin + 1);
     }
     for (uint32_t it = 0; it < nit; ++it) {
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         umma::mbar_arrive(&mbar[2]);
         if (warp < 2) {
             umma::mbar_wait(&mbar[2], it & 1u);
-            if (it + 1 < nit) issue_fwd(buf ^ 1u, warp);
+            if (it + 1 < nit) issue_fwd(warp);
             if (warp == 1 && it + 2 < nit) issue_load(st + 2);        // every thread has read the staged words by now
         }
         if (!bwd) continue;
