@@ -109,9 +109,11 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     uint8_t* sW = sA + (size_t)2 * sa_bytes;
     uint32_t* sG = reinterpret_cast<uint32_t*>(sW + C::SW);               // [NC][128] packed words of the next super-tile (bulk copy target)
     uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + (size_t)NCB * 512;
-    float2* wp2 = reinterpret_cast<float2*>(sD + C::SD);                   // tail parameters, duplicated {w, w}
-    float2* b0p2 = wp2 + ((T::n_tail() + 3) & ~3);                         // [W0P] first-layer bias with the means folded in
-    float* red = reinterpret_cast<float*>(b0p2 + W0P);                     // [NRED] reduction scratch
+    // tail parameters as plain floats: FFMA2 takes a scalar register as a broadcast operand (.F32), so no {w, w} pairs are
+    // needed and one LDS.128 brings four weights (the duplicated layout cost 2 shared-memory wavefronts per pair)
+    float* wp = reinterpret_cast<float*>(__builtin_assume_aligned(sD + C::SD, 16));   // [n_tail]
+    float* b0p = wp + ((T::n_tail() + 3) & ~3);                            // [W0P] first-layer bias with the means folded in
+    float* red = b0p + 2 * ((T::n_tail() + 3) & ~3) - ((T::n_tail() + 3) & ~3) + 2 * W0P;   // [NRED] reduction scratch (layout size as before)
     // [0] forward MMAs done, [1] backward MMAs done (tcgen05.commit); [2] next tile expanded, [3] delta pieces written
     // (128 arrivals each); [4] packed words landed (bulk copy transaction bytes)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     if (warp == 0) umma::tmem_alloc(tmem_slot, C::TMEM_COLS);
     for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += 128) {
         const float w = th[m * W0 + k];
-        wp2[k] = make_float2(w, w);
+        wp[k] = w;
     }
     __syncthreads();
     // ---- stage W' = W0 / sd (f32, in the delta buffer for the bias fold) and its three bf16 pieces
@@ -158,9 +160,9 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         float acc = 0.f;
         if (tid < W0) {
             for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], wtmp[j * W0 + tid], acc);
-            acc = wp2[T::b_off(0) + tid].x - acc;
+            acc = wp[T::b_off(0) + tid] - acc;
         }
-        b0p2[tid] = make_float2(acc, acc);
+        b0p[tid] = acc;
     }
     __syncthreads();
     for (uint32_t k = tid; k < m * W0; k += 128) wtmp[k] = 0.f;   // the pad columns of the delta operand must stay zero
@@ -288,24 +290,24 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
 #pragma unroll
         for (int c = 0; c < W0; ++c) {
             const f2 z = mk2(accA[c] + (accA[W0 + c] + accA[2 * W0 + c]), accB[c] + (accB[W0 + c] + accB[2 * W0 + c]));
-            act[0][c] = tanh2(fma2(z, dup2(8589934592.f /* 2^33 */), ld2(b0p2 + c)));
+            act[0][c] = tanh2(fma2(z, dup2(8589934592.f /* 2^33 */), dup2(b0p[c])));
         }
 #pragma unroll
         for (int l = 1; l < NLA; ++l) {
 #pragma unroll
             for (int c = 0; c < MW; ++c) {
                 if (c < T::width(l)) {
-                    f2 zz = ld2(wp2 + T::b_off(l) + c);
+                    f2 zz = dup2(wp[T::b_off(l) + c]);
 #pragma unroll
                     for (int i = 0; i < MW; ++i)
-                        if (i < T::in_w(l)) zz = fma2(act[l - 1][i], ld2(wp2 + T::w_off(l) + c * T::in_w(l) + i), zz);
+                        if (i < T::in_w(l)) zz = fma2(act[l - 1][i], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), zz);
                     act[l][c] = tanh2(zz);
                 }
             }
         }
         f2 yh = zero2;
 #pragma unroll
-        for (int i = 0; i < S; ++i) yh = fma2(act[NLA - 1][i], ld2(wp2 + T::w_off(NLA) + i), yh);
+        for (int i = 0; i < S; ++i) yh = fma2(act[NLA - 1][i], dup2(wp[T::w_off(NLA) + i]), yh);
         if (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) tg = add2(tg, yh);            // net.rs:280
         const f2 e = mul2(fma2(tg, dup2(-1.f), yh), mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f));  // branch_sampler.rs:821
         // ---- per-row outputs
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             gWo[i] = fma2(act[NLA - 1][i], e2, gWo[i]);
-            delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e2, ld2(wp2 + T::w_off(NLA) + i)));
+            delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e2, dup2(wp[T::w_off(NLA) + i])));
         }
 #pragma unroll
         for (int l = NLA - 1; l >= 1; --l) {
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
                     for (int i = 0; i < MW; ++i)
                         if (i < T::in_w(l)) {
                             gWt[l - 1][i][c] = fma2(act[l - 1][i], delta[c], gWt[l - 1][i][c]);
-                            nd[i] = fma2(delta[c], ld2(wp2 + T::w_off(l) + c * T::in_w(l) + i), nd[i]);
+                            nd[i] = fma2(delta[c], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), nd[i]);
                         }
                 }
             }
