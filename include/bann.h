@@ -111,6 +111,21 @@ int  bann_ctx_create(int device, void* stream, int rank, int world, bann_ctx** o
 void bann_ctx_destroy(bann_ctx*);
 int  bann_ctx_sync(bann_ctx*);
 
+/* ---- cross-rank sums of the sequential-exact schedule.  The reference is single-process;
+ * what these replace are its N-row reductions (`sum_all`, `dot`, `matmul(delta^T, X)` in
+ * net/branch/branch_sampler.rs:813-875,905-909 and the residual sums of net/net.rs:43-45,604-606), which
+ * with sharded rows become sums over ranks.  Each rank allocates an inbox in its own HBM and exports a
+ * handle; the host layer all-gathers the world * BANN_COMM_HANDLE_BYTES bytes (rank order) and every rank
+ * maps its peers' inboxes (CUDA IPC over NVLink; plain pointers for ranks of the same process).  From then
+ * on bann_visit_branch / bann_sweep / bann_hmc_step / bann_branch_fwd_bwd / bann_net_init_residual sum over
+ * ranks INSIDE their reduction kernels (8-byte {value, epoch} stores into peer memory, rank-ordered adds:
+ * bit-identical results on every rank), with no collective launch and no host involvement.  All ranks
+ * must issue the same sequence of calls. */
+#define BANN_COMM_HANDLE_BYTES 128
+int  bann_ctx_comm_handle(bann_ctx*, uint8_t* handle_out /* BANN_COMM_HANDLE_BYTES */);
+int  bann_ctx_comm_connect(bann_ctx*, const uint8_t* all_handles /* world * BANN_COMM_HANDLE_BYTES */);
+int  bann_ctx_comm_connected(bann_ctx*);
+
 /* ---- genotypes: replaces BedVM + MarkerGrouping + GroupedGenotypes::x_group_af
  * (io/bed.rs:123-133,193-245,325-355; group/grouping.rs:7-15; data/genotypes.rs:7-48).
  * bed_payload: PLINK variant-major 2-bit payload WITHOUT the 3-byte signature, m * ceil(n/4)

@@ -13,6 +13,7 @@ STD_NORMAL, RIDGE_BASE, RIDGE_ARD, LASSO_BASE, LASSO_ARD = range(5)
 TANH, RELU, LEAKY_RELU, SILU, IDENTITY = range(5)
 STEP_UNIFORM, STEP_RANDOM, STEP_STD_SCALED, STEP_IZMAILOV = range(4)
 HMC_REJECTED_EARLY, HMC_REJECTED, HMC_ACCEPTED = range(3)
+COMM_HANDLE_BYTES = 128
 
 MODEL_NAMES = {"std_normal": STD_NORMAL, "ridge_base": RIDGE_BASE, "ridge_ard": RIDGE_ARD,
                "lasso_base": LASSO_BASE, "lasso_ard": LASSO_ARD}
@@ -64,6 +65,9 @@ PROTOTYPES = {
     "bann_ctx_create": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "bann_ctx_destroy": (None, [_vp]),
     "bann_ctx_sync": (C.c_int, [_vp]),
+    "bann_ctx_comm_handle": (C.c_int, [_vp, _vp]),
+    "bann_ctx_comm_connect": (C.c_int, [_vp, _vp]),
+    "bann_ctx_comm_connected": (C.c_int, [_vp]),
     "bann_genotypes_create": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _fp, _fp, _u64, C.POINTER(_u64),
                                          C.POINTER(_u64), C.POINTER(_vp)]),
     "bann_genotypes_random": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _u64, C.c_float, C.c_float, _u64, C.POINTER(_u64),

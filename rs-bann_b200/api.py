@@ -76,6 +76,22 @@ class Context:
     def sync(self):
         check(lib.bann_ctx_sync(self.h))
 
+    # ---- peer-memory exchange of the sequential-exact schedule on sharded rows (include/bann.h, comm.cuh)
+    def comm_handle(self) -> bytes:
+        """Allocates this rank's inbox and returns its handle (to be all-gathered in rank order)."""
+        buf = (C.c_uint8 * _lib.COMM_HANDLE_BYTES)()
+        check(lib.bann_ctx_comm_handle(self.h, buf))
+        return bytes(buf)
+
+    def comm_connect(self, handles: Sequence[bytes]):
+        """Maps every peer's inbox; `handles[r]` = rank r's `comm_handle()`."""
+        assert len(handles) == self.world and all(len(h) == _lib.COMM_HANDLE_BYTES for h in handles)
+        blob = b"".join(handles)
+        check(lib.bann_ctx_comm_connect(self.h, (C.c_uint8 * len(blob)).from_buffer_copy(blob)))
+
+    def comm_connected(self) -> bool:
+        return bool(lib.bann_ctx_comm_connected(self.h))
+
     def close(self):
         if self.h:
             lib.bann_ctx_destroy(self.h)

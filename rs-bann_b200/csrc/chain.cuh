@@ -223,13 +223,15 @@ __global__ void __launch_bounds__(256) k_resid_stats(const float* __restrict__ r
     }
 }
 
-__global__ void k_resid_reduce(const float* __restrict__ part, uint32_t nblk, NetGlobals* G) {
+__global__ void k_resid_reduce(const float* __restrict__ part, uint32_t nblk, NetGlobals* G, XrComm xc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double ss = 0.0, s = 0.0;
         for (uint32_t i = 0; i < nblk; ++i) {
             ss += part[2 * i];
             s += part[2 * i + 1];
         }
+        ss = xr_sum(xc, 0, ss);
+        s = xr_sum(xc, 1, s);
         G->resid_ss = (float)ss;
         G->resid_sum = (float)s;
     }
@@ -339,6 +341,7 @@ struct FinishArgs {
     float* bias_old_new;       // out [2]
     int update_bias;           // 1 in a train visit, 0 in initialize_stats
     int* error_flag;
+    XrComm xc;                 // row-sharded runs: the residual sums are summed over ranks here
 };
 
 // One block: update_lpd_from_branch (net.rs:173-185) when accepted, to_cfg + global params
@@ -356,6 +359,16 @@ __global__ void __launch_bounds__(256) k_visit_finish(FinishArgs a) {
     for (uint32_t i = 0; i < a.nblk; ++i) {
         ss += a.part[2 * i];
         sb += a.part[2 * i + 1];
+    }
+    if (a.xc.world > 1) {        // one thread exchanges, everybody reads the rank-ordered totals
+        __shared__ double tot[2];
+        if (tid == 0) {
+            tot[0] = xr_sum(a.xc, 0, ss);
+            tot[1] = xr_sum(a.xc, 1, sb);
+        }
+        __syncthreads();
+        ss = tot[0];
+        sb = tot[1];
     }
     const float others = *a.ow_others;
     if (status == ST_ACCEPTED) {

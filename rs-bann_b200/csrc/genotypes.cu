@@ -246,6 +246,7 @@ int bann_ctx_create(int device, void* stream, int rank, int world, bann_ctx** ou
 
 void bann_ctx_destroy(bann_ctx* c) {
     if (!c) return;
+    bann::xr_release(c);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
 }

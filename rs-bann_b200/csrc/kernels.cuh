@@ -10,6 +10,7 @@
 //  k_hmc_init / k_accept           step sizes (a10), momenta, accept/reject (a11).
 #pragma once
 
+#include "comm.cuh"
 #include "common.cuh"
 
 namespace bann {
@@ -274,7 +275,7 @@ inline size_t k1_generic_smem(const BranchDesc& d) {
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ part, float* __restrict__ gsum, uint32_t nchunk,
                                                          uint32_t pstride, const uint32_t* __restrict__ list,
                                                          const BranchDesc* __restrict__ descs,
-                                                         const BranchState* __restrict__ states) {
+                                                         const BranchState* __restrict__ states, XrComm xc) {
     __shared__ double sm[8][32];
     const uint32_t li = blockIdx.y;
     const uint32_t b = list ? list[li] : li;
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
         double s = sm[0][lane];
 #pragma unroll
         for (int i = 1; i < 8; ++i) s += sm[i][lane];
-        gsum[(size_t)li * pstride + k] = (float)s;
+        // row-sharded sequential schedule: the sum over ranks happens right here (comm.cuh), rank order
+        gsum[(size_t)li * pstride + k] = xr_sum(xc, li * pstride + k, (float)s);
     }
 }
 

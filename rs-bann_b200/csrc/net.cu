@@ -82,7 +82,22 @@ struct K1Launch {
     const bann_genotypes* store = nullptr;
     const BranchDesc* descs_dev = nullptr;
     int single_branch = -1;  // host index of the only branch in the list (for kernel selection), -1: all
+    bool xr = false;         // sum the reduced [gW | gb | rss] over ranks inside KR (sequential schedule, world > 1)
 };
+
+static XrComm xr_none() {
+    XrComm c;
+    memset(&c, 0, sizeof(c));
+    c.world = 1;
+    return c;
+}
+// sequential-exact entry points on sharded rows need the peer-memory exchange
+static int need_comm(bann_net* net) {
+    if (net->ctx->world > 1 && !net->ctx->xr_connected)
+        BANN_FAIL("rows are sharded over ranks: call bann_ctx_comm_handle / bann_ctx_comm_connect first");
+    return 0;
+}
+static bool sharded(const bann_net* net) { return net->ctx->world > 1; }
 
 static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
     const bann_genotypes* g = L.store ? L.store : net->gen;
@@ -160,9 +175,11 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
     }
-    if (reduce && !L.fwd_only && part != net->d_gsum) {
+    if (reduce && !L.fwd_only && (part != net->d_gsum || L.xr)) {   // nchunk == 1 with L.xr: in place, exchange only
+        if (L.xr && (size_t)L.nlist * net->pstride > kXrCap) BANN_FAIL("peer-memory exchange: too many values in one launch");
         dim3 grid((net->pstride + 31) / 32, L.nlist);
-        k_reduce_partials<<<grid, 256, 0, st>>>(part, net->d_gsum, nchunk, net->pstride, L.list, a.descs, L.states);
+        k_reduce_partials<<<grid, 256, 0, st>>>(part, net->d_gsum, nchunk, net->pstride, L.list, a.descs, L.states,
+                                                L.xr ? xr_next(net->ctx, net->d_errflag) : xr_none());
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
     }
@@ -333,6 +350,7 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
     k.nlist = R.nlist;
     k.single_branch = R.single_branch;
     k.states = net->d_states;
+    k.xr = sharded(net) && R.nlist == 1 && R.list != nullptr;   // sequential schedule; grouped launches are all-reduced by the caller
     k.target_mode = R.first_mode;
     k.tgt = R.tgt;
     k.resid = resid;
@@ -421,6 +439,7 @@ static int check_error_flag(bann_net* net) {
     int flag = 0;
     BANN_CUDA(cudaMemcpyAsync(&flag, net->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, net->ctx->stream));
     BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    if (flag == 2) BANN_FAIL("peer-memory exchange timed out: a rank did not issue the matching call");
     if (flag) BANN_FAIL("Invalid output weight summary statistic (negative or NaN), params.rs:49-54");
     return 0;
 }
@@ -428,7 +447,7 @@ static int check_error_flag(bann_net* net) {
 // one iteration of the inner loop of Net::train, fully asynchronous
 static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj, uint64_t seed) {
     cudaStream_t st = net->ctx->stream;
-    if (net->ctx->world > 1) BANN_FAIL("sequential-exact visits are single-GPU in this release (use the grouped phases)");
+    BANN_CHECK(need_comm(net));
     HmcRun R;
     R.list = net->d_list_all + b;
     R.nlist = 1;
@@ -463,11 +482,13 @@ static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, cons
     f.bias_old_new = net->d_bias2;
     f.update_bias = 1;
     f.error_flag = net->d_errflag;
+    f.xc = sharded(net) ? xr_next(net->ctx, net->d_errflag) : xr_none();
     k_visit_finish<<<1, 256, 0, st>>>(f);                                                          // net.rs:296,303-305,320-330
     BANN_LAUNCHED();
     k_resid_apply_bias<<<net->rblk, 256, 0, st>>>(net->d_r, net->n, net->d_bias2, net->d_rpart);   // net.rs:321,332
     BANN_LAUNCHED();
-    k_resid_reduce<<<1, 32, 0, st>>>(net->d_rpart, net->rblk, net->d_G);
+    k_resid_reduce<<<1, 32, 0, st>>>(net->d_rpart, net->rblk, net->d_G,
+                                     sharded(net) ? xr_next(net->ctx, net->d_errflag) : xr_none());
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     net->visit_seq += 1;
@@ -491,7 +512,8 @@ static int refresh_resid_stats(bann_net* net) {
     cudaStream_t st = net->ctx->stream;
     k_resid_stats<<<net->rblk, 256, 0, st>>>(net->d_r, net->n, net->d_rpart);
     BANN_LAUNCHED();
-    k_resid_reduce<<<1, 32, 0, st>>>(net->d_rpart, net->rblk, net->d_G);
+    k_resid_reduce<<<1, 32, 0, st>>>(net->d_rpart, net->rblk, net->d_G,
+                                     (sharded(net) && net->ctx->xr_connected) ? xr_next(net->ctx, net->d_errflag) : xr_none());
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
@@ -568,6 +590,9 @@ int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int acti
     net->total_prec = qoff;
     net->pstride = (net->maxP + 1 + 3) & ~3u;
     BANN_CHECK(ensure_cap(&net->d_gsum, &net->gsum_cap, (size_t)net->B * net->pstride));   // all-reduce buffer, fixed address
+    // per-CTA partials of the largest launch (entries x chunks <= 4 CTAs per SM + entries): sized once so that no
+    // allocation (a device-wide synchronisation) ever happens between the launches of a visit
+    BANN_CHECK(ensure_cap(&net->d_part, &net->part_cap, ((size_t)ctx->num_sms * 4 + net->B + 8) * net->pstride));
     cudaStream_t st = ctx->stream;
     size_t pb = poff * sizeof(float);
     BANN_CUDA(cudaMalloc(&net->d_descs, net->B * sizeof(BranchDesc)));
@@ -781,7 +806,7 @@ int bann_net_set_residual(bann_net* net, const float* r) {
 
 int bann_net_init_residual(bann_net* net) {
     if (!net) BANN_FAIL("NULL net");
-    if (net->ctx->world > 1) BANN_FAIL("bann_net_init_residual is single-GPU in this release");
+    BANN_CHECK(need_comm(net));
     cudaStream_t st = net->ctx->stream;
     k_init_residual<<<(net->n + 255) / 256, 256, 0, st>>>(net->d_r, net->d_y, net->n, net->d_G);
     BANN_LAUNCHED();
@@ -802,6 +827,7 @@ int bann_net_init_residual(bann_net* net) {
         f.st = nullptr; f.ow_others = net->d_ow_others; f.lpd_local = net->d_lpd_local; f.hyper = net->hyper;
         f.model = net->model; f.n_total = net->n_total; f.part = net->d_rpart; f.nblk = net->rblk;
         f.bias_old_new = net->d_bias2; f.update_bias = 0; f.error_flag = net->d_errflag;
+        f.xc = sharded(net) ? xr_next(net->ctx, net->d_errflag) : xr_none();
         k_visit_finish<<<1, 256, 0, st>>>(f);                                         // net.rs:167
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
@@ -815,7 +841,7 @@ int bann_branch_fwd_bwd(bann_net* net, uint64_t b, const float* target, float* r
                         float* yhat) {
     if (!net) BANN_FAIL("NULL net");
     if (b >= net->B) BANN_FAIL("branch index out of range");
-    if (net->ctx->world > 1) BANN_FAIL("bann_branch_fwd_bwd is single-GPU in this release");
+    BANN_CHECK(need_comm(net));
     cudaStream_t st = net->ctx->stream;
     const BranchDesc& d = net->descs[b];
     const float* tgt = net->d_y;
@@ -830,6 +856,7 @@ int bann_branch_fwd_bwd(bann_net* net, uint64_t b, const float* target, float* r
     k.target_mode = TGT_SHARED;
     k.tgt = tgt;
     k.yhat_out = yhat ? net->d_ynew : nullptr;
+    k.xr = sharded(net);
     BANN_CHECK(launch_k1(net, k, true));
     if (ldg) {
         k_grad_only<<<1, 256, 0, st>>>(net->d_descs, net->d_list_all + b, net->d_theta, net->d_prec, net->d_gsum,
@@ -885,7 +912,7 @@ int bann_hmc_step(bann_net* net, uint64_t b, const float* target, const bann_mcm
                   bann_hmc_result* out, bann_trajectory* traj, float* yhat_out) {
     if (!net || !cfg) BANN_FAIL("NULL argument");
     if (b >= net->B) BANN_FAIL("branch index out of range");
-    if (net->ctx->world > 1) BANN_FAIL("bann_hmc_step is single-GPU in this release (use the grouped phases)");
+    BANN_CHECK(need_comm(net));
     cudaStream_t st = net->ctx->stream;
     const BranchDesc& d = net->descs[b];
     const float* tgt = net->d_y;

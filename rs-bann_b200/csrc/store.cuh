@@ -3,6 +3,7 @@
 
 #include <string.h>
 
+#include "comm.cuh"
 #include "common.cuh"
 
 struct bann_ctx {
@@ -13,7 +14,18 @@ struct bann_ctx {
     int cc_major = 10;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
+    // cross-rank sums over peer memory (comm.cuh / comm.cu); connected by bann_ctx_comm_connect
+    uint2* xr_inbox[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool xr_ipc[8] = {false, false, false, false, false, false, false, false};   // opened with cudaIpcOpenMemHandle
+    bool xr_connected = false;
+    uint32_t xr_epoch = 0;
 };
+
+namespace bann {
+// the descriptor of the NEXT exchange (advances the epoch); single-rank contexts get world = 1
+XrComm xr_next(bann_ctx* ctx, int* error_flag);
+void xr_release(bann_ctx* ctx);
+}  // namespace bann
 
 struct bann_genotypes {
     bann_ctx* ctx = nullptr;

@@ -3,7 +3,9 @@ for the plumbing.  Individuals (rows) are sharded on 128-row tile boundaries; pa
 momenta and precisions are replicated; the only data-path collectives are
   * an all-reduce(sum) of the per-column genotype counts at load (global column statistics),
   * an all-reduce(sum) of the per-step [gW | gb | rss] sums between K1 and K2.
-Every replica then applies the identical update (same Philox keys), so nothing is broadcast."""
+Every replica then applies the identical update (same Philox keys), so nothing is broadcast.
+The sequential-exact schedule (branch visits of Net::train) sums over ranks INSIDE the library's
+reduction kernels through peer-mapped inboxes (csrc/comm.cuh); `connect_ranks` wires them up."""
 from typing import Callable, Optional, Tuple
 
 import numpy as np
@@ -38,3 +40,20 @@ def global_col_stats(local_counts: np.ndarray, n_total: int, allreduce_sum: Opti
     if allreduce_sum is not None:
         counts = allreduce_sum(counts)
     return stats_from_counts(counts, n_total)
+
+
+def connect_ranks(ctx, all_gather_bytes: Optional[Callable] = None):
+    """Peer-memory exchange set-up: all-gather every rank's inbox handle and map the peers.
+    `all_gather_bytes(b) -> [bytes of rank 0, ..., bytes of rank world-1]`; the default uses
+    torch.distributed.all_gather_object on the default process group."""
+    if ctx.world == 1:
+        return
+    mine = ctx.comm_handle()
+    if all_gather_bytes is None:
+        import torch.distributed as dist
+        out = [None] * ctx.world
+        dist.all_gather_object(out, mine)
+        handles = out
+    else:
+        handles = all_gather_bytes(mine)
+    ctx.comm_connect([bytes(h) for h in handles])

@@ -1,0 +1,107 @@
+"""One process per GPU (torchrun): the row-sharded sequential-exact chain over the peer-memory exchange.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+      tests/multirank_worker.py [--rate]
+
+Check: every rank runs the same sweeps on its row shard; rank 0 also runs the unsharded chain on its own GPU and
+compares (same bar as tests/test_gpu_sharded_chain.py).  --rate: visits / s of the sharded chain at 100k rows.
+Prints one line starting with MULTIRANK_OK or MULTIRANK_FAIL (rank 0)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import rs_bann_b200 as rb  # noqa: E402
+from test_gpu_sharded_chain import build_problem, make_net, run_chain  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = rb.Context(local, rank=rank, world=world)
+    rb.connect_ranks(ctx)
+    ok, msgs = True, []
+    for model in ("ridge_ard", "lasso_base"):
+        P = build_problem(model, 3000, [20, 50, 9, 33], 5, 5, seed=11)
+        B = len(P["groups"])
+        r0, r1 = rb.row_shard(P["n"], rank, world)
+        gen, net = make_net(rb, ctx, P, r0, r1)
+        out = run_chain(net, rb, P["y"][r0:r1], B, sweeps=2, L=8)
+        net.close(); gen.close()
+        # replicas identical: compare a digest over ranks
+        dig = torch.tensor([float(np.sum(out["pv"].astype(np.float64))), float(np.sum(out["qv"].astype(np.float64))),
+                            out["stats"]["num_accepted"], out["globals"]["output_bias"]], dtype=torch.float64, device="cuda")
+        lo, hi = dig.clone(), dig.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+        resid = [None] * world
+        dist.all_gather_object(resid, out["resid"])
+        if rank == 0:
+            c1 = rb.Context(local)
+            g1, n1 = make_net(rb, c1, P, 0, P["n"])
+            ref = run_chain(n1, rb, P["y"], B, sweeps=2, L=8)
+            n1.close(); g1.close(); c1.close()
+            s, s1 = out["stats"], ref["stats"]
+            good = (same and s["num_accepted"] == s1["num_accepted"] and s["num_early_rejected"] == s1["num_early_rejected"]
+                    and np.allclose(out["pv"], ref["pv"], rtol=2e-4, atol=2e-5)
+                    and np.allclose(out["qv"], ref["qv"], rtol=2e-4, atol=2e-5)
+                    and np.allclose(np.concatenate(resid), ref["resid"], rtol=0, atol=5e-4)
+                    and abs(s["lpd"] - s1["lpd"]) < 5e-4 * abs(s1["lpd"]))
+            ok = ok and good
+            msgs.append(f"{model}: replicas_identical={same} accepted {s['num_accepted']}/{s['num_samples']} (single rank "
+                        f"{s1['num_accepted']}) max|dtheta|={np.max(np.abs(out['pv'] - ref['pv'])):.2e} "
+                        f"lpd {s['lpd']:.4f} vs {s1['lpd']:.4f}")
+    if "--rate" in sys.argv:
+        from bench import default_params
+        n, B, per, L = 100000, 64, 50, 100
+        r0, r1 = rb.row_shard(n, rank, world)
+        gen = rb.Genotypes.random(ctx, r1 - r0, B * per, None, seed=42, row_offset=r0, n_total=n, uniform_groups=(B, per))
+
+        def allreduce_counts(c):
+            t = torch.from_numpy(c).cuda()
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+
+        mu, sd = rb.global_col_stats(gen.col_counts(), n, allreduce_counts)
+        gen.set_col_stats(mu, sd)
+        wl = dict(B=B, per=per, widths=[5, 5, 1], model="ridge_ard")
+        net = rb.Net(ctx, gen, "ridge_ard", [[5, 5, 1]] * B)
+        pv, qv = default_params(wl)
+        net.set_all_params(pv, qv)
+        w_out = pv.reshape(B, -1)[:, per * 5 + 25:per * 5 + 30]
+        net.set_globals(2.0, 0.05, float(np.sum(w_out ** 2)), B * 5)
+        net.set_targets(np.random.default_rng(1).normal(size=n).astype(np.float32)[r0:r1])
+        net.init_residual()
+        cfg = rb.MCMCCfg(hmc_step_size_factor=0.1, hmc_integration_length=L, hmc_max_hamiltonian_error=1e30)
+        net.sweep(cfg, np.arange(B), seed=1)
+        ctx.sync()
+        dist.barrier()
+        t0 = time.perf_counter()
+        st = net.sweep(cfg, np.random.default_rng(2).permutation(B), seed=2)
+        ctx.sync()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt[0])
+        if rank == 0:
+            msgs.append(f"rate: world={world} n={n} B={B} m_b={per} L={L}: {B / dt:.1f} visits/s, "
+                        f"{dt / B / L * 1e6:.1f} us per leapfrog, accepted {st['num_accepted']}/{st['num_samples']}")
+        net.close(); gen.close()
+    ctx.close()
+    if rank == 0:
+        print(("MULTIRANK_OK " if ok else "MULTIRANK_FAIL ") + " | ".join(msgs), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
