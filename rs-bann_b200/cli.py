@@ -121,41 +121,97 @@ def net_from_device(net: Net, nf: files.NetFile) -> files.NetFile:
     return nf
 
 
-def _load_data(ctx, bfile, groups_path, phen_path=None):
+def _load_data(ctx, bfile, groups_path, phen_path=None, shard=False):
+    """BedVM::from_file + grouping + phenotypes.  shard=True (training data under torchrun): this rank keeps rows
+    [r0, r1) of every column (128-row tile boundaries); column statistics come from all-reduced value counts."""
     payload, n, m = files.read_bed(bfile)
     groups = files.read_grouping(groups_path)
-    gen = Genotypes(ctx, payload, n, m, groups)
     y = files.read_phen(phen_path) if phen_path else None
     if y is not None and y.size != n:
         sys.exit(f"{phen_path}: {y.size} phenotypes for {n} individuals")
+    if shard and ctx.world > 1:
+        import torch
+        import torch.distributed as dist
+        from .dist import global_col_stats, row_shard, shard_payload
+        r0, r1 = row_shard(n, ctx.rank, ctx.world)
+        if r1 <= r0:
+            sys.exit(f"{bfile}: {n} individuals are too few for {ctx.world} ranks (shards are whole 128-row tiles)")
+        one = np.ones(m, dtype=np.float32)
+        gen = Genotypes(ctx, shard_payload(payload, n, m, r0, r1), r1 - r0, m, groups, col_means=0 * one, col_stds=one,
+                        n_total=n)
+
+        def allreduce(c):
+            t = torch.from_numpy(c).cuda()
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+
+        gen.set_col_stats(*global_col_stats(gen.col_counts(), n, allreduce))
+        return gen, (y[r0:r1] if y is not None else None)
+    gen = Genotypes(ctx, payload, n, m, groups)
     return gen, y
+
+
+def _dist_context(device: int):
+    """One process per GPU when launched by torchrun (RANK / WORLD_SIZE / LOCAL_RANK); otherwise a single rank."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return Context(device), 0, 1
+    import torch
+    import torch.distributed as dist
+    from .dist import connect_ranks
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", os.environ["RANK"]))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local, rank=rank, world=world)
+    connect_ranks(ctx)           # peer-mapped inboxes: cross-rank sums inside the reduction kernels (csrc/comm.cuh)
+    return ctx, rank, world
+
+
+def _prepare_dist(a):
+    """Ranks must agree on every random choice made on the host (initial weights, branch orders)."""
+    a._dist = _dist_context(a.device)
+    if a._dist[2] > 1:
+        a.seed = _bcast_int(a.seed if a.seed is not None else int.from_bytes(os.urandom(4), "little"), a._dist[2])
+
+
+def _bcast_int(v: int, world: int) -> int:
+    if world == 1:
+        return v
+    import torch.distributed as dist
+    box = [v]
+    dist.broadcast_object_list(box, src=0)
+    return int(box[0])
 
 
 def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
     """Net::train (net/net.rs:201-358) with the sequential-exact schedule on the device."""
-    ctx = Context(a.device)
-    gen, y = _load_data(ctx, a.bfile_train, a.groups, a.p_train)
+    ctx, rank, world = a._dist if getattr(a, "_dist", None) else _dist_context(a.device)
+    gen, y = _load_data(ctx, a.bfile_train, a.groups, a.p_train, shard=True)
     test = None
     if a.bfile_test and a.p_test:
-        test = _load_data(ctx, a.bfile_test, a.groups, a.p_test)
-    os.makedirs(outdir, exist_ok=True)
-    with open(os.path.join(outdir, "args.json"), "w") as f:
-        json.dump(args_json, f, indent=2)
+        test = _load_data(ctx, a.bfile_test, a.groups, a.p_test)                  # replicated: predict is row-local
+    lead = rank == 0              # replicas hold identical state; rank 0 writes the files
     burn_in = a.burn_in if a.burn_in is not None else a.chain_length - 1          # mcmc_cfg.rs:152-156
     net = net_to_device(ctx, gen, model, nf)
-    with open(os.path.join(outdir, "hyperparams"), "w") as f:                     # net.rs:149-156
-        json.dump(files.hyperparams_json(nf), f)
-    if a.chain_length > burn_in:
-        os.makedirs(os.path.join(outdir, "models"), exist_ok=True)
-        os.makedirs(os.path.join(outdir, "effect_sizes"), exist_ok=True)
+    if lead:
+        os.makedirs(outdir, exist_ok=True)
+        with open(os.path.join(outdir, "args.json"), "w") as f:
+            json.dump(args_json, f, indent=2)
+        with open(os.path.join(outdir, "hyperparams"), "w") as f:                 # net.rs:149-156
+            json.dump(files.hyperparams_json(nf), f)
+        if a.chain_length > burn_in:
+            os.makedirs(os.path.join(outdir, "models"), exist_ok=True)
+            os.makedirs(os.path.join(outdir, "effect_sizes"), exist_ok=True)
     net.set_targets(y)
     net.init_residual()
     cfg = MCMCCfg(hmc_step_size_factor=a.step_size, hmc_max_hamiltonian_error=a.max_hamiltonian_error,
                   hmc_integration_length=a.integration_length, hmc_step_size_mode=a.step_size_mode,
                   fixed_param_precisions=a.fixed_param_precision is not None)
-    seed = a.seed if a.seed is not None else int.from_bytes(os.urandom(4), "little")
+    seed = _bcast_int(a.seed if a.seed is not None else int.from_bytes(os.urandom(4), "little"), world)
     rng = np.random.default_rng(seed)
-    trace = open(os.path.join(outdir, "trace"), "w") if a.trace else None
+    trace = open(os.path.join(outdir, "trace"), "w") if (a.trace and lead) else None
 
     def record_perf(st):                                                          # net.rs:597-610
         nf.lpd.append(float(st["lpd"]))
@@ -165,6 +221,8 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
             nf.mse_test = (nf.mse_test or []) + [float(np.sum(r.astype(np.float32) ** 2, dtype=np.float32) / np.float32(r.size))]
 
     def report(i, st):                                                            # net.rs:670-693
+        if not lead:
+            return
         ns = max(st["num_samples"], 1)
         acc, early = st["num_accepted"] / ns, st["num_early_rejected"] / ns
         line = (f"i: {i} \t | acc: {acc:.2f} \t | early_rej: {early:.2f} \t | end_rej: {1 - acc - early:.2f} \t | "
@@ -178,9 +236,12 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
         trace.write(json.dumps([c.to_json() for c in nf.branch_cfgs]) + "\n")
 
     def save_model(ix):
-        files.write_net(os.path.join(outdir, "models", f"{ix}.bin"), net_from_device(net, nf))
+        if lead:
+            files.write_net(os.path.join(outdir, "models", f"{ix}.bin"), net_from_device(net, nf))
 
-    print(f"Training net with {net.num_branches} branches, {net.num_params()} params", file=sys.stderr)
+    if lead:
+        print(f"Training net with {net.num_branches} branches, {net.num_params()} params"
+              + (f", rows sharded over {world} GPUs" if world > 1 else ""), file=sys.stderr)
     st = net.stats()
     record_perf(st)
     report(0, st)
@@ -199,16 +260,21 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
         if trace:
             dump_trace()
     net_from_device(net, nf)
-    with open(os.path.join(outdir, "training_stats"), "w") as f:                  # train_stats.rs:83-87
-        json.dump(nf.training_stats_json(), f)
-    if trace:
-        trace.close()
-    print("Completed training", file=sys.stderr)
+    if lead:
+        with open(os.path.join(outdir, "training_stats"), "w") as f:              # train_stats.rs:83-87
+            json.dump(nf.training_stats_json(), f)
+        if trace:
+            trace.close()
+        print("Completed training", file=sys.stderr)
     net.close(); gen.close()
     if test is not None:
         test[0].close()
     ctx.close()
-    return outdir
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return outdir if lead else None
 
 
 def _replicate_dir(parent: str, outdir: str) -> str:
@@ -222,6 +288,7 @@ def _replicate_dir(parent: str, outdir: str) -> str:
 # ------------------------------------------------------------------ subcommands
 def cmd_train_new(a):
     _check_supported(a)
+    _prepare_dist(a)
     model = a.model_type
     outdir = (f"{MODEL_JSON[model]}_{files.ACTIVATION_JSON[files.ACTIVATIONS.index(a.activation_function)]}_d{a.branch_depth}"
               f"_cl{a.chain_length}_il{a.integration_length}_{STEP_DISPLAY[a.step_size_mode]}_st{_fmt(a.step_size)}"
@@ -246,13 +313,16 @@ def cmd_train_new(a):
                      relative_summary_layer_width=a.relative_summary_layer_width,
                      fixed_summary_layer_width=a.fixed_summary_layer_width, dpk=a.dpk, dps=a.dps, spk=a.spk, sps=a.sps,
                      opk=a.opk, ops=a.ops)                                         # cli.rs:350-404
-    print(run_chain(a, model, nf, path, args_json))
+    out = run_chain(a, model, nf, path, args_json)
+    if out:
+        print(out)
 
 
 def cmd_train(a):
     _check_supported(a)
     if not os.path.isfile(a.model_file):
         sys.exit("Specified model: No such file found")                           # rs-bann.rs:1147-1150
+    _prepare_dist(a)
     stem = os.path.splitext(os.path.basename(a.model_file))[0]
     outdir = (f"{stem}_cl{a.chain_length}_il{a.integration_length}_{STEP_DISPLAY[a.step_size_mode]}_st{_fmt(a.step_size)}"
               f"_dtheta{_fmt(a.perturb_params or 0.0)}_dlambda{_fmt(a.perturb_precisions or 0.0)}")
@@ -270,7 +340,9 @@ def cmd_train(a):
                                    for p in c.weight_precisions]
     args_json = dict(model_type=MODEL_JSON[a.model_type], model_file=a.model_file, perturb_params=a.perturb_params,
                      perturb_precisions=a.perturb_precisions)                     # cli.rs:325-338
-    print(run_chain(a, a.model_type, nf, os.path.join(a.outpath, outdir) if a.outpath != "./" else outdir, args_json))
+    out = run_chain(a, a.model_type, nf, os.path.join(a.outpath, outdir) if a.outpath != "./" else outdir, args_json)
+    if out:
+        print(out)
 
 
 def _model_files(model_path: str) -> List[str]:

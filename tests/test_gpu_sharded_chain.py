@@ -201,3 +201,38 @@ def test_sharded_chain_one_process_per_gpu():
            "--master-port", "29631", os.path.join(here, "multirank_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "MULTIRANK_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_train_new_cli_under_torchrun_matches_single_gpu(tmp_path):
+    """`rs-bann train-new` launched by torchrun shards the individuals over the GPUs; with the same --seed the
+    recorded chain (mse, lpd, acceptance counts, saved model) follows the single-GPU run (needs >= 2 GPUs)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from rs_bann_b200 import files
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "rs-bann")
+    sim = subprocess.run([sys.executable, exe, "simulate-xy", "-o", str(tmp_path), "--seed", "1", "ridge-ard", "tanh", "20", "6",
+                          "2000", "3", "1", "0.6"], capture_output=True, text=True, timeout=300, check=True).stdout.strip()
+    tr, te = os.path.join(sim, "train"), os.path.join(sim, "test")
+    common = ["train-new", tr, tr + ".phen", tr + ".groups", "6", "15", "ridge-ard", "tanh", "1", "--fixed-hidden-layer-width", "3",
+              "--bfile-test", te, "--p-test", te + ".phen", "--burn-in", "6", "--step-size", "0.3", "--seed", "7"]
+    one = subprocess.run([sys.executable, exe] + common + ["-o", str(tmp_path / "one")], capture_output=True, text=True,
+                         timeout=300, check=True).stdout.strip()
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29633", exe] + common + ["-o", str(tmp_path / "two")],
+                         capture_output=True, text=True, timeout=600)
+    assert two.returncode == 0, two.stdout[-2000:] + two.stderr[-3000:]
+    two_dir = [ln for ln in two.stdout.strip().splitlines() if os.path.isdir(ln)][-1]
+    a = json.load(open(os.path.join(one, "training_stats")))
+    b = json.load(open(os.path.join(two_dir, "training_stats")))
+    assert (a["num_samples"], a["num_accepted"], a["num_early_rejected"]) == (b["num_samples"], b["num_accepted"], b["num_early_rejected"])
+    assert np.allclose(a["mse_train"], b["mse_train"], rtol=1e-4) and np.allclose(a["mse_test"], b["mse_test"], rtol=1e-4)
+    assert np.allclose(a["lpd"][1:], b["lpd"][1:], rtol=1e-3)
+    ma, mb = files.read_net(os.path.join(one, "models", "6.bin")), files.read_net(os.path.join(two_dir, "models", "6.bin"))
+    for ca, cb in zip(ma.branch_cfgs, mb.branch_cfgs):
+        assert np.allclose(ca.param_vec(), cb.param_vec(), rtol=2e-3, atol=2e-4)
