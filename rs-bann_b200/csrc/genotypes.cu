@@ -392,7 +392,7 @@ int bann_genotypes_create(bann_ctx* ctx, const uint8_t* bed_payload, uint64_t n,
     if (!ctx || !bed_payload || !branch_offsets || !col_ids || !out) BANN_FAIL("NULL argument");
     if (n == 0 || m == 0 || num_branches == 0) BANN_FAIL("empty genotype store");
     if ((col_means == nullptr) != (col_stds == nullptr)) BANN_FAIL("col_means and col_stds must both be given or both NULL");
-    if (!col_means && ctx->world > 1)
+    if (!col_means && ctx->world > 1 && n_total != 0 && n_total != n)   // a replicated store (n == n_total, e.g. test data) is fine
         BANN_FAIL("column statistics must be global: pass col_means/col_stds when rows are sharded");
     BANN_CUDA(cudaSetDevice(ctx->device));
     BANN_CHECK(check_csr(m, num_branches, branch_offsets, col_ids));

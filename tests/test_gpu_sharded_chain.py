@@ -220,9 +220,10 @@ def test_train_new_cli_under_torchrun_matches_single_gpu(tmp_path):
                           "2000", "3", "1", "0.6"], capture_output=True, text=True, timeout=300, check=True).stdout.strip()
     tr, te = os.path.join(sim, "train"), os.path.join(sim, "test")
     common = ["train-new", tr, tr + ".phen", tr + ".groups", "6", "15", "ridge-ard", "tanh", "1", "--fixed-hidden-layer-width", "3",
-              "--bfile-test", te, "--p-test", te + ".phen", "--burn-in", "6", "--step-size", "0.3", "--seed", "7"]
-    one = subprocess.run([sys.executable, exe] + common + ["-o", str(tmp_path / "one")], capture_output=True, text=True,
-                         timeout=300, check=True).stdout.strip()
+              "--bfile-test", te, "--p-test", te + ".phen", "--burn-in", "5", "--step-size", "0.3", "--seed", "7"]
+    one = subprocess.run([sys.executable, exe] + common + ["-o", str(tmp_path / "one")], capture_output=True, text=True, timeout=300)
+    assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-3000:]
+    one = one.stdout.strip()
     two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                           "127.0.0.1", "--master-port", "29633", exe] + common + ["-o", str(tmp_path / "two")],
                          capture_output=True, text=True, timeout=600)
@@ -232,7 +233,7 @@ def test_train_new_cli_under_torchrun_matches_single_gpu(tmp_path):
     b = json.load(open(os.path.join(two_dir, "training_stats")))
     assert (a["num_samples"], a["num_accepted"], a["num_early_rejected"]) == (b["num_samples"], b["num_accepted"], b["num_early_rejected"])
     assert np.allclose(a["mse_train"], b["mse_train"], rtol=1e-4) and np.allclose(a["mse_test"], b["mse_test"], rtol=1e-4)
-    assert np.allclose(a["lpd"][1:], b["lpd"][1:], rtol=1e-3)
+    assert np.allclose(a["lpd"][1:], b["lpd"][1:], rtol=1e-3, equal_nan=True)   # NaN while a never-accepted branch keeps its infinite ML bias precision (Q7)
     ma, mb = files.read_net(os.path.join(one, "models", "6.bin")), files.read_net(os.path.join(two_dir, "models", "6.bin"))
     for ca, cb in zip(ma.branch_cfgs, mb.branch_cfgs):
         assert np.allclose(ca.param_vec(), cb.param_vec(), rtol=2e-3, atol=2e-4)
