@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbann_b200.so")
+LIB_PATH = os.environ.get("BANN_LIB_PATH") or os.path.join(_HERE, "libbann_b200.so")   # override: kernel-variant experiments only
 
 MAX_LAYERS = 8
 STD_NORMAL, RIDGE_BASE, RIDGE_ARD, LASSO_BASE, LASSO_ARD = range(5)

@@ -30,6 +30,10 @@
 #include "k1_small.cuh"
 #include "umma.cuh"
 
+#ifndef BANN_TCV
+#define BANN_TCV 3      // measured switches, cfg3s K1 ms: 0 -> 1.99, bit 0 (batched word loads in expand) -> 1.86, + bit 1 (deferred MMA issue) -> 1.68
+#endif
+
 namespace bann {
 
 constexpr int kTcMaxMarkers = 64;     // one M = 64 backward accumulator, four K = 16 forward steps
@@ -215,10 +219,15 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     // expand: one AND per two operand elements, 16-byte conflict-free stores (row t and row 128 + t)
     auto expand = [&](uint32_t buf) {
         uint8_t* rowA = sA + buf * sa_bytes + tid * 16;
+        uint32_t xw[8];
+        if (BANN_TCV & 1) {          // all word loads first: the stores below are volatile asm, the compiler will not hoist loads over them
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xw[i] = ((uint32_t)i < NC) ? sG[i * 128 + tid] : 0u;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             if ((uint32_t)i < NC) {
-                const uint32_t x = sG[i * 128 + tid], y = x >> 8;
+                const uint32_t x = (BANN_TCV & 1) ? xw[i] : sG[i * 128 + tid], y = x >> 8;
                 const uint4 oa = make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
                 const uint4 ob = make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
                 *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) = oa;                   // backward operand (MN-major view)
@@ -284,13 +293,17 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         float accA[16], accB[16];
         umma::tmem_ld16x2(tlane, tlane + NN, accA, accB);
         umma::fence_before_sync();      // these reads precede the next forward MMA (ordered by the barrier below)
+        if ((BANN_TCV & 2) && bwd && it > 0 && warp >= 2) {   // deferred: by now every thread has long written its delta pieces
+            umma::mbar_wait(&mbar[3], (it - 1) & 1u);
+            issue_bwd(buf ^ 1u, warp - 2, it - 1);
+        }
 
         // ---- tail, part 1: remaining layers and the error, both rows of the pair in packed FP32
         f2 act[NLA][MW];
 #pragma unroll
         for (int c = 0; c < W0; ++c) {
             const f2 z = mk2(accA[c] + (accA[W0 + c] + accA[2 * W0 + c]), accB[c] + (accB[W0 + c] + accB[2 * W0 + c]));
-            act[0][c] = tanh2(fma2(z, dup2(8589934592.f /* 2^33 */), dup2(b0p[c])));
+            act[0][c] = tanh2(fma2(z, dup2(8589934592.f /* 2^33 */), dup2(b0p[c])));   // folding tanh's 2 log2(e) into the weights: measured no gain
         }
 #pragma unroll
         for (int l = 1; l < NLA; ++l) {
@@ -335,11 +348,14 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         // no CTA-wide barrier: every thread arrives and moves on, only the issuer warp waits for all 128 arrivals
         umma::fence_async_smem();
         umma::mbar_arrive(&mbar[2]);
-        if (warp < 2) {
-            umma::mbar_wait(&mbar[2], it & 1u);
-            if (it + 1 < nit) issue_fwd(warp);
-            if (warp == 1 && it + 2 < nit) issue_load(st + 2);        // every thread has read the staged words by now
-        }
+        auto fwd_issue_point = [&]() {
+            if (warp < 2) {
+                umma::mbar_wait(&mbar[2], it & 1u);
+                if (it + 1 < nit) issue_fwd(warp);
+                if (warp == 1 && it + 2 < nit) issue_load(st + 2);        // every thread has read the staged words by now
+            }
+        };
+        if (!(BANN_TCV & 2) || !bwd) fwd_issue_point();
         if (!bwd) continue;
 
         // ---- tail, part 2: backward deltas and the cross-row sums of the layers >= 1
@@ -372,6 +388,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
             for (int i = 0; i < MW; ++i)
                 if (i < T::in_w(l)) delta[i] = mul2(dtanh2(act[l - 1][i]), nd[i]);
         }
+        if (BANN_TCV & 2) fwd_issue_point();      // deferred: the other warps have expanded their rows while this one did the deltas
         // ---- delta_0 -> three bf16 pieces per unit by truncation (exact: 3 x 8 significand bits = f32),
         //      n = piece * W0 + unit, MN-major B operand: one 16-byte chunk per 8 n
         {
@@ -403,10 +420,14 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         }
         umma::fence_async_smem();
         umma::mbar_arrive(&mbar[3]);
-        if (warp >= 2) {
+        if (!(BANN_TCV & 2) && warp >= 2) {
             umma::mbar_wait(&mbar[3], it & 1u);
             issue_bwd(buf, warp - 2, it);
         }
+    }
+    if ((BANN_TCV & 2) && bwd && nit > 0 && warp >= 2) {       // the last super-tile's backward contraction
+        umma::mbar_wait(&mbar[3], (nit - 1) & 1u);
+        issue_bwd((nit - 1) & 1u, warp - 2, nit - 1);
     }
     const bool has_bwd = bwd && a.part && nit > 0;
     float sacc[16];
