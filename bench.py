@@ -39,7 +39,7 @@ WORKLOADS = {
 METRIC = "full_network_hmc_leapfrog_steps_per_sec"
 UNIT = "steps/s"
 # ncu --set full capture of the dominant kernel (profiles/): dram bytes per launch, filled in once measured
-NCU_TRAFFIC_BYTES = {"cfg3s": 1.8091e9, "cfg3": 1.8091e10}   # profiles/r1_k1_tc_ncu_summary.md: k1_tc dram read 1.8038 GB + write 5.3 MB per launch (cfg3 = 10 x the branches)
+NCU_TRAFFIC_BYTES = {"cfg3s": 1.8104e9, "cfg3": 1.8104e10}   # profiles/r1_k1_tc_ncu_summary.md (v10): k1_tc dram read 1.8038 GB + write 6.6 MB per launch (cfg3 = 10 x the branches)
 
 
 def default_params(wl, seed=42):
