@@ -31,7 +31,8 @@
 #include "umma.cuh"
 
 #ifndef BANN_TCV
-#define BANN_TCV 3      // measured switches, cfg3s K1 ms: 0 -> 1.99, bit 0 (batched word loads in expand) -> 1.86, + bit 1 (deferred MMA issue) -> 1.68
+#define BANN_TCV 11     // measured switches, cfg3s K1 ms: 0 -> 1.99, bit 0 (batched word loads in expand) -> 1.86, + bit 1 (deferred MMA issue) -> 1.68,
+                        // + bit 3 (no proxy fence after expand) -> 1.645.  Tried, no gain: forward issue after the delta pieces, backward issue later in part 1.
 #endif
 
 namespace bann {
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
             expand(buf ^ 1u);
         }
         // no CTA-wide barrier: every thread arrives and moves on, only the issuer warp waits for all 128 arrivals
-        umma::fence_async_smem();
+        if (!(BANN_TCV & 8) || !bwd) umma::fence_async_smem();   // bit 3: the image written above is first read by a backward MMA gated by the NEXT delta barrier, whose fence covers it
         umma::mbar_arrive(&mbar[2]);
         auto fwd_issue_point = [&]() {
             if (warp < 2) {
