@@ -56,6 +56,10 @@ typedef struct {
     uint32_t hmc_integration_length;      /* default 100 */
     int32_t  hmc_step_size_mode;          /* BANN_STEP_* , default Izmailov */
     int32_t  fixed_param_precisions;      /* skip sample_param_precisions (net.rs:273) */
+    /* flag-gated sampler modes of Net::train (net/mcmc_cfg.rs:21-26, net/net.rs:268-290); all 0 = hmc_step */
+    int32_t  joint_hmc;                   /* hmc_step_joint: precisions are part of the HMC state, no Gibbs draws */
+    int32_t  gradient_descent;            /* gradient_descent: line-search ascent on the log density */
+    int32_t  gradient_descent_joint;      /* gradient_descent_joint: fixed-step ascent on parameters and precisions */
 } bann_mcmc_cfg;
 
 /* Injected randomness for parity runs.  NULL members fall back to the built-in
@@ -86,6 +90,16 @@ typedef struct {
     float* ldg;
     float* hamiltonian;
 } bann_trajectory;
+
+/* The same for hmc_step_joint (net/branch/trajectory.rs:4-43): params L * P_b, precisions L * Q_b,
+ * ldg L * (P_b + Q_b) in BranchLogDensityGradientJoint::param_vec order (net/branch/gradient.rs:66-97:
+ * weights, biases, weight precisions, bias precisions, error precision), hamiltonian L + 1. */
+typedef struct {
+    float* params;
+    float* precisions;
+    float* ldg;
+    float* hamiltonian;
+} bann_trajectory_joint;
 
 /* net/train_stats.rs:23-32 + net/log_posterior_density.rs:62-67 */
 typedef struct {
@@ -191,6 +205,28 @@ int  bann_branch_step_sizes(bann_net*, uint64_t b, const bann_mcmc_cfg*, const f
  * yhat_out (n, may be NULL) receives the prediction at the final state. */
 int  bann_hmc_step(bann_net*, uint64_t b, const float* target, const bann_mcmc_cfg*, const bann_rng_inject*,
                    bann_hmc_result* out, bann_trajectory* traj, float* yhat_out);
+/* ---- flag-gated sampler modes.  Q_b = number of precisions of the branch
+ * (bann_net_branch_sizes); the joint state is [param_vec | BranchPrecisions::param_vec (net/params.rs:272-289)].
+ * The output-weight statistic of the other branches comes from the globals (bann_net_set_globals g[2], g[3]) minus the
+ * branch's own (net/branch/branch_struct.rs:27).  StdNormal fails: its joint density is unimplemented!() in the reference. */
+/* log_density_gradient_joint (branch_sampler.rs:406-422) + log_density_joint (:292-305) + log_density (:72-78) of the
+ * current state against `target` (NULL -> net targets).  ldg_joint: P_b + Q_b floats.  Any output may be NULL. */
+int  bann_branch_joint(bann_net*, uint64_t b, const float* target, float* rss, float* log_density_joint,
+                       float* log_density, float* ldg_joint);
+/* hmc_step_joint (branch_sampler.rs:1070-1178): Random step sizes with the joint factor (P_b + Q_b)^(-1/4) f whatever the
+ * configured mode (:1094-1101); inject->momenta / step_uniforms carry P_b + Q_b values.  The accept step evaluates the
+ * NON-joint log density against the joint initial Hamiltonian, as the reference does (:928-962,1164-1172). */
+int  bann_hmc_step_joint(bann_net*, uint64_t b, const float* target, const bann_mcmc_cfg*, const bann_rng_inject*,
+                         bann_hmc_result* out, bann_trajectory_joint* traj, float* yhat_out);
+/* gradient_descent (branch_sampler.rs:964-1017): hmc_integration_length ascent steps, each with the doubling / halving
+ * line search on probe RSS values.  Always BANN_HMC_ACCEPTED.  step_sizes_out (L, may be NULL): the step size taken in
+ * every iteration; num_probes (may be NULL): probe_gradient_step evaluations. */
+int  bann_gradient_descent(bann_net*, uint64_t b, const float* target, const bann_mcmc_cfg*, bann_hmc_result* out,
+                           float* step_sizes_out, uint32_t* num_probes, float* yhat_out);
+/* gradient_descent_joint (branch_sampler.rs:1019-1066): fixed step hmc_step_size_factor on parameters and precisions;
+ * BANN_HMC_REJECTED (state restored) when the error precision ends <= 0.  out->log_density: log_density_joint. */
+int  bann_gradient_descent_joint(bann_net*, uint64_t b, const float* target, const bann_mcmc_cfg*, bann_hmc_result* out,
+                                 float* yhat_out);
 /* sample_error_precision + sample_param_precisions against the current residual
  * (branch_sampler.rs:173-202 and the per-prior sample_prior_precisions). */
 int  bann_gibbs_branch(bann_net*, uint64_t b, const bann_mcmc_cfg*, const bann_rng_inject*);

@@ -49,6 +49,9 @@ class MCMCCfg:
     hmc_integration_length: int = 100
     hmc_step_size_mode: str = "izmailov"
     fixed_param_precisions: bool = False
+    joint_hmc: bool = False                 # mcmc_cfg.rs:21-26
+    gradient_descent: bool = False
+    gradient_descent_joint: bool = False
 
 
 @dataclass
@@ -737,6 +740,228 @@ class Branch:
             self.W, self.b = init_W, init_b  # :1293-1296
             out.update(status=REJECTED, log_density=None, y_pred=None)
         return out
+
+    # ---- joint HMC / gradient descent (flag-gated modes)
+    def precision_vec(self):
+        """BranchPrecisions::param_vec (params.rs:272-289)."""
+        return np.concatenate([np.asarray(p, dtype=self.dt).reshape(-1) for p in self.wprec]
+                              + [np.asarray(p, dtype=self.dt).reshape(-1) for p in self.bprec]
+                              + [np.array([self.eprec], dtype=self.dt)])
+
+    def load_precision_vec(self, v):
+        v = np.asarray(v, dtype=self.dt)
+        ix = 0
+        for l in range(self.num_layers):
+            n = self.wprec[l].size
+            self.wprec[l] = v[ix:ix + n].copy()
+            ix += n
+        for l in range(self.last):
+            self.bprec[l] = v[ix:ix + 1].copy()
+            ix += 1
+        self.eprec = self.dt.type(v[ix])
+
+    def split_precision_vec(self, v):
+        """precision param_vec-ordered vector -> (per-layer weight-precision arrays, per-layer bias-precision arrays, error)."""
+        v = np.asarray(v, dtype=self.dt)
+        ix, wp, bp = 0, [], []
+        for l in range(self.num_layers):
+            n = self.wprec[l].size
+            wp.append(v[ix:ix + n].copy())
+            ix += n
+        for l in range(self.last):
+            bp.append(v[ix:ix + 1].copy())
+            ix += 1
+        return wp, bp, self.dt.type(v[ix])
+
+    def log_density_gradient_joint(self, x, y, hyper: Hyper):
+        """branch_sampler.rs:406-422: backpropagate, weights under the prior, l2-regularised biases (:334-345),
+        precisions of weights (per prior), biases (:348-367) and error (:369-378, last_rss of this pass).
+        Returns (rss, gw, gb, gwp, gbp, gep)."""
+        rss, gW, gb = self.backpropagate(x, y)
+        n = np.asarray(y).size
+        return (rss, self.ldg_wrt_weights(gW), self.ldg_wrt_biases_l2(gb), self.ldg_wrt_weight_precisions(hyper),
+                [np.asarray(v, dtype=self.dt).reshape(-1) for v in self.ldg_wrt_bias_precisions(hyper)],
+                self.ldg_wrt_error_precision(rss, n, hyper))
+
+    @staticmethod
+    def join_joint_vec(gw, gb, gwp, gbp, gep):
+        """BranchLogDensityGradientJoint::param_vec order (gradient.rs:66-97): weights, biases, weight precisions,
+        bias precisions, error precision."""
+        return np.concatenate([w.reshape(-1, order="F") for w in gw] + [b.reshape(-1) for b in gb]
+                              + [p.reshape(-1) for p in gwp] + [p.reshape(-1) for p in gbp]
+                              + [np.asarray(gep).reshape(1)])
+
+    def kinetic_joint(self, pw, pb, pwp, pbp, pep):
+        """momentum.rs:83-104."""
+        dt = self.dt
+        acc = dt.type(0)
+        for grp in (pw, pb, pwp, pbp):
+            for a in grp:
+                acc = dt.type(acc + dt.type(np.sum(a * a)))
+        acc = dt.type(acc + dt.type(pep * pep))
+        return dt.type(dt.type(0.5) * acc)
+
+    def hmc_step_joint(self, x, y, cfg: MCMCCfg, hyper: Hyper, momenta, u, step_uniforms, record=False):
+        """hmc_step_joint (branch_sampler.rs:1070-1178).  momenta / step_uniforms: P + Q draws, parameters in param_vec
+        order followed by the precisions in their param_vec order.  Step sizes are always Random with the joint
+        proportionality factor (P + Q)^(-1/4) * f (:654-704).  The final accept uses the NON-joint log density
+        (accept_or_reject_hmc_state, :928-962) against the joint initial Hamiltonian -- as the reference does."""
+        dt = self.dt
+        x = np.asarray(x, dtype=dt)
+        y = np.asarray(y, dtype=dt)
+        n = y.size
+        P = self.param_vec().size
+        Q = self.precision_vec().size
+        momenta = np.asarray(momenta, dtype=dt)
+        step_uniforms = np.asarray(step_uniforms, dtype=dt)
+        init_theta, init_prec = self.param_vec().copy(), self.precision_vec().copy()
+        prop = self.f(self.f(self.f(P) + self.f(Q)) ** self.f(-0.25)) * self.f(cfg.hmc_step_size_factor)
+        ew, eb = self.split_vec((step_uniforms[:P] * prop).astype(dt))
+        ewp, ebp, eep = self.split_precision_vec((step_uniforms[P:] * prop).astype(dt))
+        pw, pb = self.split_vec(momenta[:P])
+        pwp, pbp, pep = self.split_precision_vec(momenta[P:])
+
+        def neg_h():  # neg_hamiltonian_joint, :886-903
+            return self.f(self.log_density_joint(self.rss(x, y), hyper, n) - self.kinetic_joint(pw, pb, pwp, pbp, pep))
+
+        h_init = neg_h()
+        traj = dict(params=[], precisions=[], ldg=[], hamiltonian=[float(h_init)])
+        _, gw, gb, gwp, gbp, gep = self.log_density_gradient_joint(x, y, hyper)
+        half = dt.type(0.5)
+        h_curr = h_init
+
+        def half_step():  # momentum.rs:32-58
+            nonlocal pep
+            for l in range(self.num_layers):
+                pw[l] = (pw[l] + half * ew[l] * gw[l]).astype(dt)
+            for l in range(self.last):
+                pb[l] = (pb[l] + eb[l] * half * gb[l]).astype(dt)
+            for l in range(self.num_layers):
+                pwp[l] = (pwp[l] + ewp[l] * half * gwp[l]).astype(dt)
+            for l in range(self.last):
+                pbp[l] = (pbp[l] + ebp[l] * half * gbp[l]).astype(dt)
+            pep = dt.type(pep + eep * half * gep)
+
+        for step in range(cfg.hmc_integration_length):
+            half_step()
+            for l in range(self.num_layers):  # params.rs:728-738
+                self.W[l] = (self.W[l] + ew[l] * pw[l]).astype(dt)
+            for l in range(self.last):
+                self.b[l] = (self.b[l] + eb[l] * pb[l]).astype(dt)
+            for l in range(self.num_layers):  # params.rs:344-355
+                self.wprec[l] = (self.wprec[l] + ewp[l] * pwp[l]).astype(dt)
+            for l in range(self.last):
+                self.bprec[l] = (self.bprec[l] + ebp[l] * pbp[l]).astype(dt)
+            self.eprec = dt.type(self.eprec + eep * pep)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                _, gw, gb, gwp, gbp, gep = self.log_density_gradient_joint(x, y, hyper)
+                half_step()
+                h_curr = neg_h()
+            if record:
+                traj["params"].append(self.param_vec().astype(np.float64))
+                traj["precisions"].append(self.precision_vec().astype(np.float64))
+                traj["ldg"].append(self.join_joint_vec(gw, gb, gwp, gbp, gep).astype(np.float64))
+                traj["hamiltonian"].append(float(h_curr))
+            if not (abs(h_curr - h_init) <= dt.type(cfg.hmc_max_hamiltonian_error)):  # :1146-1162 (NaN: `>` is false in Rust)
+                if not np.isnan(h_curr):
+                    self.load_param_vec(init_theta)
+                    self.load_precision_vec(init_prec)
+                    return dict(status=REJECTED_EARLY, log_density=None, y_pred=None, h_init=float(h_init),
+                                h_final=float(h_curr), steps_done=step + 1, traj=traj)
+        y_pred = self.predict(x)
+        r = y_pred - y
+        rss = dt.type(np.sum(r * r))
+        with np.errstate(invalid="ignore", over="ignore"):
+            log_density = self.log_density(rss)
+            h_final = dt.type(log_density - self.kinetic_joint(pw, pb, pwp, pbp, pep))
+            log_acc = dt.type(h_final - h_init)
+            acc_prob = dt.type(1) if log_acc >= 0 else np.exp(log_acc)
+        accepted = bool(dt.type(u) < acc_prob)
+        out = dict(h_init=float(h_init), h_final=float(h_final), steps_done=cfg.hmc_integration_length, traj=traj,
+                   log_acc=float(log_acc))
+        if accepted:
+            out.update(status=ACCEPTED, log_density=float(log_density), y_pred=y_pred)
+        else:
+            self.load_param_vec(init_theta)
+            self.load_precision_vec(init_prec)
+            out.update(status=REJECTED, log_density=None, y_pred=None)
+        return out
+
+    def _descend(self, step, gw, gb):
+        """BranchParams::descend_gradient (params.rs:740-749)."""
+        s = self.f(step)
+        for l in range(self.num_layers):
+            self.W[l] = (self.W[l] + s * gw[l]).astype(self.dt)
+        for l in range(self.last):
+            self.b[l] = (self.b[l] + s * gb[l]).astype(self.dt)
+
+    def gradient_descent(self, x, y, cfg: MCMCCfg):
+        """gradient_descent (branch_sampler.rs:964-1003): `hmc_integration_length` ascent steps on the log density, each
+        with the doubling / halving line search on the RSS of probe steps (:1005-1017).  Always Accepted.
+        Returns dict(status, log_density, y_pred, step_sizes (the accepted step size of every iteration), num_probes)."""
+        dt = self.dt
+        x = np.asarray(x, dtype=dt)
+        y = np.asarray(y, dtype=dt)
+
+        def probe(gw, gb, s):
+            keep = self.param_vec().copy()
+            self._descend(s, gw, gb)
+            res = self.rss(x, y)
+            self.load_param_vec(keep)
+            return res
+
+        _, gw, gb = self.log_density_gradient(x, y)
+        taken, nprobe = [], 0
+        for _ in range(cfg.hmc_integration_length):
+            step = self.f(cfg.hmc_step_size_factor)
+            prev = probe(gw, gb, step)
+            fac = self.f(2.0) if probe(gw, gb, self.f(2.0) * step) < prev else self.f(0.5)
+            step = self.f(step * fac)
+            curr = probe(gw, gb, step)
+            nprobe += 3
+            while curr < prev:
+                prev = curr
+                step = self.f(step * fac)
+                curr = probe(gw, gb, step)
+                nprobe += 1
+            step = self.f(step / fac)
+            self._descend(step, gw, gb)
+            taken.append(float(step))
+            _, gw, gb = self.log_density_gradient(x, y)
+        y_pred = self.predict(x)
+        r = y_pred - y
+        rss = dt.type(np.sum(r * r))
+        return dict(status=ACCEPTED, log_density=float(self.log_density(rss)), y_pred=y_pred, step_sizes=taken,
+                    num_probes=nprobe)
+
+    def gradient_descent_joint(self, x, y, cfg: MCMCCfg, hyper: Hyper):
+        """gradient_descent_joint (branch_sampler.rs:1019-1066): fixed step size `hmc_step_size_factor` on parameters and
+        precisions; Rejected (state restored) when the error precision ends <= 0."""
+        dt = self.dt
+        x = np.asarray(x, dtype=dt)
+        y = np.asarray(y, dtype=dt)
+        init_theta, init_prec = self.param_vec().copy(), self.precision_vec().copy()
+        s = self.f(cfg.hmc_step_size_factor)
+        with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+            _, gw, gb, gwp, gbp, gep = self.log_density_gradient_joint(x, y, hyper)
+            for _ in range(cfg.hmc_integration_length):
+                self._descend(s, gw, gb)
+                for l in range(self.num_layers):  # params.rs:357-367
+                    self.wprec[l] = (self.wprec[l] + s * gwp[l]).astype(dt)
+                for l in range(self.last):
+                    self.bprec[l] = (self.bprec[l] + s * gbp[l]).astype(dt)
+                self.eprec = dt.type(self.eprec + s * gep)
+                _, gw, gb, gwp, gbp, gep = self.log_density_gradient_joint(x, y, hyper)
+            y_pred = self.predict(x)
+            r = y_pred - y
+            rss = dt.type(np.sum(r * r))
+            log_density = self.log_density_joint(rss, hyper, y.size)
+        if not (self.eprec > 0):  # `<= 0.0` in the reference; NaN compares false there -> Accepted
+            if not np.isnan(self.eprec):
+                self.load_param_vec(init_theta)
+                self.load_precision_vec(init_prec)
+                return dict(status=REJECTED, log_density=None, y_pred=None)
+        return dict(status=ACCEPTED, log_density=float(log_density), y_pred=y_pred)
 
     # ---- Gibbs precision draws (standard-gamma variates injected through `gam`)
     def _ridge_post(self, k, s, stat, n, gam):

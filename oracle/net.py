@@ -211,14 +211,25 @@ def visit_branch(net: Net, b: int, x, residual, mcmc: MCMCCfg, draws: Draws, dty
     _update_cfg_globals(net, cfg)                       # :261-262
     br = Branch(cfg, dtype)                             # :268
     draws.new_visit(b)
-    br.sample_error_precision(residual, net.hyper, draws.std_gamma)   # :272
-    if not mcmc.fixed_param_precisions:
-        br.sample_param_precisions(net.hyper, draws.std_gamma)        # :275
+    joint = mcmc.gradient_descent_joint or mcmc.joint_hmc
+    if not joint:                                       # :268
+        br.sample_error_precision(residual, net.hyper, draws.std_gamma)   # :272
+        if not mcmc.fixed_param_precisions:
+            br.sample_param_precisions(net.hyper, draws.std_gamma)        # :275
     prev_pred = br.predict(x)                           # :279
     residual = (residual + prev_pred).astype(dt)        # :280
-    su = draws.step_uniforms(br.param_vec().size) if mcmc.hmc_step_size_mode == "random" else None
-    res = br.hmc_step(x, residual, mcmc, draws.momenta(br.param_vec().size), draws.uniform(),
-                      step_uniforms=su, record=record)  # :289
+    if mcmc.gradient_descent:                           # :282-290, in the reference's order
+        res = br.gradient_descent(x, residual, mcmc)
+    elif mcmc.gradient_descent_joint:
+        res = br.gradient_descent_joint(x, residual, mcmc, net.hyper)
+    elif mcmc.joint_hmc:
+        nq = br.param_vec().size + br.precision_vec().size
+        su = draws.step_uniforms(nq)
+        res = br.hmc_step_joint(x, residual, mcmc, net.hyper, draws.momenta(nq), draws.uniform(), su, record=record)
+    else:
+        su = draws.step_uniforms(br.param_vec().size) if mcmc.hmc_step_size_mode == "random" else None
+        res = br.hmc_step(x, residual, mcmc, draws.momenta(br.param_vec().size), draws.uniform(),
+                          step_uniforms=su, record=record)  # :289
     net.num_samples += 1                                # train_stats.rs:48-56
     if res["status"] == ACCEPTED:
         net.num_accepted += 1

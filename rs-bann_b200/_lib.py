@@ -29,7 +29,8 @@ class BranchLayout(C.Structure):
 class McmcCfg(C.Structure):
     _fields_ = [("hmc_step_size_factor", C.c_float), ("hmc_max_hamiltonian_error", C.c_float),
                 ("hmc_integration_length", C.c_uint32), ("hmc_step_size_mode", C.c_int32),
-                ("fixed_param_precisions", C.c_int32)]
+                ("fixed_param_precisions", C.c_int32), ("joint_hmc", C.c_int32), ("gradient_descent", C.c_int32),
+                ("gradient_descent_joint", C.c_int32)]
 
 
 class RngInject(C.Structure):
@@ -45,6 +46,11 @@ class HmcResult(C.Structure):
 
 class Trajectory(C.Structure):
     _fields_ = [("params", C.POINTER(C.c_float)), ("ldg", C.POINTER(C.c_float)),
+                ("hamiltonian", C.POINTER(C.c_float))]
+
+
+class TrajectoryJoint(C.Structure):
+    _fields_ = [("params", C.POINTER(C.c_float)), ("precisions", C.POINTER(C.c_float)), ("ldg", C.POINTER(C.c_float)),
                 ("hamiltonian", C.POINTER(C.c_float))]
 
 
@@ -97,6 +103,12 @@ PROTOTYPES = {
     "bann_branch_step_sizes": (C.c_int, [_vp, _u64, C.POINTER(McmcCfg), _fp, _fp]),
     "bann_hmc_step": (C.c_int, [_vp, _u64, _fp, C.POINTER(McmcCfg), C.POINTER(RngInject), C.POINTER(HmcResult),
                                  C.POINTER(Trajectory), _fp]),
+    "bann_branch_joint": (C.c_int, [_vp, _u64, _fp, _fp, _fp, _fp, _fp]),
+    "bann_hmc_step_joint": (C.c_int, [_vp, _u64, _fp, C.POINTER(McmcCfg), C.POINTER(RngInject), C.POINTER(HmcResult),
+                                       C.POINTER(TrajectoryJoint), _fp]),
+    "bann_gradient_descent": (C.c_int, [_vp, _u64, _fp, C.POINTER(McmcCfg), C.POINTER(HmcResult), _fp,
+                                         C.POINTER(C.c_uint32), _fp]),
+    "bann_gradient_descent_joint": (C.c_int, [_vp, _u64, _fp, C.POINTER(McmcCfg), C.POINTER(HmcResult), _fp]),
     "bann_gibbs_branch": (C.c_int, [_vp, _u64, C.POINTER(McmcCfg), C.POINTER(RngInject)]),
     "bann_visit_branch": (C.c_int, [_vp, _u64, C.POINTER(McmcCfg), C.POINTER(RngInject), C.POINTER(HmcResult)]),
     "bann_sweep": (C.c_int, [_vp, C.POINTER(McmcCfg), C.POINTER(_u64), _u64, C.c_uint32, _u64,

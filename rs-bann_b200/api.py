@@ -37,10 +37,14 @@ class MCMCCfg:
     hmc_integration_length: int = 100
     hmc_step_size_mode: str = "izmailov"
     fixed_param_precisions: bool = False
+    joint_hmc: bool = False                 # net/mcmc_cfg.rs:21-26: the flag-gated modes of Net::train (net.rs:268-290)
+    gradient_descent: bool = False
+    gradient_descent_joint: bool = False
 
     def c(self) -> _lib.McmcCfg:
         return _lib.McmcCfg(self.hmc_step_size_factor, self.hmc_max_hamiltonian_error, self.hmc_integration_length,
-                            STEP_NAMES[self.hmc_step_size_mode], int(self.fixed_param_precisions))
+                            STEP_NAMES[self.hmc_step_size_mode], int(self.fixed_param_precisions), int(self.joint_hmc),
+                            int(self.gradient_descent), int(self.gradient_descent_joint))
 
 
 @dataclass
@@ -364,6 +368,64 @@ class Net:
         if trajectory:
             out.trajectory = dict(params=tp.reshape(L, P), ldg=tl.reshape(L, P), hamiltonian=th)
         return out
+
+    # ---- flag-gated sampler modes
+    def branch_joint(self, b, target=None) -> dict:
+        """log_density_gradient_joint + log_density_joint + log_density (branch_sampler.rs:406-422,292-305,72-78).
+        `ldg`: P + Q values, parameters then precisions (gradient.rs:66-97)."""
+        P, Q = self._sizes[b]
+        t = _f32(target) if target is not None else None
+        rss, ldj, ld = C.c_float(), C.c_float(), C.c_float()
+        g = np.empty(P + Q, dtype=np.float32)
+        check(lib.bann_branch_joint(self.h, b, _ptr(t), C.byref(rss), C.byref(ldj), C.byref(ld), _ptr(g)))
+        return dict(rss=rss.value, log_density_joint=ldj.value, log_density=ld.value, ldg=g)
+
+    def hmc_step_joint(self, b, cfg: MCMCCfg, target=None, momenta=None, u=None, step_uniforms=None, trajectory=False,
+                       want_yhat=True) -> HMCStepResult:
+        """BranchSampler::hmc_step_joint (branch_sampler.rs:1070-1178); momenta / step_uniforms: P + Q values."""
+        (P, Q), L = self._sizes[b], cfg.hmc_integration_length
+        inj, keep = self._inject(momenta, u, step_uniforms)
+        t = _f32(target) if target is not None else None
+        res = _lib.HmcResult()
+        traj = _lib.TrajectoryJoint()
+        tp = tq = tl = th = None
+        if trajectory:
+            tp = np.zeros(L * P, dtype=np.float32); tq = np.zeros(L * Q, dtype=np.float32)
+            tl = np.zeros(L * (P + Q), dtype=np.float32); th = np.zeros(L + 1, dtype=np.float32)
+            traj.params, traj.precisions, traj.ldg, traj.hamiltonian = _ptr(tp), _ptr(tq), _ptr(tl), _ptr(th)
+        yh = np.empty(self.gen.n, dtype=np.float32) if want_yhat else None
+        c = cfg.c()
+        check(lib.bann_hmc_step_joint(self.h, b, _ptr(t), C.byref(c), C.byref(inj), C.byref(res),
+                                      C.byref(traj) if trajectory else None, _ptr(yh)))
+        out = HMCStepResult(res.status, res.log_density, res.neg_h_init, res.neg_h_final, res.steps_done,
+                            res.u_turn_step, yh)
+        if trajectory:
+            out.trajectory = dict(params=tp.reshape(L, P), precisions=tq.reshape(L, Q), ldg=tl.reshape(L, P + Q),
+                                  hamiltonian=th)
+        return out
+
+    def gradient_descent(self, b, cfg: MCMCCfg, target=None, want_yhat=True) -> HMCStepResult:
+        """BranchSampler::gradient_descent (branch_sampler.rs:964-1017).  `trajectory['step_sizes']`: the step taken in
+        every iteration, `trajectory['num_probes']`: probe evaluations."""
+        L = cfg.hmc_integration_length
+        t = _f32(target) if target is not None else None
+        res = _lib.HmcResult()
+        steps = np.zeros(max(L, 1), dtype=np.float32)
+        nprobe = C.c_uint32()
+        yh = np.empty(self.gen.n, dtype=np.float32) if want_yhat else None
+        c = cfg.c()
+        check(lib.bann_gradient_descent(self.h, b, _ptr(t), C.byref(c), C.byref(res), _ptr(steps), C.byref(nprobe), _ptr(yh)))
+        return HMCStepResult(res.status, res.log_density, res.neg_h_init, res.neg_h_final, res.steps_done, res.u_turn_step,
+                             yh, dict(step_sizes=steps[:L], num_probes=nprobe.value))
+
+    def gradient_descent_joint(self, b, cfg: MCMCCfg, target=None, want_yhat=True) -> HMCStepResult:
+        """BranchSampler::gradient_descent_joint (branch_sampler.rs:1019-1066)."""
+        t = _f32(target) if target is not None else None
+        res = _lib.HmcResult()
+        yh = np.empty(self.gen.n, dtype=np.float32) if want_yhat else None
+        c = cfg.c()
+        check(lib.bann_gradient_descent_joint(self.h, b, _ptr(t), C.byref(c), C.byref(res), _ptr(yh)))
+        return HMCStepResult(res.status, res.log_density, res.neg_h_init, res.neg_h_final, res.steps_done, res.u_turn_step, yh)
 
     def gibbs_branch(self, b, cfg: MCMCCfg, std_gammas=None):
         """sample_error_precision + sample_param_precisions (branch_sampler.rs:173-202)."""

@@ -5,6 +5,7 @@
 #include <cmath>
 
 #include "chain.cuh"
+#include "joint.cuh"
 #include "k1_small.cuh"
 #include "k1_tc.cuh"
 #include "k1_tc_wide.cuh"
@@ -52,6 +53,10 @@ struct bann_net {
     uint64_t visit_seq = 0;
     int k1_mode = BANN_K1_AUTO;   // which K1 kernel launch_k1 may pick (bann_net_select_k1)
     float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient
+    // joint HMC / gradient-ascent modes (joint.cuh), one branch at a time: [prec0 | pmom | pgrad | peps] x maxQ,
+    // injected momenta / step uniforms (maxP + maxQ each), accept uniform + kinetic energy + 3 outputs
+    uint32_t maxQ = 0;
+    float* d_jws = nullptr;
 };
 
 static int ensure_cap(float** p, size_t* cap, size_t need) {
@@ -383,6 +388,248 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
     return 0;
 }
 
+// ------------------------------------------------------------------ joint HMC / gradient ascent (joint.cuh)
+struct JointWs {
+    float *prec0, *pmom, *pgrad, *peps, *inj_mom, *inj_su, *tail;   // tail: [0] accept u, [1] kinetic, [2..4] eval out, [5] log density
+};
+static JointWs joint_ws(bann_net* net) {
+    JointWs w;
+    const size_t q = net->maxQ, t = (size_t)net->maxP + net->maxQ;
+    w.prec0 = net->d_jws;
+    w.pmom = w.prec0 + q;
+    w.pgrad = w.pmom + q;
+    w.peps = w.pgrad + q;
+    w.inj_mom = w.peps + q;
+    w.inj_su = w.inj_mom + t;
+    w.tail = w.inj_su + t;
+    return w;
+}
+static int joint_supported(bann_net* net) {
+    if (net->model == BANN_STD_NORMAL)
+        BANN_FAIL("joint sampling / joint gradient ascent: the joint density is unimplemented!() for StdNormal in the reference (std_normal_branch.rs)");
+    return 0;
+}
+struct JointRun {
+    uint32_t b = 0;
+    int first_mode = TGT_SHARED;     // target mode of the first evaluation (TGT_RESID_PLUS_PRED inside a train visit)
+    const float* tgt = nullptr;      // shared target
+    const float* resid = nullptr;
+    float* tgt_out = nullptr;
+    float* prev_out = nullptr;
+    float* ynew_out = nullptr;
+    const float* inj_mom = nullptr;  // device, P + Q
+    const float* inj_su = nullptr;   // device, P + Q
+    const float* inj_u = nullptr;    // device, 1
+    uint64_t seed = 0, stream = 0;
+    float *traj_params = nullptr, *traj_prec = nullptr, *traj_ldg = nullptr, *traj_h = nullptr;
+    bool ow_from_gibbs = false;      // d_ow_others already set by k_gibbs (train visit)
+};
+static JointArgs make_joint(bann_net* net, const bann_mcmc_cfg* cfg, const JointRun& R, int mode, int is_last) {
+    JointWs w = joint_ws(net);
+    JointArgs a;
+    a.descs = net->d_descs;
+    a.b = R.b;
+    a.st = net->d_states + R.b;
+    a.theta = net->d_theta;
+    a.theta0 = net->d_theta0;
+    a.mom = net->d_mom;
+    a.grad = net->d_grad;
+    a.eps = net->d_eps;
+    a.prec = net->d_prec;
+    a.prec0 = w.prec0;
+    a.pmom = w.pmom;
+    a.pgrad = w.pgrad;
+    a.peps = w.peps;
+    a.gsum = net->d_gsum;
+    a.ow_others = net->d_ow_others;
+    a.G = net->d_G;
+    a.hyper = net->hyper;
+    a.model = net->model;
+    a.n_total = net->n_total;
+    a.max_h_err = cfg ? cfg->hmc_max_hamiltonian_error : 0.f;
+    a.mode = mode;
+    a.is_last = is_last;
+    a.gd_step = cfg ? cfg->hmc_step_size_factor : 0.f;
+    a.traj_params = R.traj_params;
+    a.traj_prec = R.traj_prec;
+    a.traj_ldg = R.traj_ldg;
+    a.traj_h = R.traj_h;
+    a.out = w.tail + 2;
+    a.kin_out = w.tail + 1;
+    return a;
+}
+static K1Launch joint_k1(bann_net* net, const JointRun& R, bool first) {
+    K1Launch k;
+    k.list = net->d_list_all + R.b;
+    k.nlist = 1;
+    k.single_branch = (int)R.b;
+    k.states = net->d_states;
+    k.xr = sharded(net);
+    if (first) {
+        k.target_mode = R.first_mode;
+        k.tgt = R.tgt;
+        k.resid = R.resid;
+        k.tgt_out = R.tgt_out;
+        k.prev_out = R.prev_out;
+    } else {
+        k.target_mode = TGT_SHARED;
+        k.tgt = (R.first_mode == TGT_RESID_PLUS_PRED) ? R.tgt_out : R.tgt;
+    }
+    return k;
+}
+static int joint_prepare(bann_net* net, const JointRun& R, int hmc, const bann_mcmc_cfg* cfg) {
+    cudaStream_t st = net->ctx->stream;
+    JointWs w = joint_ws(net);
+    if (!R.ow_from_gibbs) {
+        k_ow_others<<<1, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_G, net->model, net->d_ow_others);
+        BANN_LAUNCHED();
+    }
+    JointInitArgs ia;
+    ia.descs = net->d_descs;
+    ia.b = R.b;
+    ia.st = net->d_states + R.b;
+    ia.theta = net->d_theta;
+    ia.theta0 = net->d_theta0;
+    ia.mom = net->d_mom;
+    ia.eps = net->d_eps;
+    ia.prec = net->d_prec;
+    ia.prec0 = w.prec0;
+    ia.pmom = w.pmom;
+    ia.peps = w.peps;
+    ia.factor = cfg->hmc_step_size_factor;
+    ia.hmc = hmc;
+    ia.inj_momenta = R.inj_mom;
+    ia.inj_step_uniforms = R.inj_su;
+    ia.seed = R.seed;
+    ia.stream = R.stream;
+    k_joint_init<<<1, 256, 0, st>>>(ia);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+// hmc_step_joint (branch_sampler.rs:1070-1178): always Random step sizes with the joint factor (:1094-1101)
+static int run_hmc_joint(bann_net* net, const bann_mcmc_cfg* cfg, const JointRun& R) {
+    cudaStream_t st = net->ctx->stream;
+    BANN_CHECK(joint_supported(net));
+    BANN_CHECK(joint_prepare(net, R, 1, cfg));
+    const uint32_t Ls = cfg->hmc_integration_length;
+    K1Launch k = joint_k1(net, R, true);
+    if (Ls == 0) k.yhat_out = R.ynew_out;
+    BANN_CHECK(launch_k1(net, k, true));
+    k2_joint<<<1, 256, 0, st>>>(make_joint(net, cfg, R, JM_HMC_INIT, Ls == 0));
+    BANN_LAUNCHED();
+    k = joint_k1(net, R, false);
+    for (uint32_t s = 1; s <= Ls; ++s) {
+        k.yhat_out = (s == Ls) ? R.ynew_out : nullptr;
+        BANN_CHECK(launch_k1(net, k, true));
+        k2_joint<<<1, 256, 0, st>>>(make_joint(net, cfg, R, JM_HMC_STEP, s == Ls));
+        BANN_LAUNCHED();
+    }
+    JointWs w = joint_ws(net);
+    k_joint_accept<<<1, 256, 0, st>>>(net->d_descs, R.b, net->d_states + R.b, net->d_theta, net->d_theta0, net->d_prec, w.prec0,
+                                      w.tail + 1, R.inj_u, R.seed, R.stream);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+// gradient_descent_joint (branch_sampler.rs:1019-1066)
+static int run_gd_joint(bann_net* net, const bann_mcmc_cfg* cfg, const JointRun& R) {
+    cudaStream_t st = net->ctx->stream;
+    BANN_CHECK(joint_supported(net));
+    BANN_CHECK(joint_prepare(net, R, 0, cfg));
+    const uint32_t Ls = cfg->hmc_integration_length;
+    for (uint32_t s = 0; s <= Ls; ++s) {
+        K1Launch k = joint_k1(net, R, s == 0);
+        k.yhat_out = (s == Ls) ? R.ynew_out : nullptr;
+        BANN_CHECK(launch_k1(net, k, true));
+        k2_joint<<<1, 256, 0, st>>>(make_joint(net, cfg, R, JM_GD_STEP, s == Ls));
+        BANN_LAUNCHED();
+    }
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+// gradient_descent (branch_sampler.rs:964-1017): the line search compares RSS values on the host, so every probe is one
+// K1 pass + a 4-byte read-back (a debugging / point-estimate mode in the reference, not the sampler's hot loop)
+static int run_gd(bann_net* net, const bann_mcmc_cfg* cfg, const JointRun& R, float* step_sizes_out, uint32_t* num_probes) {
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[R.b];
+    const uint32_t Ls = cfg->hmc_integration_length;
+    const unsigned gb = (d.P + 255) / 256;
+    JointWs w = joint_ws(net);
+    BANN_CHECK(joint_prepare(net, R, 0, cfg));   // theta0 = theta (the base of every probe), state RUNNING
+    auto eval_grad = [&](bool first, bool want_yhat) -> int {
+        K1Launch k = joint_k1(net, R, first);
+        k.yhat_out = want_yhat ? R.ynew_out : nullptr;
+        BANN_CHECK(launch_k1(net, k, true));
+        k_grad_only<<<1, 256, 0, st>>>(net->d_descs, net->d_list_all + R.b, net->d_theta, net->d_prec, net->d_gsum, net->pstride,
+                                       net->model, net->d_grad);
+        BANN_LAUNCHED();
+        return 0;
+    };
+    uint32_t probes = 0;
+    auto probe = [&](float s, float* rss) -> int {   // probe_gradient_step (:1005-1017)
+        k_gd_axpy<<<gb, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_theta0, net->d_grad, s);
+        BANN_LAUNCHED();
+        K1Launch k = joint_k1(net, R, false);
+        BANN_CHECK(launch_k1(net, k, true));
+        BANN_CUDA(cudaMemcpyAsync(rss, net->d_gsum + d.P, sizeof(float), cudaMemcpyDeviceToHost, st));
+        BANN_CUDA(cudaStreamSynchronize(st));
+        ++probes;
+        return 0;
+    };
+    BANN_CHECK(eval_grad(true, Ls == 0));
+    for (uint32_t it = 0; it < Ls; ++it) {
+        float step = cfg->hmc_step_size_factor, prev, r2, curr;
+        BANN_CHECK(probe(step, &prev));
+        BANN_CHECK(probe(2.0f * step, &r2));
+        const float fac = (r2 < prev) ? 2.0f : 0.5f;
+        step *= fac;
+        BANN_CHECK(probe(step, &curr));
+        while (curr < prev) {
+            prev = curr;
+            step *= fac;
+            BANN_CHECK(probe(step, &curr));
+        }
+        step /= fac;
+        if (step_sizes_out) step_sizes_out[it] = step;
+        k_gd_axpy<<<gb, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_theta0, net->d_grad, step);   // descend_gradient
+        BANN_LAUNCHED();
+        k_gd_copy<<<gb, 256, 0, st>>>(net->d_descs, R.b, net->d_theta0, net->d_theta);
+        BANN_LAUNCHED();
+        BANN_CHECK(eval_grad(false, it + 1 == Ls));
+    }
+    if (num_probes) *num_probes = probes;
+    // the last gradient evaluation ran at the final parameters: its rss / prediction are those of :991-1002
+    float rss = 0.f;
+    BANN_CUDA(cudaMemcpyAsync(&rss, net->d_gsum + d.P, sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    k_log_density<<<1, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_prec, net->model, rss, w.tail + 5);
+    BANN_LAUNCHED();
+    k_gd_finish<<<1, 1, 0, st>>>(net->d_states + R.b, net->d_gsum, d.P, w.tail + 5, (int)Ls);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+// injected randomness of the joint sampler: P + Q momenta / step uniforms, 1 accept uniform
+static int stage_inject_joint(bann_net* net, const bann_rng_inject* inj, uint32_t T, JointRun* R) {
+    if (!inj) return 0;
+    cudaStream_t st = net->ctx->stream;
+    JointWs w = joint_ws(net);
+    if (inj->momenta) {
+        BANN_CUDA(cudaMemcpyAsync(w.inj_mom, inj->momenta, T * sizeof(float), cudaMemcpyHostToDevice, st));
+        R->inj_mom = w.inj_mom;
+    }
+    if (inj->step_uniforms) {
+        BANN_CUDA(cudaMemcpyAsync(w.inj_su, inj->step_uniforms, T * sizeof(float), cudaMemcpyHostToDevice, st));
+        R->inj_su = w.inj_su;
+    }
+    if (inj->accept_uniform) {
+        BANN_CUDA(cudaMemcpyAsync(w.tail, inj->accept_uniform, sizeof(float), cudaMemcpyHostToDevice, st));
+        R->inj_u = w.tail;
+    }
+    return 0;
+}
+
 static int stage_inject(bann_net* net, const bann_rng_inject* inj, uint32_t P, HmcRun* R, const float** d_gam,
                         uint32_t* n_gam) {
     cudaStream_t st = net->ctx->stream;
@@ -459,9 +706,35 @@ static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, cons
     R.stream_base = net->visit_seq * net->B;
     const float* d_gam = nullptr;
     uint32_t n_gam = 0;
-    BANN_CHECK(stage_inject(net, inj, net->descs[b].P, &R, &d_gam, &n_gam));
-    BANN_CHECK(launch_gibbs(net, b, cfg, 1, d_gam, n_gam, seed, net->visit_seq * net->B + b));   // net.rs:261-277
-    BANN_CHECK(run_hmc(net, cfg, R, net->d_ynew, net->d_t, net->d_prev, net->d_r));               // net.rs:279-290
+    const bool joint = cfg->joint_hmc || cfg->gradient_descent_joint;
+    if (cfg->gradient_descent || joint) {   // net.rs:268-290: no Gibbs draws in the joint modes; dispatch order as the reference
+        JointRun J;
+        J.b = b;
+        J.first_mode = TGT_RESID_PLUS_PRED;
+        J.resid = net->d_r;
+        J.tgt_out = net->d_t;
+        J.prev_out = net->d_prev;
+        J.ynew_out = net->d_ynew;
+        J.seed = seed;
+        J.stream = net->visit_seq * net->B + b;
+        J.ow_from_gibbs = true;
+        if (cfg->gradient_descent) {
+            BANN_CHECK(stage_inject(net, inj, net->descs[b].P, nullptr, &d_gam, &n_gam));
+            BANN_CHECK(launch_gibbs(net, b, cfg, joint ? 0 : 1, d_gam, n_gam, seed, net->visit_seq * net->B + b));
+            BANN_CHECK(run_gd(net, cfg, J, nullptr, nullptr));
+        } else {
+            BANN_CHECK(launch_gibbs(net, b, cfg, 0, nullptr, 0, seed, net->visit_seq * net->B + b));
+            if (cfg->gradient_descent_joint) BANN_CHECK(run_gd_joint(net, cfg, J));
+            else {
+                BANN_CHECK(stage_inject_joint(net, inj, net->descs[b].P + net->descs[b].nprec, &J));
+                BANN_CHECK(run_hmc_joint(net, cfg, J));
+            }
+        }
+    } else {
+        BANN_CHECK(stage_inject(net, inj, net->descs[b].P, &R, &d_gam, &n_gam));
+        BANN_CHECK(launch_gibbs(net, b, cfg, 1, d_gam, n_gam, seed, net->visit_seq * net->B + b));   // net.rs:261-277
+        BANN_CHECK(run_hmc(net, cfg, R, net->d_ynew, net->d_t, net->d_prev, net->d_r));               // net.rs:279-290
+    }
     k_resid_after_hmc<<<net->rblk, 256, 0, st>>>(net->d_r, net->d_t, net->d_ynew, net->d_prev, net->n,
                                                  net->d_states + b, net->d_G, net->d_rpart);      // net.rs:292-300
     BANN_LAUNCHED();
@@ -581,6 +854,7 @@ int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int acti
         poff += (d.P + 3) & ~3u;
         qoff += d.nprec;
         net->maxP = std::max(net->maxP, d.P);
+        net->maxQ = std::max(net->maxQ, d.nprec);
         max_gam = std::max(max_gam, gam + 1);
         size_t sm = k1_generic_smem(d);
         net->max_generic_smem = std::max(net->max_generic_smem, sm);
@@ -657,6 +931,7 @@ int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int acti
     net->inj_gamma_cap = max_gam;
     BANN_CUDA(cudaMalloc(&net->d_inj, (2 * (size_t)net->maxP + 4 + max_gam) * sizeof(float)));
     BANN_CUDA(cudaMalloc(&net->d_scratchB, 3 * net->B * sizeof(float) + 16));
+    BANN_CUDA(cudaMalloc(&net->d_jws, (4 * (size_t)net->maxQ + 2 * ((size_t)net->maxP + net->maxQ) + 16) * sizeof(float)));
     BANN_CUDA(cudaFuncSetAttribute(k1_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)net->max_generic_smem));
     BANN_CUDA(cudaStreamSynchronize(st));
     *out = net;
@@ -671,7 +946,7 @@ void bann_net_destroy(bann_net* net) {
     cudaFree(net->d_ynew); cudaFree(net->d_part); cudaFree(net->d_gsum); cudaFree(net->d_rpart);
     cudaFree(net->d_ow_others); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
     cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj);
-    cudaFree(net->d_scratchB);
+    cudaFree(net->d_scratchB); cudaFree(net->d_jws);
     if (net->h_pin_a) cudaFreeHost(net->h_pin_a);
     if (net->h_pin_b) cudaFreeHost(net->h_pin_b);
     delete net;
@@ -946,6 +1221,111 @@ int bann_hmc_step(bann_net* net, uint64_t b, const float* target, const bann_mcm
         if (traj->ldg) BANN_CUDA(cudaMemcpyAsync(traj->ldg, R.traj_ldg, (size_t)Ls * d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (traj->hamiltonian) BANN_CUDA(cudaMemcpyAsync(traj->hamiltonian, R.traj_h, (Ls + 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
+    if (yhat_out) BANN_CUDA(cudaMemcpyAsync(yhat_out, net->d_ynew, (size_t)net->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int joint_entry_common(bann_net* net, uint64_t b, const float* target, const bann_mcmc_cfg* cfg, JointRun* R) {
+    if (!net || !cfg) BANN_FAIL("NULL argument");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    BANN_CHECK(need_comm(net));
+    R->b = (uint32_t)b;
+    R->tgt = net->d_y;
+    if (target) {
+        BANN_CUDA(cudaMemcpyAsync(net->d_t, target, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, net->ctx->stream));
+        R->tgt = net->d_t;
+    }
+    R->ynew_out = net->d_ynew;
+    R->stream = net->visit_seq * net->B + b;
+    return 0;
+}
+
+int bann_branch_joint(bann_net* net, uint64_t b, const float* target, float* rss, float* log_density_joint,
+                      float* log_density, float* ldg_joint) {
+    JointRun R;
+    bann_mcmc_cfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    BANN_CHECK(joint_entry_common(net, b, target, &cfg, &R));
+    BANN_CHECK(joint_supported(net));
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[b];
+    JointWs w = joint_ws(net);
+    k_ow_others<<<1, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_G, net->model, net->d_ow_others);
+    BANN_LAUNCHED();
+    K1Launch k = joint_k1(net, R, true);
+    k.states = nullptr;
+    BANN_CHECK(launch_k1(net, k, true));
+    k2_joint<<<1, 256, 0, st>>>(make_joint(net, &cfg, R, JM_EVAL, 1));
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    float o[3];
+    BANN_CUDA(cudaMemcpyAsync(o, w.tail + 2, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (ldg_joint) {
+        BANN_CUDA(cudaMemcpyAsync(ldg_joint, net->d_grad + d.param_off, d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+        BANN_CUDA(cudaMemcpyAsync(ldg_joint + d.P, w.pgrad, d.nprec * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    BANN_CUDA(cudaStreamSynchronize(st));
+    if (rss) *rss = o[0];
+    if (log_density_joint) *log_density_joint = o[1];
+    if (log_density) *log_density = o[2];
+    return 0;
+}
+
+int bann_hmc_step_joint(bann_net* net, uint64_t b, const float* target, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj,
+                        bann_hmc_result* out, bann_trajectory_joint* traj, float* yhat_out) {
+    JointRun R;
+    BANN_CHECK(joint_entry_common(net, b, target, cfg, &R));
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[b];
+    const size_t P = d.P, Q = d.nprec, Ls = cfg->hmc_integration_length;
+    R.seed = 0x243f6a8885a308d3ull;
+    BANN_CHECK(stage_inject_joint(net, inj, (uint32_t)(P + Q), &R));
+    const bool want_traj = traj && (traj->params || traj->precisions || traj->ldg || traj->hamiltonian);
+    if (want_traj) {
+        const size_t need = Ls * P + Ls * Q + Ls * (P + Q) + Ls + 1;
+        BANN_CHECK(ensure_cap(&net->d_traj, &net->traj_cap, need));
+        BANN_CUDA(cudaMemsetAsync(net->d_traj, 0, need * sizeof(float), st));
+        R.traj_params = net->d_traj;
+        R.traj_prec = R.traj_params + Ls * P;
+        R.traj_ldg = R.traj_prec + Ls * Q;
+        R.traj_h = R.traj_ldg + Ls * (P + Q);
+    }
+    BANN_CHECK(run_hmc_joint(net, cfg, R));
+    net->visit_seq += 1;
+    if (want_traj) {
+        if (traj->params) BANN_CUDA(cudaMemcpyAsync(traj->params, R.traj_params, Ls * P * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (traj->precisions) BANN_CUDA(cudaMemcpyAsync(traj->precisions, R.traj_prec, Ls * Q * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (traj->ldg) BANN_CUDA(cudaMemcpyAsync(traj->ldg, R.traj_ldg, Ls * (P + Q) * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (traj->hamiltonian) BANN_CUDA(cudaMemcpyAsync(traj->hamiltonian, R.traj_h, (Ls + 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (yhat_out) BANN_CUDA(cudaMemcpyAsync(yhat_out, net->d_ynew, (size_t)net->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_gradient_descent(bann_net* net, uint64_t b, const float* target, const bann_mcmc_cfg* cfg, bann_hmc_result* out,
+                          float* step_sizes_out, uint32_t* num_probes, float* yhat_out) {
+    JointRun R;
+    BANN_CHECK(joint_entry_common(net, b, target, cfg, &R));
+    cudaStream_t st = net->ctx->stream;
+    BANN_CHECK(run_gd(net, cfg, R, step_sizes_out, num_probes));
+    net->visit_seq += 1;
+    if (yhat_out) BANN_CUDA(cudaMemcpyAsync(yhat_out, net->d_ynew, (size_t)net->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_gradient_descent_joint(bann_net* net, uint64_t b, const float* target, const bann_mcmc_cfg* cfg, bann_hmc_result* out,
+                                float* yhat_out) {
+    JointRun R;
+    BANN_CHECK(joint_entry_common(net, b, target, cfg, &R));
+    cudaStream_t st = net->ctx->stream;
+    BANN_CHECK(run_gd_joint(net, cfg, R));
+    net->visit_seq += 1;
     if (yhat_out) BANN_CUDA(cudaMemcpyAsync(yhat_out, net->d_ynew, (size_t)net->n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
     BANN_CUDA(cudaStreamSynchronize(st));
