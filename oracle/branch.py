@@ -842,6 +842,8 @@ class Branch:
                 pbp[l] = (pbp[l] + ebp[l] * half * gbp[l]).astype(dt)
             pep = dt.type(pep + eep * half * gep)
 
+        err_state = np.errstate(all="ignore")   # precisions may cross zero / blow up: NaN and inf propagate as in the reference
+        err_state.__enter__()
         for step in range(cfg.hmc_integration_length):
             half_step()
             for l in range(self.num_layers):  # params.rs:728-738
@@ -853,10 +855,9 @@ class Branch:
             for l in range(self.last):
                 self.bprec[l] = (self.bprec[l] + ebp[l] * pbp[l]).astype(dt)
             self.eprec = dt.type(self.eprec + eep * pep)
-            with np.errstate(invalid="ignore", divide="ignore"):
-                _, gw, gb, gwp, gbp, gep = self.log_density_gradient_joint(x, y, hyper)
-                half_step()
-                h_curr = neg_h()
+            _, gw, gb, gwp, gbp, gep = self.log_density_gradient_joint(x, y, hyper)
+            half_step()
+            h_curr = neg_h()
             if record:
                 traj["params"].append(self.param_vec().astype(np.float64))
                 traj["precisions"].append(self.precision_vec().astype(np.float64))
@@ -866,12 +867,14 @@ class Branch:
                 if not np.isnan(h_curr):
                     self.load_param_vec(init_theta)
                     self.load_precision_vec(init_prec)
+                    err_state.__exit__(None, None, None)
                     return dict(status=REJECTED_EARLY, log_density=None, y_pred=None, h_init=float(h_init),
                                 h_final=float(h_curr), steps_done=step + 1, traj=traj)
-        y_pred = self.predict(x)
-        r = y_pred - y
-        rss = dt.type(np.sum(r * r))
-        with np.errstate(invalid="ignore", over="ignore"):
+        err_state.__exit__(None, None, None)
+        with np.errstate(all="ignore"):
+            y_pred = self.predict(x)
+            r = y_pred - y
+            rss = dt.type(np.sum(r * r))
             log_density = self.log_density(rss)
             h_final = dt.type(log_density - self.kinetic_joint(pw, pb, pwp, pbp, pep))
             log_acc = dt.type(h_final - h_init)
@@ -942,7 +945,7 @@ class Branch:
         y = np.asarray(y, dtype=dt)
         init_theta, init_prec = self.param_vec().copy(), self.precision_vec().copy()
         s = self.f(cfg.hmc_step_size_factor)
-        with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        with np.errstate(all="ignore"):
             _, gw, gb, gwp, gbp, gep = self.log_density_gradient_joint(x, y, hyper)
             for _ in range(cfg.hmc_integration_length):
                 self._descend(s, gw, gb)

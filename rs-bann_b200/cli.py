@@ -86,7 +86,7 @@ def add_mcmc(p):
 
 
 def _check_supported(a):
-    for flag in ("trajectories", "num_grad_traj", "num_grad", "gradient_descent", "gradient_descent_joint", "joint_hmc"):
+    for flag in ("trajectories", "num_grad_traj", "num_grad"):
         if getattr(a, flag):
             sys.exit(f"rs-bann (B200 build): --{flag.replace('_', '-')} is outside the hot path built so far (SURVEY 8f-4)")
 
@@ -208,7 +208,8 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
     net.init_residual()
     cfg = MCMCCfg(hmc_step_size_factor=a.step_size, hmc_max_hamiltonian_error=a.max_hamiltonian_error,
                   hmc_integration_length=a.integration_length, hmc_step_size_mode=a.step_size_mode,
-                  fixed_param_precisions=a.fixed_param_precision is not None)
+                  fixed_param_precisions=a.fixed_param_precision is not None, joint_hmc=a.joint_hmc,
+                  gradient_descent=a.gradient_descent, gradient_descent_joint=a.gradient_descent_joint)   # net.rs:282-290
     seed = _bcast_int(a.seed if a.seed is not None else int.from_bytes(os.urandom(4), "little"), world)
     rng = np.random.default_rng(seed)
     trace = open(os.path.join(outdir, "trace"), "w") if (a.trace and lead) else None

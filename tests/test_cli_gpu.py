@@ -87,3 +87,21 @@ def test_simulate_train_predict_resume(rb, tmp_path):
     first = files.read_net(os.path.join(res, "models", "0.bin"))
     assert np.array_equal(first.branch_cfgs[2].param_vec(), last.branch_cfgs[2].param_vec())   # resumed from the saved state
     assert first.mse_train[-1] == pytest.approx(last.mse_train[-1], rel=1e-4)
+
+
+@pytest.mark.parametrize("flag,step", [("--gradient-descent", "1e-4"), ("--gradient-descent-joint", "1e-5"), ("--joint-hmc", "0.003")])
+def test_train_new_flag_gated_modes(rb, tmp_path, flag, step):
+    """`train-new --gradient-descent | --gradient-descent-joint | --joint-hmc` (cli.rs mcmc args, net.rs:282-290) run through
+    the same chain driver and write the same files; the ascent modes must lower the training error."""
+    sim = run(["simulate-xy", "-o", str(tmp_path), "--seed", "2", "ridge-ard", "tanh", "12", "4", "600", "3", "1", "0.6"]).strip()
+    tr = os.path.join(sim, "train")
+    out = run(["train-new", tr, tr + ".phen", tr + ".groups", "4", "5", "ridge-ard", "tanh", "1", "--fixed-hidden-layer-width", "3",
+               "-o", str(tmp_path / "fit"), "--burn-in", "0", "--step-size", step, "--seed", "5", flag]).strip()
+    ts = json.load(open(os.path.join(out, "training_stats")))
+    assert ts["num_samples"] == 4 * 4 and len(ts["mse_train"]) == 5 and np.all(np.isfinite(ts["mse_train"]))
+    assert len(glob.glob(os.path.join(out, "models", "*.bin"))) == 5
+    if flag != "--joint-hmc":
+        assert ts["num_accepted"] == ts["num_samples"]           # the ascent modes always accept (error precision stays > 0)
+        assert ts["mse_train"][-1] < ts["mse_train"][0]
+    else:
+        assert ts["num_accepted"] + ts["num_early_rejected"] <= ts["num_samples"]

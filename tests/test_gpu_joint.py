@@ -23,7 +23,7 @@ OTHERS = 3.75      # output-weight statistic of the "other branches" of the net
 def with_globals(P, b):
     """Give branch b's cfg a global output-weight statistic (own + others) and mirror it on the device."""
     c = P.cfgs[b]
-    own = summary_stat_host(P.model, c.weights[-1])
+    own = summary_stat_host(P.model, c.weights[-1].reshape(-1))
     c.ow_reg_sum = float(np.float32(own) + np.float32(OTHERS))
     c.ow_num_params = 3 * c.weights[-1].size
     P.net.set_globals(c.error_precision, float(c.weight_precisions[-1][0]), c.ow_reg_sum, c.ow_num_params, 0.0)
@@ -182,32 +182,35 @@ def test_gradient_descent_line_search(rb, ctx, model):
 def test_gradient_descent_joint(rb, ctx, model):
     P = Problem(rb, ctx, model, 500, [20, 9], 4, 3, seed=6)
     try:
+        seen = set()
         for b in range(2):
-            for factor, expect in ((2e-5, ACCEPTED), (0.5, None)):
+            # tiny steps: plain ascent; large steps: the error precision is driven below zero -> Rejected, state restored
+            for factor, L in ((2e-5, 5), (0.02, 3), (0.05, 2)):
                 c = with_globals(P, b)
-                cfg = rb.MCMCCfg(hmc_step_size_factor=factor, hmc_integration_length=5, gradient_descent_joint=True)
-                ocfg = OCfg(hmc_step_size_factor=factor, hmc_integration_length=5)
+                cfg = rb.MCMCCfg(hmc_step_size_factor=factor, hmc_integration_length=L, gradient_descent_joint=True)
+                ocfg = OCfg(hmc_step_size_factor=factor, hmc_integration_length=L)
                 got = P.net.gradient_descent_joint(b, cfg)
                 o = {}
                 for dt in (np.float32, np.float64):
                     br = Branch(c, dt)
                     o[dt] = br.gradient_descent_joint(P.x(b, dt), P.y.astype(dt), ocfg, HYPER)
                     o[dt]["params_after"], o[dt]["prec_after"] = br.param_vec(), br.precision_vec()
-                if expect is not None:
-                    assert o[np.float64]["status"] == expect
+                t, m = o[np.float64], o[np.float32]
+                if t["status"] != m["status"] or not (np.all(np.isfinite(t["params_after"])) and np.all(np.isfinite(m["params_after"]))
+                                                      and np.all(np.isfinite(t["prec_after"])) and np.all(np.isfinite(m["prec_after"]))):
+                    continue                                      # the f32 restatement itself leaves the truth: chaotic blow-up
+                assert got.status == t["status"]
+                seen.add(t["status"])
                 pv, qv = P.net.get_branch(b)
-                if o[np.float64]["status"] == REJECTED:          # error precision driven below zero: state restored
-                    assert got.status == rb.HMC_REJECTED
+                if t["status"] == REJECTED:                       # :1053-1058
                     assert np.array_equal(pv, c.param_vec()) and np.array_equal(qv, c.precision_vec().astype(np.float32))
                     continue
-                if not np.all(np.isfinite(o[np.float64]["params_after"])):
-                    continue                                      # diverged to NaN / inf in the truth itself
-                assert got.status == rb.HMC_ACCEPTED
-                within(pv, o[np.float64]["params_after"], o[np.float32]["params_after"], rel=1e-4)
-                within(qv, o[np.float64]["prec_after"], o[np.float32]["prec_after"], rel=1e-4)
-                within(got.y_pred, o[np.float64]["y_pred"], o[np.float32]["y_pred"], rel=1e-4)
-                within(got.log_density, o[np.float64]["log_density"], o[np.float32]["log_density"],
-                       scale=abs(o[np.float64]["log_density"]) + P.n, rel=1e-4)
+                within(pv, t["params_after"], m["params_after"], rel=1e-4)
+                within(qv, t["prec_after"], m["prec_after"], rel=1e-4)
+                within(got.y_pred, t["y_pred"], m["y_pred"], rel=1e-4)
+                if np.isfinite(t["log_density"]):
+                    within(got.log_density, t["log_density"], m["log_density"], scale=abs(t["log_density"]) + P.n, rel=1e-4)
+        assert ACCEPTED in seen and REJECTED in seen, seen
     finally:
         P.close()
 
