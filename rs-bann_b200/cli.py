@@ -294,6 +294,7 @@ def cmd_train_new(a):
     outdir = (f"{MODEL_JSON[model]}_{files.ACTIVATION_JSON[files.ACTIVATIONS.index(a.activation_function)]}_d{a.branch_depth}"
               f"_cl{a.chain_length}_il{a.integration_length}_{STEP_DISPLAY[a.step_size_mode]}_st{_fmt(a.step_size)}"
               f"_dpk{_fmt(a.dpk)}_dps{_fmt(a.dps)}_spk{_fmt(a.spk)}_sps{_fmt(a.sps)}_opk{_fmt(a.opk)}_ops{_fmt(a.ops)}")
+    outdir += ("_joint" if a.joint_hmc else "") + ("_gd" if a.gradient_descent else "") + ("_gdj" if a.gradient_descent_joint else "")   # rs-bann.rs:1036-1046
     if a.fixed_param_precision is not None:
         outdir += f"_fp{_fmt(a.fixed_param_precision)}"
     outdir += f"_fhlw{a.fixed_hidden_layer_width}" if a.fixed_hidden_layer_width is not None else \
@@ -327,6 +328,7 @@ def cmd_train(a):
     stem = os.path.splitext(os.path.basename(a.model_file))[0]
     outdir = (f"{stem}_cl{a.chain_length}_il{a.integration_length}_{STEP_DISPLAY[a.step_size_mode]}_st{_fmt(a.step_size)}"
               f"_dtheta{_fmt(a.perturb_params or 0.0)}_dlambda{_fmt(a.perturb_precisions or 0.0)}")
+    outdir += ("_joint" if a.joint_hmc else "") + ("_gd" if a.gradient_descent else "") + ("_gdj" if a.gradient_descent_joint else "")   # rs-bann.rs:1164-1174
     if a.fixed_param_precision is not None:
         outdir += "_fp"
     nf = files.read_net(a.model_file)

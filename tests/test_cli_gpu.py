@@ -93,10 +93,16 @@ def test_simulate_train_predict_resume(rb, tmp_path):
 def test_train_new_flag_gated_modes(rb, tmp_path, flag, step):
     """`train-new --gradient-descent | --gradient-descent-joint | --joint-hmc` (cli.rs mcmc args, net.rs:282-290) run through
     the same chain driver and write the same files; the ascent modes must lower the training error."""
-    sim = run(["simulate-xy", "-o", str(tmp_path), "--seed", "2", "ridge-ard", "tanh", "12", "4", "600", "3", "1", "0.6"]).strip()
+    model = "ridge-ard" if flag == "--gradient-descent" else "ridge-base"   # fixed precisions exist for Base models only (:324-326)
+    sim = run(["simulate-xy", "-o", str(tmp_path), "--seed", "2", model, "tanh", "12", "4", "600", "3", "1", "0.6"]).strip()
     tr = os.path.join(sim, "train")
-    out = run(["train-new", tr, tr + ".phen", tr + ".groups", "4", "5", "ridge-ard", "tanh", "1", "--fixed-hidden-layer-width", "3",
-               "-o", str(tmp_path / "fit"), "--burn-in", "0", "--step-size", step, "--seed", "5", flag]).strip()
+    out = run(["train-new", tr, tr + ".phen", tr + ".groups", "4", "5", model, "tanh", "1", "--fixed-hidden-layer-width", "3",
+               "-o", str(tmp_path / "fit"), "--burn-in", "0", "--step-size", step, "--seed", "5", flag]
+              # the default initialisation has zero biases, i.e. infinite maximum-likelihood bias precisions
+              # (branch_cfg_builder.rs:237-283): the joint gradient is NaN there, in the reference as well
+              + (["--fixed-param-precision", "1.0"] if flag != "--gradient-descent" else [])).strip()
+    tag = {"--gradient-descent": "_gd_fhlw3", "--gradient-descent-joint": "_gdj_fp1_fhlw3", "--joint-hmc": "_joint_fp1_fhlw3"}[flag]
+    assert f"_ops1000{tag}" in os.path.basename(out)             # rs-bann.rs:1036-1050
     ts = json.load(open(os.path.join(out, "training_stats")))
     assert ts["num_samples"] == 4 * 4 and len(ts["mse_train"]) == 5 and np.all(np.isfinite(ts["mse_train"]))
     assert len(glob.glob(os.path.join(out, "models", "*.bin"))) == 5
