@@ -240,6 +240,16 @@ int  bann_sweep(bann_net*, const bann_mcmc_cfg*, const uint64_t* branch_order, u
 /* Net::predict (net/net.rs:545-559) on the training genotypes (NULL) or another store. */
 int  bann_predict(bann_net*, bann_genotypes* test_or_null, float* yhat);
 int  bann_net_stats(bann_net*, bann_sweep_stats* out);
+/* ---- per-row diagnostics of saved models (the `activations` / `population-effect-sizes` subcommands and
+ * --effect-sizes; off the sampler's hot path).  genotypes NULL -> the training store.
+ * Net::activations (net/net.rs:509-518): forward_feed of branch b (branch_sampler.rs:743-782);
+ * out = [a_0 (n x w_0) | a_1 (n x w_1) | ... | yhat (n x 1)], every block column-major, n * (sum w_l + 1) floats. */
+int  bann_branch_activations(bann_net*, uint64_t b, bann_genotypes* genotypes_or_null, float* out);
+/* BranchSampler::effect_sizes (branch_sampler.rs:784-811): the prediction back-propagated to the standardised input,
+ * seeded with yhat itself as the reference does; n x m_b column-major.  population_effect_sizes (net/net.rs:529-543):
+ * its column means, m_b floats.  Either output may be NULL. */
+int  bann_branch_effect_sizes(bann_net*, uint64_t b, bann_genotypes* genotypes_or_null, float* effect_sizes,
+                              float* population_effect_sizes);
 /* the three groups of terms of LogPosteriorDensity (net/log_posterior_density.rs:9-16), as serialised in a model file;
  * wrt_local_params: one value per branch */
 int  bann_net_lpd_terms(bann_net*, float* wrt_rss_and_error_precision, float* wrt_output_weights_and_precision,

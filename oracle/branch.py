@@ -741,6 +741,17 @@ class Branch:
             out.update(status=REJECTED, log_density=None, y_pred=None)
         return out
 
+    def effect_sizes(self, x):
+        """branch_sampler.rs:784-811: back-propagation of the prediction to the (standardised) input, seeded with
+        yhat W_last^T (the reference multiplies by the prediction itself).  Returns [n, m]."""
+        x = np.asarray(x, dtype=self.dt)
+        pre, acts = self.forward_feed(x)
+        error = acts[-1] @ self.W[self.last].T
+        for l in range(self.num_layers - 2, -1, -1):
+            delta = act_dhdx(self.activation, pre[l]) * error
+            error = delta @ self.W[l].T
+        return error
+
     # ---- joint HMC / gradient descent (flag-gated modes, SURVEY 8a15)
     def precision_vec(self):
         """BranchPrecisions::param_vec (params.rs:272-289)."""

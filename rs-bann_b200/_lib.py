@@ -114,6 +114,8 @@ PROTOTYPES = {
     "bann_sweep": (C.c_int, [_vp, C.POINTER(McmcCfg), C.POINTER(_u64), _u64, C.c_uint32, _u64,
                               C.POINTER(SweepStats)]),
     "bann_predict": (C.c_int, [_vp, _vp, _fp]),
+    "bann_branch_activations": (C.c_int, [_vp, _u64, _vp, _fp]),
+    "bann_branch_effect_sizes": (C.c_int, [_vp, _u64, _vp, _fp, _fp]),
     "bann_net_stats": (C.c_int, [_vp, C.POINTER(SweepStats)]),
     "bann_net_gradient": (C.c_int, [_vp, _fp, _fp, _fp, _fp]),
     "bann_net_gradient_begin": (C.c_int, [_vp, _fp, _fp]),

@@ -486,6 +486,33 @@ class Net:
         check(lib.bann_predict(self.h, test.h if test is not None else None, _ptr(out)))
         return out
 
+    # ---- per-row diagnostics of saved models
+    def branch_activations(self, b, genotypes: Optional[Genotypes] = None) -> List[np.ndarray]:
+        """forward_feed of branch b as Net::activations collects it (net/net.rs:509-518): [a_0 .. a_{last-1}, yhat],
+        arrays of shape [n, w_l] (the reference's column-major Array<f32>)."""
+        g = genotypes or self.gen
+        widths = self.layer_widths[b][:-1] + [1]
+        out = np.empty(g.n * sum(widths), dtype=np.float32)
+        check(lib.bann_branch_activations(self.h, b, genotypes.h if genotypes is not None else None, _ptr(out)))
+        res, off = [], 0
+        for w in widths:
+            res.append(out[off:off + g.n * w].reshape((g.n, w), order="F"))
+            off += g.n * w
+        return res
+
+    def branch_effect_sizes(self, b, genotypes: Optional[Genotypes] = None, per_row=True, population=True):
+        """BranchSampler::effect_sizes [n, m_b] and its column means (Net::population_effect_sizes, net/net.rs:529-543)."""
+        g = genotypes or self.gen
+        m = len(self.gen.groups[b])
+        es = np.empty(g.n * m, dtype=np.float32) if per_row else None
+        pop = np.empty(m, dtype=np.float32) if population else None
+        check(lib.bann_branch_effect_sizes(self.h, b, genotypes.h if genotypes is not None else None, _ptr(es), _ptr(pop)))
+        return (es.reshape((g.n, m), order="F") if per_row else None), pop
+
+    def population_effect_sizes(self, genotypes: Optional[Genotypes] = None) -> np.ndarray:
+        """Net::population_effect_sizes (net/net.rs:529-543): all branches, concatenated in branch order."""
+        return np.concatenate([self.branch_effect_sizes(b, genotypes, per_row=False)[1] for b in range(self.num_branches)])
+
     # ---- full network (grouped) operations
     def gradient(self, param_vecs=None, y=None, allreduce=None, out=None):
         """Net::gradient (net/net.rs:520-527) through HOST buffers: returns (grads, rss per branch).

@@ -434,6 +434,45 @@ def cmd_gradients(a):
     print(outdir)
 
 
+def cmd_population_effect_sizes(a):
+    """population-effect-sizes (rs-bann.rs:314-372, net.rs:529-543): column means of every branch's effect sizes, one JSON
+    list (all branches concatenated in branch order) per model under <model dir>/../population_effect_sizes/."""
+    ctx = Context(a.device)
+    gen, _ = _load_data(ctx, a.bfile, a.groups, a.phen)
+    model = _read_model_type(a.model_path)
+    outdir = os.path.join(os.path.dirname(os.path.normpath(a.model_path)), "population_effect_sizes")
+    os.makedirs(outdir, exist_ok=True)
+    for path in _model_files(a.model_path):
+        net = net_to_device(ctx, gen, model, files.read_net(path))
+        pes = net.population_effect_sizes()
+        stem = os.path.splitext(os.path.basename(path))[0]
+        json.dump([float(v) for v in pes], open(os.path.join(outdir, stem + ".json"), "w"))
+        net.close()
+    gen.close(); ctx.close()
+    print(outdir)
+
+
+def cmd_activations(a):
+    """activations (rs-bann.rs:175-224, net.rs:509-518): the forward pass of every branch, one JSON file per model under
+    <model dir>/../activations/.  (The reference serialises ArrayFire arrays through afserde; here
+    {"activations": [[{"dims": [n, w], "data": [column-major]} per layer incl. the prediction] per branch]}.)"""
+    ctx = Context(a.device)
+    gen, _ = _load_data(ctx, a.bfile, a.groups)
+    model = _read_model_type(a.model_path)
+    outdir = os.path.join(os.path.dirname(os.path.normpath(a.model_path)), "activations")
+    os.makedirs(outdir, exist_ok=True)
+    for path in _model_files(a.model_path):
+        nf = files.read_net(path)
+        net = net_to_device(ctx, gen, model, nf)
+        out = [[dict(dims=list(arr.shape), data=[float(v) for v in arr.reshape(-1, order="F")])
+                for arr in net.branch_activations(b)] for b in range(len(nf.branch_cfgs))]
+        stem = os.path.splitext(os.path.basename(path))[0]
+        json.dump(dict(activations=out), open(os.path.join(outdir, stem + ".json"), "w"))
+        net.close()
+    gen.close(); ctx.close()
+    print(outdir)
+
+
 def cmd_simulate_xy(a):
     """simulate_xy (rs-bann.rs:793-964): random genotypes (io/bed.rs:136-188), a random net, y = net(X) + noise."""
     if not 0.0 <= a.heritability <= 1.0:
@@ -524,11 +563,16 @@ def build_parser():
     p.add_argument("--device", type=int, default=0)
     p.set_defaults(func=cmd_r2)
     for name, fn, hlp in (("branch-r2", cmd_branch_r2, "Use trained model to compute r2 values for each model branch."),
-                          ("gradients", cmd_gradients, "Report gradient wrt to params in trained model.")):
+                          ("gradients", cmd_gradients, "Report gradient wrt to params in trained model."),
+                          ("population-effect-sizes", cmd_population_effect_sizes, "Report population level effect sizes in trained model.")):
         p = sub.add_parser(name, help=hlp)
         p.add_argument("bfile"); p.add_argument("phen"); p.add_argument("groups"); p.add_argument("-m", "--model-path", default="./models")
         p.add_argument("--device", type=int, default=0)
         p.set_defaults(func=fn)
+    p = sub.add_parser("activations", help="Report activations in trained model.")
+    p.add_argument("bfile"); p.add_argument("groups"); p.add_argument("-m", "--model-path", default="./models")
+    p.add_argument("--device", type=int, default=0)
+    p.set_defaults(func=cmd_activations)
     p = sub.add_parser("simulate-xy", help="Simulate marker and phenotype data under a network model.")
     p.add_argument("-o", "--outdir", default="./")
     p.add_argument("model_type", type=_model_type); p.add_argument("activation_function", type=_activation)

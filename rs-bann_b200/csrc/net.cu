@@ -6,6 +6,7 @@
 
 #include "chain.cuh"
 #include "joint.cuh"
+#include "probe.cuh"
 #include "k1_small.cuh"
 #include "k1_tc.cuh"
 #include "k1_tc_wide.cuh"
@@ -1446,6 +1447,74 @@ int bann_predict(bann_net* net, bann_genotypes* test, float* yhat) {
     cudaFree(d_out);
     if (rc == -2) BANN_FAIL("CUDA error in bann_predict");
     return rc;
+}
+
+// ------------------------------------------------------------------ per-row diagnostics (probe.cuh)
+static int run_probe(bann_net* net, uint64_t b, bann_genotypes* other, float* acts_host, float* es_host, float* pop_host) {
+    if (!net) BANN_FAIL("NULL net");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    cudaStream_t st = net->ctx->stream;
+    bann_genotypes* g = other ? other : net->gen;
+    if (g->num_branches != net->B || g->m_b[b] != net->descs[b].m) BANN_FAIL("genotypes do not match the net's grouping");
+    if (pop_host && sharded(net)) BANN_FAIL("population effect sizes on sharded rows: sum the per-rank effect sizes on the host");
+    BranchDesc d = net->descs[b];
+    d.tile_off = g->tile_off[b];
+    d.col_off = g->col_off[b];
+    const size_t n = g->n, na = n * (d.sumw + 1), ne = n * d.m;
+    const uint32_t ntiles = g->ntiles, w0 = d.widths[0];
+    const size_t smem = k1_generic_smem(d);
+    if (smem > 227 * 1024) BANN_FAIL("branch too large for the diagnostic kernel's shared memory");
+    BranchDesc* d_desc = nullptr;
+    float *d_acts = nullptr, *d_es = nullptr, *d_dsum = nullptr, *d_pop = nullptr;
+    int rc = 0;
+    do {
+        if (cudaMalloc(&d_desc, sizeof(BranchDesc)) != cudaSuccess) { rc = -2; break; }
+        if (acts_host && cudaMalloc(&d_acts, na * sizeof(float)) != cudaSuccess) { rc = -2; break; }
+        if (es_host && cudaMalloc(&d_es, ne * sizeof(float)) != cudaSuccess) { rc = -2; break; }
+        if (pop_host && (cudaMalloc(&d_dsum, (size_t)ntiles * w0 * sizeof(float)) != cudaSuccess ||
+                         cudaMalloc(&d_pop, d.m * sizeof(float)) != cudaSuccess)) { rc = -2; break; }
+        if (cudaMemcpyAsync(d_desc, &d, sizeof(d), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = -2; break; }
+        if (cudaFuncSetAttribute(k_branch_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { rc = -2; break; }
+        ProbeArgs a;
+        a.store = g->d_store;
+        a.descs = d_desc;
+        a.b = 0;
+        a.theta = net->d_theta;
+        a.mu = g->d_mu;
+        a.sd = g->d_sd;
+        a.n = (uint32_t)n;
+        a.ntiles = ntiles;
+        a.act = net->act;
+        a.acts_out = d_acts;
+        a.es_out = d_es;
+        a.dsum_part = d_dsum;
+        k_branch_probe<<<std::min<uint32_t>(ntiles, (uint32_t)net->ctx->num_sms * 2), 128, smem, st>>>(a);
+        BANN_LAUNCHED();
+        if (pop_host) {
+            k_population_effects<<<(d.m + 127) / 128, 128, w0 * sizeof(float), st>>>(d_desc, 0, net->d_theta, d_dsum, ntiles,
+                                                                                       (float)g->n_total, d_pop);
+            BANN_LAUNCHED();
+        }
+        if (cudaGetLastError() != cudaSuccess) { rc = -2; break; }
+        if (acts_host && cudaMemcpyAsync(acts_host, d_acts, na * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = -2; break; }
+        if (es_host && cudaMemcpyAsync(es_host, d_es, ne * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = -2; break; }
+        if (pop_host && cudaMemcpyAsync(pop_host, d_pop, d.m * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = -2; break; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -2; break; }
+    } while (0);
+    cudaFree(d_desc); cudaFree(d_acts); cudaFree(d_es); cudaFree(d_dsum); cudaFree(d_pop);
+    if (rc == -2) BANN_FAIL(std::string("CUDA error in the diagnostic kernels: ") + cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+int bann_branch_activations(bann_net* net, uint64_t b, bann_genotypes* genotypes_or_null, float* out) {
+    if (!out) BANN_FAIL("NULL argument");
+    return run_probe(net, b, genotypes_or_null, out, nullptr, nullptr);
+}
+
+int bann_branch_effect_sizes(bann_net* net, uint64_t b, bann_genotypes* genotypes_or_null, float* effect_sizes,
+                             float* population_effect_sizes) {
+    if (!effect_sizes && !population_effect_sizes) BANN_FAIL("NULL argument");
+    return run_probe(net, b, genotypes_or_null, nullptr, effect_sizes, population_effect_sizes);
 }
 
 // ------------------------------------------------------------------ full-network (grouped) operations

@@ -80,6 +80,15 @@ def test_simulate_train_predict_resume(rb, tmp_path):
     assert len(gj) == 5 and [len(w) for w in gj[0]["wrt_weights"]] == [60, 9, 3] and [len(b) for b in gj[0]["wrt_biases"]] == [3, 3]
     assert np.all(np.isfinite(np.concatenate([np.concatenate([np.array(w) for w in br["wrt_weights"]]) for br in gj])))
 
+    pdir = run(["population-effect-sizes", tr, tr + ".phen", tr + ".groups", "-m", os.path.join(out, "models")]).strip()
+    pes = json.load(open(os.path.join(pdir, "30.json")))
+    assert os.path.basename(pdir) == "population_effect_sizes" and len(pes) == 5 * 20 and np.all(np.isfinite(pes))
+    adir = run(["activations", te, te + ".groups", "-m", os.path.join(out, "models")]).strip()
+    aj = json.load(open(os.path.join(adir, "30.json")))["activations"]
+    assert len(aj) == 5 and [a["dims"] for a in aj[0]] == [[1200, 3], [1200, 3], [1200, 1]]
+    yhat_sum = np.sum([np.array(br[-1]["data"]) for br in aj], axis=0) + last.output_bias[2]
+    assert np.allclose(yhat_sum, preds[-1], rtol=0, atol=1e-4)                                  # sum of branch predictions + bias
+
     res = run(["train", tr, tr + ".phen", tr + ".groups", "3", "10", "ridge-base", os.path.join(out, "models", "30.bin"),
                "-o", str(tmp_path / "resume"), "--burn-in", "0", "--seed", "3"]).strip()
     assert os.path.basename(res) == "30_cl3_il10_Izmailov_st1_dtheta0_dlambda0"                # rs-bann.rs:1152-1160

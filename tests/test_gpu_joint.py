@@ -272,3 +272,44 @@ def test_train_visits_flag_gated_modes(rb, ctx, mode, model):
                 assert abs(st["lpd"] - lo) < 1e-3 * abs(lo), (st["lpd"], lo)
     finally:
         P.close()
+
+
+# ------------------------------------------------------------------ per-row diagnostics (Net::activations, effect sizes)
+@pytest.mark.parametrize("model,act,shape", [("ridge_ard", "tanh", ([30, 11, 64], 5, 5, 1)), ("lasso_base", "silu", ([9, 70], 4, 3, 2)),
+                                             ("std_normal", "relu", ([17, 5], 6, 2, 1))])
+def test_activations_and_effect_sizes(rb, ctx, model, act, shape):
+    from oracle import bed as obed
+    sizes, hidden, summary, depth = shape
+    P = Problem(rb, ctx, model, 391, sizes, hidden, summary, depth=depth, act=act, seed=41)
+    try:
+        pes_all = P.net.population_effect_sizes()
+        off = 0
+        for b in range(len(sizes)):
+            c = P.cfgs[b]
+            ref = {}
+            for dt in (np.float32, np.float64):
+                br = Branch(c, dt)
+                ref[dt] = (br.forward_feed(P.x(b, dt))[1], br.effect_sizes(P.x(b, dt)))
+            acts = P.net.branch_activations(b)
+            assert len(acts) == len(ref[np.float64][0])                       # a_0 .. a_{last-1}, yhat (net.rs:509-518)
+            for got, t, m in zip(acts, ref[np.float64][0], ref[np.float32][0]):
+                assert got.shape == t.shape
+                within(got, t, m, scale=max(1.0, np.max(np.abs(t))))
+            es, pop = P.net.branch_effect_sizes(b)
+            t, m = ref[np.float64][1], ref[np.float32][1]
+            within(es, t, m, rel=5e-5)
+            within(pop, t.sum(axis=0) / P.n, m.sum(axis=0, dtype=np.float32) / np.float32(P.n), scale=np.max(np.abs(t)), rel=5e-5)
+            assert np.array_equal(pes_all[off:off + len(P.groups[b])], pop)
+            off += len(P.groups[b])
+        # a second store (test data) with its own column statistics
+        g2 = obed.random_genotypes(77, P.m, seed=99)
+        pl2 = obed.pack_columns(g2)
+        mu2, sd2 = obed.col_stats(pl2, 77, P.m)
+        test = rb.Genotypes(ctx, pl2, 77, P.m, P.groups)
+        x2 = obed.submatrix_standardized(pl2, 77, P.groups[0], mu2, sd2, np.float64)
+        acts2 = P.net.branch_activations(0, test)
+        t2 = Branch(P.cfgs[0], np.float64).forward_feed(x2)[1]
+        assert np.allclose(acts2[-1], t2[-1], rtol=0, atol=2e-5 * max(1.0, np.max(np.abs(t2[-1]))))
+        test.close()
+    finally:
+        P.close()
