@@ -303,8 +303,12 @@ def main():
     value = args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the host-facing call (Net::gradient = full-network fwd+grad), HOST buffers
-    grads = np.empty(net.num_params(), dtype=np.float32)
-    rss = np.empty(B, dtype=np.float32)
+    # page-locked HOST buffers (bann_pinned_alloc): every step copies the inputs from them and the results into them
+    pv_h = rb.pinned_empty(pv.size); pv_h[:] = pv
+    y_h = rb.pinned_empty(y_local.size); y_h[:] = y_local
+    grads = rb.pinned_empty(net.num_params())
+    rss = rb.pinned_empty(B)
+    pv, y_local = pv_h, y_h
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         net.gradient(pv, y_local, allreduce=allreduce if world > 1 else None, out=(grads, rss))

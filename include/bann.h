@@ -260,6 +260,10 @@ int  bann_net_lpd_terms(bann_net*, float* wrt_rss_and_error_precision, float* wr
  * HOST buffers: params in (sum P_b, may be NULL = keep device state), y in (n, may be NULL),
  * grads out (sum P_b), rss out (B).  This is the host-facing full-network fwd+grad call. */
 int  bann_net_gradient(bann_net*, const float* param_vecs, const float* y, float* grads, float* rss);
+/* Page-locked host buffers for the calls above: pinned (or cudaHostRegister-ed) caller buffers are read / written by DMA
+ * directly, one copy per direction; pageable ones are staged through an internal pinned buffer (one extra memcpy each way). */
+int  bann_pinned_alloc(uint64_t bytes, void** out);
+void bann_pinned_free(void* p);
 /* the same in two halves for row-sharded runs: begin (H2D, fused fwd+bwd, raw sums into the
  * all-reduce buffer) -- caller all-reduces -- end (gradient under the prior, D2H). */
 int  bann_net_gradient_begin(bann_net*, const float* param_vecs, const float* y);

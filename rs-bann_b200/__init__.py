@@ -4,7 +4,7 @@ Importable as `rs_bann_b200` through the shim at the repository root.  The CUDA 
 must be present (`__graft_entry__.build()`); there is no CPU fallback."""
 from ._lib import (ACT_NAMES, HMC_ACCEPTED, HMC_REJECTED, HMC_REJECTED_EARLY, LIB_PATH, MODEL_NAMES, PROTOTYPES,
                    STEP_NAMES, BannError, lib)
-from .api import Context, Genotypes, HMCStepResult, MCMCCfg, Net, cuda_available, stats_from_counts
+from .api import Context, Genotypes, HMCStepResult, MCMCCfg, Net, cuda_available, pinned_empty, stats_from_counts
 
 
 def launch_count(reset: bool = False) -> int:

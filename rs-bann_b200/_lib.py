@@ -118,6 +118,8 @@ PROTOTYPES = {
     "bann_branch_effect_sizes": (C.c_int, [_vp, _u64, _vp, _fp, _fp]),
     "bann_net_stats": (C.c_int, [_vp, C.POINTER(SweepStats)]),
     "bann_net_gradient": (C.c_int, [_vp, _fp, _fp, _fp, _fp]),
+    "bann_pinned_alloc": (C.c_int, [_u64, C.POINTER(_vp)]),
+    "bann_pinned_free": (None, [_vp]),
     "bann_net_gradient_begin": (C.c_int, [_vp, _fp, _fp]),
     "bann_net_gradient_end": (C.c_int, [_vp, _fp, _fp]),
     "bann_grouped_begin": (C.c_int, [_vp, C.POINTER(McmcCfg), _u64, C.c_int]),

@@ -67,6 +67,32 @@ def cuda_available() -> bool:
     return bool(lib.bann_cuda_available())
 
 
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib.bann_pinned_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(n: int, dtype=np.float32) -> np.ndarray:
+    """Page-locked host array (bann_pinned_alloc): `Net.gradient` copies such buffers by DMA without staging."""
+    dt = np.dtype(dtype)
+    p = C.c_void_p()
+    check(lib.bann_pinned_alloc(int(n) * dt.itemsize, C.byref(p)))
+    owner = _PinnedOwner(p)
+    buf = (C.c_char * (int(n) * dt.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(n))
+    _PINNED_KEEP[id(buf)] = (owner, buf)        # the allocation lives as long as the module (arrays may be viewed anywhere)
+    return arr
+
+
+_PINNED_KEEP = {}
+
+
 class Context:
     """One per process / GPU. `stream`: a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
 

@@ -43,7 +43,7 @@ struct BranchDesc {
     uint64_t col_off;           // offset into the per-branch gathered mu / sd arrays
     uint64_t tc_off;            // byte offset of the branch in the tensor-core store (k1_tc.cuh)
     uint32_t nc;                // 8-marker chunks per row in the tensor-core store: ceil(m / 8)
-    uint32_t pad_;
+    uint32_t dense_off;         // offset (floats) of the branch in a DENSE concatenation of param vecs (host-facing layout)
 };
 
 // GlobalParams + OutputBias + LPD + TrainingStats, device resident (net/params.rs:13-56,

@@ -53,7 +53,9 @@ struct bann_net {
     float* d_scratchB = nullptr;  // [3*B] gather buffer
     uint64_t visit_seq = 0;
     int k1_mode = BANN_K1_AUTO;   // which K1 kernel launch_k1 may pick (bann_net_select_k1)
-    float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient
+    float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient (callers with pageable buffers)
+    float *d_dense_in = nullptr, *d_dense_out = nullptr;   // dense host-facing layouts of the parameters / gradients + rss
+    uint64_t sum_params = 0;
     // joint HMC / gradient-ascent modes (joint.cuh), one branch at a time: [prec0 | pmom | pgrad | peps] x maxQ,
     // injected momenta / step uniforms (maxP + maxQ each), accept uniform + kinetic energy + 3 outputs
     uint32_t maxQ = 0;
@@ -852,6 +854,9 @@ int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int acti
         d.nprec = q;
         d.param_off = poff;
         d.prec_off = qoff;
+        if (net->sum_params + d.P > 0xFFFFFFFFull) { delete net; BANN_FAIL("more than 2^32 parameters"); }
+        d.dense_off = (uint32_t)net->sum_params;
+        net->sum_params += d.P;
         poff += (d.P + 3) & ~3u;
         qoff += d.nprec;
         net->maxP = std::max(net->maxP, d.P);
@@ -947,7 +952,7 @@ void bann_net_destroy(bann_net* net) {
     cudaFree(net->d_ynew); cudaFree(net->d_part); cudaFree(net->d_gsum); cudaFree(net->d_rpart);
     cudaFree(net->d_ow_others); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
     cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj);
-    cudaFree(net->d_scratchB); cudaFree(net->d_jws);
+    cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
     if (net->h_pin_a) cudaFreeHost(net->h_pin_a);
     if (net->h_pin_b) cudaFreeHost(net->h_pin_b);
     delete net;
@@ -1521,28 +1526,51 @@ int bann_branch_effect_sizes(bann_net* net, uint64_t b, bann_genotypes* genotype
 // Net::gradient split in two so that a multi-GPU caller can all-reduce the raw sums in between:
 //   begin: H2D params / y, fused fwd+bwd over every branch, chunk reduction into the all-reduce buffer
 //   end  : gradient under the prior, D2H of gradients and rss
+// dense (host-facing: param vecs back to back) <-> arena (16-byte aligned per branch) on the device, so that the host side
+// of Net::gradient is ONE copy per direction straight from / into the caller's buffer
+__global__ void __launch_bounds__(128) k_dense_to_arena(const BranchDesc* descs, const float* __restrict__ dense, float* __restrict__ arena) {
+    const BranchDesc& d = descs[blockIdx.x];
+    for (uint32_t k = threadIdx.x; k < d.P; k += 128) arena[d.param_off + k] = dense[d.dense_off + k];
+}
+__global__ void __launch_bounds__(128) k_arena_to_dense(const BranchDesc* descs, const float* __restrict__ arena, float* __restrict__ dense) {
+    const BranchDesc& d = descs[blockIdx.x];
+    for (uint32_t k = threadIdx.x; k < d.P; k += 128) dense[d.dense_off + k] = arena[d.param_off + k];
+}
+static bool host_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int bann_net_gradient_begin(bann_net* net, const float* param_vecs, const float* y) {
     if (!net) BANN_FAIL("NULL net");
     cudaStream_t st = net->ctx->stream;
-    // pinned staging so that the copies are true async DMA (the e2e form of the benchmark)
-    if (!net->h_pin_a) {
-        BANN_CUDA(cudaMallocHost(&net->h_pin_a, (net->total_params + net->n) * sizeof(float)));
-        BANN_CUDA(cudaMallocHost(&net->h_pin_b, (net->total_params + net->B) * sizeof(float)));
+    // Pinned (page-locked / registered) caller buffers are copied by DMA directly; pageable ones go through one pinned
+    // staging buffer with a single memcpy, so that the copies stay asynchronous either way.
+    if (!net->d_dense_in) {
+        BANN_CUDA(cudaMalloc(&net->d_dense_in, std::max<uint64_t>(net->sum_params, 1) * sizeof(float)));
+        BANN_CUDA(cudaMalloc(&net->d_dense_out, (net->sum_params + net->B) * sizeof(float)));
     }
+    if (!net->h_pin_a && ((param_vecs && !host_pinned(param_vecs)) || (y && !host_pinned(y))))
+        BANN_CUDA(cudaMallocHost(&net->h_pin_a, (net->sum_params + net->n) * sizeof(float)));
     if (param_vecs) {
-        size_t k = 0;
-        for (uint64_t b = 0; b < net->B; ++b) {
-            const BranchDesc& d = net->descs[b];
-            memcpy(net->h_pin_a + d.param_off, param_vecs + k, d.P * sizeof(float));
-            k += d.P;
+        const float* src = param_vecs;
+        if (!host_pinned(param_vecs)) {
+            memcpy(net->h_pin_a, param_vecs, net->sum_params * sizeof(float));
+            src = net->h_pin_a;
         }
-        BANN_CUDA(cudaMemcpyAsync(net->d_theta, net->h_pin_a, net->total_params * sizeof(float), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaMemcpyAsync(net->d_dense_in, src, net->sum_params * sizeof(float), cudaMemcpyHostToDevice, st));
+        k_dense_to_arena<<<(unsigned)net->B, 128, 0, st>>>(net->d_descs, net->d_dense_in, net->d_theta);
+        BANN_LAUNCHED();
     }
     const float* tgt = net->d_y;
     if (y) {
-        memcpy(net->h_pin_a + net->total_params, y, (size_t)net->n * sizeof(float));
-        BANN_CUDA(cudaMemcpyAsync(net->d_t, net->h_pin_a + net->total_params, (size_t)net->n * sizeof(float),
-                                  cudaMemcpyHostToDevice, st));
+        const float* src = y;
+        if (!host_pinned(y)) {
+            memcpy(net->h_pin_a + net->sum_params, y, (size_t)net->n * sizeof(float));
+            src = net->h_pin_a + net->sum_params;
+        }
+        BANN_CUDA(cudaMemcpyAsync(net->d_t, src, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, st));
         tgt = net->d_t;
     }
     K1Launch k;
@@ -1556,27 +1584,38 @@ int bann_net_gradient_begin(bann_net* net, const float* param_vecs, const float*
 int bann_net_gradient_end(bann_net* net, float* grads, float* rss) {
     if (!net) BANN_FAIL("NULL net");
     cudaStream_t st = net->ctx->stream;
-    if (!net->h_pin_b) BANN_FAIL("bann_net_gradient_end without bann_net_gradient_begin");
+    if (!net->d_dense_out) BANN_FAIL("bann_net_gradient_end without bann_net_gradient_begin");
     k_grad_only<<<(unsigned)net->B, 256, 0, st>>>(net->d_descs, nullptr, net->d_theta, net->d_prec, net->d_gsum,
                                                   net->pstride, net->model, net->d_grad);
     BANN_LAUNCHED();
-    k_gather_rss<<<((unsigned)net->B + 255) / 256, 256, 0, st>>>(net->d_gsum, net->pstride, net->d_descs, (uint32_t)net->B,
-                                                                 net->d_scratchB);
-    BANN_LAUNCHED();
-    BANN_CUDA(cudaGetLastError());
-    if (grads) BANN_CUDA(cudaMemcpyAsync(net->h_pin_b, net->d_grad, net->total_params * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (rss) BANN_CUDA(cudaMemcpyAsync(net->h_pin_b + net->total_params, net->d_scratchB, net->B * sizeof(float), cudaMemcpyDeviceToHost, st));
-    BANN_CUDA(cudaStreamSynchronize(st));
+    const bool pin_g = !grads || host_pinned(grads), pin_r = !rss || host_pinned(rss);
+    if (!net->h_pin_b && !(pin_g && pin_r)) BANN_CUDA(cudaMallocHost(&net->h_pin_b, (net->sum_params + net->B) * sizeof(float)));
     if (grads) {
-        size_t kk = 0;
-        for (uint64_t b = 0; b < net->B; ++b) {
-            const BranchDesc& d = net->descs[b];
-            memcpy(grads + kk, net->h_pin_b + d.param_off, d.P * sizeof(float));
-            kk += d.P;
-        }
+        k_arena_to_dense<<<(unsigned)net->B, 128, 0, st>>>(net->d_descs, net->d_grad, net->d_dense_out);
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaMemcpyAsync(pin_g ? grads : net->h_pin_b, net->d_dense_out, net->sum_params * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    if (rss) memcpy(rss, net->h_pin_b + net->total_params, net->B * sizeof(float));
+    if (rss) {
+        k_gather_rss<<<((unsigned)net->B + 255) / 256, 256, 0, st>>>(net->d_gsum, net->pstride, net->d_descs, (uint32_t)net->B,
+                                                                     net->d_dense_out + net->sum_params);
+        BANN_LAUNCHED();
+        BANN_CUDA(cudaMemcpyAsync(pin_r ? rss : net->h_pin_b + net->sum_params, net->d_dense_out + net->sum_params,
+                                  net->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    BANN_CUDA(cudaGetLastError());
+    BANN_CUDA(cudaStreamSynchronize(st));
+    if (grads && !pin_g) memcpy(grads, net->h_pin_b, net->sum_params * sizeof(float));
+    if (rss && !pin_r) memcpy(rss, net->h_pin_b + net->sum_params, net->B * sizeof(float));
     return 0;
+}
+
+int bann_pinned_alloc(uint64_t bytes, void** out) {
+    if (!out) BANN_FAIL("NULL argument");
+    BANN_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return 0;
+}
+void bann_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int bann_net_gradient(bann_net* net, const float* param_vecs, const float* y, float* grads, float* rss) {

@@ -556,6 +556,27 @@ def test_predict_train_and_test_store(rb, ctx):
         P.close()
 
 
+def test_net_gradient_pinned_and_pageable_host_buffers_agree(rb, ctx):
+    """bann_net_gradient copies page-locked caller buffers by DMA directly and stages pageable ones: same results,
+    heterogeneous branch sizes (dense host layout vs the 16-byte aligned device arena)."""
+    P = Problem(rb, ctx, "ridge_ard", 700, [13, 50, 7, 64], 5, 5, seed=23)
+    try:
+        pv = np.concatenate([c.param_vec() for c in P.cfgs]).astype(np.float32)
+        g0, r0 = P.net.gradient(pv, P.y)
+        pv_h, y_h = rb.pinned_empty(pv.size), rb.pinned_empty(P.n)
+        pv_h[:], y_h[:] = pv, P.y
+        out = (rb.pinned_empty(pv.size), rb.pinned_empty(len(P.cfgs)))
+        g1, r1 = P.net.gradient(pv_h, y_h, out=out)
+        assert g1 is out[0] and np.array_equal(g0, g1) and np.array_equal(r0, r1)
+        off = 0
+        for b, c in enumerate(P.cfgs):                      # and both equal the per-branch entry point
+            one = P.net.branch_fwd_bwd(b)
+            assert np.array_equal(one["ldg"], g1[off:off + c.num_params]) and one["rss"] == r1[b]
+            off += c.num_params
+    finally:
+        P.close()
+
+
 # ------------------------------------------------------------------ full network (grouped schedule)
 def test_net_gradient_matches_per_branch(rb, ctx):
     P = Problem(rb, ctx, "ridge_ard", 900, [50, 50, 50, 13, 50], 5, 5, seed=2)
