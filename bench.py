@@ -33,6 +33,10 @@ WORKLOADS = {
                  n=10000, B=1000, per=500, widths=[5, 5, 1], model="ridge_ard"),
     "cfg3": dict(desc="configs[2] biobank: 100k individuals x 10000 branches x 50 markers (500k markers), "
                       "widths [5,5,1], RidgeARD", n=100000, B=10000, per=50, widths=[5, 5, 1], model="ridge_ard"),
+    "cfg4": dict(desc="configs[3] wide branches: 50k individuals x 2000 branches x 1000 markers, widths [16,16,16,1], RidgeARD",
+                 n=50000, B=2000, per=1000, widths=[16, 16, 16, 1], model="ridge_ard"),
+    "cfg4s": dict(desc="configs[3] at 1/20 of the branches (smoke size)", n=50000, B=100, per=1000, widths=[16, 16, 16, 1],
+                  model="ridge_ard"),
     "cfg3s": dict(desc="configs[2] at 1/10 of the branches (smoke size)", n=100000, B=1000, per=50, widths=[5, 5, 1],
                   model="ridge_ard"),
 }
