@@ -207,6 +207,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs to stdout by default: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream().cuda_stream
     ctx = rb.Context(local, stream=stream, rank=rank, world=world)
