@@ -296,7 +296,7 @@ static int build_from_device_payload(bann_ctx* ctx, uint8_t* d_payload /* consum
     g->nst = (uint32_t)((n + 255) / 256);
     g->tc_off.assign(num_branches, 0);
     bool tc_ok = true;
-    for (uint64_t b = 0; b < num_branches; ++b) tc_ok = tc_ok && g->m_b[b] <= 512;
+    for (uint64_t b = 0; b < num_branches; ++b) tc_ok = tc_ok && g->m_b[b] <= 2048;   // kTcxMaxMarkers (k1_tcx.cuh)
     g->tc_bytes = 0;
     if (tc_ok) {
         for (uint64_t b = 0; b < num_branches; ++b) {

@@ -10,6 +10,7 @@
 #include "k1_small.cuh"
 #include "k1_tc.cuh"
 #include "k1_tc_wide.cuh"
+#include "k1_tcx.cuh"
 #include "store.cuh"
 
 using namespace bann;
@@ -60,6 +61,8 @@ struct bann_net {
     // injected momenta / step uniforms (maxP + maxQ each), accept uniform + kinetic energy + 3 outputs
     uint32_t maxQ = 0;
     float* d_jws = nullptr;
+    float* d_tcx[3] = {nullptr, nullptr, nullptr};   // k1_tcx.cuh work buffers
+    size_t tcx_cap[3] = {0, 0, 0};
 };
 
 static int ensure_cap(float** p, size_t* cap, size_t need) {
@@ -169,8 +172,13 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
                               L.fwd_only ? nullptr : &part, net);
             if (r != 0) return r;
         }
+        if (!launched) {   // wide first layers (up to 16 units) / more markers: the three-pass variant
+            r = launch_k1_tcx(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched, &nchunk,
+                              L.fwd_only ? nullptr : &part, net);
+            if (r != 0) return r;
+        }
         if (!launched && net->k1_mode == BANN_K1_TENSOR)
-            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (tanh, <= 512 markers, 3 * width <= 16)");
+            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (tanh, homogeneous architecture, widths in the instantiated set)");
     }
     if (!launched && net->k1_mode != BANN_K1_GENERIC) {
         int r = launch_k1_small(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
@@ -200,6 +208,13 @@ float* bann_net_partials(bann_net* net, size_t need) {
     return net->d_part;
 }
 float* bann_net_gsum(bann_net* net) { return net->d_gsum; }
+// work buffers of the three-pass wide kernel (k1_tcx.cuh): 0 = W' pieces, 1 = first-layer activations, 2 = delta pieces
+namespace bann {
+float* bann_net_tcx_buffer(bann_net* net, int which, size_t bytes) {
+    if (ensure_cap(&net->d_tcx[which], &net->tcx_cap[which], (bytes + 3) / 4 + 64) != 0) return nullptr;
+    return net->d_tcx[which];
+}
+}  // namespace bann
 uint32_t bann_net_pstride(bann_net* net) { return net->pstride; }
 
 // gradient under the prior without touching the HMC state (log_density_gradient, a8)
@@ -953,6 +968,7 @@ void bann_net_destroy(bann_net* net) {
     cudaFree(net->d_ow_others); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
     cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj);
     cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
+    for (int i = 0; i < 3; ++i) cudaFree(net->d_tcx[i]);
     if (net->h_pin_a) cudaFreeHost(net->h_pin_a);
     if (net->h_pin_b) cudaFreeHost(net->h_pin_b);
     delete net;
