@@ -26,9 +26,10 @@ struct TcxShape {
     static constexpr uint32_t WBLK = kTcwBlockChunks * NN * 16;          // bytes of W' pieces per marker block
     static constexpr uint32_t SLOT = kTcwBlockChunks * 512 + WBLK;       // ring slot: packed words + W' pieces of one block
     static constexpr uint32_t DP_ST = NQ * kTcChunkStride;               // delta pieces of one super-tile
-    static constexpr size_t SMEM_A = 2 * (size_t)kTcwBlockBytes + kTcxRing * (size_t)SLOT + 256 + 128;
+    static constexpr uint32_t RING_A = 8;                                // KA ring slots (its operand buffers are in tensor memory)
+    static constexpr size_t SMEM_A = RING_A * (size_t)SLOT + 256 + 128;
     static constexpr size_t SMEM_B = 2 * (size_t)kTcwBlockBytes + kTcxRing * (size_t)kTcwBlockChunks * 512 + DP_ST + 512 + 128;
-    static constexpr int TMEM_A = 128;                                   // 2 x NN <= 96
+    static constexpr int TMEM_A = 256;                                   // 2 x NN accumulators + 2 x 2 x 32 operand columns <= 224
     static constexpr int TMEM_B = 256;                                   // kTcxSlabBlocks x NN <= 192
 };
 
@@ -123,10 +124,16 @@ __device__ __forceinline__ void tcx_expand(const uint32_t* src, uint8_t* rowA, u
 }
 
 // ------------------------------------------------------------------ KA: a_0 = tanh(X W' + b')
+// The forward A operand lives in TENSOR MEMORY (lanes = rows, 32-bit columns = marker pairs, as in k1_tc): the expansion is a
+// tcgen05.st per 8 markers and row, no shared-memory operand image, no proxy fence.  Shared memory only holds the ring of
+// (packed words | W' pieces) per marker block, 8 slots deep; a slot is reloaded once the MMAs that read its W' pieces are done.
+// Warps 0-3 expand (one row pair per thread) and run the epilogue; warp 4 only requests the ring loads and issues the MMAs, so that
+// the ~40 clk per tcgen05.mma of the issuing lane never sits on the expansion's critical path.
 template <int W0>
-__global__ void __launch_bounds__(128, 2) k_tcx_fwd(TcxArgs a) {
+__global__ void __launch_bounds__(160, 2) k_tcx_fwd(TcxArgs a) {
     using X = TcxShape<W0>;
     constexpr int NN = X::NN;
+    constexpr uint32_t RING = X::RING_A;
     extern __shared__ __align__(16) uint8_t smraw[];
     const uint32_t tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
@@ -134,18 +141,17 @@ __global__ void __launch_bounds__(128, 2) k_tcx_fwd(TcxArgs a) {
     if (a.k.states && a.k.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = a.k.descs[b];
     const uint32_t NC = d.nc, NKB = (NC + kTcwBlockChunks - 1) / kTcwBlockChunks;
-    uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // 2 operand buffers
-    uint8_t* sR = sA + 2 * kTcwBlockBytes;                                  // ring: [slot][words 4 KB | W' pieces]
-    float* b0s = reinterpret_cast<float*>(sR + kTcxRing * X::SLOT);         // [W0]
+    uint8_t* sR = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // ring: [slot][words 4 KB | W' pieces]
+    float* b0s = reinterpret_cast<float*>(sR + RING * X::SLOT);             // [W0]
     // mbarriers: [0..1] MMAs that read operand buffer 0/1 (and their ring slot) done; [2..3] buffer expanded (128 arrivals);
-    //            [4..7] ring slot landed
+    //            [4..4+RING) ring slot landed
     uint64_t* mbar = reinterpret_cast<uint64_t*>(b0s + 16);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4 + RING);
     const uint8_t* wp_g = a.wp + (size_t)li * a.wp_stride;
     if (tid == 0) {
         umma::mbar_init(&mbar[0], 1); umma::mbar_init(&mbar[1], 1);
         umma::mbar_init(&mbar[2], 128); umma::mbar_init(&mbar[3], 128);
-        for (int k = 0; k < (int)kTcxRing; ++k) umma::mbar_init(&mbar[4 + k], 1);
+        for (int k = 0; k < (int)RING; ++k) umma::mbar_init(&mbar[4 + k], 1);
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, X::TMEM_A);
@@ -155,9 +161,10 @@ __global__ void __launch_bounds__(128, 2) k_tcx_fwd(TcxArgs a) {
     umma::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tlane = tmem + ((warp * 32u) << 16);
-    const uint32_t sA_u = umma::smem_u32(sA), sR_u = umma::smem_u32(sR);
+    // tensor memory: accumulators [0, 2 NN); operand buffer p, row half h at columns 2 NN + 64 p + 32 h (4 columns per chunk)
+    const uint32_t tA = 2 * NN;
+    const uint32_t sR_u = umma::smem_u32(sR);
     constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
-    const uint64_t dA_f = umma::make_desc(sA_u, kTcChunkStride, 128);
 
     const uint32_t t_begin = chunk * a.k.st_per_chunk;
     const uint32_t t_end = min(a.k.nst, t_begin + a.k.st_per_chunk);
@@ -167,50 +174,73 @@ __global__ void __launch_bounds__(128, 2) k_tcx_fwd(TcxArgs a) {
     auto chunks_of = [&](uint32_t kb) { return min((uint32_t)kTcwBlockChunks, NC - kb * kTcwBlockChunks); };
     auto issue_load = [&](uint32_t q, uint32_t it, uint32_t kb) {   // whole issuer warp enters
         if (umma::elect_one()) {
-            uint8_t* slot = sR + (q % kTcxRing) * X::SLOT;
+            uint8_t* slot = sR + (q % RING) * X::SLOT;
             const uint32_t wb = chunks_of(kb) * 512u;
-            umma::expect_tx(&mbar[4 + (q % kTcxRing)], wb + X::WBLK);
-            umma::bulk_copy(slot, gwords + ((size_t)(t_begin + it) * NC + kb * kTcwBlockChunks) * 128, wb, &mbar[4 + (q % kTcxRing)]);
-            umma::bulk_copy(slot + kTcwBlockChunks * 512, wp_g + (size_t)kb * X::WBLK, X::WBLK, &mbar[4 + (q % kTcxRing)]);
+            umma::expect_tx(&mbar[4 + (q % RING)], wb + X::WBLK);
+            umma::bulk_copy(slot, gwords + ((size_t)(t_begin + it) * NC + kb * kTcwBlockChunks) * 128, wb, &mbar[4 + (q % RING)]);
+            umma::bulk_copy(slot + kTcwBlockChunks * 512, wp_g + (size_t)kb * X::WBLK, X::WBLK, &mbar[4 + (q % RING)]);
         }
         __syncwarp();
     };
-    // stream position of the next load (issuer warp): block q + 2 is requested while block q is expanded
+    // stream position of the next load (issuer warp): block q + RING - 2 is requested while block q is expanded
     uint32_t l_it = 0, l_kb = 0, lq = 0;
     auto advance_l = [&]() { if (++l_kb == NKB) { l_kb = 0; ++l_it; } ++lq; };
-    if (warp == 0)
-        for (; lq < 2 && lq < nblk;) { issue_load(lq, l_it, l_kb); advance_l(); }
     float* a0_g = a.a0 + (size_t)li * a.a0_stride;
+    if (warp == 4) {                 // ---- issuer warp
+        for (; lq < RING - 2 && lq < nblk;) { issue_load(lq, l_it, l_kb); advance_l(); }
+        uint32_t kb = 0;
+        for (uint32_t q = 0; q < nblk; ++q) {
+            const uint32_t buf = q & 1u, nch = chunks_of(kb);
+            if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);     // MMAs of block q - 2 done: their ring slot is free
+            if (lq < nblk) { issue_load(lq, l_it, l_kb); advance_l(); }
+            umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);                   // block q expanded by all 128 threads
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                const uint32_t nks = (nch + 1) >> 1;
+                const uint64_t wbase = umma::make_desc(sR_u + (q % RING) * X::SLOT + kTcwBlockChunks * 512, NN * 16, 128);
+#pragma unroll
+                for (uint32_t h = 0; h < 2; ++h)
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks)
+                        if (ks < nks)
+                            umma::mma_f16_ts(tmem + h * NN, tmem + tA + buf * 64u + h * 32u + ks * 8u,
+                                             wbase + ((ks * 2u * (NN * 16)) >> 4), idesc_f, (kb | ks) != 0);
+                umma::commit(&mbar[buf]);
+            }
+            __syncwarp();
+            if (++kb == NKB) kb = 0;
+        }
+        if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
+        if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
+        umma::fence_before_sync();
+        __syncthreads();
+        return;
+    }
 
     uint32_t q = 0;
     for (uint32_t it = 0; it < nit; ++it) {
         const uint32_t st = t_begin + it;
         for (uint32_t kb = 0; kb < NKB; ++kb, ++q) {
             const uint32_t buf = q & 1u, nch = chunks_of(kb);
-            if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);     // MMAs of block q - 2 done: buffer and ring slot (q + 2) % 4 free
-            if (warp == 0 && lq < nblk) { issue_load(lq, l_it, l_kb); advance_l(); }
-            umma::mbar_wait(&mbar[4 + (q % kTcxRing)], (q / kTcxRing) & 1u);
-            tcx_expand(reinterpret_cast<const uint32_t*>(sR + (q % kTcxRing) * X::SLOT) + tid, sA + buf * kTcwBlockBytes + tid * 16, nch);
-            umma::fence_async_smem();
-            umma::mbar_arrive(&mbar[2 + buf]);
-            if (warp == 0) {
-                umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);
+            if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);     // MMAs of block q - 2 done: operand buffer free
+            umma::mbar_wait(&mbar[4 + (q % RING)], (q / RING) & 1u);
+            {
                 umma::fence_after_sync();
-                if (umma::elect_one()) {
-                    const uint32_t nks = (nch + 1) >> 1;
-                    const uint64_t base = dA_f + ((buf * kTcwBlockBytes) >> 4);
-                    const uint64_t wbase = umma::make_desc(sR_u + (q % kTcxRing) * X::SLOT + kTcwBlockChunks * 512, NN * 16, 128);
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(sR + (q % RING) * X::SLOT) + tid;
+                uint32_t x[kTcwBlockChunks];
 #pragma unroll
-                    for (uint32_t h = 0; h < 2; ++h)
+                for (int i = 0; i < kTcwBlockChunks; ++i) x[i] = (uint32_t)i < nch ? src[i * 128] : 0u;
+                const uint32_t ta = tlane + tA + buf * 64u;
 #pragma unroll
-                        for (uint32_t ks = 0; ks < 4; ++ks)
-                            if (ks < nks)
-                                umma::mma_f16(tmem + h * NN, base + ((h * 2048u + ks * 2u * kTcChunkStride) >> 4),
-                                              wbase + ((ks * 2u * (NN * 16)) >> 4), idesc_f, (kb | ks) != 0);
-                    umma::commit(&mbar[buf]);
+                for (int i = 0; i < kTcwBlockChunks; ++i) {
+                    const uint32_t y = x[i] >> 8;
+                    umma::tmem_st4(ta + 4 * i, x[i] & 0x00030003u, x[i] & 0x000C000Cu, x[i] & 0x00300030u, x[i] & 0x00C000C0u);
+                    umma::tmem_st4(ta + 32 + 4 * i, y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
                 }
-                __syncwarp();
+                umma::tmem_st_wait();
+                umma::fence_before_sync();
             }
+            umma::mbar_arrive(&mbar[2 + buf]);
         }
         // z0 complete when the MMAs of the last block are (commits complete in issue order)
         umma::mbar_wait(&mbar[(q - 1) & 1u], ((q - 1) >> 1) & 1u);
@@ -219,8 +249,7 @@ __global__ void __launch_bounds__(128, 2) k_tcx_fwd(TcxArgs a) {
 #pragma unroll
         for (uint32_t h = 0; h < 2; ++h) {
             const uint32_t tb = tlane + h * NN;
-            // n = piece * W0 + c: read 3 W0 consecutive columns in 16-column loads
-            float v[NN];
+            float v[NN];                 // n = piece * W0 + c
 #pragma unroll
             for (int g = 0; g < NN / 16; ++g) umma::tmem_ld16(tb + 16 * g, v + 16 * g);
             const uint32_t row = h ? rowB_g : rowA_g;
@@ -508,8 +537,9 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
 }
 
 // ------------------------------------------------------------------ KB: S = X^T delta_0 for one slab of 4 marker blocks
+// Warps 0-3 expand and run the epilogue, warp 4 requests the loads and issues the MMAs (as in KA).
 template <int W0>
-__global__ void __launch_bounds__(128, 2) k_tcx_bwd(TcxArgs a) {
+__global__ void __launch_bounds__(160, 2) k_tcx_bwd(TcxArgs a) {
     using X = TcxShape<W0>;
     constexpr int NN = X::NN;
     extern __shared__ __align__(16) uint8_t smraw[];
@@ -570,29 +600,22 @@ __global__ void __launch_bounds__(128, 2) k_tcx_bwd(TcxArgs a) {
     };
     uint32_t l_it = 0, l_kb = 0, lq = 0;
     auto advance_l = [&]() { if (++l_kb == nkb) { l_kb = 0; ++l_it; } ++lq; };
-    if (warp == 0) {
+    if (warp == 4) {                 // ---- issuer warp
         for (; lq < kTcxRing && lq < nblk;) { issue_load(lq, l_it, l_kb); advance_l(); }
         if (nit > 0) issue_dp(0);
-    }
-    uint32_t q = 0;
-    for (uint32_t it = 0; it < nit; ++it) {
-        if (it > 0) {
-            // the delta buffer is read by the MMAs of the previous super-tile: all of them must be complete before the reload
-            umma::mbar_wait(&mbar[(q - 1) & 1u], ((q - 1) >> 1) & 1u);
-            if (q >= 2) umma::mbar_wait(&mbar[(q - 2) & 1u], ((q - 2) >> 1) & 1u);
-            if (warp == 0) issue_dp(it);
-        }
-        for (uint32_t kbl = 0; kbl < nkb; ++kbl, ++q) {
-            const uint32_t buf = q & 1u, nch = chunks_of(kb0 + kbl);
-            umma::mbar_wait(&mbar[4 + (q % kTcxRing)], (q / kTcxRing) & 1u);
-            const uint32_t* src = sG + (q % kTcxRing) * (kTcwBlockChunks * 128) + tid;
-            if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);
-            tcx_expand(src, sA + buf * kTcwBlockBytes + tid * 16, nch);
-            umma::fence_async_smem();
-            umma::mbar_arrive(&mbar[2 + buf]);
-            if (warp == 0) {
-                umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);
-                if (kbl == 0) umma::mbar_wait(&mbar[8], it & 1u);            // delta pieces of this super-tile
+        uint32_t q = 0;
+        for (uint32_t it = 0; it < nit; ++it) {
+            if (it > 0) {
+                // the delta buffer is read by the MMAs of the previous super-tile: all of them must be complete before the reload
+                umma::mbar_wait(&mbar[(q - 1) & 1u], ((q - 1) >> 1) & 1u);
+                if (q >= 2) umma::mbar_wait(&mbar[(q - 2) & 1u], ((q - 2) >> 1) & 1u);
+                issue_dp(it);
+            }
+            for (uint32_t kbl = 0; kbl < nkb; ++kbl, ++q) {
+                const uint32_t buf = q & 1u;
+                umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);               // block q expanded by all 128 threads
+                if (lq < nblk) { issue_load(lq, l_it, l_kb); advance_l(); }   // every thread has consumed ring slot q % 4
+                if (kbl == 0) umma::mbar_wait(&mbar[8], it & 1u);             // delta pieces of this super-tile
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
                     const uint64_t base = dA_b + ((buf * kTcwBlockBytes) >> 4);
@@ -602,9 +625,24 @@ __global__ void __launch_bounds__(128, 2) k_tcx_bwd(TcxArgs a) {
                     umma::commit(&mbar[buf]);
                 }
                 __syncwarp();
-                if (lq < nblk) { issue_load(lq, l_it, l_kb); advance_l(); }   // every thread has consumed ring slot q % 4
             }
         }
+        if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
+        if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
+        umma::fence_before_sync();
+        __syncthreads();
+        return;
+    }
+    for (uint32_t q = 0; q < nblk; ++q) {
+        const uint32_t buf = q & 1u;
+        const uint32_t kbl = q % nkb;
+        const uint32_t nch = chunks_of(kb0 + kbl);
+        umma::mbar_wait(&mbar[4 + (q % kTcxRing)], (q / kTcxRing) & 1u);
+        const uint32_t* src = sG + (q % kTcxRing) * (kTcwBlockChunks * 128) + tid;
+        if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);         // MMAs of block q - 2 done: operand buffer free
+        tcx_expand(src, sA + buf * kTcwBlockBytes + tid * 16, nch);
+        umma::fence_async_smem();
+        umma::mbar_arrive(&mbar[2 + buf]);
     }
     if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
     if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
@@ -654,13 +692,13 @@ int launch_one_tcx(TcxArgs& a, uint32_t nlist, uint32_t nslab, bool bwd, cudaStr
     k_tcx_prep<T::W0><<<nlist, 128, 0, st>>>(a);
     BANN_LAUNCHED();
     dim3 grid(a.k.nchunk, nlist);
-    k_tcx_fwd<T::W0><<<grid, 128, X::SMEM_A, st>>>(a);
+    k_tcx_fwd<T::W0><<<grid, 160, X::SMEM_A, st>>>(a);
     BANN_LAUNCHED();
     k_tcx_tail<H, S, D><<<grid, 128, smem_t, st>>>(a);
     BANN_LAUNCHED();
     if (bwd) {
         dim3 gridb(a.k.nchunk, nlist, nslab);
-        k_tcx_bwd<T::W0><<<gridb, 128, X::SMEM_B, st>>>(a);
+        k_tcx_bwd<T::W0><<<gridb, 160, X::SMEM_B, st>>>(a);
         BANN_LAUNCHED();
     }
     BANN_CUDA(cudaGetLastError());
