@@ -291,7 +291,8 @@ int  bann_allreduce_buffer(bann_net*, void** dev_ptr, uint64_t* num_floats);
 /* test hook: route every K1 launch through the shape-agnostic kernel (cross-checks the tuned one) */
 int  bann_net_force_generic(bann_net*, int on);
 /* test / profiling hook: which fused forward+backward kernel launches may use.  AUTO tries the tensor-core
- * kernels (tcgen05; <= 64 markers per branch, or K-blocked up to 512), then the FFMA kernel, then the shape-agnostic one. */
+ * kernels (tcgen05: <= 64 markers per branch; K-blocked up to 512; the three-pass wide variant for first-layer widths up
+ * to 16 and up to 2048 markers), then the FFMA kernel, then the shape-agnostic one. */
 enum { BANN_K1_AUTO = 0, BANN_K1_TENSOR = 1, BANN_K1_FFMA = 2, BANN_K1_GENERIC = 3 };
 int  bann_net_select_k1(bann_net*, int which);
 

@@ -40,7 +40,7 @@ struct bann_genotypes {
     std::vector<uint32_t> m_b, m_pad4;
     std::vector<uint64_t> tile_off, col_off;
     uint8_t* d_store = nullptr;
-    // tensor-core store (only when every branch has <= 512 markers): per branch, per 256-row super-tile,
+    // tensor-core store (only when every branch has <= 2048 markers): per branch, per 256-row super-tile,
     // [ceil(m/8) chunks][128 row pairs] 32-bit words, see k_build_tc
     uint32_t* d_store_tc = nullptr;
     uint32_t nst = 0;            // super-tiles of 256 rows
