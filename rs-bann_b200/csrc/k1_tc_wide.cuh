@@ -33,8 +33,13 @@ struct TcwShape {
     static constexpr size_t SMEM = 2 * (size_t)kTcwBlockBytes + kTcwRing * (size_t)kTcwBlockChunks * 512 + C::SD + SW + C::MISC + 128 + 128;
 };
 
+#ifndef BANN_TCW_ISSUER_WARP
+#define BANN_TCW_ISSUER_WARP 1    // 1: a fifth warp requests the ring loads and issues the MMAs (measured on cfg2)
+#endif
+constexpr int kTcwThreads = BANN_TCW_ISSUER_WARP ? 160 : 128;
+
 template <int H, int S, int D, bool LEAN>
-__global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
+__global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
     using CW = TcwShape<H, S, D>;
@@ -46,7 +51,7 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
     if (a.states && a.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = a.descs[b];
     const uint32_t m = d.m, NC = d.nc, NKB = (NC + kTcwBlockChunks - 1) / kTcwBlockChunks;
-    const uint32_t issuer = 0;
+    const uint32_t issuer = BANN_TCW_ISSUER_WARP ? 4 : 0;
     // ---- shared memory carve-up
     uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);       // 2 operand buffers of 8 chunks
     uint32_t* sG = reinterpret_cast<uint32_t*>(sA + 2 * kTcwBlockBytes);           // ring: [slot][chunk][128] packed words
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
     // ---- one-time setup
     {
         const uint32_t nz = (uint32_t)((sW + CW::SW - sA) / 16);
-        for (uint32_t k = tid; k < nz; k += 128) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
+        for (uint32_t k = tid; k < nz; k += kTcwThreads) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
         umma::mbar_init(&mbar[0], 1); umma::mbar_init(&mbar[1], 1);
@@ -76,7 +81,7 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, CW::TMEM_COLS);
-    for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += 128) {
+    for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += kTcwThreads) {
         const float w = th[m * W0 + k];
         wp2[k] = make_float2(w, w);
     }
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
     float bacc[W0];
 #pragma unroll
     for (int c = 0; c < W0; ++c) bacc[c] = 0.f;
-    for (uint32_t j = tid; j < m; j += 128) {
+    for (uint32_t j = tid; j < m && tid < 128; j += 128) {
 #pragma unroll
         for (int c = 0; c < W0; ++c) {
             const float w = __fdiv_rn(th[c * m + j], sd[j]);
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
         float v = bacc[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[warp * W0 + c] = v;
+        if (lane == 0 && warp < 4) red[warp * W0 + c] = v;
     }
     __syncthreads();
     if (tid < W0P) {
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
             }
         umma::fence_async_smem();
         umma::mbar_arrive(&mbar[2 + buf]);
-        if (warp == issuer) {
+        if (!BANN_TCW_ISSUER_WARP && warp == issuer) {
             umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);
             issue_mma(q, pos);
             if (lq < nblk) { issue_load(lq, lpos); ++lq; advance(lpos); }   // every thread has consumed ring slot q % 4
@@ -232,6 +237,22 @@ __global__ void __launch_bounds__(128, 2) k1_tcw(K1Args a) {
     if (warp == issuer)
         for (; lq < kTcwRing && lq < nblk; ++lq) { issue_load(lq, lpos); advance(lpos); }
 
+    if (BANN_TCW_ISSUER_WARP && warp == issuer) {
+        // ---- issuing warp: the whole block stream in order -- wait "expanded" (128 arrivals: also publishes the delta pieces
+        // written before a backward pass), issue the MMAs, recycle the ring slot every thread has consumed
+        for (uint32_t qq = 0; qq < nblk; ++qq) {
+            umma::mbar_wait(&mbar[2 + (qq & 1u)], (qq >> 1) & 1u);
+            issue_mma(qq, pos);
+            if (lq < nblk) { issue_load(lq, lpos); ++lq; advance(lpos); }
+            advance(pos);
+        }
+        if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
+        if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
+        umma::fence_before_sync();
+        __syncthreads();                       // the compute warps' exits below: one barrier without an epilogue, three with it
+        if (bwd && a.part) { __syncthreads(); __syncthreads(); }
+        return;
+    }
     uint32_t q = 0;
     for (uint32_t it = 0; it < nit; ++it) {
         const uint32_t st = t_begin + it;
@@ -447,8 +468,8 @@ int launch_one_tcw(K1Args& a, uint32_t nlist, cudaStream_t st) {
     }
     dim3 grid(a.nchunk, nlist);
     const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
-    if (lean) k1_tcw<H, S, D, true><<<grid, 128, CW::SMEM, st>>>(a);
-    else k1_tcw<H, S, D, false><<<grid, 128, CW::SMEM, st>>>(a);
+    if (lean) k1_tcw<H, S, D, true><<<grid, kTcwThreads, CW::SMEM, st>>>(a);
+    else k1_tcw<H, S, D, false><<<grid, kTcwThreads, CW::SMEM, st>>>(a);
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
