@@ -233,6 +233,12 @@ int  bann_gibbs_branch(bann_net*, uint64_t b, const bann_mcmc_cfg*, const bann_r
 /* one iteration of the inner loop of Net::train (net/net.rs:258-334): globals -> cfg, Gibbs,
  * prev_pred, HMC against residual + prev_pred, residual / LPD / globals / output-bias update. */
 int  bann_visit_branch(bann_net*, uint64_t b, const bann_mcmc_cfg*, const bann_rng_inject*, bann_hmc_result* out);
+/* the same with the built-in RNG keyed by `seed` and the per-step trajectory of the visit's HMC transition recorded
+ * (net/branch/trajectory.rs:4-43, the `traj` file of --trajectories): params L * P_b, ldg L * P_b, hamiltonian L + 1; with
+ * cfg->joint_hmc also precisions L * Q_b and ldg L * (P_b + Q_b).  Rows after an early rejection stay zero (out->steps_done
+ * tells how many are valid).  The ascent modes record nothing. */
+int  bann_visit_branch_traj(bann_net*, uint64_t b, const bann_mcmc_cfg*, uint64_t seed, bann_hmc_result* out,
+                            bann_trajectory_joint* traj);
 /* a full pass over `branch_order` (sequential-exact schedule, group_size must be 1 in this
  * release) with the built-in RNG keyed by seed; asynchronous, one sync at the end. */
 int  bann_sweep(bann_net*, const bann_mcmc_cfg*, const uint64_t* branch_order, uint64_t num, uint32_t group_size,

@@ -111,6 +111,7 @@ PROTOTYPES = {
     "bann_gradient_descent_joint": (C.c_int, [_vp, _u64, _fp, C.POINTER(McmcCfg), C.POINTER(HmcResult), _fp]),
     "bann_gibbs_branch": (C.c_int, [_vp, _u64, C.POINTER(McmcCfg), C.POINTER(RngInject)]),
     "bann_visit_branch": (C.c_int, [_vp, _u64, C.POINTER(McmcCfg), C.POINTER(RngInject), C.POINTER(HmcResult)]),
+    "bann_visit_branch_traj": (C.c_int, [_vp, _u64, C.POINTER(McmcCfg), _u64, C.POINTER(HmcResult), C.POINTER(TrajectoryJoint)]),
     "bann_sweep": (C.c_int, [_vp, C.POINTER(McmcCfg), C.POINTER(_u64), _u64, C.c_uint32, _u64,
                               C.POINTER(SweepStats)]),
     "bann_predict": (C.c_int, [_vp, _vp, _fp]),

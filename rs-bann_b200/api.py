@@ -469,6 +469,25 @@ class Net:
         return HMCStepResult(res.status, res.log_density, res.neg_h_init, res.neg_h_final, res.steps_done,
                              res.u_turn_step)
 
+    def visit_branch_traj(self, b, cfg: MCMCCfg, seed: int = 0) -> HMCStepResult:
+        """One visit with the built-in RNG and the trajectory of its HMC transition (trajectory.rs:4-43): `trajectory` holds
+        only the steps that ran (params / ldg / hamiltonian, plus precisions in the joint mode)."""
+        (P, Q), L = self._sizes[b], cfg.hmc_integration_length
+        jt = cfg.joint_hmc and not (cfg.gradient_descent or cfg.gradient_descent_joint)
+        Q = Q if jt else 0
+        res = _lib.HmcResult()
+        traj = _lib.TrajectoryJoint()
+        tp = np.zeros(L * P, dtype=np.float32); tq = np.zeros(max(L * Q, 1), dtype=np.float32)
+        tl = np.zeros(L * (P + Q), dtype=np.float32); th = np.zeros(L + 1, dtype=np.float32)
+        traj.params, traj.precisions, traj.ldg, traj.hamiltonian = _ptr(tp), _ptr(tq), _ptr(tl), _ptr(th)
+        c = cfg.c()
+        check(lib.bann_visit_branch_traj(self.h, b, C.byref(c), seed, C.byref(res), C.byref(traj)))
+        n = 0 if (cfg.gradient_descent or cfg.gradient_descent_joint) else min(res.steps_done, L)
+        out = HMCStepResult(res.status, res.log_density, res.neg_h_init, res.neg_h_final, res.steps_done, res.u_turn_step)
+        out.trajectory = dict(params=tp.reshape(L, P)[:n], precisions=tq[:L * Q].reshape(L, Q)[:n] if Q else np.zeros((0, 0), np.float32),
+                              ldg=tl.reshape(L, P + Q)[:n], hamiltonian=th[:n + 1])
+        return out
+
     def sweep(self, cfg: MCMCCfg, order, seed: int = 0):
         order = np.ascontiguousarray(order, dtype=np.uint64)
         st = _lib.SweepStats()

@@ -86,7 +86,7 @@ def add_mcmc(p):
 
 
 def _check_supported(a):
-    for flag in ("trajectories", "num_grad_traj", "num_grad"):
+    for flag in ("num_grad_traj", "num_grad"):
         if getattr(a, flag):
             sys.exit(f"rs-bann (B200 build): --{flag.replace('_', '-')} is outside the hot path built so far (SURVEY 8f-4)")
 
@@ -213,6 +213,7 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
     seed = _bcast_int(a.seed if a.seed is not None else int.from_bytes(os.urandom(4), "little"), world)
     rng = np.random.default_rng(seed)
     trace = open(os.path.join(outdir, "trace"), "w") if (a.trace and lead) else None
+    traj_file = open(os.path.join(outdir, "traj"), "a") if (a.trajectories and lead) else None   # mcmc_cfg.rs:247-249, appended
 
     def record_perf(st):                                                          # net.rs:597-610
         nf.lpd.append(float(st["lpd"]))
@@ -252,7 +253,18 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
         save_model(0)
     for chain_ix in range(1, a.chain_length + 1):
         order = rng.permutation(net.num_branches)                                 # net.rs:257
-        st = net.sweep(cfg, order, seed=seed + chain_ix)
+        if a.trajectories:                                                        # branch_sampler.rs:1198-1207,1286-1289: one JSON line per transition
+            for b in order:
+                res = net.visit_branch_traj(int(b), cfg, seed=seed + chain_ix)
+                if traj_file is not None:
+                    t = res.trajectory
+                    traj_file.write(json.dumps(dict(params=[[float(v) for v in r] for r in t["params"]],
+                                                    precisions=[[float(v) for v in r] for r in t["precisions"]],
+                                                    ldg=[[float(v) for v in r] for r in t["ldg"]], num_ldg=[],
+                                                    hamiltonian=[float(v) for v in t["hamiltonian"]])) + "\n")
+            st = net.stats()
+        else:
+            st = net.sweep(cfg, order, seed=seed + chain_ix)
         record_perf(st)
         if chain_ix >= burn_in:
             save_model(chain_ix)
@@ -266,6 +278,8 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
             json.dump(nf.training_stats_json(), f)
         if trace:
             trace.close()
+        if traj_file:
+            traj_file.close()
         print("Completed training", file=sys.stderr)
     net.close(); gen.close()
     if test is not None:

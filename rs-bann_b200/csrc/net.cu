@@ -710,10 +710,15 @@ static int check_error_flag(bann_net* net) {
 }
 
 // one iteration of the inner loop of Net::train, fully asynchronous
-static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj, uint64_t seed) {
+struct VisitTraj {   // device buffers of one visit's trajectory (trajectory.rs:4-43), all optional
+    float *params = nullptr, *prec = nullptr, *ldg = nullptr, *h = nullptr;
+};
+static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj, uint64_t seed,
+                       const VisitTraj* vt = nullptr) {
     cudaStream_t st = net->ctx->stream;
     BANN_CHECK(need_comm(net));
     HmcRun R;
+    if (vt) { R.traj_params = vt->params; R.traj_ldg = vt->ldg; R.traj_h = vt->h; }
     R.list = net->d_list_all + b;
     R.nlist = 1;
     R.single_branch = (int)b;
@@ -736,6 +741,9 @@ static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, cons
         J.seed = seed;
         J.stream = net->visit_seq * net->B + b;
         J.ow_from_gibbs = true;
+        if (vt && cfg->joint_hmc && !cfg->gradient_descent && !cfg->gradient_descent_joint) {
+            J.traj_params = vt->params; J.traj_prec = vt->prec; J.traj_ldg = vt->ldg; J.traj_h = vt->h;
+        }
         if (cfg->gradient_descent) {
             BANN_CHECK(stage_inject(net, inj, net->descs[b].P, nullptr, &d_gam, &n_gam));
             BANN_CHECK(launch_gibbs(net, b, cfg, joint ? 0 : 1, d_gam, n_gam, seed, net->visit_seq * net->B + b));
@@ -1371,6 +1379,32 @@ int bann_visit_branch(bann_net* net, uint64_t b, const bann_mcmc_cfg* cfg, const
     if (!net || !cfg) BANN_FAIL("NULL argument");
     if (b >= net->B) BANN_FAIL("branch index out of range");
     BANN_CHECK(visit_async(net, (uint32_t)b, cfg, inj, 0x452821e638d01377ull));
+    if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
+    BANN_CHECK(check_error_flag(net));
+    return 0;
+}
+
+int bann_visit_branch_traj(bann_net* net, uint64_t b, const bann_mcmc_cfg* cfg, uint64_t seed, bann_hmc_result* out,
+                           bann_trajectory_joint* traj) {
+    if (!net || !cfg || !traj) BANN_FAIL("NULL argument");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[b];
+    const bool jt = cfg->joint_hmc && !cfg->gradient_descent && !cfg->gradient_descent_joint;
+    const size_t P = d.P, Q = jt ? d.nprec : 0, Ls = cfg->hmc_integration_length;
+    const size_t need = Ls * P + Ls * Q + Ls * (P + Q) + Ls + 1;
+    BANN_CHECK(ensure_cap(&net->d_traj, &net->traj_cap, need));
+    BANN_CUDA(cudaMemsetAsync(net->d_traj, 0, need * sizeof(float), st));
+    VisitTraj vt;
+    vt.params = net->d_traj;
+    vt.prec = vt.params + Ls * P;
+    vt.ldg = vt.prec + Ls * Q;
+    vt.h = vt.ldg + Ls * (P + Q);
+    BANN_CHECK(visit_async(net, (uint32_t)b, cfg, nullptr, seed, &vt));
+    if (traj->params) BANN_CUDA(cudaMemcpyAsync(traj->params, vt.params, Ls * P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (traj->precisions && Q) BANN_CUDA(cudaMemcpyAsync(traj->precisions, vt.prec, Ls * Q * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (traj->ldg) BANN_CUDA(cudaMemcpyAsync(traj->ldg, vt.ldg, Ls * (P + Q) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (traj->hamiltonian) BANN_CUDA(cudaMemcpyAsync(traj->hamiltonian, vt.h, (Ls + 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
     BANN_CHECK(check_error_flag(net));
     return 0;

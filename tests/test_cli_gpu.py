@@ -120,3 +120,31 @@ def test_train_new_flag_gated_modes(rb, tmp_path, flag, step):
         assert ts["mse_train"][-1] < ts["mse_train"][0]
     else:
         assert ts["num_accepted"] + ts["num_early_rejected"] <= ts["num_samples"]
+
+
+def test_train_new_trajectories_file(rb, tmp_path):
+    """--trajectories: one JSON line per HMC transition in <outdir>/traj (trajectory.rs:4-43, mcmc_cfg.rs:247-249), and the
+    chain itself is the one `bann_sweep` samples with the same seed."""
+    sim = run(["simulate-xy", "-o", str(tmp_path), "--seed", "4", "ridge-base", "tanh", "10", "3", "500", "3", "1", "0.5"]).strip()
+    tr = os.path.join(sim, "train")
+    common = [tr, tr + ".phen", tr + ".groups", "3", "7", "ridge-base", "tanh", "1", "--fixed-hidden-layer-width", "3",
+              "--burn-in", "0", "--step-size", "0.3", "--seed", "11"]
+    out_t = run(["train-new"] + common + ["-o", str(tmp_path / "a"), "--trajectories"]).strip()
+    out_s = run(["train-new"] + common + ["-o", str(tmp_path / "b")]).strip()
+    lines = [json.loads(l) for l in open(os.path.join(out_t, "traj"))]
+    assert len(lines) == 3 * 3                                    # chain_length x branches
+    P = 10 * 3 + 3 * 3 + 3 + 3 + 3
+    for t in lines:
+        assert set(t) == {"params", "precisions", "ldg", "num_ldg", "hamiltonian"}
+        n = len(t["params"])
+        assert 1 <= n <= 7 and len(t["hamiltonian"]) == n + 1 and len(t["ldg"]) == n
+        assert all(len(r) == P for r in t["params"]) and all(len(r) == P for r in t["ldg"])
+        assert np.all(np.isfinite(t["hamiltonian"]))
+    a = json.load(open(os.path.join(out_t, "training_stats")))
+    b = json.load(open(os.path.join(out_s, "training_stats")))
+    assert a["num_accepted"] == b["num_accepted"] and a["mse_train"] == pytest.approx(b["mse_train"], rel=1e-6)
+    # joint mode: precisions ride along
+    out_j = run(["train-new"] + common + ["-o", str(tmp_path / "c"), "--trajectories", "--joint-hmc", "--fixed-param-precision", "1.0"]).strip()
+    tj = [json.loads(l) for l in open(os.path.join(out_j, "traj"))]
+    Q = 3 + 2 + 1
+    assert len(tj) == 9 and all(len(r) == Q for t in tj for r in t["precisions"]) and all(len(r) == P + Q for t in tj for r in t["ldg"])
