@@ -6,7 +6,7 @@
 // the fused kernel of k1_tc / k1_tcw is cut into three passes over a (branch, row chunk):
 //   KA  k_tcx_fwd  : a_0 = tanh(X W' + b')          tcgen05, all marker blocks streamed once, accumulators 2 x 48 columns
 //   KT  k_tcx_tail : layers >= 1, error, deltas, cross-row sums of the layers >= 1, delta_0 as bf16 pieces   (FP32)
-//   KB  k_tcx_bwd  : S = X^T delta_0                 tcgen05, one CTA per 256-marker slab, accumulators 4 x 48 columns
+//   KB  k_tcx_bwd  : S = X^T delta_0                 tcgen05 (M = 128: two marker blocks per MMA), one CTA per 512-marker slab
 // Same operands as k1_tc: genotypes expanded to bf16 subnormals by one AND per two elements, W' and delta_0 as three bf16 pieces
 // whose sum is the f32 value (exact products, f32 accumulation).  The price of the cut is traffic: the packed genotypes are read
 // twice and a_0 (64 B per row) / the delta pieces (96 B per row) travel through HBM / L2 once.
@@ -16,7 +16,7 @@
 namespace bann {
 
 constexpr int kTcxMaxMarkers = 2048;       // tensor-core store limit (genotypes.cu)
-constexpr int kTcxSlabBlocks = 4;          // marker blocks (of 64) per KB CTA: 4 x NN accumulator columns
+constexpr int kTcxSlabPairs = 4;           // pairs of marker blocks (128 markers each) per KB CTA: 4 x NN accumulator columns
 constexpr uint32_t kTcxRing = 4;
 
 template <int W0>
@@ -28,9 +28,9 @@ struct TcxShape {
     static constexpr uint32_t DP_ST = NQ * kTcChunkStride;               // delta pieces of one super-tile
     static constexpr uint32_t RING_A = 8;                                // KA ring slots (its operand buffers are in tensor memory)
     static constexpr size_t SMEM_A = RING_A * (size_t)SLOT + 256 + 128;
-    static constexpr size_t SMEM_B = 2 * (size_t)kTcwBlockBytes + kTcxRing * (size_t)kTcwBlockChunks * 512 + DP_ST + 512 + 128;
+    static constexpr size_t SMEM_B = 2 * (size_t)kTcwBlockBytes + 2 * (size_t)(2 * kTcwBlockChunks) * 512 + DP_ST + 512 + 128;
     static constexpr int TMEM_A = 256;                                   // 2 x NN accumulators + 2 x 2 x 32 operand columns <= 224
-    static constexpr int TMEM_B = 256;                                   // kTcxSlabBlocks x NN <= 192
+    static constexpr int TMEM_B = 256;                                   // kTcxSlabPairs x NN <= 192
 };
 
 namespace umma {
@@ -536,12 +536,16 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
     }
 }
 
-// ------------------------------------------------------------------ KB: S = X^T delta_0 for one slab of 4 marker blocks
-// Warps 0-3 expand and run the epilogue, warp 4 requests the loads and issues the MMAs (as in KA).
+// ------------------------------------------------------------------ KB: S = X^T delta_0 for one slab of 512 markers
+// The unit is a PAIR of marker blocks (128 markers): one M = 128 MMA per 16 rows covers both (at M = 64 the tensor core runs at
+// half rate), its accumulator fills all 128 lanes x NN columns.  One 64 KB operand image per CTA (the second resident CTA covers
+// the MMA latency), a 2-slot ring of packed words, the delta pieces of the current super-tile.  Warps 0-3 expand and run the
+// epilogue, warp 4 requests the loads and issues the MMAs (as in KA).
 template <int W0>
 __global__ void __launch_bounds__(160, 2) k_tcx_bwd(TcxArgs a) {
     using X = TcxShape<W0>;
     constexpr int NN = X::NN;
+    constexpr uint32_t PAIR_CH = 2 * kTcwBlockChunks;                        // 16 chunks of 8 markers
     extern __shared__ __align__(16) uint8_t smraw[];
     const K1Args& k = a.k;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -549,22 +553,22 @@ __global__ void __launch_bounds__(160, 2) k_tcx_bwd(TcxArgs a) {
     const uint32_t b = k.list ? k.list[li] : li;
     if (k.states && k.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = k.descs[b];
-    const uint32_t m = d.m, NC = d.nc, NKB = (NC + kTcwBlockChunks - 1) / kTcwBlockChunks;
-    const uint32_t kb0 = slab * kTcxSlabBlocks;
-    if (kb0 >= NKB) return;
-    const uint32_t nkb = min((uint32_t)kTcxSlabBlocks, NKB - kb0);
-    uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // 2 operand buffers
-    uint32_t* sG = reinterpret_cast<uint32_t*>(sA + 2 * kTcwBlockBytes);     // ring [slot][chunk][128] packed words
-    uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + kTcxRing * kTcwBlockChunks * 512;   // delta pieces of the current super-tile
+    const uint32_t m = d.m, NC = d.nc, NP = (NC + PAIR_CH - 1) / PAIR_CH;     // pairs of the branch
+    const uint32_t p0 = slab * kTcxSlabPairs;
+    if (p0 >= NP) return;
+    const uint32_t np = min((uint32_t)kTcxSlabPairs, NP - p0);
+    uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // operand image: 16 chunks x 256 rows x 16 B
+    uint32_t* sG = reinterpret_cast<uint32_t*>(sA + 2 * kTcwBlockBytes);     // ring [2 slots][16 chunks][128] packed words
+    uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + 2 * PAIR_CH * 512;        // delta pieces of the current super-tile
     float* gb0 = reinterpret_cast<float*>(sD + X::DP_ST);                    // [W0]
-    // mbarriers: [0..1] MMAs that read operand buffer 0/1 done; [2..3] buffer expanded (128 arrivals); [4..7] ring slot landed;
+    // mbarriers: [0] MMAs that read the operand image done; [2] image expanded (128 arrivals); [4..5] ring slot landed;
     //            [8] delta pieces landed
     uint64_t* mbar = reinterpret_cast<uint64_t*>(gb0 + 16);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 10);
     if (tid == 0) {
-        umma::mbar_init(&mbar[0], 1); umma::mbar_init(&mbar[1], 1);
-        umma::mbar_init(&mbar[2], 128); umma::mbar_init(&mbar[3], 128);
-        for (int i = 0; i < (int)kTcxRing; ++i) umma::mbar_init(&mbar[4 + i], 1);
+        umma::mbar_init(&mbar[0], 1);
+        umma::mbar_init(&mbar[2], 128);
+        umma::mbar_init(&mbar[4], 1); umma::mbar_init(&mbar[5], 1);
         umma::mbar_init(&mbar[8], 1);
         umma::fence_mbar_init();
     }
@@ -577,94 +581,86 @@ __global__ void __launch_bounds__(160, 2) k_tcx_bwd(TcxArgs a) {
     const uint32_t tmem = *tmem_slot;
     const uint32_t tlane = tmem + ((warp * 32u) << 16);
     const uint32_t sA_u = umma::smem_u32(sA), sD_u = umma::smem_u32(sD);
-    constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
+    constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 128, NN);
     const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
 
     const uint32_t t_begin = chunk * k.st_per_chunk;
     const uint32_t t_end = min(k.nst, t_begin + k.st_per_chunk);
     const uint32_t nit = t_end > t_begin ? t_end - t_begin : 0;
-    const uint32_t nblk = nit * nkb;
+    const uint32_t nq = nit * np;                                            // length of the pair stream of this CTA
     const uint32_t* gwords = k.store_tc + (d.tc_off >> 2);
     const uint8_t* dp_g = a.dp + (size_t)li * a.dp_stride;
-    auto chunks_of = [&](uint32_t kb) { return min((uint32_t)kTcwBlockChunks, NC - kb * kTcwBlockChunks); };
-    auto issue_load = [&](uint32_t q, uint32_t it, uint32_t kbl) {   // whole issuer warp enters
+    auto chunks_of = [&](uint32_t p) { return min(PAIR_CH, NC - p * PAIR_CH); };     // chunks of pair p
+    auto issue_load = [&](uint32_t q, uint32_t it, uint32_t pl) {   // whole issuer warp enters
         if (umma::elect_one())
-            umma::bulk_load(sG + (q % kTcxRing) * (kTcwBlockChunks * 128),
-                            gwords + ((size_t)(t_begin + it) * NC + (kb0 + kbl) * kTcwBlockChunks) * 128, chunks_of(kb0 + kbl) * 512u,
-                            &mbar[4 + (q % kTcxRing)]);
+            umma::bulk_load(sG + (q & 1u) * (PAIR_CH * 128), gwords + ((size_t)(t_begin + it) * NC + (p0 + pl) * PAIR_CH) * 128,
+                            chunks_of(p0 + pl) * 512u, &mbar[4 + (q & 1u)]);
         __syncwarp();
     };
     auto issue_dp = [&](uint32_t it) {
         if (umma::elect_one()) umma::bulk_load(sD, dp_g + (size_t)(t_begin + it) * X::DP_ST, X::DP_ST, &mbar[8]);
         __syncwarp();
     };
-    uint32_t l_it = 0, l_kb = 0, lq = 0;
-    auto advance_l = [&]() { if (++l_kb == nkb) { l_kb = 0; ++l_it; } ++lq; };
     if (warp == 4) {                 // ---- issuer warp
-        for (; lq < kTcxRing && lq < nblk;) { issue_load(lq, l_it, l_kb); advance_l(); }
+        uint32_t l_it = 0, l_p = 0, lq = 0;
+        auto advance_l = [&]() { if (++l_p == np) { l_p = 0; ++l_it; } ++lq; };
+        for (; lq < 2 && lq < nq;) { issue_load(lq, l_it, l_p); advance_l(); }
         if (nit > 0) issue_dp(0);
         uint32_t q = 0;
         for (uint32_t it = 0; it < nit; ++it) {
             if (it > 0) {
-                // the delta buffer is read by the MMAs of the previous super-tile: all of them must be complete before the reload
-                umma::mbar_wait(&mbar[(q - 1) & 1u], ((q - 1) >> 1) & 1u);
-                if (q >= 2) umma::mbar_wait(&mbar[(q - 2) & 1u], ((q - 2) >> 1) & 1u);
+                // the delta buffer is read by the MMAs of the previous super-tile (they complete in order): reload after the last one
+                umma::mbar_wait(&mbar[0], (q - 1) & 1u);
                 issue_dp(it);
             }
-            for (uint32_t kbl = 0; kbl < nkb; ++kbl, ++q) {
-                const uint32_t buf = q & 1u;
-                umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);               // block q expanded by all 128 threads
-                if (lq < nblk) { issue_load(lq, l_it, l_kb); advance_l(); }   // every thread has consumed ring slot q % 4
-                if (kbl == 0) umma::mbar_wait(&mbar[8], it & 1u);             // delta pieces of this super-tile
+            for (uint32_t pl = 0; pl < np; ++pl, ++q) {
+                umma::mbar_wait(&mbar[2], q & 1u);                            // pair q expanded by all 128 threads
+                if (lq < nq) { issue_load(lq, l_it, l_p); advance_l(); }      // every thread has consumed ring slot q % 2
+                if (pl == 0) umma::mbar_wait(&mbar[8], it & 1u);              // delta pieces of this super-tile
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
-                    const uint64_t base = dA_b + ((buf * kTcwBlockBytes) >> 4);
 #pragma unroll
                     for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
-                        umma::mma_f16(tmem + kbl * NN, base + ks * 16u, dD_b + ks * 16u, idesc_b, (it | ks) != 0);
-                    umma::commit(&mbar[buf]);
+                        umma::mma_f16(tmem + pl * NN, dA_b + ks * 16u, dD_b + ks * 16u, idesc_b, (it | ks) != 0);
+                    umma::commit(&mbar[0]);
                 }
                 __syncwarp();
             }
         }
-        if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
-        if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
+        if (nq >= 1) umma::mbar_wait(&mbar[0], (nq - 1) & 1u);
         umma::fence_before_sync();
         __syncthreads();
         return;
     }
-    for (uint32_t q = 0; q < nblk; ++q) {
-        const uint32_t buf = q & 1u;
-        const uint32_t kbl = q % nkb;
-        const uint32_t nch = chunks_of(kb0 + kbl);
-        umma::mbar_wait(&mbar[4 + (q % kTcxRing)], (q / kTcxRing) & 1u);
-        const uint32_t* src = sG + (q % kTcxRing) * (kTcwBlockChunks * 128) + tid;
-        if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);         // MMAs of block q - 2 done: operand buffer free
-        tcx_expand(src, sA + buf * kTcwBlockBytes + tid * 16, nch);
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t pl = q % np;
+        const uint32_t nch = chunks_of(p0 + pl);
+        umma::mbar_wait(&mbar[4 + (q & 1u)], (q >> 1) & 1u);
+        const uint32_t* src = sG + (q & 1u) * (PAIR_CH * 128) + tid;
+        if (q >= 1) umma::mbar_wait(&mbar[0], (q - 1) & 1u);                  // MMAs of pair q - 1 done: operand image free
+        tcx_expand(src, sA + tid * 16, min(nch, (uint32_t)kTcwBlockChunks));
+        tcx_expand(src + kTcwBlockChunks * 128, sA + kTcwBlockBytes + tid * 16, nch > kTcwBlockChunks ? nch - kTcwBlockChunks : 0u);
         umma::fence_async_smem();
-        umma::mbar_arrive(&mbar[2 + buf]);
+        umma::mbar_arrive(&mbar[2]);
     }
-    if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
-    if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
+    if (nq >= 1) umma::mbar_wait(&mbar[0], (nq - 1) & 1u);
     umma::fence_after_sync();
-    // first-layer weight gradient of the slab: accumulator row r of block kbl lives in lane r % 16 of warp r / 16
+    // first-layer weight gradient of the slab: accumulator row r of pair pl lives in lane r (M = 128 layout)
     const float* mu = k.mu + d.col_off;
     const float* sd = k.sd + d.col_off;
-    for (uint32_t kbl = 0; kbl < nkb; ++kbl) {
+    for (uint32_t pl = 0; pl < np; ++pl) {
         float v[NN];
         if (nit > 0) {
 #pragma unroll
-            for (int g = 0; g < NN / 16; ++g) umma::tmem_ld16(tlane + kbl * NN + 16 * g, v + 16 * g);
+            for (int g = 0; g < NN / 16; ++g) umma::tmem_ld16(tlane + pl * NN + 16 * g, v + 16 * g);
         }
-        if (lane < 16) {
-            const uint32_t j = (kb0 + kbl) * 64 + warp * 16 + lane;
-            if (j < m) {
-                const float unscale = pow2f(33 - 2 * (int)((j & 7u) >> 1));
+        const uint32_t j = (p0 + pl) * 128 + tid;
+        if (j < m) {
+            const float unscale = pow2f(33 - 2 * (int)((j & 7u) >> 1));
 #pragma unroll
-                for (int c = 0; c < W0; ++c) {
-                    const float s = (nit > 0 ? (v[c] + (v[W0 + c] + v[2 * W0 + c])) : 0.f) * unscale;
-                    pp[c * m + j] = __fdiv_rn(s - mu[j] * gb0[c], sd[j]);
-                }
+            for (int c = 0; c < W0; ++c) {
+                const float s = (nit > 0 ? (v[c] + (v[W0 + c] + v[2 * W0 + c])) : 0.f) * unscale;
+                pp[c * m + j] = __fdiv_rn(s - mu[j] * gb0[c], sd[j]);
             }
         }
     }
@@ -728,7 +724,7 @@ inline int launch_k1_tcx(const std::vector<BranchDesc>& descs, int single_branch
         if ((int)d0.widths[l] != H) return 0;
     const uint32_t nst = k.nst;
     const uint32_t nkb_max = ((max_m + 7) / 8 + kTcwBlockChunks - 1) / kTcwBlockChunks;
-    const uint32_t nslab = (nkb_max + kTcxSlabBlocks - 1) / kTcxSlabBlocks;
+    const uint32_t nslab = ((nkb_max + 1) / 2 + kTcxSlabPairs - 1) / kTcxSlabPairs;
     uint32_t want = (uint32_t)std::max<uint64_t>(1, ((uint64_t)num_sms * 2 + nlist - 1) / nlist);
     uint32_t nchunk = std::min<uint32_t>(want, std::max<uint32_t>(1, nst));
     uint32_t spc = (nst + nchunk - 1) / nchunk;
