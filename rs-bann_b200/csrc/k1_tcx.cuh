@@ -313,15 +313,14 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
     uint8_t* dp_g = a.dp + (size_t)li * a.dp_stride;
     // register-tiled cross-row products: row group rg (rows r * 8 + rg), block (ib, cb) of 4 x 4 entries
     const uint32_t rg = tid >> 4, blk = tid & 15, ib = blk >> 2, cb = blk & 3;
-    float gacc[NLA > 1 ? NLA - 1 : 1][4][4];
+    auto swz = [](uint32_t row, uint32_t col) { return row * 16 + ((((col >> 2) ^ (row >> 1)) & 3u) << 2) + (col & 3u); };   // staged element (row, col)
+    f2 gacc[NLA > 1 ? NLA - 1 : 1][4][2];        // 4 x 4 block, packed over column pairs
     float gbacc[NLA], gwo = 0.f;
     f2 rss = zero2;
 #pragma unroll
     for (int l = 0; l < (NLA > 1 ? NLA - 1 : 1); ++l)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) gacc[l][i][c] = 0.f;
+        for (int i = 0; i < 4; ++i) { gacc[l][i][0] = zero2; gacc[l][i][1] = zero2; }
 #pragma unroll
     for (int l = 0; l < NLA; ++l) gbacc[l] = 0.f;
 
@@ -381,17 +380,21 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
         // stage (input, delta) of a layer for the whole super-tile, then every thread accumulates its 4 x 4 block over 32 rows
         auto stage = [&](const f2* in, int nin, const f2* dl, int nout) {
             __syncthreads();                                   // the previous product has been read
+            // rows are 64 B apart: the 16-byte group g of row r sits at group g ^ ((r >> 1) & 3), which makes the 128-bit
+            // stores of eight consecutive rows (one quarter-warp) hit eight different bank groups (rows t and 128 + t swizzle alike)
             float* ra = As + tid * 16; float* rb = As + (128 + tid) * 16;
             float* da = Ds + tid * 16; float* db = Ds + (128 + tid) * 16;
+            const int sw = (int)((tid >> 1) & 3u);
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
+                const int o = ((i >> 2) ^ sw) << 2;
                 if (i < nin) {
-                    *reinterpret_cast<float4*>(ra + i) = make_float4(lo2(in[i]), lo2(in[i + 1]), lo2(in[i + 2]), lo2(in[i + 3]));
-                    *reinterpret_cast<float4*>(rb + i) = make_float4(hi2(in[i]), hi2(in[i + 1]), hi2(in[i + 2]), hi2(in[i + 3]));
+                    *reinterpret_cast<float4*>(ra + o) = make_float4(lo2(in[i]), lo2(in[i + 1]), lo2(in[i + 2]), lo2(in[i + 3]));
+                    *reinterpret_cast<float4*>(rb + o) = make_float4(hi2(in[i]), hi2(in[i + 1]), hi2(in[i + 2]), hi2(in[i + 3]));
                 }
                 if (i < nout) {
-                    *reinterpret_cast<float4*>(da + i) = make_float4(lo2(dl[i]), lo2(dl[i + 1]), lo2(dl[i + 2]), lo2(dl[i + 3]));
-                    *reinterpret_cast<float4*>(db + i) = make_float4(hi2(dl[i]), hi2(dl[i + 1]), hi2(dl[i + 2]), hi2(dl[i + 3]));
+                    *reinterpret_cast<float4*>(da + o) = make_float4(lo2(dl[i]), lo2(dl[i + 1]), lo2(dl[i + 2]), lo2(dl[i + 3]));
+                    *reinterpret_cast<float4*>(db + o) = make_float4(hi2(dl[i]), hi2(dl[i + 1]), hi2(dl[i + 2]), hi2(dl[i + 3]));
                 }
             }
             __syncthreads();
@@ -408,19 +411,21 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
             if ((int)(4 * ib) < T::in_w(l) && (int)(4 * cb) < T::width(l)) {
 #pragma unroll 4
                 for (uint32_t r = 0; r < 32; ++r) {
-                    const uint32_t row = r * 8 + rg;
-                    const float4 x = *reinterpret_cast<const float4*>(As + row * 16 + 4 * ib);
-                    const float4 y = *reinterpret_cast<const float4*>(Ds + row * 16 + 4 * cb);
-                    const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+                    const uint32_t row = r * 8 + rg, sw = (row >> 1) & 3u;
+                    const float4 x = *reinterpret_cast<const float4*>(As + row * 16 + 4 * (ib ^ sw));
+                    const float4 y = *reinterpret_cast<const float4*>(Ds + row * 16 + 4 * (cb ^ sw));
+                    const float xs[4] = {x.x, x.y, x.z, x.w};
+                    const f2 y01 = mk2(y.x, y.y), y23 = mk2(y.z, y.w);      // packed over the delta columns: 8 FFMA2 per row
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) gacc[l - 1][i][c] = fmaf(xs[i], ys[c], gacc[l - 1][i][c]);
+                    for (int i = 0; i < 4; ++i) {
+                        gacc[l - 1][i][0] = fma2(y01, dup2(xs[i]), gacc[l - 1][i][0]);
+                        gacc[l - 1][i][1] = fma2(y23, dup2(xs[i]), gacc[l - 1][i][1]);
+                    }
                 }
             }
             if (blk < (uint32_t)T::width(l)) {                  // bias of layer l: column sums of the staged deltas
                 float s = gbacc[l];
-                for (uint32_t r = 0; r < 32; ++r) s += Ds[(r * 8 + rg) * 16 + blk];
+                for (uint32_t r = 0; r < 32; ++r) s += Ds[swz(r * 8 + rg, blk)];
                 gbacc[l] = s;
             }
             f2 nd[MW];
@@ -441,12 +446,12 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
         stage(act[NLA - 1], S, delta, W0);
         if (blk < (uint32_t)W0) {
             float s = gbacc[0];
-            for (uint32_t r = 0; r < 32; ++r) s += Ds[(r * 8 + rg) * 16 + blk];
+            for (uint32_t r = 0; r < 32; ++r) s += Ds[swz(r * 8 + rg, blk)];
             gbacc[0] = s;
         }
         if (blk < (uint32_t)S) {
             float s = gwo;
-            for (uint32_t r = 0; r < 32; ++r) s = fmaf(As[(r * 8 + rg) * 16 + blk], Es[r * 8 + rg], s);
+            for (uint32_t r = 0; r < 32; ++r) s = fmaf(As[swz(r * 8 + rg, blk)], Es[r * 8 + rg], s);
             gwo = s;
         }
         // delta_0 -> three bf16 pieces per unit by truncation (exact), n = piece * W0 + unit, in KB's operand layout
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) mine[idx++] = gacc[l][i][c];
+                for (int c = 0; c < 4; ++c) mine[idx++] = (c & 1) ? hi2(gacc[l][i][c >> 1]) : lo2(gacc[l][i][c >> 1]);
 #pragma unroll
         for (int l = 0; l < NLA; ++l) mine[idx++] = gbacc[l];
         mine[idx++] = gwo;
