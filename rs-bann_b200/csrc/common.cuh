@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
+#include <utility>
 #include <vector>
 
 #include "../../include/bann.h"
@@ -107,6 +109,40 @@ void set_error(const std::string& s);
 
 extern unsigned long long g_launch_count;
 #define BANN_LAUNCHED() (++::bann::g_launch_count)
+
+// ---------------------------------------------------------------- programmatic dependent launch (sm_90+)
+// The kernels on the critical path of a leapfrog step of the sequential schedule (K1 -> KR -> K2 -> K1 ...) are launched with
+// programmatic stream serialisation: a kernel may be scheduled -- and run the part of its prologue that touches no global data
+// of its predecessors -- while the previous kernel is still running; pdl_wait() returns once the previous kernel has completed
+// and its writes are visible.  EVERY path of such a kernel executes pdl_wait() before it exits or touches dependent data, so that
+// "kernel N complete" implies "kernel N - 1 complete".  Launched the ordinary way both calls are no-ops.
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+#if defined(__CUDACC__)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 // ---------------------------------------------------------------- Philox4x32-10
 struct Philox {

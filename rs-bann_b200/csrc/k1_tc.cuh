@@ -101,8 +101,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
     const uint32_t b = a.list ? a.list[li] : li;
-    if (a.states && a.states[b].status != ST_RUNNING) return;
-    const BranchDesc& d = a.descs[b];
+    const BranchDesc& d = a.descs[b];        // descriptors and branch lists are written once, at net creation
     const uint32_t m = d.m, NC = NCT ? (uint32_t)NCT : d.nc, NKS = (NC + 1) >> 1, NCB = a.ncb;
     // Issuing a tcgen05.mma costs the issuing warp ~40 clk (measured: 8 forward MMAs + bulk copy 600 clk, 16 backward MMAs
     // 630 clk); on one warp that made it the straggler every other warp waited for (~1250 clk per super-tile).  The work is
@@ -142,6 +141,17 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    // Programmatic dependent launch (common.cuh): everything above touched only shared / tensor memory and ran under the
+    // previous kernel (K2 of the last leapfrog step); parameters, targets and the branch status are read from here on.
+    pdl_launch_dependents();
+    pdl_wait();
+    if (a.states && a.states[b].status != ST_RUNNING) {      // early-rejected / finished branch: release the tensor memory and leave
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        if (warp == 0) umma::tmem_dealloc(*tmem_slot, C::TMEM_COLS);
+        return;
+    }
     for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += 128) {
         const float w = th[m * W0 + k];
         wp[k] = w;
@@ -526,9 +536,9 @@ int launch_one_tc(K1Args& a, uint32_t nlist, cudaStream_t st) {
     const size_t smem = C::smem(a.ncb);
     dim3 grid(a.nchunk, nlist);
     const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
-    if (lean && a.nc_uniform == 7) k1_tc<H, S, D, true, 7><<<grid, 128, smem, st>>>(a);   // 49..56 markers in every listed branch
-    else if (lean) k1_tc<H, S, D, true, 0><<<grid, 128, smem, st>>>(a);
-    else k1_tc<H, S, D, false, 0><<<grid, 128, smem, st>>>(a);
+    if (lean && a.nc_uniform == 7) BANN_CUDA(launch_pdl(k1_tc<H, S, D, true, 7>, grid, dim3(128), smem, st, a));   // 49..56 markers in every listed branch
+    else if (lean) BANN_CUDA(launch_pdl(k1_tc<H, S, D, true, 0>, grid, dim3(128), smem, st, a));
+    else BANN_CUDA(launch_pdl(k1_tc<H, S, D, false, 0>, grid, dim3(128), smem, st, a));
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
@@ -562,7 +572,10 @@ inline int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch,
     for (int l = 0; l < D; ++l)
         if ((int)d0.widths[l] != H) return 0;
     const uint32_t nst = a.nst;
-    uint32_t want = (uint32_t)std::max<uint64_t>(1, ((uint64_t)num_sms * 4 + nlist - 1) / nlist);
+    // single-branch launches (sequential schedule): 2 CTAs per SM instead of 4 -- fewer chunks for the reduction kernel on the
+    // critical path of every leapfrog step (measured 27.7 -> 25.7 us per leapfrog at N = 100k); grouped launches as before
+    const uint32_t want_mult = nlist == 1 ? 2 : 4;
+    uint32_t want = (uint32_t)std::max<uint64_t>(1, ((uint64_t)num_sms * want_mult + nlist - 1) / nlist);
     uint32_t nchunk = std::min<uint32_t>(want, std::max<uint32_t>(1, nst));
     uint32_t spc = (nst + nchunk - 1) / nchunk;
     nchunk = (nst + spc - 1) / spc;

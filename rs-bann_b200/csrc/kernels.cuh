@@ -277,6 +277,8 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
                                                          const BranchDesc* __restrict__ descs,
                                                          const BranchState* __restrict__ states, XrComm xc) {
     __shared__ double sm[8][32];
+    pdl_wait();                    // the partials come from the kernel launched just before
+    pdl_launch_dependents();
     const uint32_t li = blockIdx.y;
     const uint32_t b = list ? list[li] : li;
     if (states && states[b].status != ST_RUNNING) return;
@@ -342,11 +344,19 @@ struct K2Args {
 __global__ void __launch_bounds__(256) k2_step(K2Args a) {
     __shared__ float red[8];
     __shared__ int s_status;
+    __shared__ BranchDesc s_desc;
     const uint32_t li = blockIdx.x, tid = threadIdx.x;
     const uint32_t b = a.list ? a.list[li] : li;
+    pdl_launch_dependents();       // the next K1 may run its shared-memory / tensor-memory prologue under this kernel
+    pdl_wait();                    // gsum comes from the kernel launched just before
     BranchState& st = a.states[b];
     if (st.status != ST_RUNNING) return;
-    const BranchDesc& d = a.descs[b];
+    // the descriptor in shared memory: locate_param walks its offset tables for every parameter, and from global memory every
+    // step of that walk was a dependent L2 round trip on the critical path of a leapfrog step
+    static_assert(sizeof(BranchDesc) % 4 == 0 && sizeof(BranchDesc) / 4 <= 256, "descriptor copy assumes <= 256 words");
+    if (tid < sizeof(BranchDesc) / 4) reinterpret_cast<uint32_t*>(&s_desc)[tid] = reinterpret_cast<const uint32_t*>(&a.descs[b])[tid];
+    __syncthreads();
+    const BranchDesc& d = s_desc;
     const uint32_t P = d.P;
     float* th = a.theta + d.param_off;
     const float* th0 = a.theta0 + d.param_off;

@@ -194,8 +194,8 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
     if (reduce && !L.fwd_only && (part != net->d_gsum || L.xr)) {   // nchunk == 1 with L.xr: in place, exchange only
         if (L.xr && (size_t)L.nlist * net->pstride > kXrCap) BANN_FAIL("peer-memory exchange: too many values in one launch");
         dim3 grid((net->pstride + 31) / 32, L.nlist);
-        k_reduce_partials<<<grid, 256, 0, st>>>(part, net->d_gsum, nchunk, net->pstride, L.list, a.descs, L.states,
-                                                L.xr ? xr_next(net->ctx, net->d_errflag) : xr_none());
+        BANN_CUDA(launch_pdl(k_reduce_partials, grid, dim3(256), 0, st, (const float*)part, net->d_gsum, nchunk, net->pstride, L.list,
+                             a.descs, L.states, L.xr ? xr_next(net->ctx, net->d_errflag) : xr_none()));
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
     }
@@ -382,7 +382,7 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
     if (Lsteps == 0) k.yhat_out = ynew_out;
     BANN_CHECK(launch_k1(net, k, true));
     K2Args a = make_k2(net, cfg, R, 1, Lsteps == 0);
-    k2_step<<<R.nlist, 256, 0, st>>>(a);
+    BANN_CUDA(launch_pdl(k2_step, dim3(R.nlist), dim3(256), 0, st, a));
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     k.target_mode = R.later_mode;
@@ -395,7 +395,7 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
         BANN_CHECK(launch_k1(net, k, true));
         a.mode_init = 0;
         a.is_last = (s == Lsteps);
-        k2_step<<<R.nlist, 256, 0, st>>>(a);
+        BANN_CUDA(launch_pdl(k2_step, dim3(R.nlist), dim3(256), 0, st, a));
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
     }
@@ -1716,7 +1716,7 @@ int bann_grouped_begin(bann_net* net, const bann_mcmc_cfg* cfg, uint64_t seed, i
     BANN_CHECK(grouped_k1(net, 1));
     if (net->ctx->world > 1) return 0;   // caller all-reduces, then bann_grouped_phase_b(is_init = 1)
     K2Args a = make_k2(net, cfg, R, 1, 0);
-    k2_step<<<R.nlist, 256, 0, net->ctx->stream>>>(a);
+    BANN_CUDA(launch_pdl(k2_step, dim3(R.nlist), dim3(256), 0, net->ctx->stream, a));
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
@@ -1731,7 +1731,7 @@ int bann_grouped_phase_b(bann_net* net, const bann_mcmc_cfg* cfg, int is_init, i
     if (!net || !cfg) BANN_FAIL("NULL argument");
     HmcRun R = grouped_run(net);
     K2Args a = make_k2(net, cfg, R, is_init, is_last);
-    k2_step<<<R.nlist, 256, 0, net->ctx->stream>>>(a);
+    BANN_CUDA(launch_pdl(k2_step, dim3(R.nlist), dim3(256), 0, net->ctx->stream, a));
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
