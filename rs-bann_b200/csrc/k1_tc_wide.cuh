@@ -48,8 +48,7 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
     const uint32_t b = a.list ? a.list[li] : li;
-    if (a.states && a.states[b].status != ST_RUNNING) return;
-    const BranchDesc& d = a.descs[b];
+    const BranchDesc& d = a.descs[b];        // descriptors and branch lists are written once, at net creation
     const uint32_t m = d.m, NC = d.nc, NKB = (NC + kTcwBlockChunks - 1) / kTcwBlockChunks;
     const uint32_t issuer = BANN_TCW_ISSUER_WARP ? 4 : 0;
     // ---- shared memory carve-up
@@ -81,6 +80,16 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, CW::TMEM_COLS);
+    // programmatic dependent launch (common.cuh): the shared / tensor memory prologue above ran under the previous kernel
+    pdl_launch_dependents();
+    pdl_wait();
+    if (a.states && a.states[b].status != ST_RUNNING) {      // early-rejected / finished branch: release the tensor memory and leave
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        if (warp == 0) umma::tmem_dealloc(*tmem_slot, CW::TMEM_COLS);
+        return;
+    }
     for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += kTcwThreads) {
         const float w = th[m * W0 + k];
         wp2[k] = make_float2(w, w);
@@ -468,8 +477,8 @@ int launch_one_tcw(K1Args& a, uint32_t nlist, cudaStream_t st) {
     }
     dim3 grid(a.nchunk, nlist);
     const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
-    if (lean) k1_tcw<H, S, D, true><<<grid, kTcwThreads, CW::SMEM, st>>>(a);
-    else k1_tcw<H, S, D, false><<<grid, kTcwThreads, CW::SMEM, st>>>(a);
+    if (lean) BANN_CUDA(launch_pdl(k1_tcw<H, S, D, true>, grid, dim3(kTcwThreads), CW::SMEM, st, a));
+    else BANN_CUDA(launch_pdl(k1_tcw<H, S, D, false>, grid, dim3(kTcwThreads), CW::SMEM, st, a));
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
