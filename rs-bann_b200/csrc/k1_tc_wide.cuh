@@ -1,18 +1,16 @@
 // Tensor-core K1 for branches with 65 .. 512 markers (first-layer width <= 5): the k1_tc scheme, K-blocked.
 //
-// A branch is cut into blocks of 64 markers (8 chunks of 8).  Per 256-row super-tile the CTA streams the blocks through
-// two operand buffers TWICE:
-//   forward pass : expand block kb -> MMA fwd (M128 N16 K16 x 4, two row halves) accumulating z0 over all blocks in
-//                  tensor memory;
+// A branch is cut into blocks of 64 markers (8 chunks of 8).  Per 256-row super-tile the CTA streams the blocks TWICE:
+//   forward pass : packed words -> TENSOR MEMORY (tcgen05.st of the AND-expanded words: the A operand of the TS-form MMA, no
+//                  shared-memory traffic) -> MMA fwd (M128 N16 K16 x 4, two row halves) accumulating z0 over all blocks;
 //   tail         : exactly as in k1_tc (packed f32x2, one row pair per thread), delta_0 pieces -> shared memory;
-//   backward pass: expand block kb again -> MMA bwd (M64 N16 K16 x 16) into the block's own 16 accumulator columns,
-//                  which keep accumulating over ALL super-tiles of the CTA.
+//   backward pass: packed words -> one of two shared-memory operand buffers -> MMA bwd (M64 N16 K16 x 16) into the block's own
+//                  16 accumulator columns, which keep accumulating over ALL super-tiles of the CTA.
 // The packed words of a block (8 chunks x 128 row pairs x 4 B = 4 KB, contiguous in the tensor-core store) arrive by bulk
 // async copies into a 4-slot ring, requested 4 blocks ahead; the second pass re-reads them (from L2).  Every stage is
-// decoupled by mbarriers: "block expanded" (128 arrivals, one barrier per operand buffer), "buffer free" (tcgen05.commit of
-// the MMAs that read it), "words landed" (transaction bytes, one barrier per ring slot).
+// decoupled by mbarriers; warps 0-3 expand / run the tail, warp 4 requests the loads and issues every MMA.
 // Shared memory: 2 x 32 KB operands + 16 KB ring + 8 KB delta pieces + 16 KB weight pieces -> 2 CTAs per SM;
-// tensor memory: 32 + 16 x ceil(m/64) <= 160 columns (256 allocated).
+// tensor memory: 32 + 16 x ceil(m/64) accumulator columns + 64 forward-operand columns <= 224 (256 allocated).
 #pragma once
 #include "k1_tc.cuh"
 
@@ -33,10 +31,7 @@ struct TcwShape {
     static constexpr size_t SMEM = 2 * (size_t)kTcwBlockBytes + kTcwRing * (size_t)kTcwBlockChunks * 512 + C::SD + SW + C::MISC + 128 + 128;
 };
 
-#ifndef BANN_TCW_ISSUER_WARP
-#define BANN_TCW_ISSUER_WARP 1    // 1: a fifth warp requests the ring loads and issues the MMAs (measured on cfg2)
-#endif
-constexpr int kTcwThreads = BANN_TCW_ISSUER_WARP ? 160 : 128;
+constexpr int kTcwThreads = 160;   // warps 0-3: expansion, tail, epilogue; warp 4: ring loads + MMA issue (measured on cfg2: +50 %)
 
 template <int H, int S, int D, bool LEAN>
 __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
@@ -50,7 +45,7 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     const uint32_t b = a.list ? a.list[li] : li;
     const BranchDesc& d = a.descs[b];        // descriptors and branch lists are written once, at net creation
     const uint32_t m = d.m, NC = d.nc, NKB = (NC + kTcwBlockChunks - 1) / kTcwBlockChunks;
-    const uint32_t issuer = BANN_TCW_ISSUER_WARP ? 4 : 0;
+    const uint32_t issuer = 4;
     // ---- shared memory carve-up
     uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);       // 2 operand buffers of 8 chunks
     uint32_t* sG = reinterpret_cast<uint32_t*>(sA + 2 * kTcwBlockBytes);           // ring: [slot][chunk][128] packed words
@@ -59,10 +54,10 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     float2* wp2 = reinterpret_cast<float2*>(sW + CW::SW);
     float2* b0p2 = wp2 + ((T::n_tail() + 3) & ~3);
     float* red = reinterpret_cast<float*>(b0p2 + W0P);
-    // mbarriers: [0..1] MMAs that read operand buffer 0/1 done; [2..3] buffer 0/1 expanded (128 arrivals);
-    //            [4..7] ring slot 0..3 landed
+    // mbarriers: [0..1] backward MMAs that read operand buffer 0/1 done; [2..3] buffer 0/1 expanded (128 arrivals);
+    //            [4..7] ring slot 0..3 landed; [8] forward MMAs of a block done; [9] forward block expanded (128 arrivals)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 10);
 
     const float* th = a.theta + d.param_off;
     const float* mu = a.mu + d.col_off;
@@ -77,6 +72,7 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
         umma::mbar_init(&mbar[0], 1); umma::mbar_init(&mbar[1], 1);
         umma::mbar_init(&mbar[2], 128); umma::mbar_init(&mbar[3], 128);
         for (int k = 0; k < (int)kTcwRing; ++k) umma::mbar_init(&mbar[4 + k], 1);
+        umma::mbar_init(&mbar[8], 1); umma::mbar_init(&mbar[9], 128);
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, CW::TMEM_COLS);
@@ -135,7 +131,7 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     const uint32_t sA_u = umma::smem_u32(sA), sD_u = umma::smem_u32(sD), sW_u = umma::smem_u32(sW);
     constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
     constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
-    const uint64_t dA_f = umma::make_desc(sA_u, kTcChunkStride, 128), dW_f = umma::make_desc(sW_u, NN * 16, 128);
+    const uint64_t dW_f = umma::make_desc(sW_u, NN * 16, 128);
     const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
 
     // ---- persistent per-thread accumulators (as in k1_tc)
@@ -181,42 +177,74 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
                             &mbar[4 + (q % kTcwRing)]);
         __syncwarp();
     };
-    auto issue_mma = [&](uint32_t q, const Pos& p) {    // whole issuer warp enters; the MMAs of stream block q
-        const uint32_t buf = q & 1u;
+    // Forward operand in TENSOR MEMORY (as in k1_tc / k1_tcx): one buffer of 2 x 32 columns behind the accumulators (32 + 16 x 8
+    // columns), written by tcgen05.st -- the forward pass costs no shared-memory traffic at all (the kernel was shared-memory
+    // bandwidth bound: every block was written and read twice); single-buffered, the second resident CTA covers the MMA latency.
+    // Backward blocks go through the two shared-memory operand buffers as before.  qf / qb count forward / backward blocks.
+    constexpr uint32_t tA = 160;
+    auto issue_fwd = [&](uint32_t qf, uint32_t kb) {          // whole issuer warp enters
+        umma::mbar_wait(&mbar[9], qf & 1u);
         umma::fence_after_sync();
         if (umma::elect_one()) {
-            if (p.pass == 0) {
-                const uint32_t nks = (chunks_of(p.kb) + 1) >> 1;
-                const uint64_t base = dA_f + ((buf * kTcwBlockBytes) >> 4), wbase = dW_f + ((p.kb * kTcwBlockChunks * (NN * 16)) >> 4);
+            const uint32_t nks = (chunks_of(kb) + 1) >> 1;
+            const uint64_t wbase = dW_f + ((kb * kTcwBlockChunks * (NN * 16)) >> 4);
 #pragma unroll
-                for (uint32_t h = 0; h < 2; ++h)
+            for (uint32_t h = 0; h < 2; ++h)
 #pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks)
-                        if (ks < nks)
-                            umma::mma_f16(tmem + h * NN, base + ((h * 2048u + ks * 2u * kTcChunkStride) >> 4),
-                                          wbase + ((ks * 2u * (NN * 16)) >> 4), idesc_f, (p.kb | ks) != 0);
-            } else {
-                const uint64_t base = dA_b + ((buf * kTcwBlockBytes) >> 4);
+                for (uint32_t ks = 0; ks < 4; ++ks)
+                    if (ks < nks)
+                        umma::mma_f16_ts(tmem + h * NN, tmem + tA + h * 32u + ks * 8u, wbase + ((ks * 2u * (NN * 16)) >> 4), idesc_f,
+                                         (kb | ks) != 0);
+            umma::commit(&mbar[8]);
+        }
+        __syncwarp();
+    };
+    auto issue_bwd = [&](uint32_t qb, uint32_t it, uint32_t kb) {   // whole issuer warp enters
+        const uint32_t buf = qb & 1u;
+        umma::mbar_wait(&mbar[2 + buf], (qb >> 1) & 1u);
+        umma::fence_after_sync();
+        if (umma::elect_one()) {
+            const uint64_t base = dA_b + ((buf * kTcwBlockBytes) >> 4);
 #pragma unroll
-                for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
-                    umma::mma_f16(tmem + (2 + p.kb) * NN, base + ks * 16u, dD_b + ks * 16u, idesc_b, (p.it | ks) != 0);
-            }
+            for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
+                umma::mma_f16(tmem + (2 + kb) * NN, base + ks * 16u, dD_b + ks * 16u, idesc_b, (it | ks) != 0);
             umma::commit(&mbar[buf]);
         }
         __syncwarp();
     };
-    Pos pos{0, 0, 0};           // position of stream block q (all threads)
+    Pos pos{0, 0, 0};           // position of stream block q
     Pos lpos{0, 0, 0};          // position of the next block whose words get requested (issuer warp)
     uint32_t lq = 0;
-    // expand stream block q into operand buffer q % 2 (waits: its words, and the MMAs that last read the buffer)
-    auto expand_block = [&](uint32_t q) {
-        const uint32_t buf = q & 1u, nch = chunks_of(pos.kb);
+    // forward block: packed words of ring slot q % 4 -> tensor memory (waits: the words, the previous forward block's MMAs)
+    auto expand_fwd = [&](uint32_t q, uint32_t qf, uint32_t kb) {
+        const uint32_t nch = chunks_of(kb);
         umma::mbar_wait(&mbar[4 + (q % kTcwRing)], (q / kTcwRing) & 1u);
         const uint32_t* src = sG + (q % kTcwRing) * (kTcwBlockChunks * 128) + tid;
         uint32_t x[kTcwBlockChunks];
 #pragma unroll
         for (int i = 0; i < kTcwBlockChunks; ++i) x[i] = (uint32_t)i < nch ? src[i * 128] : 0u;   // all loads first
-        if (q >= 2) umma::mbar_wait(&mbar[buf], ((q >> 1) - 1) & 1u);
+        if (qf >= 1) umma::mbar_wait(&mbar[8], (qf - 1) & 1u);
+        umma::fence_after_sync();
+        const uint32_t ta = tlane + tA;
+#pragma unroll
+        for (int i = 0; i < kTcwBlockChunks; ++i) {
+            const uint32_t y = x[i] >> 8;
+            umma::tmem_st4(ta + 4 * i, x[i] & 0x00030003u, x[i] & 0x000C000Cu, x[i] & 0x00300030u, x[i] & 0x00C000C0u);
+            umma::tmem_st4(ta + 32 + 4 * i, y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
+        }
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
+        umma::mbar_arrive(&mbar[9]);
+    };
+    // backward block: packed words -> operand buffer qb % 2 in shared memory (waits: the words, the MMAs that last read the buffer)
+    auto expand_bwd = [&](uint32_t q, uint32_t qb, uint32_t kb) {
+        const uint32_t buf = qb & 1u, nch = chunks_of(kb);
+        umma::mbar_wait(&mbar[4 + (q % kTcwRing)], (q / kTcwRing) & 1u);
+        const uint32_t* src = sG + (q % kTcwRing) * (kTcwBlockChunks * 128) + tid;
+        uint32_t x[kTcwBlockChunks];
+#pragma unroll
+        for (int i = 0; i < kTcwBlockChunks; ++i) x[i] = (uint32_t)i < nch ? src[i * 128] : 0u;   // all loads first
+        if (qb >= 2) umma::mbar_wait(&mbar[buf], ((qb >> 1) - 1) & 1u);
         uint8_t* rowA = sA + buf * kTcwBlockBytes + tid * 16;
 #pragma unroll
         for (int i = 0; i < kTcwBlockChunks; ++i)
@@ -229,12 +257,6 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
             }
         umma::fence_async_smem();
         umma::mbar_arrive(&mbar[2 + buf]);
-        if (!BANN_TCW_ISSUER_WARP && warp == issuer) {
-            umma::mbar_wait(&mbar[2 + buf], (q >> 1) & 1u);
-            issue_mma(q, pos);
-            if (lq < nblk) { issue_load(lq, lpos); ++lq; advance(lpos); }   // every thread has consumed ring slot q % 4
-        }
-        advance(pos);
     };
 
     auto load_targets = [&](uint32_t st) -> f2 {
@@ -246,23 +268,25 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     if (warp == issuer)
         for (; lq < kTcwRing && lq < nblk; ++lq) { issue_load(lq, lpos); advance(lpos); }
 
-    if (BANN_TCW_ISSUER_WARP && warp == issuer) {
-        // ---- issuing warp: the whole block stream in order -- wait "expanded" (128 arrivals: also publishes the delta pieces
-        // written before a backward pass), issue the MMAs, recycle the ring slot every thread has consumed
+    if (warp == issuer) {
+        // ---- issuing warp: the whole block stream in order -- wait "expanded" (128 arrivals: for the first backward block this also
+        // publishes the delta pieces), issue the MMAs, recycle the ring slot every thread has consumed
+        uint32_t qf = 0, qb = 0;
         for (uint32_t qq = 0; qq < nblk; ++qq) {
-            umma::mbar_wait(&mbar[2 + (qq & 1u)], (qq >> 1) & 1u);
-            issue_mma(qq, pos);
+            if (pos.pass == 0) issue_fwd(qf++, pos.kb);
+            else issue_bwd(qb++, pos.it, pos.kb);
             if (lq < nblk) { issue_load(lq, lpos); ++lq; advance(lpos); }
             advance(pos);
         }
-        if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
-        if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
+        if (qf >= 1) umma::mbar_wait(&mbar[8], (qf - 1) & 1u);
+        if (qb >= 1) umma::mbar_wait(&mbar[(qb - 1) & 1u], ((qb - 1) >> 1) & 1u);
+        if (qb >= 2) umma::mbar_wait(&mbar[(qb - 2) & 1u], ((qb - 2) >> 1) & 1u);
         umma::fence_before_sync();
         __syncthreads();                       // the compute warps' exits below: one barrier without an epilogue, three with it
         if (bwd && a.part) { __syncthreads(); __syncthreads(); }
         return;
     }
-    uint32_t q = 0;
+    uint32_t q = 0, qf = 0, qb = 0;
     for (uint32_t it = 0; it < nit; ++it) {
         const uint32_t st = t_begin + it;
         const uint32_t rowA_g = st * kTcRows + tid, rowB_g = rowA_g + 128;
@@ -270,9 +294,9 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
         f2 tg = tg_next;
         tg_next = load_targets(st + 1);
         // ---- forward pass over the marker blocks
-        for (uint32_t kb = 0; kb < NKB; ++kb, ++q) expand_block(q);
+        for (uint32_t kb = 0; kb < NKB; ++kb, ++q, ++qf) expand_fwd(q, qf, kb);
         // z0 is complete when the MMAs of the last forward block are (commits complete in issue order)
-        umma::mbar_wait(&mbar[(q - 1) & 1u], ((q - 1) >> 1) & 1u);
+        umma::mbar_wait(&mbar[8], (qf - 1) & 1u);
         umma::fence_after_sync();
         float accA[16], accB[16];
         umma::tmem_ld16x2(tlane, tlane + NN, accA, accB);
@@ -349,8 +373,10 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
             for (int i = 0; i < MW; ++i)
                 if (i < T::in_w(l)) delta[i] = mul2(dtanh2(act[l - 1][i]), nd[i]);
         }
-        // delta_0 pieces.  The delta buffer was last read by the previous super-tile's backward MMAs, all of which completed
-        // before the forward pass above could recycle their operand buffers (NKB >= 2).
+        // delta_0 pieces.  The delta buffer was last read by the previous super-tile's backward MMAs: wait for its last two
+        // commits (both operand buffers), long complete after a forward pass and a tail.
+        if (qb >= 1) umma::mbar_wait(&mbar[(qb - 1) & 1u], ((qb - 1) >> 1) & 1u);
+        if (qb >= 2) umma::mbar_wait(&mbar[(qb - 2) & 1u], ((qb - 2) >> 1) & 1u);
         {
             uint32_t pa[NN], pb[NN];
 #pragma unroll
@@ -379,11 +405,11 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
             }
         }
         // ---- backward pass over the marker blocks (the first arrival below also publishes the delta pieces)
-        for (uint32_t kb = 0; kb < NKB; ++kb, ++q) expand_block(q);
+        for (uint32_t kb = 0; kb < NKB; ++kb, ++q, ++qb) expand_bwd(q, qb, kb);
     }
-    // ---- drain: all MMAs done (the last two stream blocks cover both operand buffers)
-    if (nblk >= 1) umma::mbar_wait(&mbar[(nblk - 1) & 1u], ((nblk - 1) >> 1) & 1u);
-    if (nblk >= 2) umma::mbar_wait(&mbar[(nblk - 2) & 1u], ((nblk - 2) >> 1) & 1u);
+    // ---- drain: all MMAs done (the forward ones were waited for above; the last two backward blocks cover both operand buffers)
+    if (qb >= 1) umma::mbar_wait(&mbar[(qb - 1) & 1u], ((qb - 1) >> 1) & 1u);
+    if (qb >= 2) umma::mbar_wait(&mbar[(qb - 2) & 1u], ((qb - 2) >> 1) & 1u);
     umma::fence_after_sync();
     const bool has_bwd = bwd && a.part && nit > 0;
     if (!bwd || !a.part) {
