@@ -17,7 +17,6 @@ namespace bann {
 
 constexpr int kTcxMaxMarkers = 2048;       // tensor-core store limit (genotypes.cu)
 constexpr int kTcxSlabPairs = 4;           // pairs of marker blocks (128 markers each) per KB CTA: 4 x NN accumulator columns
-constexpr uint32_t kTcxRing = 4;
 
 template <int W0>
 struct TcxShape {
