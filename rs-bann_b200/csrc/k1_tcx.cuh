@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(160, 2) k_tcx_fwd(TcxArgs a) {
     const uint32_t tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
     const uint32_t b = a.k.list ? a.k.list[li] : li;
-    if (a.k.states && a.k.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = a.k.descs[b];
     const uint32_t NC = d.nc, NKB = (NC + kTcwBlockChunks - 1) / kTcwBlockChunks;
     uint8_t* sR = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // ring: [slot][words 4 KB | W' pieces]
@@ -154,6 +153,15 @@ __global__ void __launch_bounds__(160, 2) k_tcx_fwd(TcxArgs a) {
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, X::TMEM_A);
+    pdl_launch_dependents();       // programmatic dependent launch (common.cuh): the prologue above ran under k_tcx_prep
+    pdl_wait();
+    if (a.k.states && a.k.states[b].status != ST_RUNNING) {
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        if (warp == 0) umma::tmem_dealloc(*tmem_slot, X::TMEM_A);
+        return;
+    }
     if (tid < W0) b0s[tid] = reinterpret_cast<const float*>(wp_g + (size_t)a.nkb_max * X::WBLK)[tid];
     umma::fence_before_sync();
     __syncthreads();
@@ -289,7 +297,6 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
     const uint32_t b = k.list ? k.list[li] : li;
-    if (k.states && k.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = k.descs[b];
     const uint32_t m = d.m, P = d.P;
     float* wp = reinterpret_cast<float*>(smraw);                       // tail parameters [n_tail]
@@ -298,7 +305,12 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
     float* Es = Ds + 256 * 16;                                         // [256] errors
     float* red = Es + 256;                                             // [8 row groups][...] final reduction scratch
     const float* th = k.theta + d.param_off;
+    // programmatic dependent launch: the parameters were written before k_tcx_prep was launched (an ordinary launch), so staging
+    // them may run under KA; its activations are read after the wait
     for (uint32_t i = tid; i < (uint32_t)T::n_tail(); i += 128) wp[i] = th[m * W0 + i];
+    pdl_launch_dependents();
+    pdl_wait();
+    if (k.states && k.states[b].status != ST_RUNNING) return;
     __syncthreads();
 
     const f2 zero2 = dup2(0.f);
@@ -555,11 +567,10 @@ __global__ void __launch_bounds__(160, 2) k_tcx_bwd(TcxArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t li = blockIdx.y, chunk = blockIdx.x, slab = blockIdx.z;
     const uint32_t b = k.list ? k.list[li] : li;
-    if (k.states && k.states[b].status != ST_RUNNING) return;
     const BranchDesc& d = k.descs[b];
     const uint32_t m = d.m, NC = d.nc, NP = (NC + PAIR_CH - 1) / PAIR_CH;     // pairs of the branch
     const uint32_t p0 = slab * kTcxSlabPairs;
-    if (p0 >= NP) return;
+    if (p0 >= NP) { pdl_launch_dependents(); pdl_wait(); return; }
     const uint32_t np = min((uint32_t)kTcxSlabPairs, NP - p0);
     uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);   // operand image: 16 chunks x 256 rows x 16 B
     uint32_t* sG = reinterpret_cast<uint32_t*>(sA + 2 * kTcwBlockBytes);     // ring [2 slots][16 chunks][128] packed words
@@ -577,6 +588,15 @@ __global__ void __launch_bounds__(160, 2) k_tcx_bwd(TcxArgs a) {
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, X::TMEM_B);
+    pdl_launch_dependents();       // programmatic dependent launch: the prologue above ran under KT
+    pdl_wait();
+    if (k.states && k.states[b].status != ST_RUNNING) {
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        if (warp == 0) umma::tmem_dealloc(*tmem_slot, X::TMEM_B);
+        return;
+    }
     float* pp = k.part + ((size_t)li * k.nchunk + chunk) * k.pstride;
     if (tid < W0) gb0[tid] = pp[d.b_off[0] + tid];          // written by KT for the same (entry, chunk)
     umma::fence_before_sync();
@@ -692,13 +712,13 @@ int launch_one_tcx(TcxArgs& a, uint32_t nlist, uint32_t nslab, bool bwd, cudaStr
     k_tcx_prep<T::W0><<<nlist, 128, 0, st>>>(a);
     BANN_LAUNCHED();
     dim3 grid(a.k.nchunk, nlist);
-    k_tcx_fwd<T::W0><<<grid, 160, X::SMEM_A, st>>>(a);
+    BANN_CUDA(launch_pdl(k_tcx_fwd<T::W0>, grid, dim3(160), X::SMEM_A, st, a));
     BANN_LAUNCHED();
-    k_tcx_tail<H, S, D><<<grid, 128, smem_t, st>>>(a);
+    BANN_CUDA(launch_pdl(k_tcx_tail<H, S, D>, grid, dim3(128), smem_t, st, a));
     BANN_LAUNCHED();
     if (bwd) {
         dim3 gridb(a.k.nchunk, nlist, nslab);
-        k_tcx_bwd<T::W0><<<gridb, 160, X::SMEM_B, st>>>(a);
+        BANN_CUDA(launch_pdl(k_tcx_bwd<T::W0>, gridb, dim3(160), X::SMEM_B, st, a));
         BANN_LAUNCHED();
     }
     BANN_CUDA(cudaGetLastError());
