@@ -207,7 +207,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs to stdout by default: keep stdout to the one JSON line
+        # NCCL writes its version / debug lines to the process's stdout: route fd 1 to stderr until the JSON line is printed
+        sys.stdout.flush()
+        _saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream().cuda_stream
     ctx = rb.Context(local, stream=stream, rank=rank, world=world)
@@ -355,7 +358,10 @@ def main():
                 line["cpu_baseline"], _ = cpu_reference_rate(wl, seconds=12.0)
             except Exception as ex:   # the oracle is test infrastructure; never let it break the GPU number
                 line["cpu_baseline"] = dict(error=str(ex))
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if world > 1:
+            os.dup2(_saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     net.close()
     gen.close()
     ctx.close()
