@@ -83,7 +83,26 @@ class ClockSampler:
         self.rows, self.stop_flag, self.idx = [], False, gpu_index
         self.t = threading.Thread(target=self.run, daemon=True)
 
+    def run_nvml(self):
+        """Fast path: NVML (nvidia_ml_py) polled every 10 ms -- a 0.3 s timed region still gets ~30 samples."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+        while not self.stop_flag:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            self.rows.append([str(self.idx), str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            time.sleep(0.01)
+
     def run(self):
+        try:
+            self.run_nvml()
+            return
+        except Exception:
+            pass                      # no NVML binding: fall back to polling nvidia-smi
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
