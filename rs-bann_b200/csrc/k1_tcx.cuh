@@ -784,8 +784,12 @@ inline int launch_k1_tcx(const std::vector<BranchDesc>& descs, int single_branch
     }
     BANN_TRY_TCX(16, 16, 2)
     BANN_TRY_TCX(16, 16, 1)
+    BANN_TRY_TCX(12, 12, 2)
+    BANN_TRY_TCX(12, 12, 1)
+    BANN_TRY_TCX(8, 8, 2)
     BANN_TRY_TCX(8, 8, 1)
     BANN_TRY_TCX(8, 4, 1)
+    BANN_TRY_TCX(4, 4, 1)
 #undef BANN_TRY_TCX
     return 0;
 }

@@ -18,6 +18,10 @@ WIDE_SHAPES = [
     (257, [64, 65], 8, 8, 1),
     (1030, [300, 8], 8, 4, 1),           # several super-tiles; a branch with a single 8-marker chunk
     (128, [2048], 16, 16, 1),            # the tensor-core store's marker limit
+    (400, [90, 700], 12, 12, 2),         # first-layer width 12: 36 of 48 accumulator columns used
+    (300, [130], 12, 12, 1),
+    (600, [64, 200], 8, 8, 2),
+    (257, [40, 600], 4, 4, 1),
 ]
 
 
