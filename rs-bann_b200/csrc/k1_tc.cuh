@@ -603,6 +603,9 @@ inline int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch,
     BANN_TRY_TC(4, 3, 2)
     BANN_TRY_TC(5, 3, 2)
     BANN_TRY_TC(2, 2, 0)
+    BANN_TRY_TC(3, 3, 1)
+    BANN_TRY_TC(4, 4, 1)
+    BANN_TRY_TC(5, 5, 2)
 #undef BANN_TRY_TC
     return 0;
 }

@@ -559,6 +559,9 @@ inline int launch_k1_tcw(const std::vector<BranchDesc>& descs, int single_branch
     BANN_TRY_TCW(5, 5, 1)
     BANN_TRY_TCW(2, 2, 1)
     BANN_TRY_TCW(4, 3, 1)
+    BANN_TRY_TCW(3, 3, 1)
+    BANN_TRY_TCW(4, 4, 1)
+    BANN_TRY_TCW(5, 5, 2)
 #undef BANN_TRY_TCW
     return 0;
 }

@@ -214,6 +214,13 @@ TC_SHAPES = [  # n, group sizes, hidden, summary, depth
     (1030, [500, 65], 5, 5, 1),
     (515, [128, 129], 2, 2, 1),
     (700, [512], 4, 3, 1),
+    # further instantiations: [3,3,1] (the CLI test's architecture), [4,4,1], two hidden layers of 5
+    (600, [20, 64], 3, 3, 1),
+    (300, [33, 8], 4, 4, 1),
+    (515, [50, 64], 5, 5, 2),
+    (700, [100, 400], 3, 3, 1),
+    (300, [65, 200], 4, 4, 1),
+    (515, [256, 90], 5, 5, 2),
 ]
 
 
