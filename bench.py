@@ -81,13 +81,18 @@ class ClockSampler:
 
     def __init__(self, gpu_index=0):
         self.rows, self.stop_flag, self.idx = [], False, gpu_index
+        self.nv = self.nv_handle = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.nv_handle = nv, nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.nv = None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run_nvml(self):
         """Fast path: NVML (nvidia_ml_py) polled every 10 ms -- a 0.3 s timed region still gets ~30 samples."""
-        import pynvml as nv
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+        nv, h = self.nv, self.nv_handle          # initialised in the constructor: the first sample lands inside the timed region
         mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         bits = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
@@ -98,11 +103,12 @@ class ClockSampler:
             time.sleep(0.01)
 
     def run(self):
-        try:
-            self.run_nvml()
-            return
-        except Exception:
-            pass                      # no NVML binding: fall back to polling nvidia-smi
+        if self.nv is not None:
+            try:
+                self.run_nvml()
+                return
+            except Exception:
+                pass                  # NVML query failed: fall back to polling nvidia-smi
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
