@@ -37,6 +37,8 @@ WORKLOADS = {
                  n=50000, B=2000, per=1000, widths=[16, 16, 16, 1], model="ridge_ard"),
     "cfg4s": dict(desc="configs[3] at 1/20 of the branches (smoke size)", n=50000, B=100, per=1000, widths=[16, 16, 16, 1],
                   model="ridge_ard"),
+    "cfg3r8": dict(desc="configs[2] with 1/8 of the rows: the per-GPU shard of the 8-GPU run on one GPU (prologue / epilogue share of K1)",
+                   n=12544, B=10000, per=50, widths=[5, 5, 1], model="ridge_ard"),
     "cfg3s": dict(desc="configs[2] at 1/10 of the branches (smoke size)", n=100000, B=1000, per=50, widths=[5, 5, 1],
                   model="ridge_ard"),
 }
