@@ -235,7 +235,7 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
 
     def dump_trace():
         net_from_device(net, nf)
-        trace.write(json.dumps([c.to_json() for c in nf.branch_cfgs]) + "\n")
+        trace.write(files.json_dumps([c.to_json() for c in nf.branch_cfgs]) + "\n")
 
     def save_model(ix):
         if lead:
@@ -258,7 +258,7 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
                 res = net.visit_branch_traj(int(b), cfg, seed=seed + chain_ix)
                 if traj_file is not None:
                     t = res.trajectory
-                    traj_file.write(json.dumps(dict(params=[[float(v) for v in r] for r in t["params"]],
+                    traj_file.write(files.json_dumps(dict(params=[[float(v) for v in r] for r in t["params"]],
                                                     precisions=[[float(v) for v in r] for r in t["precisions"]],
                                                     ldg=[[float(v) for v in r] for r in t["ldg"]], num_ldg=[],
                                                     hamiltonian=[float(v) for v in t["hamiltonian"]])) + "\n")
@@ -275,7 +275,7 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
     net_from_device(net, nf)
     if lead:
         with open(os.path.join(outdir, "training_stats"), "w") as f:              # train_stats.rs:83-87
-            json.dump(nf.training_stats_json(), f)
+            files.json_dump(nf.training_stats_json(), f)
         if trace:
             trace.close()
         if traj_file:
@@ -532,7 +532,7 @@ def cmd_simulate_xy(a):
         break
     files.write_net(os.path.join(path, "model.bin"), nf)
     with open(os.path.join(path, "model.params"), "w") as f:
-        f.write(json.dumps([c.to_json() for c in nf.branch_cfgs]) + "\n")
+        f.write(files.json_dumps([c.to_json() for c in nf.branch_cfgs]) + "\n")
     for split, (payload, gv, y, resid_var) in out.items():
         stem = os.path.join(path, split)
         files.write_bed(stem, payload, n, m)

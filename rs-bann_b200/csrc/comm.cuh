@@ -15,7 +15,9 @@
 // and adds the values in RANK ORDER.  All ranks therefore compute bit-identical sums and take identical
 // accept / reject decisions.  Parities alternate with the epoch: a peer can only write epoch e + 2 into a
 // slot after it has completed epoch e + 1, which needed this rank's e + 1 contribution, which this rank
-// sent after it had consumed epoch e (stream order) -- two parities suffice.
+// sent after it had consumed epoch e (stream order) -- two parities suffice.  That argument needs EVERY epoch
+// the host hands out (xr_next) to be exchanged by every rank: a kernel that received an XrComm must run its
+// exchange unconditionally (k_reduce_partials does so for early-rejected branches too, with values nobody uses).
 // A rank that never shows up trips a wall-clock limit: the error flag is raised and the kernel returns.
 #pragma once
 
@@ -34,13 +36,16 @@ struct XrComm {
     int* error_flag;
 };
 
+// {payload, epoch} travel as ONE 64-bit word (a single st.b64 / ld.b64: 8-byte aligned accesses are single-copy atomic, so the
+// flag can never be seen without its data; a .v2.u32 access is modelled as two scalar accesses and gives no such guarantee)
 __device__ __forceinline__ void xr_store(uint2* p, uint32_t payload, uint32_t epoch) {
-    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
+    const unsigned long long w = (unsigned long long)payload | ((unsigned long long)epoch << 32);
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ uint2 xr_load(const uint2* p) {
-    uint2 v;
-    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
 }
 __device__ __forceinline__ unsigned long long xr_now() {
     unsigned long long t;

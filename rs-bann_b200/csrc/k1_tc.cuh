@@ -30,10 +30,8 @@
 #include "k1_small.cuh"
 #include "umma.cuh"
 
-#ifndef BANN_TCV
-#define BANN_TCV 11     // measured switches, cfg3s K1 ms: 0 -> 1.99, bit 0 (batched word loads in expand) -> 1.86, + bit 1 (deferred MMA issue) -> 1.68,
-                        // + bit 3 (no proxy fence after expand) -> 1.645.  Tried, no gain: forward issue after the delta pieces, backward issue later in part 1.
-#endif
+// Round-1 history of this kernel (cfg3s K1 ms): separate word loads 1.99 -> batched word loads in expand 1.86 -> deferred MMA issue
+// 1.68 -> no proxy fence after expand 1.645.  Tried, no gain: forward issue after the delta pieces, backward issue later in part 1.
 
 namespace bann {
 
@@ -69,6 +67,57 @@ __device__ __forceinline__ f2 tanh2(f2 x) {
 // 1 - a^2 (activation_functions.rs:33-45 for tanh, evaluated from the activation)
 __device__ __forceinline__ f2 dtanh2(f2 a) { return fma2(a, mul2(a, dup2(-1.f)), dup2(1.f)); }
 
+// ---- activations of the tensor-core tails (activation_functions.rs:23-45), on packed pairs.
+// The pre-activation arrives PRE-SCALED by act_prescale<ACT>() (folded into the staged weights and biases, so the
+// scaling costs no instruction): tanh wants 2 x log2(e), everything else the plain value.
+template <int ACT> __host__ __device__ constexpr float act_prescale() { return ACT == BANN_TANH ? 2.8853900817779268f : 1.f; }
+// activation of a pre-scaled pair; `aux` = what the derivative needs besides the activation (SiLU: the sigmoid)
+template <int ACT>
+__device__ __forceinline__ f2 act2(f2 t, f2& aux) {
+    if constexpr (ACT == BANN_TANH) {          // 1 - 2 / (2^t + 1), t = 2 x log2(e); saturates correctly (ex2 -> inf / 0)
+        float e0, e1, r0, r1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(lo2(t)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(hi2(t)));
+        const f2 s = add2(mk2(e0, e1), dup2(1.f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(lo2(s)));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(hi2(s)));
+        aux = t;
+        return fma2(mk2(r0, r1), dup2(-2.f), dup2(1.f));
+    } else if constexpr (ACT == BANN_RELU) {
+        aux = t;
+        return mk2(fmaxf(lo2(t), 0.f), fmaxf(hi2(t), 0.f));
+    } else if constexpr (ACT == BANN_LEAKY_RELU) {   // max(x, 0.01 x): x for x > 0, 0.01 x for x < 0, 0 at 0
+        const f2 s = mul2(t, dup2(0.01f));
+        aux = t;
+        return mk2(fmaxf(lo2(t), lo2(s)), fmaxf(hi2(t), hi2(s)));
+    } else if constexpr (ACT == BANN_SILU) {         // x * sigma(x), sigma = 1 / (1 + 2^(-x log2 e))
+        const f2 u = mul2(t, dup2(-1.4426950408889634f));
+        float e0, e1, r0, r1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(lo2(u)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(hi2(u)));
+        const f2 s = add2(mk2(e0, e1), dup2(1.f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(lo2(s)));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(hi2(s)));
+        aux = mk2(r0, r1);
+        // rcp(inf) = 0 and x -> -inf: 0 * (-inf) would be NaN; the reference's x * (1 / (1 + exp(-x))) has the same hazard only at -inf itself
+        return mul2(t, aux);
+    } else {
+        aux = t;
+        return t;
+    }
+}
+// MINUS the derivative of the activation at the pre-activation, from the activation (and aux): the backward pass carries
+// alternating signs so that tanh's a^2 - 1 needs one instruction instead of two
+template <int ACT>
+__device__ __forceinline__ f2 neg_dact2(f2 a, f2 aux) {
+    if constexpr (ACT == BANN_TANH) return fma2(a, a, dup2(-1.f));
+    else if constexpr (ACT == BANN_RELU) return mk2(lo2(a) > 0.f ? -1.f : 0.f, hi2(a) > 0.f ? -1.f : 0.f);     // a > 0 <=> x > 0
+    else if constexpr (ACT == BANN_LEAKY_RELU)
+        return mk2(lo2(a) > 0.f ? -1.f : (lo2(a) < 0.f ? -0.01f : 0.f), hi2(a) > 0.f ? -1.f : (hi2(a) < 0.f ? -0.01f : 0.f));
+    else if constexpr (ACT == BANN_SILU) return fma2(aux, a, mul2(add2(a, aux), dup2(-1.f)));   // -(f + s (1 - f)), f = x s = a
+    else return dup2(-1.f);
+}
+
 template <int H, int S, int D>
 struct TcShape {
     using T = TailShape<H, S, D>;
@@ -91,12 +140,215 @@ struct TcShape {
     }
 };
 
+// ---- the FP32 tail shared by the tensor-core kernels (k1_tc, k1_tcw): thread = row pair (t, 128 + t) as packed f32x2.
+// part1: remaining layers, error, and every part of the backward pass that needs no other data than the thread's own rows:
+//   all deltas are linear in the error, delta_l = e * rho_l with rho_{NLA-1} = phi'(z) (.) W_out and
+//   rho_{l-1} = phi'(z_{l-1}) (.) (rho_l W_l^T)  (branch_sampler.rs:813-875 with the error factored out), so rho_l is computed right
+//   behind the forward pass, while the weights of layer l are still in registers: one shared-memory read per weight and
+//   super-tile instead of two (the kernels are shared-memory-wavefront bound, profiles/r2_k1_tc_ncu_summary.md).
+//   Signs alternate -- sg_l = (-1)^(NLA-l) cA^(NLA-1-l) rho_l -- so that tanh's a^2 - 1 is one instruction and the pre-scaled
+//   weights are used as they are; the factor is undone on the error, one multiplication per layer.
+// part2: delta_0 = sg_0 * (signed, unscaled error) -> three bf16 pieces per unit by truncation (exact: 3 x 8 significand bits).
+template <int H, int S, int D, int ACT>
+struct TcTail {
+    using T = TailShape<H, S, D>;
+    static constexpr int NLA = T::NLA, W0 = T::W0, MW = T::MW, NN = 16;
+    static constexpr int NL1 = NLA > 1 ? NLA - 1 : 1;
+    static constexpr float cA = act_prescale<ACT>();
+    struct Acc {                          // cross-row sums, persistent over the super-tiles of a CTA
+        f2 gb0[W0], gWo[S], rss, gWt[NL1][MW][MW], gbt[NL1][MW];
+        __device__ __forceinline__ void clear() {
+            const f2 z = dup2(0.f);
+            rss = z;
+#pragma unroll
+            for (int c = 0; c < W0; ++c) gb0[c] = z;
+#pragma unroll
+            for (int c = 0; c < S; ++c) gWo[c] = z;
+#pragma unroll
+            for (int l = 0; l < NL1; ++l)
+#pragma unroll
+                for (int i = 0; i < MW; ++i) {
+                    gbt[l][i] = z;
+#pragma unroll
+                    for (int c = 0; c < MW; ++c) gWt[l][i][c] = z;
+                }
+        }
+    };
+    // wp: tail parameters (weights / biases feeding an activated layer >= 1 pre-scaled by cA), b0p: cA * mean-folded first-layer bias
+    __device__ __forceinline__ static void part1(const float* accA, const float* accB, const float* wp, const float* b0p, f2& tg,
+                                                 bool add_pred_to_target, f2 valid, bool bwd, Acc& A, f2& yh, f2 (&sg0)[W0], f2& ef0) {
+        const f2 zero2 = dup2(0.f);
+        f2 act[NLA][MW], aux[NLA][MW];
+#pragma unroll
+        for (int c = 0; c < W0; ++c) {
+            const f2 z = mk2(accA[c] + (accA[W0 + c] + accA[2 * W0 + c]), accB[c] + (accB[W0 + c] + accB[2 * W0 + c]));
+            act[0][c] = act2<ACT>(fma2(z, dup2(8589934592.f /* 2^33 */ * cA), dup2(b0p[c])), aux[0][c]);
+        }
+#pragma unroll
+        for (int l = 1; l < NLA; ++l) {
+#pragma unroll
+            for (int c = 0; c < MW; ++c) {
+                if (c < T::width(l)) {
+                    f2 zz = dup2(wp[T::b_off(l) + c]);
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) zz = fma2(act[l - 1][i], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), zz);
+                    act[l][c] = act2<ACT>(zz, aux[l][c]);
+                }
+            }
+        }
+        yh = zero2;
+#pragma unroll
+        for (int i = 0; i < S; ++i) yh = fma2(act[NLA - 1][i], dup2(wp[T::w_off(NLA) + i]), yh);
+        if (add_pred_to_target) tg = add2(tg, yh);                         // net.rs:280
+        const f2 e = mul2(fma2(tg, dup2(-1.f), yh), valid);                // branch_sampler.rs:821
+        ef0 = zero2;
+#pragma unroll
+        for (int c = 0; c < W0; ++c) sg0[c] = zero2;
+        if (!bwd) return;
+        f2 sg[MW];
+#pragma unroll
+        for (int i = 0; i < S; ++i) sg[i] = mul2(neg_dact2<ACT>(act[NLA - 1][i], aux[NLA - 1][i]), dup2(wp[T::w_off(NLA) + i]));
+        A.rss = fma2(e, e, A.rss);
+#pragma unroll
+        for (int i = 0; i < S; ++i) A.gWo[i] = fma2(act[NLA - 1][i], e, A.gWo[i]);
+        float fac = -1.f;                  // (-1)^(NLA-l) cA^-(NLA-1-l) at l = NLA - 1
+#pragma unroll
+        for (int l = NLA - 1; l >= 1; --l) {
+            f2 nd[MW];                     // sg of the layer below, from the weights the forward pass of layer l just used
+#pragma unroll
+            for (int i = 0; i < MW; ++i) nd[i] = zero2;
+#pragma unroll
+            for (int c = 0; c < MW; ++c)
+                if (c < T::width(l)) {
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) nd[i] = fma2(sg[c], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), nd[i]);
+                }
+            const f2 ef = mul2(e, dup2(fac));        // cross-row sums of layer l
+#pragma unroll
+            for (int c = 0; c < MW; ++c)
+                if (c < T::width(l)) {
+                    const f2 dl = mul2(sg[c], ef);
+                    A.gbt[l - 1][c] = add2(A.gbt[l - 1][c], dl);
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) A.gWt[l - 1][i][c] = fma2(act[l - 1][i], dl, A.gWt[l - 1][i][c]);
+                }
+#pragma unroll
+            for (int i = 0; i < MW; ++i)
+                if (i < T::in_w(l)) sg[i] = mul2(neg_dact2<ACT>(act[l - 1][i], aux[l - 1][i]), nd[i]);
+            fac = -fac / cA;
+        }
+#pragma unroll
+        for (int c = 0; c < W0; ++c) sg0[c] = sg[c];
+        ef0 = mul2(e, dup2(fac));
+    }
+    // delta_0 of the pair, accumulated into gb0 and lifted by 2^100 (exact) for the piece split
+    __device__ __forceinline__ static void delta0(const f2 (&sg0)[W0], f2 ef0, Acc& A, f2 (&v)[W0]) {
+#pragma unroll
+        for (int c = 0; c < W0; ++c) {
+            const f2 d0 = mul2(sg0[c], ef0);
+            A.gb0[c] = add2(A.gb0[c], d0);
+            v[c] = mul2(d0, dup2(1.2676506002282294e30f));
+        }
+    }
+    // three bf16 pieces per unit -> the MN-major B operand rows of this thread: n = piece * W0 + unit, one 16-byte chunk per 8 n
+    __device__ __forceinline__ static void store_pieces(f2 (&v)[W0], uint8_t* dst /* sD + tid * 16 */) {
+        uint32_t pa[NN], pb[NN];      // f32 bit patterns whose upper halves are the bf16 pieces (row A / row B)
+#pragma unroll
+        for (int n = 0; n < NN; ++n) { pa[n] = 0u; pb[n] = 0u; }
+#pragma unroll
+        for (int c = 0; c < W0; ++c) {
+#pragma unroll
+            for (int piece = 0; piece < 3; ++piece) {
+                const uint32_t ua = __float_as_uint(lo2(v[c])) & 0xFFFF0000u, ub = __float_as_uint(hi2(v[c])) & 0xFFFF0000u;
+                pa[piece * W0 + c] = ua; pb[piece * W0 + c] = ub;
+                if (piece < 2) v[c] = add2(v[c], mk2(-__uint_as_float(ua), -__uint_as_float(ub)));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NN / 8; ++q) {
+            uint4 wa, wb;
+            wa.x = __byte_perm(pa[8 * q], pa[8 * q + 1], 0x7632); wa.y = __byte_perm(pa[8 * q + 2], pa[8 * q + 3], 0x7632);
+            wa.z = __byte_perm(pa[8 * q + 4], pa[8 * q + 5], 0x7632); wa.w = __byte_perm(pa[8 * q + 6], pa[8 * q + 7], 0x7632);
+            wb.x = __byte_perm(pb[8 * q], pb[8 * q + 1], 0x7632); wb.y = __byte_perm(pb[8 * q + 2], pb[8 * q + 3], 0x7632);
+            wb.z = __byte_perm(pb[8 * q + 4], pb[8 * q + 5], 0x7632); wb.w = __byte_perm(pb[8 * q + 6], pb[8 * q + 7], 0x7632);
+            *reinterpret_cast<uint4*>(dst + q * kTcChunkStride) = wa;
+            *reinterpret_cast<uint4*>(dst + q * kTcChunkStride + 128 * 16) = wb;
+        }
+    }
+    // stage the tail parameters of a branch: th_tail = theta + m * W0, n_tail floats
+    __device__ __forceinline__ static void stage_tail(const float* th_tail, float* wp, uint32_t tid, uint32_t nthreads) {
+        for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += nthreads) {
+            const float w = th_tail[k];
+            const bool scaled = NLA > 1 && ((int)k < T::w_off(NLA) || (int)k >= T::b_off(NLA > 1 ? 1 : 0));
+            wp[k] = scaled ? w * cA : w;
+        }
+    }
+    // CTA epilogue, first half: fixed-order reduction of the cross-row sums over row pairs, lanes and the four compute warps,
+    // written to the partial slot `pp` in param_vec order (rss at [P]); gb0 also to s_gb0 for the standardisation unfold
+    __device__ __forceinline__ static void reduce_and_store(const Acc& A, float* red, uint32_t warp, uint32_t lane, uint32_t tid, float* pp,
+                                                            uint32_t m, uint32_t P, float* s_gb0) {
+        constexpr int NTACC = T::NTACC;
+        if (warp < 4) {
+            float* rw = red + warp * NTACC;
+            int idx = 0;
+            auto put = [&](f2 v2) {
+                float v = lo2(v2) + hi2(v2);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) rw[idx] = v;
+                ++idx;
+            };
+            put(A.rss);
+#pragma unroll
+            for (int c = 0; c < S; ++c) put(A.gWo[c]);
+#pragma unroll
+            for (int c = 0; c < W0; ++c) put(A.gb0[c]);
+#pragma unroll
+            for (int l = 1; l < NLA; ++l) {
+#pragma unroll
+                for (int c = 0; c < MW; ++c) put(A.gbt[l - 1][c]);
+#pragma unroll
+                for (int i = 0; i < MW; ++i)
+#pragma unroll
+                    for (int c = 0; c < MW; ++c) put(A.gWt[l - 1][i][c]);
+            }
+        }
+        __syncthreads();
+        if (tid < NTACC) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) s += red[w * NTACC + tid];
+            int idx = tid;
+            if (idx == 0) pp[P] = s;
+            else if (idx < 1 + S) pp[m * W0 + T::w_off(NLA) + (idx - 1)] = s;                       // output weights
+            else if (idx < 1 + S + W0) { pp[m * W0 + T::b_off(0) + (idx - 1 - S)] = s; s_gb0[idx - 1 - S] = s; }
+            else {
+                int k = idx - (1 + S + W0);
+                const int per = MW + MW * MW;
+                const int l = 1 + k / per;
+                k %= per;
+                if (k < MW) {
+                    if (k < T::width(l)) pp[m * W0 + T::b_off(l) + k] = s;
+                } else {
+                    k -= MW;
+                    const int i = k / MW, c = k % MW;
+                    if (i < T::in_w(l) && c < T::width(l)) pp[m * W0 + T::w_off(l) + c * T::in_w(l) + i] = s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+};
+
 // LEAN: gradient / leapfrog launches (targets given, no per-row outputs, backward always) -- the hot configuration
-template <int H, int S, int D, bool LEAN, int NCT>
+template <int H, int S, int D, int ACT, bool LEAN, int NCT>
 __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
-    constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, MW = T::MW, NTACC = T::NTACC, NN = C::NN;
+    constexpr int W0 = T::W0, W0P = T::W0P, NN = C::NN;
     extern __shared__ __align__(16) uint8_t smraw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
@@ -152,10 +404,10 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         if (warp == 0) umma::tmem_dealloc(*tmem_slot, C::TMEM_COLS);
         return;
     }
-    for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += 128) {
-        const float w = th[m * W0 + k];
-        wp[k] = w;
-    }
+    // tail parameters; what feeds an activated layer >= 1 (its weights and biases) carries the activation's pre-scale
+    using TT = TcTail<H, S, D, ACT>;
+    constexpr float cA = TT::cA;
+    TT::stage_tail(th + m * W0, wp, tid, 128);
     __syncthreads();
     // ---- stage W' = W0 / sd (f32, in the delta buffer for the bias fold) and its three bf16 pieces
     float* wtmp = reinterpret_cast<float*>(sD);                // [m][W0], transient
@@ -175,7 +427,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         float acc = 0.f;
         if (tid < W0) {
             for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], wtmp[j * W0 + tid], acc);
-            acc = wp[T::b_off(0) + tid] - acc;
+            acc = (th[m * W0 + T::b_off(0) + tid] - acc) * cA;
         }
         b0p[tid] = acc;
     }
@@ -198,20 +450,8 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
 
     // ---- persistent per-thread accumulators (cross-row sums of the layers >= 1), one lane per row of the pair
     const f2 zero2 = dup2(0.f);
-    f2 gb0[W0], gWo[S], rss = zero2;
-    f2 gWt[NLA > 1 ? NLA - 1 : 1][MW][MW], gbt[NLA > 1 ? NLA - 1 : 1][MW];
-#pragma unroll
-    for (int c = 0; c < W0; ++c) gb0[c] = zero2;
-#pragma unroll
-    for (int c = 0; c < S; ++c) gWo[c] = zero2;
-#pragma unroll
-    for (int l = 0; l < (NLA > 1 ? NLA - 1 : 1); ++l)
-#pragma unroll
-        for (int i = 0; i < MW; ++i) {
-            gbt[l][i] = zero2;
-#pragma unroll
-            for (int c = 0; c < MW; ++c) gWt[l][i][c] = zero2;
-        }
+    typename TT::Acc A;
+    A.clear();
 
     const size_t eoff = a.out_per_entry ? (size_t)li * a.n : 0;
     const size_t toff = (a.target_mode == TGT_PER_ENTRY) ? (size_t)li * a.n : 0;
@@ -231,14 +471,13 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     auto expand = [&](uint32_t buf) {
         uint8_t* rowA = sA + buf * sa_bytes + tid * 16;
         uint32_t xw[8];
-        if (BANN_TCV & 1) {          // all word loads first: the stores below are volatile asm, the compiler will not hoist loads over them
+        // all word loads first: the stores below are volatile asm, the compiler will not hoist loads over them
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xw[i] = ((uint32_t)i < NC) ? sG[i * 128 + tid] : 0u;
-        }
+        for (int i = 0; i < 8; ++i) xw[i] = ((uint32_t)i < NC) ? sG[i * 128 + tid] : 0u;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             if ((uint32_t)i < NC) {
-                const uint32_t x = (BANN_TCV & 1) ? xw[i] : sG[i * 128 + tid], y = x >> 8;
+                const uint32_t x = xw[i], y = x >> 8;
                 const uint4 oa = make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
                 const uint4 ob = make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
                 *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) = oa;                   // backward operand (MN-major view)
@@ -304,36 +543,15 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         float accA[16], accB[16];
         umma::tmem_ld16x2(tlane, tlane + NN, accA, accB);
         umma::fence_before_sync();      // these reads precede the next forward MMA (ordered by the barrier below)
-        if ((BANN_TCV & 2) && bwd && it > 0 && warp >= 2) {   // deferred: by now every thread has long written its delta pieces
+        if (bwd && it > 0 && warp >= 2) {   // deferred: by now every thread has long written its delta pieces
             umma::mbar_wait(&mbar[3], (it - 1) & 1u);
             issue_bwd(buf ^ 1u, warp - 2, it - 1);
         }
 
-        // ---- tail, part 1: remaining layers and the error, both rows of the pair in packed FP32
-        f2 act[NLA][MW];
-#pragma unroll
-        for (int c = 0; c < W0; ++c) {
-            const f2 z = mk2(accA[c] + (accA[W0 + c] + accA[2 * W0 + c]), accB[c] + (accB[W0 + c] + accB[2 * W0 + c]));
-            act[0][c] = tanh2(fma2(z, dup2(8589934592.f /* 2^33 */), dup2(b0p[c])));   // folding tanh's 2 log2(e) into the weights: measured no gain
-        }
-#pragma unroll
-        for (int l = 1; l < NLA; ++l) {
-#pragma unroll
-            for (int c = 0; c < MW; ++c) {
-                if (c < T::width(l)) {
-                    f2 zz = dup2(wp[T::b_off(l) + c]);
-#pragma unroll
-                    for (int i = 0; i < MW; ++i)
-                        if (i < T::in_w(l)) zz = fma2(act[l - 1][i], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), zz);
-                    act[l][c] = tanh2(zz);
-                }
-            }
-        }
-        f2 yh = zero2;
-#pragma unroll
-        for (int i = 0; i < S; ++i) yh = fma2(act[NLA - 1][i], dup2(wp[T::w_off(NLA) + i]), yh);
-        if (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) tg = add2(tg, yh);            // net.rs:280
-        const f2 e = mul2(fma2(tg, dup2(-1.f), yh), mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f));  // branch_sampler.rs:821
+        // ---- tail, part 1 (TcTail): remaining layers, error, rho_l and the cross-row sums of the layers >= 1
+        f2 yh, sg0[W0], ef0;
+        TT::part1(accA, accB, wp, b0p, tg, !LEAN && a.target_mode == TGT_RESID_PLUS_PRED, mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f), bwd, A,
+                  yh, sg0, ef0);
         // ---- per-row outputs
         if (!LEAN) {
             auto put = [&](float* dst, uint32_t row, float v, int accumulate) {
@@ -357,7 +575,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
             expand(buf ^ 1u);
         }
         // no CTA-wide barrier: every thread arrives and moves on, only the issuer warp waits for all 128 arrivals
-        if (!(BANN_TCV & 8) || !bwd) umma::fence_async_smem();   // bit 3: the image written above is first read by a backward MMA gated by the NEXT delta barrier, whose fence covers it
+        if (!bwd) umma::fence_async_smem();   // with a backward pass the image written above is first read by a backward MMA gated by the NEXT delta barrier, whose fence covers it
         umma::mbar_arrive(&mbar[2]);
         auto fwd_issue_point = [&]() {
             if (warp < 2) {
@@ -366,77 +584,19 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
                 if (warp == 1 && it + 2 < nit) issue_load(st + 2);        // every thread has read the staged words by now
             }
         };
-        if (!(BANN_TCV & 2) || !bwd) fwd_issue_point();
-        if (!bwd) continue;
+        if (!bwd) { fwd_issue_point(); continue; }
 
-        // ---- tail, part 2: backward deltas and the cross-row sums of the layers >= 1
-        const f2 e2 = e;
-        rss = fma2(e2, e2, rss);
-        f2 delta[MW];
-#pragma unroll
-        for (int i = 0; i < S; ++i) {
-            gWo[i] = fma2(act[NLA - 1][i], e2, gWo[i]);
-            delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e2, dup2(wp[T::w_off(NLA) + i])));
-        }
-#pragma unroll
-        for (int l = NLA - 1; l >= 1; --l) {
-            f2 nd[MW];
-#pragma unroll
-            for (int i = 0; i < MW; ++i) nd[i] = zero2;
-#pragma unroll
-            for (int c = 0; c < MW; ++c) {
-                if (c < T::width(l)) {
-                    gbt[l - 1][c] = add2(gbt[l - 1][c], delta[c]);
-#pragma unroll
-                    for (int i = 0; i < MW; ++i)
-                        if (i < T::in_w(l)) {
-                            gWt[l - 1][i][c] = fma2(act[l - 1][i], delta[c], gWt[l - 1][i][c]);
-                            nd[i] = fma2(delta[c], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), nd[i]);
-                        }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < MW; ++i)
-                if (i < T::in_w(l)) delta[i] = mul2(dtanh2(act[l - 1][i]), nd[i]);
-        }
-        if (BANN_TCV & 2) fwd_issue_point();      // deferred: the other warps have expanded their rows while this one did the deltas
-        // ---- delta_0 -> three bf16 pieces per unit by truncation (exact: 3 x 8 significand bits = f32),
-        //      n = piece * W0 + unit, MN-major B operand: one 16-byte chunk per 8 n
+        // ---- tail, part 2: delta_0 -> three bf16 pieces per unit in the backward B operand
         {
-            uint32_t pa[NN], pb[NN];      // f32 bit patterns whose upper halves are the bf16 pieces (row A / row B)
-#pragma unroll
-            for (int n = 0; n < NN; ++n) { pa[n] = 0u; pb[n] = 0u; }
-#pragma unroll
-            for (int c = 0; c < W0; ++c) {
-                gb0[c] = add2(gb0[c], delta[c]);
-                f2 v = mul2(delta[c], dup2(1.2676506002282294e30f));   // 2^100, exact
-#pragma unroll
-                for (int piece = 0; piece < 3; ++piece) {
-                    const uint32_t ua = __float_as_uint(lo2(v)) & 0xFFFF0000u, ub = __float_as_uint(hi2(v)) & 0xFFFF0000u;
-                    pa[piece * W0 + c] = ua; pb[piece * W0 + c] = ub;
-                    if (piece < 2) v = add2(v, mk2(-__uint_as_float(ua), -__uint_as_float(ub)));
-                }
-            }
-            uint8_t* dst = sD + tid * 16;
-#pragma unroll
-            for (int q = 0; q < NN / 8; ++q) {
-                uint4 wa, wb;
-                wa.x = __byte_perm(pa[8 * q], pa[8 * q + 1], 0x7632); wa.y = __byte_perm(pa[8 * q + 2], pa[8 * q + 3], 0x7632);
-                wa.z = __byte_perm(pa[8 * q + 4], pa[8 * q + 5], 0x7632); wa.w = __byte_perm(pa[8 * q + 6], pa[8 * q + 7], 0x7632);
-                wb.x = __byte_perm(pb[8 * q], pb[8 * q + 1], 0x7632); wb.y = __byte_perm(pb[8 * q + 2], pb[8 * q + 3], 0x7632);
-                wb.z = __byte_perm(pb[8 * q + 4], pb[8 * q + 5], 0x7632); wb.w = __byte_perm(pb[8 * q + 6], pb[8 * q + 7], 0x7632);
-                *reinterpret_cast<uint4*>(dst + q * kTcChunkStride) = wa;
-                *reinterpret_cast<uint4*>(dst + q * kTcChunkStride + 128 * 16) = wb;
-            }
+            f2 v[W0];
+            TT::delta0(sg0, ef0, A, v);
+            fwd_issue_point();            // deferred: the other warps have expanded their rows while this one did the above
+            TT::store_pieces(v, sD + tid * 16);
         }
         umma::fence_async_smem();
         umma::mbar_arrive(&mbar[3]);
-        if (!(BANN_TCV & 2) && warp >= 2) {
-            umma::mbar_wait(&mbar[3], it & 1u);
-            issue_bwd(buf, warp - 2, it);
-        }
     }
-    if ((BANN_TCV & 2) && bwd && nit > 0 && warp >= 2) {       // the last super-tile's backward contraction
+    if (bwd && nit > 0 && warp >= 2) {       // the last super-tile's backward contraction
         umma::mbar_wait(&mbar[3], (nit - 1) & 1u);
         issue_bwd((nit - 1) & 1u, warp - 2, nit - 1);
     }
@@ -457,57 +617,8 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
 
     // ---- CTA epilogue: fixed-order reduction over row pairs, lanes and warps; unfold the standardisation
     float* pp = a.part + ((size_t)li * a.nchunk + chunk) * a.pstride;
-    const uint32_t P = d.P;
-    {
-        float* rw = red + warp * NTACC;
-        int idx = 0;
-        auto put = [&](f2 v2) {
-            float v = lo2(v2) + hi2(v2);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) rw[idx] = v;
-            ++idx;
-        };
-        put(rss);
-#pragma unroll
-        for (int c = 0; c < S; ++c) put(gWo[c]);
-#pragma unroll
-        for (int c = 0; c < W0; ++c) put(gb0[c]);
-#pragma unroll
-        for (int l = 1; l < NLA; ++l) {
-#pragma unroll
-            for (int c = 0; c < MW; ++c) put(gbt[l - 1][c]);
-#pragma unroll
-            for (int i = 0; i < MW; ++i)
-#pragma unroll
-                for (int c = 0; c < MW; ++c) put(gWt[l - 1][i][c]);
-        }
-    }
-    __syncthreads();
     __shared__ float s_gb0[W0];
-    if (tid < NTACC) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) s += red[w * NTACC + tid];
-        int idx = tid;
-        if (idx == 0) pp[P] = s;
-        else if (idx < 1 + S) pp[m * W0 + T::w_off(NLA) + (idx - 1)] = s;                       // output weights
-        else if (idx < 1 + S + W0) { pp[m * W0 + T::b_off(0) + (idx - 1 - S)] = s; s_gb0[idx - 1 - S] = s; }
-        else {
-            int k = idx - (1 + S + W0);
-            const int per = MW + MW * MW;
-            const int l = 1 + k / per;
-            k %= per;
-            if (k < MW) {
-                if (k < T::width(l)) pp[m * W0 + T::b_off(l) + k] = s;
-            } else {
-                k -= MW;
-                const int i = k / MW, c = k % MW;
-                if (i < T::in_w(l) && c < T::width(l)) pp[m * W0 + T::w_off(l) + c * T::in_w(l) + i] = s;
-            }
-        }
-    }
-    __syncthreads();
+    TT::reduce_and_store(A, red, warp, lane, tid, pp, m, d.P, s_gb0);
     // first-layer weight gradient: accumulator row j lives in lane (j % 16) of warp j / 16 (M = 64 layout);
     // S_jc = sum of the three pieces * 2^33 / 4^p(j), then (S_jc - mu_j * gb0_c) / sd_j
     if (lane < 16) {
@@ -523,33 +634,44 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     }
 }
 
-template <int H, int S, int D>
-int launch_one_tc(K1Args& a, uint32_t nlist, cudaStream_t st) {
+template <int H, int S, int D, int ACT>
+int launch_one_tc_act(K1Args& a, uint32_t nlist, cudaStream_t st) {
     using C = TcShape<H, S, D>;
+    constexpr bool kNct7 = ACT == BANN_TANH;      // the 49..56-marker specialisation exists for the benchmarked activation only
     static bool configured = false;
     if (!configured) {
-        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
-        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
-        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, ACT, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
+        if (kNct7) BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, ACT, true, kNct7 ? 7 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tc<H, S, D, ACT, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(8)));
         configured = true;
     }
     const size_t smem = C::smem(a.ncb);
     dim3 grid(a.nchunk, nlist);
     const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
-    if (lean && a.nc_uniform == 7) BANN_CUDA(launch_pdl(k1_tc<H, S, D, true, 7>, grid, dim3(128), smem, st, a));   // 49..56 markers in every listed branch
-    else if (lean) BANN_CUDA(launch_pdl(k1_tc<H, S, D, true, 0>, grid, dim3(128), smem, st, a));
-    else BANN_CUDA(launch_pdl(k1_tc<H, S, D, false, 0>, grid, dim3(128), smem, st, a));
+    if (lean && kNct7 && a.nc_uniform == 7) BANN_CUDA(launch_pdl(k1_tc<H, S, D, ACT, true, kNct7 ? 7 : 0>, grid, dim3(128), smem, st, a));   // 49..56 markers in every listed branch
+    else if (lean) BANN_CUDA(launch_pdl(k1_tc<H, S, D, ACT, true, 0>, grid, dim3(128), smem, st, a));
+    else BANN_CUDA(launch_pdl(k1_tc<H, S, D, ACT, false, 0>, grid, dim3(128), smem, st, a));
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
 }
+template <int H, int S, int D>
+int launch_one_tc(K1Args& a, uint32_t nlist, cudaStream_t st) {
+    switch (a.act) {
+        case BANN_TANH: return launch_one_tc_act<H, S, D, BANN_TANH>(a, nlist, st);
+        case BANN_RELU: return launch_one_tc_act<H, S, D, BANN_RELU>(a, nlist, st);
+        case BANN_LEAKY_RELU: return launch_one_tc_act<H, S, D, BANN_LEAKY_RELU>(a, nlist, st);
+        case BANN_SILU: return launch_one_tc_act<H, S, D, BANN_SILU>(a, nlist, st);
+        default: return launch_one_tc_act<H, S, D, BANN_IDENTITY>(a, nlist, st);
+    }
+}
 
-// Tensor-core K1 for a homogeneous launch: tanh, every listed branch of the same architecture with at
+// Tensor-core K1 for a homogeneous launch: any of the five activations, every listed branch of the same architecture with at
 // most 64 markers and 3 * W0 <= 16, and a tensor-core store present.  Otherwise *launched stays false.
 inline int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
                         cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
-    if (a.act != BANN_TANH || !a.store_tc) return 0;
+    if (!a.store_tc) return 0;
     const BranchDesc& d0 = descs[single_branch >= 0 ? single_branch : 0];
     uint32_t max_m = d0.m;
     if (single_branch < 0) {

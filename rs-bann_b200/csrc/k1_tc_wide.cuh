@@ -33,12 +33,13 @@ struct TcwShape {
 
 constexpr int kTcwThreads = 160;   // warps 0-3: expansion, tail, epilogue; warp 4: ring loads + MMA issue (measured on cfg2: +50 %)
 
-template <int H, int S, int D, bool LEAN>
+template <int H, int S, int D, int ACT, bool LEAN>
 __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
     using CW = TcwShape<H, S, D>;
-    constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, MW = T::MW, NTACC = T::NTACC, NN = C::NN;
+    using TT = TcTail<H, S, D, ACT>;
+    constexpr int W0 = T::W0, W0P = T::W0P, NN = C::NN;
     extern __shared__ __align__(16) uint8_t smraw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t li = blockIdx.y, chunk = blockIdx.x;
@@ -51,9 +52,9 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     uint32_t* sG = reinterpret_cast<uint32_t*>(sA + 2 * kTcwBlockBytes);           // ring: [slot][chunk][128] packed words
     uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + kTcwRing * kTcwBlockChunks * 512;
     uint8_t* sW = sD + C::SD;                                                     // [k-chunk][n] x 16 B, all blocks
-    float2* wp2 = reinterpret_cast<float2*>(sW + CW::SW);
-    float2* b0p2 = wp2 + ((T::n_tail() + 3) & ~3);
-    float* red = reinterpret_cast<float*>(b0p2 + W0P);
+    float* wp = reinterpret_cast<float*>(sW + CW::SW);              // tail parameters, plain floats (FFMA2 broadcasts a scalar register)
+    float* b0p = wp + 2 * ((T::n_tail() + 3) & ~3);                  // (layout size as before)
+    float* red = b0p + 2 * W0P;
     // mbarriers: [0..1] backward MMAs that read operand buffer 0/1 done; [2..3] buffer 0/1 expanded (128 arrivals);
     //            [4..7] ring slot 0..3 landed; [8] forward MMAs of a block done; [9] forward block expanded (128 arrivals)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);
@@ -86,10 +87,7 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
         if (warp == 0) umma::tmem_dealloc(*tmem_slot, CW::TMEM_COLS);
         return;
     }
-    for (uint32_t k = tid; k < (uint32_t)T::n_tail(); k += kTcwThreads) {
-        const float w = th[m * W0 + k];
-        wp2[k] = make_float2(w, w);
-    }
+    TT::stage_tail(th + m * W0, wp, tid, kTcwThreads);
     __syncthreads();
     // first-layer weights: W' = W0 / sd, its three bf16 pieces (scaled as in k1_tc), and the mean-folded bias
     float bacc[W0];
@@ -119,8 +117,8 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     __syncthreads();
     if (tid < W0P) {
         float acc = 0.f;
-        if (tid < W0) acc = wp2[T::b_off(0) + tid].x - (red[tid] + red[W0 + tid] + red[2 * W0 + tid] + red[3 * W0 + tid]);
-        b0p2[tid] = make_float2(acc, acc);
+        if (tid < W0) acc = (th[m * W0 + T::b_off(0) + tid] - (red[tid] + red[W0 + tid] + red[2 * W0 + tid] + red[3 * W0 + tid])) * TT::cA;
+        b0p[tid] = acc;
     }
     umma::fence_async_smem();
     umma::fence_before_sync();
@@ -136,20 +134,8 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
 
     // ---- persistent per-thread accumulators (as in k1_tc)
     const f2 zero2 = dup2(0.f);
-    f2 gb0[W0], gWo[S], rss = zero2;
-    f2 gWt[NLA > 1 ? NLA - 1 : 1][MW][MW], gbt[NLA > 1 ? NLA - 1 : 1][MW];
-#pragma unroll
-    for (int c = 0; c < W0; ++c) gb0[c] = zero2;
-#pragma unroll
-    for (int c = 0; c < S; ++c) gWo[c] = zero2;
-#pragma unroll
-    for (int l = 0; l < (NLA > 1 ? NLA - 1 : 1); ++l)
-#pragma unroll
-        for (int i = 0; i < MW; ++i) {
-            gbt[l][i] = zero2;
-#pragma unroll
-            for (int c = 0; c < MW; ++c) gWt[l][i][c] = zero2;
-        }
+    typename TT::Acc A;
+    A.clear();
 
     const size_t eoff = a.out_per_entry ? (size_t)li * a.n : 0;
     const size_t toff = (a.target_mode == TGT_PER_ENTRY) ? (size_t)li * a.n : 0;
@@ -302,31 +288,10 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
         umma::tmem_ld16x2(tlane, tlane + NN, accA, accB);
         umma::fence_before_sync();
 
-        // ---- tail, part 1
-        f2 act[NLA][MW];
-#pragma unroll
-        for (int c = 0; c < W0; ++c) {
-            const f2 z = mk2(accA[c] + (accA[W0 + c] + accA[2 * W0 + c]), accB[c] + (accB[W0 + c] + accB[2 * W0 + c]));
-            act[0][c] = tanh2(fma2(z, dup2(8589934592.f /* 2^33 */), ld2(b0p2 + c)));
-        }
-#pragma unroll
-        for (int l = 1; l < NLA; ++l) {
-#pragma unroll
-            for (int c = 0; c < MW; ++c) {
-                if (c < T::width(l)) {
-                    f2 zz = ld2(wp2 + T::b_off(l) + c);
-#pragma unroll
-                    for (int i = 0; i < MW; ++i)
-                        if (i < T::in_w(l)) zz = fma2(act[l - 1][i], ld2(wp2 + T::w_off(l) + c * T::in_w(l) + i), zz);
-                    act[l][c] = tanh2(zz);
-                }
-            }
-        }
-        f2 yh = zero2;
-#pragma unroll
-        for (int i = 0; i < S; ++i) yh = fma2(act[NLA - 1][i], ld2(wp2 + T::w_off(NLA) + i), yh);
-        if (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) tg = add2(tg, yh);            // net.rs:280
-        const f2 e = mul2(fma2(tg, dup2(-1.f), yh), mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f));  // branch_sampler.rs:821
+        // ---- tail (TcTail, k1_tc.cuh): remaining layers, error, rho_l, cross-row sums of the layers >= 1
+        f2 yh, sg0[W0], ef0;
+        TT::part1(accA, accB, wp, b0p, tg, !LEAN && a.target_mode == TGT_RESID_PLUS_PRED, mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f), bwd, A,
+                  yh, sg0, ef0);
         if (!LEAN) {
             auto put = [&](float* dst, uint32_t row, float v, int accumulate) {
                 if (!dst || row >= a.n) return;
@@ -344,65 +309,14 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
         }
         if (!bwd) continue;
 
-        // ---- tail, part 2
-        rss = fma2(e, e, rss);
-        f2 delta[MW];
-#pragma unroll
-        for (int i = 0; i < S; ++i) {
-            gWo[i] = fma2(act[NLA - 1][i], e, gWo[i]);
-            delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e, ld2(wp2 + T::w_off(NLA) + i)));
-        }
-#pragma unroll
-        for (int l = NLA - 1; l >= 1; --l) {
-            f2 nd[MW];
-#pragma unroll
-            for (int i = 0; i < MW; ++i) nd[i] = zero2;
-#pragma unroll
-            for (int c = 0; c < MW; ++c) {
-                if (c < T::width(l)) {
-                    gbt[l - 1][c] = add2(gbt[l - 1][c], delta[c]);
-#pragma unroll
-                    for (int i = 0; i < MW; ++i)
-                        if (i < T::in_w(l)) {
-                            gWt[l - 1][i][c] = fma2(act[l - 1][i], delta[c], gWt[l - 1][i][c]);
-                            nd[i] = fma2(delta[c], ld2(wp2 + T::w_off(l) + c * T::in_w(l) + i), nd[i]);
-                        }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < MW; ++i)
-                if (i < T::in_w(l)) delta[i] = mul2(dtanh2(act[l - 1][i]), nd[i]);
-        }
         // delta_0 pieces.  The delta buffer was last read by the previous super-tile's backward MMAs: wait for its last two
         // commits (both operand buffers), long complete after a forward pass and a tail.
         if (qb >= 1) umma::mbar_wait(&mbar[(qb - 1) & 1u], ((qb - 1) >> 1) & 1u);
         if (qb >= 2) umma::mbar_wait(&mbar[(qb - 2) & 1u], ((qb - 2) >> 1) & 1u);
         {
-            uint32_t pa[NN], pb[NN];
-#pragma unroll
-            for (int n = 0; n < NN; ++n) { pa[n] = 0u; pb[n] = 0u; }
-#pragma unroll
-            for (int c = 0; c < W0; ++c) {
-                gb0[c] = add2(gb0[c], delta[c]);
-                f2 v = mul2(delta[c], dup2(1.2676506002282294e30f));   // 2^100, exact
-#pragma unroll
-                for (int piece = 0; piece < 3; ++piece) {
-                    const uint32_t ua = __float_as_uint(lo2(v)) & 0xFFFF0000u, ub = __float_as_uint(hi2(v)) & 0xFFFF0000u;
-                    pa[piece * W0 + c] = ua; pb[piece * W0 + c] = ub;
-                    if (piece < 2) v = add2(v, mk2(-__uint_as_float(ua), -__uint_as_float(ub)));
-                }
-            }
-            uint8_t* dst = sD + tid * 16;
-#pragma unroll
-            for (int qq = 0; qq < NN / 8; ++qq) {
-                uint4 wa, wb;
-                wa.x = __byte_perm(pa[8 * qq], pa[8 * qq + 1], 0x7632); wa.y = __byte_perm(pa[8 * qq + 2], pa[8 * qq + 3], 0x7632);
-                wa.z = __byte_perm(pa[8 * qq + 4], pa[8 * qq + 5], 0x7632); wa.w = __byte_perm(pa[8 * qq + 6], pa[8 * qq + 7], 0x7632);
-                wb.x = __byte_perm(pb[8 * qq], pb[8 * qq + 1], 0x7632); wb.y = __byte_perm(pb[8 * qq + 2], pb[8 * qq + 3], 0x7632);
-                wb.z = __byte_perm(pb[8 * qq + 4], pb[8 * qq + 5], 0x7632); wb.w = __byte_perm(pb[8 * qq + 6], pb[8 * qq + 7], 0x7632);
-                *reinterpret_cast<uint4*>(dst + qq * kTcChunkStride) = wa;
-                *reinterpret_cast<uint4*>(dst + qq * kTcChunkStride + 128 * 16) = wb;
-            }
+            f2 v[W0];
+            TT::delta0(sg0, ef0, A, v);
+            TT::store_pieces(v, sD + tid * 16);
         }
         // ---- backward pass over the marker blocks (the first arrival below also publishes the delta pieces)
         for (uint32_t kb = 0; kb < NKB; ++kb, ++q, ++qb) expand_bwd(q, qb, kb);
@@ -421,57 +335,8 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
 
     // ---- CTA epilogue: cross-row sums of the layers >= 1 (fixed order), then the first-layer gradient per marker block
     float* pp = a.part + ((size_t)li * a.nchunk + chunk) * a.pstride;
-    const uint32_t P = d.P;
-    {
-        float* rw = red + warp * NTACC;
-        int idx = 0;
-        auto put = [&](f2 v2) {
-            float v = lo2(v2) + hi2(v2);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) rw[idx] = v;
-            ++idx;
-        };
-        put(rss);
-#pragma unroll
-        for (int c = 0; c < S; ++c) put(gWo[c]);
-#pragma unroll
-        for (int c = 0; c < W0; ++c) put(gb0[c]);
-#pragma unroll
-        for (int l = 1; l < NLA; ++l) {
-#pragma unroll
-            for (int c = 0; c < MW; ++c) put(gbt[l - 1][c]);
-#pragma unroll
-            for (int i = 0; i < MW; ++i)
-#pragma unroll
-                for (int c = 0; c < MW; ++c) put(gWt[l - 1][i][c]);
-        }
-    }
-    __syncthreads();
     __shared__ float s_gb0[W0];
-    if (tid < NTACC) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) s += red[w * NTACC + tid];
-        int idx = tid;
-        if (idx == 0) pp[P] = s;
-        else if (idx < 1 + S) pp[m * W0 + T::w_off(NLA) + (idx - 1)] = s;
-        else if (idx < 1 + S + W0) { pp[m * W0 + T::b_off(0) + (idx - 1 - S)] = s; s_gb0[idx - 1 - S] = s; }
-        else {
-            int k = idx - (1 + S + W0);
-            const int per = MW + MW * MW;
-            const int l = 1 + k / per;
-            k %= per;
-            if (k < MW) {
-                if (k < T::width(l)) pp[m * W0 + T::b_off(l) + k] = s;
-            } else {
-                k -= MW;
-                const int i = k / MW, c = k % MW;
-                if (i < T::in_w(l) && c < T::width(l)) pp[m * W0 + T::w_off(l) + c * T::in_w(l) + i] = s;
-            }
-        }
-    }
-    __syncthreads();
+    TT::reduce_and_store(A, red, warp, lane, tid, pp, m, d.P, s_gb0);
     for (uint32_t kb = 0; kb < NKB; ++kb) {
         float sacc[16];
         if (has_bwd) umma::tmem_ld16(tlane + (2 + kb) * NN, sacc);
@@ -492,30 +357,40 @@ __global__ void __launch_bounds__(kTcwThreads, 2) k1_tcw(K1Args a) {
     if (warp == 0) umma::tmem_dealloc(tmem, CW::TMEM_COLS);
 }
 
-template <int H, int S, int D>
-int launch_one_tcw(K1Args& a, uint32_t nlist, cudaStream_t st) {
+template <int H, int S, int D, int ACT>
+int launch_one_tcw_act(K1Args& a, uint32_t nlist, cudaStream_t st) {
     using CW = TcwShape<H, S, D>;
     static bool configured = false;
     if (!configured) {
-        BANN_CUDA(cudaFuncSetAttribute(k1_tcw<H, S, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM));
-        BANN_CUDA(cudaFuncSetAttribute(k1_tcw<H, S, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tcw<H, S, D, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM));
+        BANN_CUDA(cudaFuncSetAttribute(k1_tcw<H, S, D, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM));
         configured = true;
     }
     dim3 grid(a.nchunk, nlist);
     const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
-    if (lean) BANN_CUDA(launch_pdl(k1_tcw<H, S, D, true>, grid, dim3(kTcwThreads), CW::SMEM, st, a));
-    else BANN_CUDA(launch_pdl(k1_tcw<H, S, D, false>, grid, dim3(kTcwThreads), CW::SMEM, st, a));
+    if (lean) BANN_CUDA(launch_pdl(k1_tcw<H, S, D, ACT, true>, grid, dim3(kTcwThreads), CW::SMEM, st, a));
+    else BANN_CUDA(launch_pdl(k1_tcw<H, S, D, ACT, false>, grid, dim3(kTcwThreads), CW::SMEM, st, a));
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
 }
+template <int H, int S, int D>
+int launch_one_tcw(K1Args& a, uint32_t nlist, cudaStream_t st) {
+    switch (a.act) {
+        case BANN_TANH: return launch_one_tcw_act<H, S, D, BANN_TANH>(a, nlist, st);
+        case BANN_RELU: return launch_one_tcw_act<H, S, D, BANN_RELU>(a, nlist, st);
+        case BANN_LEAKY_RELU: return launch_one_tcw_act<H, S, D, BANN_LEAKY_RELU>(a, nlist, st);
+        case BANN_SILU: return launch_one_tcw_act<H, S, D, BANN_SILU>(a, nlist, st);
+        default: return launch_one_tcw_act<H, S, D, BANN_IDENTITY>(a, nlist, st);
+    }
+}
 
-// K-blocked tensor-core K1: homogeneous architecture, tanh, every listed branch with 65..512 markers (so that each has at
+// K-blocked tensor-core K1: homogeneous architecture, any of the five activations, every listed branch with 65..512 markers (so that each has at
 // least two marker blocks), 3 * W0 <= 16, tensor-core store present.
 inline int launch_k1_tcw(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
                          cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
-    if (a.act != BANN_TANH || !a.store_tc) return 0;
+    if (!a.store_tc) return 0;
     const BranchDesc& d0 = descs[single_branch >= 0 ? single_branch : 0];
     uint32_t max_m = d0.m, min_m = d0.m;
     if (single_branch < 0) {

@@ -86,7 +86,6 @@ struct K1Args {
     uint32_t nst;              // 256-row super-tiles
     uint32_t st_per_chunk;
     uint32_t ncb;              // 8-marker chunks per expanded-genotype buffer (max over the listed branches)
-    uint32_t issuer_warp;      // warp that issues the MMAs (>= 4: rotate over CTAs)
     uint32_t nc_uniform;       // chunks per row when every listed branch has the same count, else 0
 };
 
@@ -281,7 +280,9 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
     pdl_launch_dependents();
     const uint32_t li = blockIdx.y;
     const uint32_t b = list ? list[li] : li;
-    if (states && states[b].status != ST_RUNNING) return;
+    // single rank: nothing to do for an early-rejected / finished branch.  Sharded rows: the host has handed out an epoch for
+    // this launch, so the exchange below must run on every rank whatever the status (comm.cuh; the sums are not used then).
+    if (states && states[b].status != ST_RUNNING && xc.world <= 1) return;
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t k = blockIdx.x * 32 + lane;
     const bool live = k <= descs[b].P;

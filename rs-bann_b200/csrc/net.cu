@@ -160,7 +160,6 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
     a.st_per_chunk = 0;
     a.ncb = 8;
     a.nc_uniform = 0;
-    { const char* e = getenv("BANN_TC_ISSUER"); a.issuer_warp = e ? (uint32_t)atoi(e) : 0u; }
 
     bool launched = false;
     if (net->k1_mode == BANN_K1_AUTO || net->k1_mode == BANN_K1_TENSOR) {

@@ -7,12 +7,34 @@ u64 length followed by the elements, `Option<T>` as a u8 tag, unit enum variants
 fields in declaration order, `PhantomData` as nothing.
 """
 import json
+import math
 import os
 import struct
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
 import numpy as np
+
+
+def _finite(o):
+    """serde_json writes `null` for non-finite f32 (a fresh net has +inf bias precisions and -inf / NaN LPD terms);
+    Python's json would emit the invalid tokens Infinity / NaN."""
+    if isinstance(o, float):
+        return o if math.isfinite(o) else None
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    return o
+
+
+def json_dumps(obj, **kw):
+    return json.dumps(_finite(obj), allow_nan=False, **kw)
+
+
+def json_dump(obj, fp, **kw):
+    fp.write(json_dumps(obj, **kw))
+
 
 BED_SIGNATURE = bytes([0x6C, 0x1B, 0x01])            # io/bed.rs:193-213 (variant-major only)
 ACTIVATIONS = ["tanh", "relu", "leaky_relu", "silu", "identity"]       # activation_functions.rs:6-12 (variant order)

@@ -271,16 +271,24 @@ def test_tensor_core_kernel_refuses_ineligible_launch(rb, ctx):
 
 
 @pytest.mark.parametrize("act", ["relu", "leaky_relu", "silu", "identity"])
-def test_fwd_bwd_activations(rb, ctx, act):
-    P = Problem(rb, ctx, "ridge_ard", 500, [40, 21], 5, 5, act=act, seed=5)
+@pytest.mark.parametrize("shape", [(500, [40, 21], 5, 5, 1),        # k1_tc
+                                   (300, [20, 64], 5, 3, 2),        # k1_tc, two hidden layers (alternating-sign backward)
+                                   (515, [128, 129], 5, 5, 1),      # k1_tcw (65..512 markers)
+                                   (150, [12, 7], 4, 2, 0)])        # summary layer reads the markers
+def test_fwd_bwd_activations(rb, ctx, act, shape):
+    """activation_functions.rs:23-45 through the shape-agnostic kernel AND the tensor-core kernels (K1_TENSOR fails loudly
+    when a launch is not eligible: no silent fall-back to the slow kernel for ReLU / LeakyReLU / SiLU / identity nets)."""
+    n, gs, h, s, d = shape
+    P = Problem(rb, ctx, "ridge_ard", n, gs, h, s, depth=d, act=act, seed=5)
     try:
-        for generic in (True, False):
-            P.net.force_generic(generic)
-            for b in range(2):
+        for k1 in (P.net.K1_GENERIC, P.net.K1_TENSOR):
+            P.net.select_k1(k1)
+            for b in range(len(gs)):
                 got = P.net.branch_fwd_bwd(b)
                 t64, t32 = oracle_fwd_bwd(P, b, P.y, np.float64), oracle_fwd_bwd(P, b, P.y, np.float32)
                 within(got["yhat"], t64["yhat"], t32["yhat"])
                 within(got["rss"], t64["rss"], t32["rss"])
+                within(got["d_rss"], t64["d_rss"], t32["d_rss"])
                 within(got["ldg"], t64["ldg"], t32["ldg"])
     finally:
         P.close()
