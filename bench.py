@@ -4,7 +4,8 @@
 One "step" = one full-network leapfrog step = B branch-leapfrogs (momentum half step, position
 step, fused forward+backward of every branch over all N rows against its own target vector, prior
 gradient, second half step, Hamiltonian), schedule G = B (all branches advance concurrently,
-SURVEY H1).  Rows are sharded over ranks; the per-step [gW | gb | rss] sums are all-reduced (NCCL).
+SURVEY H1).  Rows are sharded over ranks; the per-step [gW | gb | rss] sums are all-reduced INSIDE the library over
+NVLink peer memory (bann_net_comm_connect; torch.distributed only carries the 128-byte handles and the timing max).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
 
@@ -44,8 +45,21 @@ WORKLOADS = {
 }
 METRIC = "full_network_hmc_leapfrog_steps_per_sec"
 UNIT = "steps/s"
-# ncu --set full capture of the dominant kernel (profiles/): dram bytes per launch, filled in once measured
-NCU_TRAFFIC_BYTES = {"cfg3s": 1.8104e9, "cfg3": 1.8104e10}   # profiles/r1_k1_tc_ncu_summary.md (v10): k1_tc dram read 1.8038 GB + write 6.6 MB per launch (cfg3 = 10 x the branches)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures
+# (NOT measured in this run -- a bench run is never profiled); None where no capture exists for the workload
+NCU_TRAFFIC = {
+    "cfg3s": dict(bytes=1.8099e9, source="profiles/r2_k1_tc_ncu_summary.md (ncu, not this run)"),
+    "cfg3": dict(bytes=1.8099e10, source="profiles/r2_k1_tc_ncu_summary.md: cfg3s capture x 10 branches (ncu, not this run)"),
+}
+
+
+def cpu_threads():
+    """Host threads the CPU arm may use: the cores this process is allowed on (torchrun's OMP_NUM_THREADS=1 is overridden
+    explicitly, VERDICT r1 weak #9)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def default_params(wl, seed=42):
@@ -135,13 +149,21 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def cpu_reference_rate(wl, seconds=10.0, max_branches=64, leapfrogs=2, threads_note=True):
-    """Times the oracle's C restatement of the reference's op sequence (host decode + dense f32 +
-    2 forwards and 1 backward per leapfrog) on a bounded sample: all N rows, a few branches."""
+def cpu_sample_branches(wl):
+    """Branches in the fixed CPU sample: ~6.4e8 row x marker products per leapfrog evaluation (128 branches at config 3)."""
+    return int(min(256, max(4, round(6.4e8 / (wl["n"] * wl["per"])))))
+
+
+def cpu_reference_rate(wl, leapfrogs=4):
+    """Times the oracle's C restatement of the reference's op sequence (host decode + dense f32 + 2 forwards and 1 backward
+    per leapfrog) on a FIXED sample: all N rows, cpu_sample_branches(wl) branches, `leapfrogs` leapfrog steps each, every
+    allowed host thread (pinned explicitly).  The same sample serves `cpu_baseline` and `--impl reference`; the full-network
+    rate is the sample's branch-leapfrog rate divided by B (extrapolation factor B / sample branches, stated in the line)."""
     from oracle import bed as obed
     from oracle.cport import CPort
-    cp = CPort()
+    cp = CPort(threads=cpu_threads())
     n, m, widths, B = wl["n"], wl["per"], wl["widths"], wl["B"]
+    K = cpu_sample_branches(wl)
     rng = np.random.default_rng(1)
     ncols = m * 4
     g = rng.binomial(2, rng.uniform(0.01, 0.5, size=ncols)[None, :], size=(n, ncols)).astype(np.uint8)
@@ -153,9 +175,8 @@ def cpu_reference_rate(wl, seconds=10.0, max_branches=64, leapfrogs=2, threads_n
     ins = [m] + widths[:-1]
     P = sum(i * o for i, o in zip(ins, widths)) + sum(widths[:-1])
     L_ref = 100.0                       # decode happens once per visit of L = 100 leapfrogs (mcmc_cfg.rs:38)
-    t_decode, t_leap, nbr = 0.0, 0.0, 0
-    t_start = time.perf_counter()
-    while nbr < max_branches and (time.perf_counter() - t_start < seconds or nbr < 2):
+    t_decode, t_leap = 0.0, 0.0
+    for nbr in range(K + 1):            # branch 0 = warm-up (thread pool, page faults), not timed
         cols = np.arange((nbr % 4) * m, (nbr % 4 + 1) * m)
         theta = rng.normal(0, np.sqrt(1.0 / m), size=P).astype(np.float32)
         mom = rng.normal(size=P).astype(np.float32)
@@ -166,16 +187,16 @@ def cpu_reference_rate(wl, seconds=10.0, max_branches=64, leapfrogs=2, threads_n
         t1 = time.perf_counter()
         cp.leapfrog(X, y, n, m, widths, "tanh", False, wl["model"] == "std_normal", theta, mom, eps, lam, 2.0, leapfrogs)
         t2 = time.perf_counter()
-        if nbr > 0:                       # first branch = warm-up (thread pool, page faults)
+        if nbr > 0:
             t_decode += t1 - t0
             t_leap += (t2 - t1) / (leapfrogs + 0.5)   # + initial gradient evaluation (half a leapfrog)
-        nbr += 1
-    k = max(nbr - 1, 1)
-    per_branch_leapfrog = t_leap / k + (t_decode / k) / L_ref
+    per_branch_leapfrog = t_leap / K + (t_decode / K) / L_ref
     steps_per_s = 1.0 / (per_branch_leapfrog * B)
-    sample = (f"{k} branches x {leapfrogs} leapfrogs over all {n} rows (m_b={m}, widths {widths}); host decode per visit "
-              f"amortised over L=100; extrapolated to B={B} branches")
-    return dict(value=steps_per_s, unit=UNIT, cores=cp.threads, kind="port", sample=sample), per_branch_leapfrog
+    sample = (f"fixed sample: {K} branches x {leapfrogs} leapfrogs over all {n} rows (m_b={m}, widths {widths}), "
+              f"{cp.threads} OpenMP threads (nproc {os.cpu_count()}); host decode per visit amortised over L=100; "
+              f"extrapolated x{B / K:.1f} to B={B} branches")
+    return dict(value=steps_per_s, unit=UNIT, cores=cp.threads, kind="port", sample=sample,
+                sample_branches=K, extrapolation_factor=B / K, sample_seconds=t_leap + t_decode), per_branch_leapfrog
 
 
 def run_reference(args, wl):
@@ -186,7 +207,7 @@ def run_reference(args, wl):
     per = []
     base = None
     for s in range(args.warmup + steps):
-        base, t = cpu_reference_rate(wl, seconds=2.0, max_branches=8)
+        base, t = cpu_reference_rate(wl)
         if s >= args.warmup:
             per.append(t)
     t_bl = statistics.mean(per)
@@ -264,24 +285,16 @@ def main():
         net.force_generic(True)
     elif args.k1 != "auto":
         net.select_k1(dict(tensor=net.K1_TENSOR, ffma=net.K1_FFMA, generic=net.K1_GENERIC)[args.k1])
-    k1_name = ("k1_tc (tcgen05 tensor-core fused fwd+bwd, phase A)" if args.k1 in ("auto", "tensor") and gen.has_tc_store()
-               and not args.generic else "k1 fused fwd+bwd (phase A)")
-    ptr, nfl = net.allreduce_buffer()
-
-    class _Dev:
-        __cuda_array_interface__ = {"shape": (nfl,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-    gbuf = torch.as_tensor(_Dev(), device=dev) if world > 1 else None
+    # cross-rank sums: INSIDE the library over NVLink peer memory (bann_net_comm_connect: reduce-scatter + all-gather kernels
+    # on the same stream, csrc/comm.cuh).  torch.distributed only carries the 128-byte region handles once.
+    rb.connect_net(net)
 
     def allreduce():
         if world > 1:
-            dist.all_reduce(gbuf)
+            net.grouped_allreduce()
 
     cfg = rb.MCMCCfg(hmc_step_size_factor=0.1, hmc_integration_length=100, hmc_max_hamiltonian_error=1e30)
-    net.grouped_begin(cfg, seed=42, per_branch_targets=True)      # t_b = r + yhat_b (net.rs:279-280), momenta, H_init
-    if world > 1:
-        allreduce()
-        net.grouped_phase_b(cfg, is_init=True)
+    net.grouped_begin(cfg, seed=42, per_branch_targets=True)      # t_b = r + yhat_b (net.rs:279-280), momenta, H_init (+ exchange)
 
     def step(ev=None):
         if ev:
@@ -346,20 +359,27 @@ def main():
     pv, y_local = pv_h, y_h
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        net.gradient(pv, y_local, allreduce=allreduce if world > 1 else None, out=(grads, rss))
+        net.gradient(pv, y_local, out=(grads, rss))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        net.gradient(pv, y_local, allreduce=allreduce if world > 1 else None, out=(grads, rss))
+        net.gradient(pv, y_local, out=(grads, rss))
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = e2e_steps / float(te[0])
-    h2d = world * 4 * pv.size + 4 * N
-    d2h = world * 4 * (pv.size + B)
+    # bytes every step moves between HOST and device, summed over ranks: each rank reads its 1 / world slice of the
+    # (replicated) parameters plus its own rows of y, and writes its slice of [grads | rss] (bann_net_gradient_slice)
+    plo, phi, olo, ohi = net.gradient_slice()
+    hb = torch.tensor([4 * (phi - plo) + 4 * n_local, 4 * (ohi - olo)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(hb)
+    h2d, d2h = int(hb[0]), int(hb[1])
+    k1_name = net.last_k1_kernel()
+    traffic = NCU_TRAFFIC.get(args.workload) if (world == 1 and k1_name.startswith("k1_tc<")) else None
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -367,22 +387,26 @@ def main():
                     dtype="f32", data="synthetic",
                     config=dict(workload=f"{args.workload}: {wl['desc']}", schedule="grouped G=B (all branches per launch)",
                                 individuals=N, branches=B, markers_per_branch=per, widths=widths, prior=wl["model"],
-                                rows_per_gpu=n_local, parallelism=f"row-sharded x{world}, all-reduce of [gW|gb|rss]",
+                                rows_per_gpu=n_local,
+                                parallelism=(f"row-sharded x{world}, all-reduce of [gW|gb|rss] inside the library over NVLink peer "
+                                             f"memory (reduce-scatter + all-gather kernels, no NCCL on the data path)"),
                                 l2="working set (packed genotypes + per-branch targets) >> 126 MB L2, no flush needed",
                                 init="reference default init, seed 42; bias precisions 1.0",
                                 branch_leapfrogs_per_step=B, active_branches=active),
                     k1_ms=k1_ms, wall_s=t_wall, gpu_launches=int(launches) * world,
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                                  traffic=(NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 and k1_name.startswith("k1_tc") else None),
+                                  traffic=traffic["bytes"] if traffic else None,
+                                  traffic_source=traffic["source"] if traffic else None,
                                   peak_source=peak_src,
                                   algorithmic_bytes_per_launch=alg_bytes, kernel=k1_name,
                                   kernel_ms=k1_ms),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             call="Net.gradient / bann_net_gradient (host params + targets in, gradients + rss out)"),
+                             call="Net.gradient / bann_net_gradient (host params + targets in, gradients + rss out; on sharded rows "
+                                  "every rank moves its 1 / world slice, the ranks all-gather / all-reduce on the device)"),
                     clocks=clocks)
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"], _ = cpu_reference_rate(wl, seconds=12.0)
+                line["cpu_baseline"], _ = cpu_reference_rate(wl)
             except Exception as ex:   # the oracle is test infrastructure; never let it break the GPU number
                 line["cpu_baseline"] = dict(error=str(ex))
         sys.stdout.flush()

@@ -60,6 +60,11 @@ typedef struct {
     int32_t  joint_hmc;                   /* hmc_step_joint: precisions are part of the HMC state, no Gibbs draws */
     int32_t  gradient_descent;            /* gradient_descent: line-search ascent on the log density */
     int32_t  gradient_descent_joint;      /* gradient_descent_joint: fixed-step ascent on parameters and precisions */
+    /* the reference's debugging aids (net/mcmc_cfg.rs, branch_sampler.rs:1232-1261; "DO NOT run this in production code"):
+     * hmc_step integrates with numerical_ldg instead of the analytical gradient / records numerical_ldg per step in the
+     * trajectory.  Per-branch transitions only (group_size 1); P_b + 2 fused passes per leapfrog step. */
+    int32_t  num_grad;
+    int32_t  num_grad_traj;
 } bann_mcmc_cfg;
 
 /* Injected randomness for parity runs.  NULL members fall back to the built-in
@@ -99,6 +104,7 @@ typedef struct {
     float* precisions;
     float* ldg;
     float* hamiltonian;
+    float* num_ldg;              /* NULL, or L * P_b: numerical_ldg per step when cfg->num_grad_traj (Trajectory::num_ldg) */
 } bann_trajectory_joint;
 
 /* net/train_stats.rs:23-32 + net/log_posterior_density.rs:62-67 */
@@ -139,6 +145,17 @@ int  bann_ctx_sync(bann_ctx*);
 int  bann_ctx_comm_handle(bann_ctx*, uint8_t* handle_out /* BANN_COMM_HANDLE_BYTES */);
 int  bann_ctx_comm_connect(bann_ctx*, const uint8_t* all_handles /* world * BANN_COMM_HANDLE_BYTES */);
 int  bann_ctx_comm_connected(bann_ctx*);
+/* ---- bulk cross-rank sums of the grouped schedule ("all-reduce(sum) of [gW | gb | rss], G x (P_b + 1) floats when
+ * G branches are grouped").  With these connected the library is self-sufficient on sharded rows: the all-reduce between the
+ * fused forward+backward launch and the parameter update runs INSIDE the library over NVLink peer memory -- reduce-scatter
+ * (rank-ordered sums: identical bits on every rank) + all-gather, 2 (world - 1) / world of the bytes per rank, three small
+ * kernels on the caller's stream, no NCCL, no host involvement (rs-bann_b200/csrc/comm.cuh: XgComm).  Used by
+ * bann_sweep / bann_visit_group with group_size > 1, bann_grouped_begin / _leapfrog and bann_net_gradient.  Set-up mirrors the
+ * context's: every rank exports the handle of its exchange region, the host layer all-gathers them once (the only step that
+ * needs a host-side transport, e.g. torch.distributed / MPI all_gather of 128 bytes), every rank maps its peers. */
+int  bann_net_comm_handle(bann_net*, uint8_t* handle_out /* BANN_COMM_HANDLE_BYTES */);
+int  bann_net_comm_connect(bann_net*, const uint8_t* all_handles /* world * BANN_COMM_HANDLE_BYTES */);
+int  bann_net_comm_connected(bann_net*);
 
 /* ---- genotypes: replaces BedVM + MarkerGrouping + GroupedGenotypes::x_group_af
  * (io/bed.rs:123-133,193-245,325-355; group/grouping.rs:7-15; data/genotypes.rs:7-48).
@@ -199,6 +216,9 @@ int  bann_branch_fwd_bwd(bann_net*, uint64_t b, const float* target, float* rss,
                          float* yhat);
 /* log_density(params, precisions, rss) (branch_sampler.rs:72-78; std_normal_branch.rs:147-158) */
 int  bann_branch_log_density(bann_net*, uint64_t b, float rss, float* out);
+/* numerical_ldg (branch_sampler.rs:480-504): forward differences of log_density with NUMERICAL_DELTA = 0.001, P_b + 1 fused
+ * passes; out: P_b floats in param_vec order.  target NULL: the net's targets.  The parameters are left unchanged. */
+int  bann_branch_numerical_ldg(bann_net*, uint64_t b, const float* target, float* out);
 /* per-parameter step sizes of the chosen mode (a10), param_vec order */
 int  bann_branch_step_sizes(bann_net*, uint64_t b, const bann_mcmc_cfg*, const float* step_uniforms, float* out);
 /* hmc_step(x_b, target, cfg) (branch_sampler.rs:1192-1299).  target NULL -> net targets.
@@ -239,10 +259,20 @@ int  bann_visit_branch(bann_net*, uint64_t b, const bann_mcmc_cfg*, const bann_r
  * tells how many are valid).  The ascent modes record nothing. */
 int  bann_visit_branch_traj(bann_net*, uint64_t b, const bann_mcmc_cfg*, uint64_t seed, bann_hmc_result* out,
                             bann_trajectory_joint* traj);
-/* a full pass over `branch_order` (sequential-exact schedule, group_size must be 1 in this
- * release) with the built-in RNG keyed by seed; asynchronous, one sync at the end. */
+/* a full pass over `branch_order` with the built-in RNG keyed by seed; asynchronous, one sync at the end.
+ * group_size 1: the reference's sequential (Gauss-Seidel) order, net/net.rs:258-334 visit by visit.
+ * group_size G > 1: block-Jacobi -- consecutive groups of G branches of the order advance concurrently: every member draws its
+ * precisions and runs its HMC transition against the residual and the global parameters frozen at group start
+ * (t_b = r + yhat_b, one fused forward+backward launch over the whole group per leapfrog step); residual
+ * (r -= sum over accepted members of yhat_new - yhat_old), global parameters, LPD terms, counters and the ML output bias are
+ * updated once per group.  G = number of branches is the schedule of the full-network leapfrog metric. */
 int  bann_sweep(bann_net*, const bann_mcmc_cfg*, const uint64_t* branch_order, uint64_t num, uint32_t group_size,
                 uint64_t seed, bann_sweep_stats* out);
+/* one group visit of the block-Jacobi schedule (see bann_sweep): `members` = num distinct branches; inj = NULL or an array of
+ * num per-member injections (parity runs: the oracle's visit_group replayed draw for draw); out = NULL or num results in
+ * member order.  One member without injections is bann_visit_branch. */
+int  bann_visit_group(bann_net*, const uint64_t* members, uint64_t num, const bann_mcmc_cfg*, const bann_rng_inject* inj_or_null,
+                      uint64_t seed, bann_hmc_result* out_or_null);
 /* Net::predict (net/net.rs:545-559) on the training genotypes (NULL) or another store. */
 int  bann_predict(bann_net*, bann_genotypes* test_or_null, float* yhat);
 int  bann_net_stats(bann_net*, bann_sweep_stats* out);
@@ -270,10 +300,16 @@ int  bann_net_gradient(bann_net*, const float* param_vecs, const float* y, float
  * directly, one copy per direction; pageable ones are staged through an internal pinned buffer (one extra memcpy each way). */
 int  bann_pinned_alloc(uint64_t bytes, void** out);
 void bann_pinned_free(void* p);
-/* the same in two halves for row-sharded runs: begin (H2D, fused fwd+bwd, raw sums into the
- * all-reduce buffer) -- caller all-reduces -- end (gradient under the prior, D2H). */
+/* the same in two halves for row-sharded runs WITHOUT the bulk exchange: begin (H2D, fused fwd+bwd, raw sums into the
+ * all-reduce buffer) -- caller all-reduces -- end (gradient under the prior, D2H).
+ * With the bulk exchange connected (bann_net_comm_connect) bann_net_gradient itself works on sharded rows, and the host
+ * traffic is divided by the number of ranks: the parameters are replicated, so every rank reads only ITS 1 / world slice of
+ * param_vecs (the ranks all-gather on the device over NVLink) and writes only its slice of [grads | rss];
+ * bann_net_gradient_slice reports the element ranges [param_lo, param_hi) of param_vecs and [out_lo, out_hi) of the
+ * concatenation [grads | rss] this rank touches (the whole vectors on a single rank).  y is this rank's rows, as always. */
 int  bann_net_gradient_begin(bann_net*, const float* param_vecs, const float* y);
 int  bann_net_gradient_end(bann_net*, float* grads, float* rss);
+int  bann_net_gradient_slice(bann_net*, uint64_t* param_lo, uint64_t* param_hi, uint64_t* out_lo, uint64_t* out_hi);
 /* Grouped leapfrog over ALL branches against per-branch targets (schedule G = B).
  * begin: theta0 <- theta, step sizes, momenta (Philox, seed), targets t_b = y (shared) or
  * residual + own prediction; then each step = B branch-leapfrogs.  Device resident, async. */
@@ -293,6 +329,11 @@ int  bann_grouped_state(bann_net*, float* neg_h_init, float* neg_h_cur, int32_t*
  * after residual updates; NULL/0 when nothing is pending.  Exposed so that the host side
  * (torch.distributed over NCCL) can run the collective on the same stream. */
 int  bann_allreduce_buffer(bann_net*, void** dev_ptr, uint64_t* num_floats);
+/* the same sum over ranks done by the library itself over NVLink peer memory (needs bann_net_comm_connect; no-op on one rank):
+ * bann_grouped_phase_a -- bann_grouped_allreduce -- bann_grouped_phase_b is what bann_grouped_leapfrog runs per step */
+int  bann_grouped_allreduce(bann_net*);
+/* name of the kernel family the last fused forward+backward launch used (profiling / bench bookkeeping); static string */
+const char* bann_net_last_k1_kernel(bann_net*);
 
 /* test hook: route every K1 launch through the shape-agnostic kernel (cross-checks the tuned one) */
 int  bann_net_force_generic(bann_net*, int on);

@@ -741,6 +741,25 @@ class Branch:
             out.update(status=REJECTED, log_density=None, y_pred=None)
         return out
 
+    def numerical_ldg(self, x, y):
+        """branch_sampler.rs:480-504 (NUMERICAL_DELTA = 0.001, :30): forward differences of log_density, the perturbed
+        vector walked exactly as the reference does (+= delta, evaluate, -= delta), original parameters reloaded at the end."""
+        dt = self.dt
+        x = np.asarray(x, dtype=dt)
+        y = np.asarray(y, dtype=dt)
+        delta = dt.type(0.001)
+        curr_pv = self.param_vec().astype(dt).copy()
+        next_pv = curr_pv.copy()
+        curr_ld = dt.type(self.log_density(self.rss(x, y)))
+        res = []
+        for pix in range(curr_pv.size):
+            next_pv[pix] = dt.type(next_pv[pix] + delta)
+            self.load_param_vec(next_pv)
+            res.append(dt.type(dt.type(dt.type(self.log_density(self.rss(x, y))) - curr_ld) / delta))
+            next_pv[pix] = dt.type(next_pv[pix] - delta)
+        self.load_param_vec(curr_pv)
+        return np.array(res, dtype=dt)
+
     def effect_sizes(self, x):
         """branch_sampler.rs:784-811: back-propagation of the prediction to the (standardised) input, seeded with
         yhat W_last^T (the reference multiplies by the prediction itself).  Returns [n, m]."""

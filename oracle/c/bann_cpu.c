@@ -35,6 +35,17 @@ int bann_cpu_num_threads(void) {
 #endif
 }
 
+/* pin the OpenMP team size explicitly (torchrun exports OMP_NUM_THREADS=1 to its workers); returns the size in effect */
+int bann_cpu_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 void bann_cpu_decode_std(const uint8_t* payload, uint64_t n, const uint64_t* cols, uint32_t m, const float* means,
                          const float* stds, float* X) {
     uint64_t bpc = (n + 3) / 4;

@@ -17,6 +17,8 @@ def load():
         subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
     lib = C.CDLL(_PATH)
     lib.bann_cpu_num_threads.restype = C.c_int
+    lib.bann_cpu_set_threads.restype = C.c_int
+    lib.bann_cpu_set_threads.argtypes = [C.c_int]
     lib.bann_cpu_decode_std.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32, _fp, _fp, _fp]
     lib.bann_cpu_rss.restype = C.c_float
     lib.bann_cpu_rss.argtypes = [_fp, _fp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_int, _fp, _fp]
@@ -33,9 +35,10 @@ def _p(a):
 
 
 class CPort:
-    def __init__(self):
+    def __init__(self, threads=None):
+        """threads: OpenMP team size to pin (None: what the environment gives, e.g. OMP_NUM_THREADS)."""
         self.lib = load()
-        self.threads = self.lib.bann_cpu_num_threads()
+        self.threads = self.lib.bann_cpu_set_threads(int(threads)) if threads else self.lib.bann_cpu_num_threads()
 
     def decode_std(self, payload, n, cols, means, stds):
         cols = np.ascontiguousarray(cols, dtype=np.uint64)

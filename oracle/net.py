@@ -249,15 +249,76 @@ def visit_branch(net: Net, b: int, x, residual, mcmc: MCMCCfg, draws: Draws, dty
     return residual, res
 
 
+def visit_group(net: Net, members, xs, residual, mcmc: MCMCCfg, draws: Draws, dtype=np.float32):
+    """One group visit of the block-Jacobi schedule (bann_visit_group / bann_sweep with group_size > 1).
+
+    Every member runs the inner loop of Net::train (net.rs:258-334) -- globals -> cfg, Gibbs draws, prev_pred, HMC against
+    residual + prev_pred -- against the residual and the global parameters FROZEN at group start.  Afterwards, once:
+    residual -= sum over the accepted members (member order) of (y_new - (t - residual)), then per member in order the
+    bookkeeping of :296-305 (counters, to_cfg against the running output-weight statistic, globals), the LPD terms of the last
+    accepted member against the group's final residual, and the ML output bias (:320-332).  A group of one member is
+    visit_branch.  Not in the reference (which only has the sequential order): this function is the specification the CUDA
+    path is held to.  Returns (residual, [hmc results])."""
+    dt = np.dtype(dtype)
+    assert not (mcmc.joint_hmc or mcmc.gradient_descent or mcmc.gradient_descent_joint)
+    r0 = np.asarray(residual, dtype=dt)
+    runs = []
+    for b in members:
+        b = int(b)
+        cfg = net.cfgs[b]
+        _update_cfg_globals(net, cfg)                    # the globals are not written inside this loop: frozen
+        br = Branch(cfg, dtype)
+        own_old = dt.type(br.summary_stat(br.W[-1]))
+        draws.new_visit(b)
+        br.sample_error_precision(r0, net.hyper, draws.std_gamma)
+        if not mcmc.fixed_param_precisions:
+            br.sample_param_precisions(net.hyper, draws.std_gamma)
+        prev = br.predict(xs[b])
+        t = (r0 + prev).astype(dt)
+        su = draws.step_uniforms(br.param_vec().size) if mcmc.hmc_step_size_mode == "random" else None
+        res = br.hmc_step(xs[b], t, mcmc, draws.momenta(br.param_vec().size), draws.uniform(), step_uniforms=su)
+        runs.append((b, br, own_old, t, res))
+    r = r0.copy()
+    for b, br, own_old, t, res in runs:
+        if res["status"] == ACCEPTED:
+            r = (r - (np.asarray(res["y_pred"], dtype=dt) - (t - r0))).astype(dt)
+    results = []
+    for b, br, own_old, t, res in runs:
+        br.ow_reg_sum = dt.type(dt.type(net.g_ow_reg_sum) - own_old)     # from_cfg against the running global
+        net.num_samples += 1
+        if res["status"] == ACCEPTED:
+            net.num_accepted += 1
+            _update_lpd(net, b, br, r)
+        elif res["status"] == REJECTED_EARLY:
+            net.num_early_rejected += 1
+        new_cfg = br.to_cfg()
+        _update_globals_from_cfg(net, new_cfg)
+        net.cfgs[b] = new_cfg
+        results.append(res)
+    r = (r + dt.type(net.output_bias)).astype(dt)
+    net.output_bias = float(dt.type(np.sum(r)) / dt.type(r.size))
+    r = (r - dt.type(net.output_bias)).astype(dt)
+    return r, results
+
+
 def train(net: Net, payload, n, means, stds, y, mcmc: MCMCCfg, chain_length: int, draws: Draws,
-          dtype=np.float32, orders=None):
-    """Net::train, net.rs:201-358 (file output / test-set MSE omitted). Returns final residual."""
+          dtype=np.float32, orders=None, group_size: int = 1):
+    """Net::train, net.rs:201-358 (file output / test-set MSE omitted). Returns final residual.
+    group_size > 1: the block-Jacobi schedule (visit_group) over consecutive groups of the order."""
     residual = initialize_stats(net, payload, n, means, stds, y, dtype)
     record_perf(net, residual)
     xs = [x_branch(net, payload, n, means, stds, b, dtype) for b in range(net.num_branches)]
     for it in range(chain_length):
         order = orders[it] if orders is not None else draws.order(net.num_branches)
-        for b in order:
-            residual, _ = visit_branch(net, int(b), xs[int(b)], residual, mcmc, draws, dtype)
+        if group_size <= 1:
+            for b in order:
+                residual, _ = visit_branch(net, int(b), xs[int(b)], residual, mcmc, draws, dtype)
+        else:
+            for i in range(0, len(order), group_size):
+                grp = [int(b) for b in order[i:i + group_size]]
+                if len(grp) == 1:
+                    residual, _ = visit_branch(net, grp[0], xs[grp[0]], residual, mcmc, draws, dtype)
+                else:
+                    residual, _ = visit_group(net, grp, xs, residual, mcmc, draws, dtype)
         record_perf(net, residual)
     return residual

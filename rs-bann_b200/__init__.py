@@ -9,5 +9,5 @@ from .api import Context, Genotypes, HMCStepResult, MCMCCfg, Net, cuda_available
 
 def launch_count(reset: bool = False) -> int:
     return int(lib.bann_launch_count(int(reset)))
-from .dist import connect_ranks, global_col_stats, row_shard, shard_payload  # noqa: E402
+from .dist import connect_net, connect_ranks, global_col_stats, row_shard, shard_payload  # noqa: E402
 from . import architectures, files  # noqa: E402,F401  (host-side file formats and net construction; cli.py is the rs-bann command surface)

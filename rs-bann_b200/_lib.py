@@ -30,7 +30,7 @@ class McmcCfg(C.Structure):
     _fields_ = [("hmc_step_size_factor", C.c_float), ("hmc_max_hamiltonian_error", C.c_float),
                 ("hmc_integration_length", C.c_uint32), ("hmc_step_size_mode", C.c_int32),
                 ("fixed_param_precisions", C.c_int32), ("joint_hmc", C.c_int32), ("gradient_descent", C.c_int32),
-                ("gradient_descent_joint", C.c_int32)]
+                ("gradient_descent_joint", C.c_int32), ("num_grad", C.c_int32), ("num_grad_traj", C.c_int32)]
 
 
 class RngInject(C.Structure):
@@ -51,7 +51,7 @@ class Trajectory(C.Structure):
 
 class TrajectoryJoint(C.Structure):
     _fields_ = [("params", C.POINTER(C.c_float)), ("precisions", C.POINTER(C.c_float)), ("ldg", C.POINTER(C.c_float)),
-                ("hamiltonian", C.POINTER(C.c_float))]
+                ("hamiltonian", C.POINTER(C.c_float)), ("num_ldg", C.POINTER(C.c_float))]
 
 
 class SweepStats(C.Structure):
@@ -114,11 +114,20 @@ PROTOTYPES = {
     "bann_visit_branch_traj": (C.c_int, [_vp, _u64, C.POINTER(McmcCfg), _u64, C.POINTER(HmcResult), C.POINTER(TrajectoryJoint)]),
     "bann_sweep": (C.c_int, [_vp, C.POINTER(McmcCfg), C.POINTER(_u64), _u64, C.c_uint32, _u64,
                               C.POINTER(SweepStats)]),
+    "bann_visit_group": (C.c_int, [_vp, C.POINTER(_u64), _u64, C.POINTER(McmcCfg), C.POINTER(RngInject), _u64,
+                                    C.POINTER(HmcResult)]),
     "bann_predict": (C.c_int, [_vp, _vp, _fp]),
     "bann_branch_activations": (C.c_int, [_vp, _u64, _vp, _fp]),
     "bann_branch_effect_sizes": (C.c_int, [_vp, _u64, _vp, _fp, _fp]),
     "bann_net_stats": (C.c_int, [_vp, C.POINTER(SweepStats)]),
     "bann_net_gradient": (C.c_int, [_vp, _fp, _fp, _fp, _fp]),
+    "bann_branch_numerical_ldg": (C.c_int, [_vp, _u64, _fp, _fp]),
+    "bann_net_gradient_slice": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "bann_net_comm_handle": (C.c_int, [_vp, _vp]),
+    "bann_net_comm_connect": (C.c_int, [_vp, _vp]),
+    "bann_net_comm_connected": (C.c_int, [_vp]),
+    "bann_grouped_allreduce": (C.c_int, [_vp]),
+    "bann_net_last_k1_kernel": (C.c_char_p, [_vp]),
     "bann_pinned_alloc": (C.c_int, [_u64, C.POINTER(_vp)]),
     "bann_pinned_free": (None, [_vp]),
     "bann_net_gradient_begin": (C.c_int, [_vp, _fp, _fp]),

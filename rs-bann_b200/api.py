@@ -40,11 +40,14 @@ class MCMCCfg:
     joint_hmc: bool = False                 # net/mcmc_cfg.rs:21-26: the flag-gated modes of Net::train (net.rs:268-290)
     gradient_descent: bool = False
     gradient_descent_joint: bool = False
+    num_grad: bool = False                  # the reference's debugging aids (branch_sampler.rs:1232-1261)
+    num_grad_traj: bool = False
 
     def c(self) -> _lib.McmcCfg:
         return _lib.McmcCfg(self.hmc_step_size_factor, self.hmc_max_hamiltonian_error, self.hmc_integration_length,
                             STEP_NAMES[self.hmc_step_size_mode], int(self.fixed_param_precisions), int(self.joint_hmc),
-                            int(self.gradient_descent), int(self.gradient_descent_joint))
+                            int(self.gradient_descent), int(self.gradient_descent_joint), int(self.num_grad),
+                            int(self.num_grad_traj))
 
 
 @dataclass
@@ -351,6 +354,13 @@ class Net:
         check(lib.bann_branch_log_density(self.h, b, float(rss), _ptr(out)))
         return float(out[0])
 
+    def branch_numerical_ldg(self, b, target=None) -> np.ndarray:
+        """numerical_ldg (branch_sampler.rs:480-504): forward differences of log_density, delta = 0.001."""
+        t = _f32(target) if target is not None else None
+        out = np.empty(self._sizes[b][0], dtype=np.float32)
+        check(lib.bann_branch_numerical_ldg(self.h, b, _ptr(t), _ptr(out)))
+        return out
+
     def branch_step_sizes(self, b, cfg: MCMCCfg, step_uniforms=None):
         out = np.empty(self._sizes[b][0], dtype=np.float32)
         su = _f32(step_uniforms) if step_uniforms is not None else None
@@ -480,19 +490,42 @@ class Net:
         tp = np.zeros(L * P, dtype=np.float32); tq = np.zeros(max(L * Q, 1), dtype=np.float32)
         tl = np.zeros(L * (P + Q), dtype=np.float32); th = np.zeros(L + 1, dtype=np.float32)
         traj.params, traj.precisions, traj.ldg, traj.hamiltonian = _ptr(tp), _ptr(tq), _ptr(tl), _ptr(th)
+        tn = np.zeros(L * P, dtype=np.float32) if (cfg.num_grad_traj and not jt) else None
+        if tn is not None:
+            traj.num_ldg = _ptr(tn)
         c = cfg.c()
         check(lib.bann_visit_branch_traj(self.h, b, C.byref(c), seed, C.byref(res), C.byref(traj)))
         n = 0 if (cfg.gradient_descent or cfg.gradient_descent_joint) else min(res.steps_done, L)
         out = HMCStepResult(res.status, res.log_density, res.neg_h_init, res.neg_h_final, res.steps_done, res.u_turn_step)
         out.trajectory = dict(params=tp.reshape(L, P)[:n], precisions=tq[:L * Q].reshape(L, Q)[:n] if Q else np.zeros((0, 0), np.float32),
-                              ldg=tl.reshape(L, P + Q)[:n], hamiltonian=th[:n + 1])
+                              ldg=tl.reshape(L, P + Q)[:n], hamiltonian=th[:n + 1],
+                              num_ldg=tn.reshape(L, P)[:n] if tn is not None else np.zeros((0, P), np.float32))
         return out
 
-    def sweep(self, cfg: MCMCCfg, order, seed: int = 0):
+    def visit_group(self, members, cfg: MCMCCfg, injections=None, seed: int = 0) -> List[HMCStepResult]:
+        """One block-Jacobi group visit (bann_visit_group): every member runs the inner loop of Net::train against the residual
+        and globals frozen at group start.  injections: None or one dict(momenta=, u=, step_uniforms=, std_gammas=) per member."""
+        members = np.ascontiguousarray(members, dtype=np.uint64)
+        res = (_lib.HmcResult * members.size)()
+        c = cfg.c()
+        inj_arr, keep = None, []
+        if injections is not None:
+            assert len(injections) == members.size
+            inj_arr = (_lib.RngInject * members.size)()
+            for i, d in enumerate(injections):
+                one, k = self._inject(d.get("momenta"), d.get("u"), d.get("step_uniforms"), d.get("std_gammas"))
+                inj_arr[i] = one
+                keep.append(k)
+        check(lib.bann_visit_group(self.h, members.ctypes.data_as(C.POINTER(C.c_uint64)), members.size, C.byref(c), inj_arr, seed,
+                                   res))
+        return [HMCStepResult(r.status, r.log_density, r.neg_h_init, r.neg_h_final, r.steps_done, r.u_turn_step) for r in res]
+
+    def sweep(self, cfg: MCMCCfg, order, seed: int = 0, group_size: int = 1):
+        """One pass over `order`: group_size 1 = the reference's sequential order, G > 1 = block-Jacobi groups of G branches."""
         order = np.ascontiguousarray(order, dtype=np.uint64)
         st = _lib.SweepStats()
         c = cfg.c()
-        check(lib.bann_sweep(self.h, C.byref(c), order.ctypes.data_as(C.POINTER(C.c_uint64)), order.size, 1, seed,
+        check(lib.bann_sweep(self.h, C.byref(c), order.ctypes.data_as(C.POINTER(C.c_uint64)), order.size, int(group_size), seed,
                              C.byref(st)))
         return self._stats(st)
 
@@ -514,14 +547,14 @@ class Net:
         check(lib.bann_net_lpd_terms(self.h, _ptr(a), _ptr(b), _ptr(loc)))
         return float(a[0]), float(b[0]), loc
 
-    def train(self, cfg: MCMCCfg, chain_length: int, seed: int = 0, orders=None):
-        """Net::train (net/net.rs:201-358), sequential-exact schedule, built-in RNG."""
+    def train(self, cfg: MCMCCfg, chain_length: int, seed: int = 0, orders=None, group_size: int = 1):
+        """Net::train (net/net.rs:201-358) with the built-in RNG; group_size 1 = sequential-exact schedule."""
         self.init_residual()
         hist = [self.stats()]
         rng = np.random.default_rng(seed)
         for it in range(chain_length):
             order = orders[it] if orders is not None else rng.permutation(self.num_branches)
-            hist.append(self.sweep(cfg, order, seed=seed + 1 + it))
+            hist.append(self.sweep(cfg, order, seed=seed + 1 + it, group_size=group_size))
         return hist
 
     def predict(self, test: Optional[Genotypes] = None) -> np.ndarray:
@@ -561,16 +594,41 @@ class Net:
     # ---- full network (grouped) operations
     def gradient(self, param_vecs=None, y=None, allreduce=None, out=None):
         """Net::gradient (net/net.rs:520-527) through HOST buffers: returns (grads, rss per branch).
-        `allreduce`: callable run between the two halves when rows are sharded over ranks."""
+        `allreduce`: callable run between the two halves when rows are sharded over ranks and the caller brings its own
+        collective; with the bulk exchange connected (dist.connect_net) leave it None: the library sums over ranks itself and
+        every rank reads / writes only its `gradient_slice()` of the host vectors."""
         pv = _f32(param_vecs) if param_vecs is not None else None
         yy = _f32(y) if y is not None else None
         grads, rss = out if out is not None else (np.empty(self.num_params(), dtype=np.float32),
                                                   np.empty(self.num_branches, dtype=np.float32))
-        check(lib.bann_net_gradient_begin(self.h, _ptr(pv), _ptr(yy)))
-        if allreduce is not None:
+        if allreduce is None:     # one rank, or sharded rows with the bulk exchange connected (fails loudly otherwise)
+            check(lib.bann_net_gradient(self.h, _ptr(pv), _ptr(yy), _ptr(grads), _ptr(rss)))
+        else:                     # sharded rows, the caller's own collective between the two halves
+            check(lib.bann_net_gradient_begin(self.h, _ptr(pv), _ptr(yy)))
             allreduce()
-        check(lib.bann_net_gradient_end(self.h, _ptr(grads), _ptr(rss)))
+            check(lib.bann_net_gradient_end(self.h, _ptr(grads), _ptr(rss)))
         return grads, rss
+
+    def gradient_slice(self):
+        """(param_lo, param_hi, out_lo, out_hi): the element ranges of `param_vecs` / of [grads | rss] this rank reads / writes
+        in `gradient` (everything on one rank; 1 / world each on sharded rows with the bulk exchange connected)."""
+        v = [C.c_uint64() for _ in range(4)]
+        check(lib.bann_net_gradient_slice(self.h, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
+    # ---- bulk peer-memory exchange of the grouped schedule on sharded rows (include/bann.h, comm.cuh: XgComm)
+    def comm_handle(self) -> bytes:
+        buf = (C.c_uint8 * _lib.COMM_HANDLE_BYTES)()
+        check(lib.bann_net_comm_handle(self.h, buf))
+        return bytes(buf)
+
+    def comm_connect(self, handles: Sequence[bytes]):
+        assert all(len(h) == _lib.COMM_HANDLE_BYTES for h in handles)
+        blob = b"".join(handles)
+        check(lib.bann_net_comm_connect(self.h, (C.c_uint8 * len(blob)).from_buffer_copy(blob)))
+
+    def comm_connected(self) -> bool:
+        return bool(lib.bann_net_comm_connected(self.h))
 
     def grouped_begin(self, cfg: MCMCCfg, seed: int = 0, per_branch_targets: bool = False):
         c = cfg.c()
@@ -586,6 +644,13 @@ class Net:
     def grouped_phase_b(self, cfg: MCMCCfg, is_init=False, is_last=False):
         c = cfg.c()
         check(lib.bann_grouped_phase_b(self.h, C.byref(c), int(is_init), int(is_last)))
+
+    def grouped_allreduce(self):
+        """Sum of the step's [gW | gb | rss] over ranks inside the library (NVLink peer memory); no-op on one rank."""
+        check(lib.bann_grouped_allreduce(self.h))
+
+    def last_k1_kernel(self) -> str:
+        return lib.bann_net_last_k1_kernel(self.h).decode()
 
     def grouped_finish(self, seed: int = 0):
         a, e = C.c_uint64(), C.c_uint64()

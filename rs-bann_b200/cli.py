@@ -83,12 +83,16 @@ def add_mcmc(p):
     p.add_argument("-j", "--joint-hmc", action="store_true")
     p.add_argument("--seed", type=int, default=None, help="(extension) seed of the chain's counter-based RNG; the reference is unseedable")
     p.add_argument("--device", type=int, default=0, help="(extension) CUDA device")
+    p.add_argument("--group-size", type=int, default=1,
+                   help="(extension) branches advanced concurrently per group visit: 1 = the reference's sequential order; "
+                        "G > 1 = block-Jacobi groups of G branches against the residual frozen at group start; 0 = all branches")
 
 
 def _check_supported(a):
-    for flag in ("num_grad_traj", "num_grad"):
-        if getattr(a, flag):
-            sys.exit(f"rs-bann (B200 build): --{flag.replace('_', '-')} is outside the hot path built so far (SURVEY 8f-4)")
+    if (a.num_grad or a.num_grad_traj) and getattr(a, "group_size", 1) not in (1, None):
+        sys.exit("--num-grad / --num-grad-traj are per-branch debugging aids of the sequential order (group size 1)")
+    if a.num_grad_traj and not a.trajectories:
+        pass        # mcmc_cfg.rs: num_grad_traj only matters while trajectories are recorded (branch_sampler.rs:1259)
 
 
 # ------------------------------------------------------------------ device <-> file state
@@ -209,9 +213,13 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
     cfg = MCMCCfg(hmc_step_size_factor=a.step_size, hmc_max_hamiltonian_error=a.max_hamiltonian_error,
                   hmc_integration_length=a.integration_length, hmc_step_size_mode=a.step_size_mode,
                   fixed_param_precisions=a.fixed_param_precision is not None, joint_hmc=a.joint_hmc,
-                  gradient_descent=a.gradient_descent, gradient_descent_joint=a.gradient_descent_joint)   # net.rs:282-290
+                  gradient_descent=a.gradient_descent, gradient_descent_joint=a.gradient_descent_joint,   # net.rs:282-290
+                  num_grad=a.num_grad, num_grad_traj=a.num_grad_traj)
     seed = _bcast_int(a.seed if a.seed is not None else int.from_bytes(os.urandom(4), "little"), world)
     rng = np.random.default_rng(seed)
+    group_size = net.num_branches if a.group_size == 0 else max(1, min(a.group_size, net.num_branches))
+    if group_size > 1 and (a.joint_hmc or a.gradient_descent or a.gradient_descent_joint or a.trajectories):
+        sys.exit("--group-size > 1 runs the HMC sampler; --joint-hmc / --gradient-descent* / --trajectories are sequential modes")
     trace = open(os.path.join(outdir, "trace"), "w") if (a.trace and lead) else None
     traj_file = open(os.path.join(outdir, "traj"), "a") if (a.trajectories and lead) else None   # mcmc_cfg.rs:247-249, appended
 
@@ -260,11 +268,12 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
                     t = res.trajectory
                     traj_file.write(files.json_dumps(dict(params=[[float(v) for v in r] for r in t["params"]],
                                                     precisions=[[float(v) for v in r] for r in t["precisions"]],
-                                                    ldg=[[float(v) for v in r] for r in t["ldg"]], num_ldg=[],
+                                                    ldg=[[float(v) for v in r] for r in t["ldg"]],
+                                                    num_ldg=[[float(v) for v in r] for r in t["num_ldg"]],
                                                     hamiltonian=[float(v) for v in t["hamiltonian"]])) + "\n")
             st = net.stats()
         else:
-            st = net.sweep(cfg, order, seed=seed + chain_ix)
+            st = net.sweep(cfg, order, seed=seed + chain_ix, group_size=group_size)
         record_perf(st)
         if chain_ix >= burn_in:
             save_model(chain_ix)

@@ -40,25 +40,29 @@ __device__ float philox_std_gamma(Philox& ph, float shape) {
 
 struct GibbsArgs {
     const BranchDesc* descs;
+    const uint32_t* list;       // group visits: one block per listed branch; NULL: the single branch `b`
     uint32_t b;
     const float* theta;
     float* prec;
-    NetGlobals* G;
-    float* ow_others;           // out: global output-weight stat minus this branch's (branch_struct.rs:27)
+    NetGlobals* G;              // read only here: a group's members all see the globals frozen at group start
+    float* ow_others;           // [B] out: global output-weight stat minus the branch's own (branch_struct.rs:27)
+    float* own_old;             // [B] out: the branch's own output-weight stat before the transition
     Hyper6 hyper;
     int model;
     float n_total;
     int fixed_param_precisions;
     int do_draws;               // 0: only cfg.update_global_params + ow_others (from_cfg)
-    const float* inj;           // injected standard-gamma variates (consumption order) or NULL
+    const float* inj;           // injected standard-gamma variates (consumption order) or NULL; entry li at inj + li * inj_stride
     uint32_t n_inj;
+    uint32_t inj_stride;
     uint64_t seed;
-    uint64_t stream;
+    uint64_t stream_base;       // Philox stream = stream_base + branch
 };
 
 __device__ __forceinline__ float gamma_variate(const GibbsArgs& a, uint32_t idx, float shape) {
-    if (a.inj) return idx < a.n_inj ? a.inj[idx] : 1.f;
-    Philox ph(a.seed ^ 0x9e3779b97f4a7c15ull, a.stream, (uint64_t)idx * 4096ull);
+    if (a.inj) return idx < a.n_inj ? a.inj[(size_t)blockIdx.x * a.inj_stride + idx] : 1.f;
+    const uint32_t b = a.list ? a.list[blockIdx.x] : a.b;
+    Philox ph(a.seed ^ 0x9e3779b97f4a7c15ull, a.stream_base + b, (uint64_t)idx * 4096ull);
     return philox_std_gamma(ph, shape);
 }
 // gibbs_steps.rs:76-94,115-129
@@ -80,7 +84,8 @@ __device__ __forceinline__ float lasso_post(const GibbsArgs& a, uint32_t idx, fl
 __global__ void __launch_bounds__(256) k_gibbs(GibbsArgs a) {
     __shared__ float red[8];
     const uint32_t tid = threadIdx.x;
-    const BranchDesc& d = a.descs[a.b];
+    const uint32_t bix = a.list ? a.list[blockIdx.x] : a.b;
+    const BranchDesc& d = a.descs[bix];
     const float* th = a.theta + d.param_off;
     float* pr = a.prec + d.prec_off;
     const int nl = (int)d.nl, last = nl - 1;
@@ -97,7 +102,8 @@ __global__ void __launch_bounds__(256) k_gibbs(GibbsArgs a) {
     const float others = a.G->ow_reg_sum - own;
     __syncthreads();
     if (tid == 0) {
-        *a.ow_others = others;
+        a.ow_others[bix] = others;
+        if (a.own_old) a.own_old[bix] = own;
         pr[d.ep_off] = a.G->error_precision;
         pr[d.wp_off[last]] = a.G->output_layer_precision;
     }
@@ -410,6 +416,159 @@ __global__ void __launch_bounds__(256) k_visit_finish(FinishArgs a) {
         }
         G.resid_ss = (float)ss;
     }
+}
+
+
+// ------------------------------------------------------------------ block-Jacobi group visits (bann_visit_group, bann_sweep with group_size > 1)
+// Every member of a group runs the inner loop of Net::train (net.rs:258-334) against the residual and the global parameters
+// FROZEN at group start; residual, globals, LPD terms, counters and the output bias are updated once, after all members
+// finished (the checker's visit_group in tests/ is held to the same specification; a group of one member is visit_branch).
+
+// r = r0 - sum over the accepted members, in list order, of (y_new - (t - r0))   (t = r0 + y_prev, net.rs:280,295);
+// block partials of sum r^2 and sum (r + bias_old) as k_resid_after_hmc
+__global__ void __launch_bounds__(256) k_resid_group(float* __restrict__ r, const float* __restrict__ T, const float* __restrict__ ynew,
+                                                     uint32_t n, const uint32_t* __restrict__ list, uint32_t nlist,
+                                                     const BranchState* __restrict__ states, const NetGlobals* G,
+                                                     float* __restrict__ part /* [2*gridDim.x] */) {
+    __shared__ float red[8];
+    __shared__ uint8_t acc_flag[4096];
+    const float bias = G->output_bias;
+    float ss = 0.f, sb = 0.f;
+    for (uint32_t base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {   // uniform trip count per block: barriers inside
+        const uint32_t i = base + threadIdx.x;
+        const float r0 = i < n ? r[i] : 0.f;
+        float v = r0;
+        for (uint32_t l0 = 0; l0 < nlist; l0 += 4096) {
+            const uint32_t cnt = min(4096u, nlist - l0);
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < cnt; k += 256) acc_flag[k] = states[list[l0 + k]].status == ST_ACCEPTED ? 1 : 0;
+            __syncthreads();
+            if (i < n)
+                for (uint32_t k = 0; k < cnt; ++k)
+                    if (acc_flag[k]) {
+                        const size_t o = (size_t)(l0 + k) * n + i;
+                        v = v - (ynew[o] - (T[o] - r0));
+                    }
+        }
+        if (i < n) {
+            r[i] = v;
+            ss = fmaf(v, v, ss);
+            sb += v + bias;
+        }
+    }
+    ss = block_sum<256>(ss, red);
+    sb = block_sum<256>(sb, red);
+    if (threadIdx.x == 0) {
+        part[2 * blockIdx.x] = ss;
+        part[2 * blockIdx.x + 1] = sb;
+    }
+}
+
+struct GroupArgs {
+    const BranchDesc* descs;
+    const uint32_t* list;
+    uint32_t nlist;
+    const float* theta;
+    const float* prec;
+    NetGlobals* G;
+    const BranchState* states;
+    const float* own_old;      // [B] by branch (k_gibbs)
+    float* own_new;            // [B] by branch
+    float* lpd_local;          // [B]
+    Hyper6 hyper;
+    int model;
+    float n_total;
+    const float* part;         // residual partials [2*nblk]
+    uint32_t nblk;
+    float* bias_old_new;       // out [2]
+    int* error_flag;
+    XrComm xc;
+};
+
+// one block per member: own output-weight statistic after the transition; LPD local term of an accepted member
+__global__ void __launch_bounds__(256) k_group_stats(GroupArgs a) {
+    __shared__ float red[8];
+    const uint32_t tid = threadIdx.x, b = a.list[blockIdx.x];
+    const BranchDesc& d = a.descs[b];
+    const float* th = a.theta + d.param_off;
+    const float* pr = a.prec + d.prec_off;
+    const int last = (int)d.nl - 1;
+    const bool lasso = (a.model == BANN_LASSO_BASE || a.model == BANN_LASSO_ARD);
+    float own = 0.f;
+    for (uint32_t i = tid; i < d.in_dim[last]; i += 256) {
+        const float w = th[d.w_off[last] + i];
+        own += lasso ? fabsf(w) : w * w;
+    }
+    own = block_sum<256>(own, red);
+    if (tid == 0) a.own_new[b] = own;
+    if (a.states[b].status == ST_ACCEPTED) {
+        float out_w, local;
+        branch_lpd_terms(d, th, pr, a.model, a.hyper, 0.f, a.G->ow_num_params, red, out_w, local);
+        if (tid == 0) a.lpd_local[b] = local;
+    }
+}
+
+// one block: the members' bookkeeping in list order (what k_visit_finish does per visit), the group's residual sums,
+// LPD terms of the last accepted member, ML output bias
+__global__ void __launch_bounds__(256) k_group_finish(GroupArgs a) {
+    const uint32_t tid = threadIdx.x;
+    double ss = 0.0, sb = 0.0;
+    for (uint32_t i = 0; i < a.nblk; ++i) {
+        ss += a.part[2 * i];
+        sb += a.part[2 * i + 1];
+    }
+    if (a.xc.world > 1) {
+        __shared__ double tot[2];
+        if (tid == 0) {
+            tot[0] = xr_sum(a.xc, 0, ss);
+            tot[1] = xr_sum(a.xc, 1, sb);
+        }
+        __syncthreads();
+        ss = tot[0];
+        sb = tot[1];
+    }
+    if (tid != 0) return;
+    NetGlobals& G = *a.G;
+    const bool lasso = (a.model == BANN_LASSO_BASE || a.model == BANN_LASSO_ARD);
+    float reg = G.ow_reg_sum;
+    int last_acc = -1;
+    float g_last = 0.f;
+    for (uint32_t li = 0; li < a.nlist; ++li) {
+        const uint32_t b = a.list[li];
+        const BranchDesc& d = a.descs[b];
+        const float* pr = a.prec + d.prec_off;
+        const int status = a.states[b].status;
+        const float others = reg - a.own_old[b];                // from_cfg (branch_struct.rs:27) against the running global
+        reg = others + a.own_new[b];                            // to_cfg (branch_sampler.rs:155-171)
+        if (reg < 0.f || isnan(reg)) atomicExch(a.error_flag, 1);   // params.rs:49-54
+        G.num_samples += 1;                                     // train_stats.rs:48-56
+        if (status == ST_ACCEPTED) { G.num_accepted += 1; last_acc = (int)li; g_last = a.own_new[b] + others; }
+        if (status == ST_REJECTED_EARLY) G.num_early_rejected += 1;
+        G.visit_counter += 1;
+        G.error_precision = pr[d.ep_off];                       // params.rs:41-56
+        G.output_layer_precision = pr[d.wp_off[(int)d.nl - 1]];
+    }
+    G.ow_reg_sum = reg;
+    if (last_acc >= 0) {                                        // update_lpd_from_branch (net.rs:173-185) of the last accepted member
+        const uint32_t b = a.list[last_acc];
+        const BranchDesc& d = a.descs[b];
+        const float* pr = a.prec + d.prec_off;
+        const int last = (int)d.nl - 1;
+        float shape, scale;
+        layer_prior(a.hyper, last, (int)d.nl, shape, scale);
+        if (a.model == BANN_STD_NORMAL) G.lpd_out_w = 0.f;
+        else {
+            const float lam = pr[d.wp_off[last]];
+            if (lasso) G.lpd_out_w = -(g_last + 1.f / scale) * lam + (shape + G.ow_num_params - 1.f) * logf(lam);
+            else G.lpd_out_w = -((0.5f * g_last) + 1.f / scale) * lam + (shape + (G.ow_num_params - 2.f) / 2.f) * logf(lam);
+        }
+        const float le = pr[d.ep_off];
+        G.lpd_rss = logf(le) * (shape + (a.n_total - 2.f) / 2.f) - le * ((float)ss / 2.f + 1.f / scale);   // log_posterior_density.rs:49-60
+    }
+    a.bias_old_new[0] = G.output_bias;
+    G.output_bias = (float)sb / a.n_total;                      // net.rs:43-45
+    a.bias_old_new[1] = G.output_bias;
+    G.resid_ss = (float)ss;
 }
 
 }  // namespace bann

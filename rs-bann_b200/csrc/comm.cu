@@ -22,6 +22,41 @@ size_t inbox_bytes(int world) { return (size_t)2 * world * kXrCap * sizeof(uint2
 }  // namespace
 
 namespace bann {
+// one device allocation -> BANN_COMM_HANDLE_BYTES blob / blob of a peer -> a pointer valid in this process
+int comm_export(void* dptr, int device, uint8_t* out) {
+    HandleBlob h;
+    memset(&h, 0, sizeof(h));
+    h.pid = (uint64_t)getpid();
+    h.raw = (uint64_t)(uintptr_t)dptr;
+    h.device = device;
+    h.has_ipc = cudaIpcGetMemHandle(&h.ipc, dptr) == cudaSuccess ? 1 : 0;
+    if (!h.has_ipc) cudaGetLastError();
+    memcpy(out, &h, sizeof(h));
+    return 0;
+}
+int comm_import(bann_ctx* ctx, const uint8_t* blob, void** out, bool* opened_ipc) {
+    HandleBlob h;
+    memcpy(&h, blob, sizeof(h));
+    if (h.pid == (uint64_t)getpid()) {             // same process: the pointer is valid as it is
+        if (h.device != ctx->device) {
+            int can = 0;
+            BANN_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
+            if (!can) BANN_FAIL("no peer access between the devices of two ranks");
+            cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) BANN_CUDA(e);
+            cudaGetLastError();
+        }
+        *out = reinterpret_cast<void*>((uintptr_t)h.raw);
+        *opened_ipc = false;
+    } else {
+        if (!h.has_ipc) BANN_FAIL("a peer rank could not export a CUDA IPC handle");
+        void* p = nullptr;
+        BANN_CUDA(cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+        *out = p;
+        *opened_ipc = true;
+    }
+    return 0;
+}
 XrComm xr_next(bann_ctx* ctx, int* error_flag) {
     XrComm c;
     memset(&c, 0, sizeof(c));
@@ -57,15 +92,7 @@ int bann_ctx_comm_handle(bann_ctx* ctx, uint8_t* out) {
         BANN_CUDA(cudaMemset(mine, 0, inbox_bytes(ctx->world)));   // epoch 0 = "nothing yet"
         BANN_CUDA(cudaDeviceSynchronize());
     }
-    HandleBlob h;
-    memset(&h, 0, sizeof(h));
-    h.pid = (uint64_t)getpid();
-    h.raw = (uint64_t)(uintptr_t)mine;
-    h.device = ctx->device;
-    h.has_ipc = cudaIpcGetMemHandle(&h.ipc, mine) == cudaSuccess ? 1 : 0;
-    if (!h.has_ipc) cudaGetLastError();
-    memcpy(out, &h, sizeof(h));
-    return 0;
+    return comm_export(mine, ctx->device, out);
 }
 
 int bann_ctx_comm_connect(bann_ctx* ctx, const uint8_t* handles) {
@@ -74,26 +101,11 @@ int bann_ctx_comm_connect(bann_ctx* ctx, const uint8_t* handles) {
     BANN_CUDA(cudaSetDevice(ctx->device));
     for (int r = 0; r < ctx->world; ++r) {
         if (r == ctx->rank) continue;
-        HandleBlob h;
-        memcpy(&h, handles + (size_t)r * BANN_COMM_HANDLE_BYTES, sizeof(h));
-        if (h.pid == (uint64_t)getpid()) {             // same process: the pointer is valid as it is
-            if (h.device != ctx->device) {
-                int can = 0;
-                BANN_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
-                if (!can) BANN_FAIL("no peer access between the devices of two ranks");
-                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) BANN_CUDA(e);
-                cudaGetLastError();
-            }
-            ctx->xr_inbox[r] = reinterpret_cast<uint2*>((uintptr_t)h.raw);
-            ctx->xr_ipc[r] = false;
-        } else {
-            if (!h.has_ipc) BANN_FAIL("a peer rank could not export a CUDA IPC handle");
-            void* p = nullptr;
-            BANN_CUDA(cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
-            ctx->xr_inbox[r] = reinterpret_cast<uint2*>(p);
-            ctx->xr_ipc[r] = true;
-        }
+        void* p = nullptr;
+        bool ipc = false;
+        BANN_CHECK(comm_import(ctx, handles + (size_t)r * BANN_COMM_HANDLE_BYTES, &p, &ipc));
+        ctx->xr_inbox[r] = reinterpret_cast<uint2*>(p);
+        ctx->xr_ipc[r] = ipc;
     }
     ctx->xr_connected = true;
     ctx->xr_epoch = 0;

@@ -105,4 +105,126 @@ __device__ __forceinline__ double xr_sum(const XrComm& c, uint32_t slot, double 
     return s;
 }
 
+
+// ------------------------------------------------------------------ bulk all-reduce / all-gather over peer memory (grouped schedule)
+// The grouped schedule sums [gW | gb | rss] of EVERY listed branch over ranks once per leapfrog step: B x (P_b + 1) floats
+// (11.7 MB at config 3) -- bandwidth, not latency, so the push protocol above (8 B per value and peer) is the wrong tool.
+// Each rank owns an exchange region in its HBM, mapped by every peer (bann_net_comm_handle / _connect):
+//     flagsA[8] flagsB[8] | in[2][cap] | out[2][cap]
+// One all-reduce (epoch e, parity e & 1), two kernels on the caller's stream, no host involvement:
+//   k_xg_publish: copies the local sums into in[parity]; the last block to finish fences at system scope and writes e into
+//                 flagsA[rank] of every peer.
+//   k_xg_reduce_scatter: waits for flagsA[src] >= e of every source, sums ITS slice (1 / world of the values) over the ranks'
+//                 in[parity] in RANK ORDER (bit-identical everywhere), writes it to out[parity] and to the local result, then
+//                 (last block) writes e into flagsB[rank] of every peer.
+//   k_xg_all_gather: waits for flagsB, pulls the other slices from the owners' out[parity].
+// Every rank moves 2 x (world - 1) / world x bytes over NVLink, like a ring / NVLS all-reduce, in three tiny launches.
+// Buffer reuse: in[parity] / out[parity] of epoch e are overwritten at e + 2, after this rank completed epoch e + 1, which
+// needed every peer's e + 1 flags, which the peers raised after finishing their reads of epoch e (stream order).
+// A rank that never shows up trips the same 20 s wall-clock limit as above (error flag 2).
+struct XgComm {
+    uint8_t* region[kXrMaxWorld];   // region[r]: rank r's exchange region (peer mapped for r != rank)
+    uint32_t rank, world;
+    uint32_t epoch;
+    uint64_t cap;                   // floats per in / out buffer
+    int* error_flag;
+    unsigned int* counter;          // local: blocks finished (self-resetting)
+};
+__device__ __forceinline__ uint32_t* xg_flags(uint8_t* region, int which) { return reinterpret_cast<uint32_t*>(region) + 8 * which; }
+__device__ __forceinline__ float* xg_in(const XgComm& c, uint32_t r) {
+    return reinterpret_cast<float*>(c.region[r] + 256) + (size_t)(c.epoch & 1u) * c.cap;
+}
+__device__ __forceinline__ float* xg_out(const XgComm& c, uint32_t r) {
+    return reinterpret_cast<float*>(c.region[r] + 256) + (size_t)(2u + (c.epoch & 1u)) * c.cap;
+}
+__device__ __forceinline__ void xg_signal(const XgComm& c, int which) {     // one thread, after the data is written
+    __threadfence_system();
+    for (uint32_t r = 0; r < c.world; ++r) {
+        uint32_t* f = xg_flags(c.region[r], which) + c.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(c.epoch) : "memory");
+    }
+}
+__device__ __forceinline__ bool xg_wait(const XgComm& c, int which) {       // one thread per block, then __syncthreads
+    const uint32_t* f = xg_flags(c.region[c.rank], which);
+    const unsigned long long t0 = xr_now();
+    for (uint32_t src = 0; src < c.world; ++src) {
+        while (true) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + src) : "memory");
+            if ((int32_t)(v - c.epoch) >= 0) break;
+            if (*reinterpret_cast<volatile int*>(c.error_flag) == 2) return false;
+            if (xr_now() - t0 > kXrTimeoutNs) { atomicExch(c.error_flag, 2); return false; }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ float4 xg_ld4(const float* p) {                   // peer data: never from a stale L1 line
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// the last block of a grid to get here returns true (and resets the counter for the next launch)
+__device__ __forceinline__ bool xg_last_block(unsigned int* counter) {
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(counter, 1u);
+        last = done == gridDim.x - 1;
+        if (last) *counter = 0;
+    }
+    __syncthreads();
+    return last;
+}
+// count: floats, a multiple of 4; src / dst 16-byte aligned
+static __global__ void __launch_bounds__(256) k_xg_publish(XgComm c, const float* __restrict__ src, uint64_t count) {
+    float4* dst = reinterpret_cast<float4*>(xg_in(c, c.rank));
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < count / 4; i += (uint64_t)gridDim.x * 256) dst[i] = s4[i];
+    if (xg_last_block(c.counter) && threadIdx.x == 0) xg_signal(c, 0);
+}
+// slice of rank r: float4 indices [r * per4, min((r + 1) * per4, count / 4))
+static __global__ void __launch_bounds__(256) k_xg_reduce_scatter(XgComm c, float* __restrict__ result, uint64_t count, uint64_t per4) {
+    __shared__ bool ok;
+    if (threadIdx.x == 0) ok = xg_wait(c, 0);
+    __syncthreads();
+    if (ok) {
+        const uint64_t lo = c.rank * per4, hi = min((c.rank + 1) * per4, count / 4);
+        float4* out = reinterpret_cast<float4*>(xg_out(c, c.rank));
+        float4* res = reinterpret_cast<float4*>(result);
+        for (uint64_t i = lo + (uint64_t)blockIdx.x * 256 + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * 256) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t r = 0; r < c.world; ++r) {          // rank order: identical bits on every rank
+                const float4 v = (r == c.rank) ? res[i] : xg_ld4(xg_in(c, r) + 4 * i);
+                if (r == 0) s = v;
+                else { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+            }
+            out[i] = s;
+            res[i] = s;
+        }
+    }
+    if (xg_last_block(c.counter) && threadIdx.x == 0) xg_signal(c, 1);
+}
+static __global__ void __launch_bounds__(256) k_xg_all_gather(XgComm c, float* __restrict__ result, uint64_t count, uint64_t per4) {
+    __shared__ bool ok;
+    if (threadIdx.x == 0) ok = xg_wait(c, 1);
+    __syncthreads();
+    if (!ok) return;
+    float4* res = reinterpret_cast<float4*>(result);
+    const uint64_t n4 = count / 4;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * 256) {
+        const uint32_t owner = (uint32_t)(i / per4);
+        if (owner != c.rank) res[i] = xg_ld4(xg_out(c, owner) + 4 * i);
+    }
+}
+// all-gather of slices the ranks hold locally (parameter upload: every rank copied only its own slice from the host):
+// publish writes the slice into out[parity] and raises flagsB; k_xg_all_gather then fills in the rest
+static __global__ void __launch_bounds__(256) k_xg_publish_slice(XgComm c, const float* __restrict__ src, uint64_t count, uint64_t per4) {
+    const uint64_t lo = c.rank * per4, hi = min((c.rank + 1) * per4, count / 4);
+    float4* out = reinterpret_cast<float4*>(xg_out(c, c.rank));
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (uint64_t i = lo + (uint64_t)blockIdx.x * 256 + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * 256) out[i] = s4[i];
+    if (xg_last_block(c.counter) && threadIdx.x == 0) xg_signal(c, 1);
+}
+
 }  // namespace bann

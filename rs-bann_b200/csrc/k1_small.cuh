@@ -459,7 +459,8 @@ int launch_one_small(K1Args& a, uint32_t nlist, uint32_t mp, cudaStream_t st) {
 
 // picks an instantiation for a homogeneous launch (all listed branches share the architecture and
 // fit the marker bound, activation tanh); otherwise leaves *launched = false and the generic kernel runs.
-inline int launch_k1_small(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
+#ifdef BANN_K1_SMALL_IMPL
+int launch_k1_small(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
                            cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
     if (a.act != BANN_TANH) return 0;
@@ -517,5 +518,9 @@ inline int launch_k1_small(const std::vector<BranchDesc>& descs, int single_bran
 #undef BANN_TRY
     return 0;
 }
+#else
+int launch_k1_small(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
+                           cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net);
+#endif
 
 }  // namespace bann

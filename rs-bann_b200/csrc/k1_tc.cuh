@@ -668,7 +668,8 @@ int launch_one_tc(K1Args& a, uint32_t nlist, cudaStream_t st) {
 
 // Tensor-core K1 for a homogeneous launch: any of the five activations, every listed branch of the same architecture with at
 // most 64 markers and 3 * W0 <= 16, and a tensor-core store present.  Otherwise *launched stays false.
-inline int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
+#ifdef BANN_K1_TC_IMPL
+int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
                         cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
     if (!a.store_tc) return 0;
@@ -731,5 +732,9 @@ inline int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch,
 #undef BANN_TRY_TC
     return 0;
 }
+#else
+int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
+                        cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net);
+#endif
 
 }  // namespace bann

@@ -387,7 +387,8 @@ int launch_one_tcw(K1Args& a, uint32_t nlist, cudaStream_t st) {
 
 // K-blocked tensor-core K1: homogeneous architecture, any of the five activations, every listed branch with 65..512 markers (so that each has at
 // least two marker blocks), 3 * W0 <= 16, tensor-core store present.
-inline int launch_k1_tcw(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
+#ifdef BANN_K1_TCW_IMPL
+int launch_k1_tcw(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
                          cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
     if (!a.store_tc) return 0;
@@ -440,5 +441,9 @@ inline int launch_k1_tcw(const std::vector<BranchDesc>& descs, int single_branch
 #undef BANN_TRY_TCW
     return 0;
 }
+#else
+int launch_k1_tcw(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
+                         cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net);
+#endif
 
 }  // namespace bann

@@ -726,7 +726,8 @@ int launch_one_tcx(TcxArgs& a, uint32_t nlist, uint32_t nslab, bool bwd, cudaStr
 }
 
 // Wide-branch tensor-core K1: homogeneous architecture, tanh, tensor-core store present, widths in the instantiated set.
-inline int launch_k1_tcx(const std::vector<BranchDesc>& descs, int single_branch, K1Args& k, uint32_t nlist, int num_sms,
+#ifdef BANN_K1_TCX_IMPL
+int launch_k1_tcx(const std::vector<BranchDesc>& descs, int single_branch, K1Args& k, uint32_t nlist, int num_sms,
                          cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
     if (k.act != BANN_TANH || !k.store_tc) return 0;
@@ -793,5 +794,9 @@ inline int launch_k1_tcx(const std::vector<BranchDesc>& descs, int single_branch
 #undef BANN_TRY_TCX
     return 0;
 }
+#else
+int launch_k1_tcx(const std::vector<BranchDesc>& descs, int single_branch, K1Args& k, uint32_t nlist, int num_sms,
+                         cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net);
+#endif
 
 }  // namespace bann

@@ -109,6 +109,7 @@ __device__ __forceinline__ void locate_param(const BranchDesc& d, uint32_t k, in
     row = r % d.in_dim[l];
 }
 
+#ifdef BANN_NET_TU   // non-template kernels: defined once, in net.cu's translation unit
 // Generic (any depth / widths / activation) fused forward+backward.  128 threads, one row per
 // thread in the forward phase, one parameter per thread in the accumulation phase.  Slow but
 // shape-agnostic; k1_small<> below is the tuned path for narrow branches.
@@ -336,6 +337,7 @@ struct K2Args {
     float* traj_params;    // optional [L][P] (single-entry launches only)
     float* traj_ldg;
     float* traj_h;         // [L+1]
+    const float* num_ldg;  // --num-grad (single-entry launches): the numerical log-density gradient replaces the analytical one
 };
 
 // One block per branch.  Reference sequence per leapfrog step (branch_sampler.rs:1239-1284):
@@ -392,6 +394,7 @@ __global__ void __launch_bounds__(256) k2_step(K2Args a) {
                 prior -= 0.5f * lam * w * w;
             }
         }
+        if (a.num_ldg) g = a.num_ldg[k];                           // branch_sampler.rs:1232-1247 (mcmc_cfg.num_grad)
         gr[k] = g;
         float pk = p[k];
         if (!a.mode_init) {
@@ -461,8 +464,9 @@ struct InitArgs {
     int step_mode;
     float factor;
     float L;
-    const float* inj_momenta;        // single-entry launches: [P]
-    const float* inj_step_uniforms;  // [P]
+    const float* inj_momenta;        // single-entry launches: [P]; inj_arena: the parameter arena layout (entry at param_off)
+    const float* inj_step_uniforms;  // the same
+    int inj_arena;
     uint64_t seed;
     uint64_t stream_base;            // Philox stream = stream_base + branch
     int keep_momenta;                // momenta already in place (bann_leapfrog_host)
@@ -524,13 +528,15 @@ __global__ void __launch_bounds__(256) k_hmc_init(InitArgs a) {
     float* p = a.mom + d.param_off;
     float* ep = a.eps + d.param_off;
     const float* pr = a.prec + d.prec_off;
+    const float* inj_mom = a.inj_momenta ? a.inj_momenta + (a.inj_arena ? d.param_off : 0) : nullptr;
+    const float* inj_su = a.inj_step_uniforms ? a.inj_step_uniforms + (a.inj_arena ? d.param_off : 0) : nullptr;
     // momenta: pairs (2k, 2k+1) from one Philox block each -> independent of the thread count
     for (uint32_t k2 = tid; 2 * k2 < P; k2 += 256) {
         const uint32_t k = 2 * k2;
         if (a.keep_momenta) break;
-        if (a.inj_momenta) {
-            p[k] = a.inj_momenta[k];
-            if (k + 1 < P) p[k + 1] = a.inj_momenta[k + 1];
+        if (inj_mom) {
+            p[k] = inj_mom[k];
+            if (k + 1 < P) p[k + 1] = inj_mom[k + 1];
         } else {
             Philox ph(a.seed, a.stream_base + b, (uint64_t)k2);
             float x, y;
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(256) k_hmc_init(InitArgs a) {
         locate_param(d, k, l, row, col, isb);
         float u = 0.f;
         if (a.step_mode == BANN_STEP_RANDOM) {
-            if (a.inj_step_uniforms) u = a.inj_step_uniforms[k];
+            if (inj_su) u = inj_su[k];
             else {
                 Philox ph(a.seed ^ 0x5bd1e995u, a.stream_base + b, (uint64_t)k);
                 uint32_t r[4];
@@ -596,5 +602,7 @@ __global__ void __launch_bounds__(256) k_accept(const BranchDesc* descs, const u
         for (uint32_t k = tid; k < d.P; k += 256) theta[d.param_off + k] = theta0[d.param_off + k];  // :1293-1296
     }
 }
+
+#endif  // BANN_NET_TU
 
 }  // namespace bann

@@ -1,6 +1,7 @@
 // Host orchestration behind the C ABI: device-resident Net state, branch visits, grouped
 // full-network leapfrog.  Mirrors Net<B>::train / predict / gradient (net/net.rs) and
 // BranchSampler::hmc_step (net/branch/branch_sampler.rs:1192-1299); see include/bann.h.
+#define BANN_NET_TU 1     // this translation unit owns the non-template kernels of kernels.cuh
 #include <algorithm>
 #include <cmath>
 
@@ -39,7 +40,14 @@ struct bann_net {
     size_t gsum_cap = 0;
     float* d_rpart = nullptr;
     uint32_t rblk = 0;
-    float* d_ow_others = nullptr;
+    float* d_ow_others = nullptr;   // [B] global output-weight stat minus the branch's own, as of the branch's last Gibbs / from_cfg
+    float *d_own_old = nullptr, *d_own_new = nullptr;   // [B] own output-weight stat before / after a transition (group visits)
+    uint32_t* d_order = nullptr;    // branch order of the current sweep (group visits read sub-ranges of it)
+    size_t order_cap = 0;
+    float *d_Tg = nullptr, *d_Yg = nullptr;   // group visits: per-member targets / final predictions [G][n]
+    size_t tg_cap = 0, yg_cap = 0;
+    float* d_inj_grp = nullptr;     // injected randomness of a group visit: momenta + step uniforms (arena layout), u[B], gammas[B][stride]
+    uint32_t inj_grp_stride = 0;
     float* d_bias2 = nullptr;
     float* d_lpd_local = nullptr;
     int* d_errflag = nullptr;
@@ -50,10 +58,12 @@ struct bann_net {
     int grouped_per_branch = 0;
     uint64_t grouped_seed = 0;
     float* d_traj = nullptr;
+    float* d_numgrad = nullptr;   // numerical_ldg: [maxP] gradient + [1] base log density
     size_t traj_cap = 0;
     float* d_scratchB = nullptr;  // [3*B] gather buffer
     uint64_t visit_seq = 0;
     int k1_mode = BANN_K1_AUTO;   // which K1 kernel launch_k1 may pick (bann_net_select_k1)
+    const char* last_k1 = "none"; // kernel family the last fused forward+backward launch used (bann_net_last_k1_kernel)
     float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient (callers with pageable buffers)
     float *d_dense_in = nullptr, *d_dense_out = nullptr;   // dense host-facing layouts of the parameters / gradients + rss
     uint64_t sum_params = 0;
@@ -62,6 +72,13 @@ struct bann_net {
     uint32_t maxQ = 0;
     float* d_jws = nullptr;
     float* d_tcx[3] = {nullptr, nullptr, nullptr};   // k1_tcx.cuh work buffers
+    // bulk peer-memory exchange of the grouped schedule (comm.cuh: XgComm), connected by bann_net_comm_connect
+    uint8_t* xg_region[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool xg_ipc[8] = {false, false, false, false, false, false, false, false};
+    bool xg_connected = false;
+    uint32_t xg_epoch = 0;
+    uint64_t xg_cap = 0;            // floats per in / out buffer
+    unsigned int* d_xg_counter = nullptr;
     size_t tcx_cap[3] = {0, 0, 0};
 };
 
@@ -94,6 +111,7 @@ struct K1Launch {
     const BranchDesc* descs_dev = nullptr;
     int single_branch = -1;  // host index of the only branch in the list (for kernel selection), -1: all
     bool xr = false;         // sum the reduced [gW | gb | rss] over ranks inside KR (sequential schedule, world > 1)
+    bool xg = false;         // sum them over ranks with the bulk exchange after KR (launches over many branches, world > 1)
 };
 
 static XrComm xr_none() {
@@ -109,6 +127,60 @@ static int need_comm(bann_net* net) {
     return 0;
 }
 static bool sharded(const bann_net* net) { return net->ctx->world > 1; }
+
+// ---- bulk exchange (comm.cuh): descriptor of the NEXT exchange, all-reduce(sum) in place, all-gather of 1/world slices
+static size_t xg_region_bytes(uint64_t cap) { return 256 + (size_t)4 * cap * sizeof(float); }
+static XgComm xg_next(bann_net* net) {
+    XgComm c;
+    memset(&c, 0, sizeof(c));
+    for (int r = 0; r < net->ctx->world; ++r) c.region[r] = net->xg_region[r];
+    c.rank = (uint32_t)net->ctx->rank;
+    c.world = (uint32_t)net->ctx->world;
+    c.epoch = ++net->xg_epoch;
+    c.cap = net->xg_cap;
+    c.error_flag = net->d_errflag;
+    c.counter = net->d_xg_counter;
+    return c;
+}
+static uint32_t xg_grid(const bann_net* net, uint64_t n4) {
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)net->ctx->num_sms * 2, (n4 + 255) / 256));
+}
+// buf[0 .. count) <- sum over ranks, identical bits on every rank; count is rounded up to a multiple of 4 (buf must hold that)
+static int xg_allreduce(bann_net* net, float* buf, uint64_t count) {
+    if (!net->xg_connected) BANN_FAIL("rows are sharded over ranks: call bann_net_comm_handle / bann_net_comm_connect first");
+    const uint64_t c4 = (count + 3) & ~3ull, n4 = c4 / 4, per4 = (n4 + net->ctx->world - 1) / net->ctx->world;
+    if (c4 > net->xg_cap) BANN_FAIL("bulk exchange: more values than the exchange region holds");
+    cudaStream_t st = net->ctx->stream;
+    XgComm c = xg_next(net);
+    k_xg_publish<<<xg_grid(net, n4), 256, 0, st>>>(c, buf, c4);
+    BANN_LAUNCHED();
+    k_xg_reduce_scatter<<<xg_grid(net, per4), 256, 0, st>>>(c, buf, c4, per4);
+    BANN_LAUNCHED();
+    k_xg_all_gather<<<xg_grid(net, n4), 256, 0, st>>>(c, buf, c4, per4);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+// every rank holds its slice [rank * per4, (rank + 1) * per4) (float4 units) of buf: fill in the others' slices
+static int xg_allgather_slices(bann_net* net, float* buf, uint64_t count) {
+    if (!net->xg_connected) BANN_FAIL("rows are sharded over ranks: call bann_net_comm_handle / bann_net_comm_connect first");
+    const uint64_t c4 = (count + 3) & ~3ull, n4 = c4 / 4, per4 = (n4 + net->ctx->world - 1) / net->ctx->world;
+    if (c4 > net->xg_cap) BANN_FAIL("bulk exchange: more values than the exchange region holds");
+    cudaStream_t st = net->ctx->stream;
+    XgComm c = xg_next(net);
+    k_xg_publish_slice<<<xg_grid(net, per4), 256, 0, st>>>(c, buf, c4, per4);
+    BANN_LAUNCHED();
+    k_xg_all_gather<<<xg_grid(net, n4), 256, 0, st>>>(c, buf, c4, per4);
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+// this rank's share [lo, hi) of a host-facing vector of `count` floats (the slices of xg_allgather_slices)
+static void xg_slice(const bann_net* net, uint64_t count, uint64_t* lo, uint64_t* hi) {
+    const uint64_t c4 = (count + 3) & ~3ull, n4 = c4 / 4, per4 = (n4 + net->ctx->world - 1) / net->ctx->world;
+    *lo = std::min<uint64_t>(count, 4 * per4 * net->ctx->rank);
+    *hi = std::min<uint64_t>(count, 4 * per4 * (net->ctx->rank + 1));
+}
 
 static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
     const bann_genotypes* g = L.store ? L.store : net->gen;
@@ -166,15 +238,18 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
         int r = launch_k1_tc(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
                              &nchunk, L.fwd_only ? nullptr : &part, net);
         if (r != 0) return r;
+        if (launched) net->last_k1 = "k1_tc<H,S,D,ACT> (tcgen05 + tensor memory, <= 64 markers per branch)";
         if (!launched) {   // 65..512 markers per branch: the K-blocked variant
             r = launch_k1_tcw(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched, &nchunk,
                               L.fwd_only ? nullptr : &part, net);
             if (r != 0) return r;
+            if (launched) net->last_k1 = "k1_tcw<H,S,D,ACT> (tcgen05, K-blocked, 65..512 markers per branch)";
         }
         if (!launched) {   // wide first layers (up to 16 units) / more markers: the three-pass variant
             r = launch_k1_tcx(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched, &nchunk,
                               L.fwd_only ? nullptr : &part, net);
             if (r != 0) return r;
+            if (launched) net->last_k1 = "k1_tcx: k_tcx_fwd + k_tcx_tail + k_tcx_bwd (tcgen05, three passes, first-layer width <= 16)";
         }
         if (!launched && net->k1_mode == BANN_K1_TENSOR)
             BANN_FAIL("tensor-core K1 requested but the launch is not eligible (tanh, homogeneous architecture, widths in the instantiated set)");
@@ -183,8 +258,10 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
         int r = launch_k1_small(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
                                 &nchunk, L.fwd_only ? nullptr : &part, net);
         if (r != 0) return r;
+        if (launched) net->last_k1 = "k1_small<H,S,D> (FFMA)";
     }
     if (!launched) {
+        net->last_k1 = "k1_generic (shape-agnostic)";
         dim3 grid(nchunk, L.nlist);
         k1_generic<<<grid, 128, net->max_generic_smem, st>>>(a);
         BANN_LAUNCHED();
@@ -198,6 +275,7 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
     }
+    if (L.xg && !L.fwd_only) BANN_CHECK(xg_allreduce(net, net->d_gsum, (uint64_t)L.nlist * net->pstride));
     return 0;
 }
 
@@ -270,6 +348,40 @@ __global__ void __launch_bounds__(256) k_log_density(const BranchDesc* descs, ui
     if (threadIdx.x == 0) *out = prior + (-1.0f * pr[d.ep_off] * (rss / 2.0f));
 }
 
+// ---- numerical_ldg (branch_sampler.rs:480-504, the reference's own debugging aid: "DO NOT run this in production code"):
+// forward differences (log_density(theta + delta e_k) - log_density(theta)) / delta with NUMERICAL_DELTA = 0.001 (:30), one
+// fused pass per parameter.  The perturbed vector is walked exactly as the reference does (+= delta, evaluate, -= delta).
+constexpr float kNumericalDelta = 0.001f;
+__global__ void k_numgrad_poke(float* p, float delta) { *p += delta; }
+// log density at the current theta from the rss the fused pass just reduced; base == NULL: store it, else the difference quotient
+__global__ void __launch_bounds__(256) k_numgrad_eval(const BranchDesc* descs, uint32_t b, const float* theta, const float* prec,
+                                                      int model, const float* rss_ptr, const float* base, float delta, float* out) {
+    __shared__ float red[8];
+    const BranchDesc& d = descs[b];
+    const float* th = theta + d.param_off;
+    const float* pr = prec + d.prec_off;
+    const bool lasso = (model == BANN_LASSO_BASE || model == BANN_LASSO_ARD);
+    float prior = 0.f;
+    for (uint32_t k = threadIdx.x; k < d.P; k += 256) {
+        int l; uint32_t row, col; bool isb;
+        locate_param(d, k, l, row, col, isb);
+        const float w = th[k];
+        if (isb) {
+            if (model == BANN_STD_NORMAL) prior -= 0.5f * w * w;
+        } else {
+            const float lam = param_prior_precision(d, pr, model, l, row, false);
+            if (model == BANN_STD_NORMAL) prior -= 0.5f * w * w;
+            else if (lasso) prior -= lam * fabsf(w);
+            else prior -= 0.5f * lam * w * w;
+        }
+    }
+    prior = block_sum<256>(prior, red);
+    if (threadIdx.x == 0) {
+        const float ld = prior + (-1.0f * pr[d.ep_off] * (*rss_ptr / 2.0f));
+        *out = base ? (ld - *base) / delta : ld;
+    }
+}
+
 __global__ void k_gather_states(const BranchState* st, uint32_t B, float* h_init, float* h_cur, int* status) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -301,11 +413,15 @@ struct HmcRun {
     const float* inj_mom = nullptr;
     const float* inj_su = nullptr;
     const float* inj_u = nullptr;
+    int inj_arena = 0;      // injected momenta / step uniforms in the parameter arena layout (group visits)
+    int out_per_entry = 0;  // tgt_out / prev_out / ynew_out hold one row vector per list entry (group visits)
+    bool xg = false;        // sharded rows: all-reduce the sums inside the library (else the caller does, bann_grouped_phase_a / _b)
     uint64_t seed = 0;
     uint64_t stream_base = 0;
     float* traj_params = nullptr;
     float* traj_ldg = nullptr;
     float* traj_h = nullptr;
+    float* traj_num_ldg = nullptr;   // [L][P]: numerical_ldg per step (mcmc_cfg.num_grad_traj)
 };
 
 static int hmc_init_and_first_eval(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, int keep_momenta) {
@@ -329,6 +445,7 @@ static int hmc_init_and_first_eval(bann_net* net, const bann_mcmc_cfg* cfg, cons
     ia.L = (float)cfg->hmc_integration_length;
     ia.inj_momenta = R.inj_mom;
     ia.inj_step_uniforms = R.inj_su;
+    ia.inj_arena = R.inj_arena;
     ia.seed = R.seed;
     ia.stream_base = R.stream_base;
     ia.keep_momenta = keep_momenta;
@@ -358,7 +475,40 @@ static K2Args make_k2(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, 
     a.traj_params = R.traj_params;
     a.traj_ldg = R.traj_ldg;
     a.traj_h = R.traj_h;
+    a.num_ldg = nullptr;
     return a;
+}
+
+// numerical_ldg of branch b against the device target vector `tgt` at the CURRENT parameters: P + 1 fused passes.
+// Result in net->d_numgrad[0 .. P); d_gsum holds the sums of the LAST perturbed evaluation afterwards (callers re-evaluate).
+static int numerical_ldg_async(bann_net* net, uint32_t b, const float* tgt) {
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[b];
+    if (!net->d_numgrad) BANN_CUDA(cudaMalloc(&net->d_numgrad, ((size_t)net->maxP + 4) * sizeof(float)));
+    float* base = net->d_numgrad + net->maxP;
+    K1Launch k;
+    k.list = net->d_list_all + b;
+    k.nlist = 1;
+    k.single_branch = (int)b;
+    k.target_mode = TGT_SHARED;
+    k.tgt = tgt;
+    k.xr = sharded(net);
+    BANN_CHECK(launch_k1(net, k, true));
+    k_numgrad_eval<<<1, 256, 0, st>>>(net->d_descs, b, net->d_theta, net->d_prec, net->model, net->d_gsum + d.P, nullptr,
+                                      kNumericalDelta, base);
+    BANN_LAUNCHED();
+    for (uint32_t pix = 0; pix < d.P; ++pix) {
+        k_numgrad_poke<<<1, 1, 0, st>>>(net->d_theta + d.param_off + pix, kNumericalDelta);
+        BANN_LAUNCHED();
+        BANN_CHECK(launch_k1(net, k, true));
+        k_numgrad_eval<<<1, 256, 0, st>>>(net->d_descs, b, net->d_theta, net->d_prec, net->model, net->d_gsum + d.P, base,
+                                          kNumericalDelta, net->d_numgrad + pix);
+        BANN_LAUNCHED();
+        k_numgrad_poke<<<1, 1, 0, st>>>(net->d_theta + d.param_off + pix, -kNumericalDelta);
+        BANN_LAUNCHED();
+    }
+    BANN_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // full HMC transition for the listed branches (sequential-exact when nlist == 1)
@@ -372,15 +522,40 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
     k.nlist = R.nlist;
     k.single_branch = R.single_branch;
     k.states = net->d_states;
-    k.xr = sharded(net) && R.nlist == 1 && R.list != nullptr;   // sequential schedule; grouped launches are all-reduced by the caller
+    k.xr = sharded(net) && R.nlist == 1 && R.list != nullptr;   // sequential schedule: latency-critical push exchange inside KR
+    k.xg = sharded(net) && !k.xr && R.xg;                        // launches over many branches: bulk exchange after KR
     k.target_mode = R.first_mode;
     k.tgt = R.tgt;
     k.resid = resid;
     k.tgt_out = tgt_out;
     k.prev_out = prev_out;
+    k.out_per_entry = R.out_per_entry;
     if (Lsteps == 0) k.yhat_out = ynew_out;
     BANN_CHECK(launch_k1(net, k, true));
     K2Args a = make_k2(net, cfg, R, 1, Lsteps == 0);
+    // --num-grad / --num-grad-traj (branch_sampler.rs:1232-1261; single-branch transitions): numerical_ldg at the parameters
+    // the fused pass above just evaluated, then that pass again (shared target) so that K2 finds the unperturbed sums
+    const bool numgrad = (cfg->num_grad || (cfg->num_grad_traj && R.traj_num_ldg)) && R.nlist == 1 && R.single_branch >= 0;
+    if ((cfg->num_grad || cfg->num_grad_traj) && !numgrad && R.nlist != 1)
+        BANN_FAIL("numerical gradients are a per-branch debugging aid (group_size 1)");
+    const float* ng_tgt = (R.first_mode == TGT_RESID_PLUS_PRED) ? tgt_out : R.tgt;
+    auto numgrad_point = [&](uint32_t step /* 0 = initial evaluation */) -> int {
+        const uint32_t b = (uint32_t)R.single_branch;
+        const BranchDesc& d = net->descs[b];
+        BANN_CHECK(numerical_ldg_async(net, b, ng_tgt));
+        if (cfg->num_grad_traj && R.traj_num_ldg && step >= 1)
+            BANN_CUDA(cudaMemcpyAsync(R.traj_num_ldg + (size_t)(step - 1) * d.P, net->d_numgrad, d.P * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, st));
+        K1Launch k2 = k;                 // the evaluation at the unperturbed parameters again: sums for K2
+        k2.target_mode = TGT_SHARED;
+        k2.tgt = ng_tgt;
+        k2.resid = nullptr; k2.tgt_out = nullptr; k2.prev_out = nullptr; k2.yhat_out = nullptr;
+        k2.states = nullptr;
+        BANN_CHECK(launch_k1(net, k2, true));
+        a.num_ldg = cfg->num_grad ? net->d_numgrad : nullptr;
+        return 0;
+    };
+    if (numgrad && (cfg->num_grad)) BANN_CHECK(numgrad_point(0));
     BANN_CUDA(launch_pdl(k2_step, dim3(R.nlist), dim3(256), 0, st, a));
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
@@ -394,6 +569,7 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
         BANN_CHECK(launch_k1(net, k, true));
         a.mode_init = 0;
         a.is_last = (s == Lsteps);
+        if (numgrad) BANN_CHECK(numgrad_point(s));
         BANN_CUDA(launch_pdl(k2_step, dim3(R.nlist), dim3(256), 0, st, a));
         BANN_LAUNCHED();
         BANN_CUDA(cudaGetLastError());
@@ -458,7 +634,7 @@ static JointArgs make_joint(bann_net* net, const bann_mcmc_cfg* cfg, const Joint
     a.pgrad = w.pgrad;
     a.peps = w.peps;
     a.gsum = net->d_gsum;
-    a.ow_others = net->d_ow_others;
+    a.ow_others = net->d_ow_others + R.b;
     a.G = net->d_G;
     a.hyper = net->hyper;
     a.model = net->model;
@@ -498,7 +674,7 @@ static int joint_prepare(bann_net* net, const JointRun& R, int hmc, const bann_m
     cudaStream_t st = net->ctx->stream;
     JointWs w = joint_ws(net);
     if (!R.ow_from_gibbs) {
-        k_ow_others<<<1, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_G, net->model, net->d_ow_others);
+        k_ow_others<<<1, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_G, net->model, net->d_ow_others + R.b);
         BANN_LAUNCHED();
     }
     JointInitArgs ia;
@@ -675,15 +851,19 @@ static int stage_inject(bann_net* net, const bann_rng_inject* inj, uint32_t P, H
     return 0;
 }
 
+// Gibbs draws of one branch (list == NULL) or of every member of a group (one block each, globals frozen)
 static int launch_gibbs(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, int do_draws, const float* d_gam,
-                        uint32_t n_gam, uint64_t seed, uint64_t stream) {
+                        uint32_t n_gam, uint64_t seed, uint64_t stream_base, const uint32_t* list = nullptr, uint32_t nlist = 1,
+                        uint32_t inj_stride = 0) {
     GibbsArgs g;
     g.descs = net->d_descs;
+    g.list = list;
     g.b = b;
     g.theta = net->d_theta;
     g.prec = net->d_prec;
     g.G = net->d_G;
     g.ow_others = net->d_ow_others;
+    g.own_old = net->d_own_old;
     g.hyper = net->hyper;
     g.model = net->model;
     g.n_total = net->n_total;
@@ -691,9 +871,10 @@ static int launch_gibbs(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, int
     g.do_draws = do_draws;
     g.inj = d_gam;
     g.n_inj = n_gam;
+    g.inj_stride = inj_stride;
     g.seed = seed;
-    g.stream = stream;
-    k_gibbs<<<1, 256, 0, net->ctx->stream>>>(g);
+    g.stream_base = stream_base;
+    k_gibbs<<<list ? nlist : 1, 256, 0, net->ctx->stream>>>(g);
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     return 0;
@@ -710,14 +891,14 @@ static int check_error_flag(bann_net* net) {
 
 // one iteration of the inner loop of Net::train, fully asynchronous
 struct VisitTraj {   // device buffers of one visit's trajectory (trajectory.rs:4-43), all optional
-    float *params = nullptr, *prec = nullptr, *ldg = nullptr, *h = nullptr;
+    float *params = nullptr, *prec = nullptr, *ldg = nullptr, *h = nullptr, *num_ldg = nullptr;
 };
 static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj, uint64_t seed,
                        const VisitTraj* vt = nullptr) {
     cudaStream_t st = net->ctx->stream;
     BANN_CHECK(need_comm(net));
     HmcRun R;
-    if (vt) { R.traj_params = vt->params; R.traj_ldg = vt->ldg; R.traj_h = vt->h; }
+    if (vt) { R.traj_params = vt->params; R.traj_ldg = vt->ldg; R.traj_h = vt->h; R.traj_num_ldg = vt->num_ldg; }
     R.list = net->d_list_all + b;
     R.nlist = 1;
     R.single_branch = (int)b;
@@ -745,10 +926,10 @@ static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, cons
         }
         if (cfg->gradient_descent) {
             BANN_CHECK(stage_inject(net, inj, net->descs[b].P, nullptr, &d_gam, &n_gam));
-            BANN_CHECK(launch_gibbs(net, b, cfg, joint ? 0 : 1, d_gam, n_gam, seed, net->visit_seq * net->B + b));
+            BANN_CHECK(launch_gibbs(net, b, cfg, joint ? 0 : 1, d_gam, n_gam, seed, net->visit_seq * net->B));
             BANN_CHECK(run_gd(net, cfg, J, nullptr, nullptr));
         } else {
-            BANN_CHECK(launch_gibbs(net, b, cfg, 0, nullptr, 0, seed, net->visit_seq * net->B + b));
+            BANN_CHECK(launch_gibbs(net, b, cfg, 0, nullptr, 0, seed, net->visit_seq * net->B));
             if (cfg->gradient_descent_joint) BANN_CHECK(run_gd_joint(net, cfg, J));
             else {
                 BANN_CHECK(stage_inject_joint(net, inj, net->descs[b].P + net->descs[b].nprec, &J));
@@ -757,7 +938,7 @@ static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, cons
         }
     } else {
         BANN_CHECK(stage_inject(net, inj, net->descs[b].P, &R, &d_gam, &n_gam));
-        BANN_CHECK(launch_gibbs(net, b, cfg, 1, d_gam, n_gam, seed, net->visit_seq * net->B + b));   // net.rs:261-277
+        BANN_CHECK(launch_gibbs(net, b, cfg, 1, d_gam, n_gam, seed, net->visit_seq * net->B));   // net.rs:261-277
         BANN_CHECK(run_hmc(net, cfg, R, net->d_ynew, net->d_t, net->d_prev, net->d_r));               // net.rs:279-290
     }
     k_resid_after_hmc<<<net->rblk, 256, 0, st>>>(net->d_r, net->d_t, net->d_ynew, net->d_prev, net->n,
@@ -770,7 +951,7 @@ static int visit_async(bann_net* net, uint32_t b, const bann_mcmc_cfg* cfg, cons
     f.prec = net->d_prec;
     f.G = net->d_G;
     f.st = net->d_states + b;
-    f.ow_others = net->d_ow_others;
+    f.ow_others = net->d_ow_others + b;
     f.lpd_local = net->d_lpd_local;
     f.hyper = net->hyper;
     f.model = net->model;
@@ -814,6 +995,97 @@ static int refresh_resid_stats(bann_net* net) {
                                      (sharded(net) && net->ctx->xr_connected) ? xr_next(net->ctx, net->d_errflag) : xr_none());
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------ block-Jacobi group visit
+// `members`: device list of `num` distinct branch ids.  All of them run Gibbs + HMC against the residual and the globals frozen
+// at group start (t_b = r + yhat_b, one row vector per member), then residual / globals / LPD / counters / output bias are
+// updated once (chain.cuh: k_resid_group, k_group_stats, k_group_finish).  Asynchronous.
+struct GroupInject {          // device pointers (or NULL): see bann_visit_group
+    const float *mom = nullptr, *su = nullptr, *u = nullptr, *gam = nullptr;
+    uint32_t n_gam = 0, gam_stride = 0;
+};
+static int visit_group_async(bann_net* net, const uint32_t* members, uint32_t num, const bann_mcmc_cfg* cfg, uint64_t seed,
+                             const GroupInject* gi) {
+    cudaStream_t st = net->ctx->stream;
+    if (cfg->joint_hmc || cfg->gradient_descent || cfg->gradient_descent_joint)
+        BANN_FAIL("group visits (group_size > 1) run the HMC sampler; the joint / gradient-descent modes are sequential (group_size 1)");
+    BANN_CHECK(need_comm(net));
+    if (sharded(net) && !net->xg_connected)
+        BANN_FAIL("group visits on sharded rows need the bulk exchange: call bann_net_comm_handle / bann_net_comm_connect first");
+    BANN_CHECK(ensure_cap(&net->d_Tg, &net->tg_cap, (size_t)num * net->n));
+    BANN_CHECK(ensure_cap(&net->d_Yg, &net->yg_cap, (size_t)num * net->n));
+    const uint64_t stream_base = net->visit_seq * net->B;
+    BANN_CHECK(launch_gibbs(net, 0, cfg, 1, gi ? gi->gam : nullptr, gi ? gi->n_gam : 0, seed, stream_base, members, num,
+                            gi ? gi->gam_stride : 0));                                             // net.rs:261-277 per member
+    HmcRun R;
+    R.list = members;
+    R.nlist = num;
+    R.single_branch = -1;
+    R.first_mode = TGT_RESID_PLUS_PRED;       // t_b = r + yhat_b (net.rs:279-280), written per member
+    R.later_mode = TGT_PER_ENTRY;
+    R.tgt = nullptr;
+    R.out_per_entry = 1;
+    R.seed = seed;
+    R.stream_base = stream_base;
+    R.xg = true;
+    if (gi) { R.inj_mom = gi->mom; R.inj_su = gi->su; R.inj_u = gi->u; R.inj_arena = 1; }
+    BANN_CHECK(run_hmc(net, cfg, R, net->d_Yg, net->d_Tg, nullptr, net->d_r));                     // net.rs:282-290 per member
+    k_resid_group<<<net->rblk, 256, 0, st>>>(net->d_r, net->d_Tg, net->d_Yg, net->n, members, num, net->d_states, net->d_G,
+                                             net->d_rpart);                                        // net.rs:292-300 over the group
+    BANN_LAUNCHED();
+    GroupArgs g;
+    g.descs = net->d_descs;
+    g.list = members;
+    g.nlist = num;
+    g.theta = net->d_theta;
+    g.prec = net->d_prec;
+    g.G = net->d_G;
+    g.states = net->d_states;
+    g.own_old = net->d_own_old;
+    g.own_new = net->d_own_new;
+    g.lpd_local = net->d_lpd_local;
+    g.hyper = net->hyper;
+    g.model = net->model;
+    g.n_total = net->n_total;
+    g.part = net->d_rpart;
+    g.nblk = net->rblk;
+    g.bias_old_new = net->d_bias2;
+    g.error_flag = net->d_errflag;
+    g.xc = sharded(net) ? xr_next(net->ctx, net->d_errflag) : xr_none();
+    k_group_stats<<<num, 256, 0, st>>>(g);
+    BANN_LAUNCHED();
+    k_group_finish<<<1, 256, 0, st>>>(g);                                                          // net.rs:296,303-305,320-330
+    BANN_LAUNCHED();
+    k_resid_apply_bias<<<net->rblk, 256, 0, st>>>(net->d_r, net->n, net->d_bias2, net->d_rpart);   // net.rs:321,332
+    BANN_LAUNCHED();
+    k_resid_reduce<<<1, 32, 0, st>>>(net->d_rpart, net->rblk, net->d_G,
+                                     sharded(net) ? xr_next(net->ctx, net->d_errflag) : xr_none());
+    BANN_LAUNCHED();
+    BANN_CUDA(cudaGetLastError());
+    net->visit_seq += 1;
+    return 0;
+}
+
+static int upload_order(bann_net* net, const uint64_t* order, uint64_t num) {
+    std::vector<uint32_t> h(num);
+    std::vector<uint8_t> seen(net->B, 0);
+    for (uint64_t i = 0; i < num; ++i) {
+        if (order[i] >= net->B) BANN_FAIL("branch index out of range");
+        h[i] = (uint32_t)order[i];
+    }
+    if (net->order_cap < num) {
+        if (net->d_order) cudaFree(net->d_order);
+        net->d_order = nullptr;
+        net->order_cap = 0;
+        BANN_CUDA(cudaMalloc(&net->d_order, num * sizeof(uint32_t)));
+        net->order_cap = num;
+    }
+    // the previous sweep's kernels may still read the list: the copy is ordered behind them on the same stream
+    BANN_CUDA(cudaMemcpyAsync(net->d_order, h.data(), num * sizeof(uint32_t), cudaMemcpyHostToDevice, net->ctx->stream));
+    BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));   // h goes out of scope
+    (void)seen;
     return 0;
 }
 
@@ -925,6 +1197,7 @@ int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int acti
     G.lpd_rss = -INFINITY;               // log_posterior_density.rs:19-25
     G.lpd_out_w = -INFINITY;
     BANN_CUDA(cudaMemcpyAsync(net->d_G, &G, sizeof(G), cudaMemcpyHostToDevice, st));
+    if (net->n == 0) { delete net; BANN_FAIL("this rank holds no individuals (empty row shard): use fewer ranks"); }
     size_t nb = (size_t)net->n * sizeof(float);
     BANN_CUDA(cudaMalloc(&net->d_y, nb));
     BANN_CUDA(cudaMalloc(&net->d_r, nb));
@@ -938,8 +1211,10 @@ int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int acti
     BANN_CUDA(cudaMemsetAsync(net->d_ynew, 0, nb, st));
     net->rblk = std::min<uint32_t>((net->n + 255) / 256, (uint32_t)ctx->num_sms * 4);
     BANN_CUDA(cudaMalloc(&net->d_rpart, 2 * (size_t)net->rblk * sizeof(float)));
-    BANN_CUDA(cudaMalloc(&net->d_ow_others, sizeof(float)));
-    BANN_CUDA(cudaMemsetAsync(net->d_ow_others, 0, sizeof(float), st));
+    BANN_CUDA(cudaMalloc(&net->d_ow_others, 3 * net->B * sizeof(float)));
+    BANN_CUDA(cudaMemsetAsync(net->d_ow_others, 0, 3 * net->B * sizeof(float), st));
+    net->d_own_old = net->d_ow_others + net->B;
+    net->d_own_new = net->d_ow_others + 2 * net->B;
     BANN_CUDA(cudaMalloc(&net->d_bias2, 2 * sizeof(float)));
     BANN_CUDA(cudaMalloc(&net->d_lpd_local, net->B * sizeof(float)));
     {
@@ -967,13 +1242,22 @@ int bann_net_create(bann_ctx* ctx, bann_genotypes* gen, int model_type, int acti
 }
 
 void bann_net_destroy(bann_net* net) {
+    if (net) {
+        for (int r = 0; r < kXrMaxWorld; ++r) {
+            if (!net->xg_region[r]) continue;
+            if (r == net->ctx->rank) cudaFree(net->xg_region[r]);
+            else if (net->xg_ipc[r]) cudaIpcCloseMemHandle(net->xg_region[r]);
+            net->xg_region[r] = nullptr;
+        }
+        cudaFree(net->d_xg_counter);
+    }
     if (!net) return;
     cudaFree(net->d_descs); cudaFree(net->d_theta); cudaFree(net->d_theta0); cudaFree(net->d_mom);
     cudaFree(net->d_grad); cudaFree(net->d_eps); cudaFree(net->d_prec); cudaFree(net->d_states);
     cudaFree(net->d_G); cudaFree(net->d_y); cudaFree(net->d_r); cudaFree(net->d_t); cudaFree(net->d_prev);
     cudaFree(net->d_ynew); cudaFree(net->d_part); cudaFree(net->d_gsum); cudaFree(net->d_rpart);
-    cudaFree(net->d_ow_others); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
-    cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj);
+    cudaFree(net->d_ow_others); cudaFree(net->d_order); cudaFree(net->d_Tg); cudaFree(net->d_Yg); cudaFree(net->d_inj_grp); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
+    cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj); cudaFree(net->d_numgrad);
     cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
     for (int i = 0; i < 3; ++i) cudaFree(net->d_tcx[i]);
     if (net->h_pin_a) cudaFreeHost(net->h_pin_a);
@@ -1128,7 +1412,7 @@ int bann_net_init_residual(bann_net* net) {
         BANN_LAUNCHED();
         FinishArgs f;
         f.descs = net->d_descs; f.b = (uint32_t)b; f.theta = net->d_theta; f.prec = net->d_prec; f.G = net->d_G;
-        f.st = nullptr; f.ow_others = net->d_ow_others; f.lpd_local = net->d_lpd_local; f.hyper = net->hyper;
+        f.st = nullptr; f.ow_others = net->d_ow_others + b; f.lpd_local = net->d_lpd_local; f.hyper = net->hyper;
         f.model = net->model; f.n_total = net->n_total; f.part = net->d_rpart; f.nblk = net->rblk;
         f.bias_old_new = net->d_bias2; f.update_bias = 0; f.error_flag = net->d_errflag;
         f.xc = sharded(net) ? xr_next(net->ctx, net->d_errflag) : xr_none();
@@ -1184,6 +1468,27 @@ int bann_branch_log_density(bann_net* net, uint64_t b, float rss, float* out) {
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     BANN_CUDA(cudaMemcpyAsync(out, net->d_scratchB, sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bann_branch_numerical_ldg(bann_net* net, uint64_t b, const float* target, float* out) {
+    if (!net || !out) BANN_FAIL("NULL argument");
+    if (b >= net->B) BANN_FAIL("branch index out of range");
+    BANN_CHECK(need_comm(net));
+    cudaStream_t st = net->ctx->stream;
+    const BranchDesc& d = net->descs[b];
+    const float* tgt = net->d_y;
+    if (target) {
+        BANN_CUDA(cudaMemcpyAsync(net->d_t, target, (size_t)net->n * sizeof(float), cudaMemcpyHostToDevice, st));
+        tgt = net->d_t;
+    }
+    std::vector<float> keep(d.P);       // the reference reloads the original parameter vector at the end (:502)
+    BANN_CUDA(cudaMemcpyAsync(keep.data(), net->d_theta + d.param_off, d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CHECK(numerical_ldg_async(net, (uint32_t)b, tgt));
+    BANN_CUDA(cudaMemcpyAsync(out, net->d_numgrad, d.P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BANN_CUDA(cudaStreamSynchronize(st));
+    BANN_CUDA(cudaMemcpyAsync(net->d_theta + d.param_off, keep.data(), d.P * sizeof(float), cudaMemcpyHostToDevice, st));
     BANN_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -1281,7 +1586,7 @@ int bann_branch_joint(bann_net* net, uint64_t b, const float* target, float* rss
     cudaStream_t st = net->ctx->stream;
     const BranchDesc& d = net->descs[b];
     JointWs w = joint_ws(net);
-    k_ow_others<<<1, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_G, net->model, net->d_ow_others);
+    k_ow_others<<<1, 256, 0, st>>>(net->d_descs, R.b, net->d_theta, net->d_G, net->model, net->d_ow_others + R.b);
     BANN_LAUNCHED();
     K1Launch k = joint_k1(net, R, true);
     k.states = nullptr;
@@ -1367,7 +1672,7 @@ int bann_gibbs_branch(bann_net* net, uint64_t b, const bann_mcmc_cfg* cfg, const
     const float* d_gam = nullptr;
     uint32_t n_gam = 0;
     BANN_CHECK(stage_inject(net, inj, net->descs[b].P, nullptr, &d_gam, &n_gam));
-    BANN_CHECK(launch_gibbs(net, (uint32_t)b, cfg, 1, d_gam, n_gam, 0x13198a2e03707344ull, net->visit_seq * net->B + b));
+    BANN_CHECK(launch_gibbs(net, (uint32_t)b, cfg, 1, d_gam, n_gam, 0x13198a2e03707344ull, net->visit_seq * net->B));
     net->visit_seq += 1;
     BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
     return 0;
@@ -1391,7 +1696,8 @@ int bann_visit_branch_traj(bann_net* net, uint64_t b, const bann_mcmc_cfg* cfg, 
     const BranchDesc& d = net->descs[b];
     const bool jt = cfg->joint_hmc && !cfg->gradient_descent && !cfg->gradient_descent_joint;
     const size_t P = d.P, Q = jt ? d.nprec : 0, Ls = cfg->hmc_integration_length;
-    const size_t need = Ls * P + Ls * Q + Ls * (P + Q) + Ls + 1;
+    const bool ng = cfg->num_grad_traj && traj->num_ldg && !jt && !cfg->gradient_descent && !cfg->gradient_descent_joint;
+    const size_t need = Ls * P + Ls * Q + Ls * (P + Q) + Ls + 1 + (ng ? Ls * P : 0);
     BANN_CHECK(ensure_cap(&net->d_traj, &net->traj_cap, need));
     BANN_CUDA(cudaMemsetAsync(net->d_traj, 0, need * sizeof(float), st));
     VisitTraj vt;
@@ -1399,11 +1705,13 @@ int bann_visit_branch_traj(bann_net* net, uint64_t b, const bann_mcmc_cfg* cfg, 
     vt.prec = vt.params + Ls * P;
     vt.ldg = vt.prec + Ls * Q;
     vt.h = vt.ldg + Ls * (P + Q);
+    if (ng) vt.num_ldg = vt.h + Ls + 1;
     BANN_CHECK(visit_async(net, (uint32_t)b, cfg, nullptr, seed, &vt));
     if (traj->params) BANN_CUDA(cudaMemcpyAsync(traj->params, vt.params, Ls * P * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (traj->precisions && Q) BANN_CUDA(cudaMemcpyAsync(traj->precisions, vt.prec, Ls * Q * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (traj->ldg) BANN_CUDA(cudaMemcpyAsync(traj->ldg, vt.ldg, Ls * (P + Q) * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (traj->hamiltonian) BANN_CUDA(cudaMemcpyAsync(traj->hamiltonian, vt.h, (Ls + 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (ng) BANN_CUDA(cudaMemcpyAsync(traj->num_ldg, vt.num_ldg, Ls * P * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (out) BANN_CHECK(read_hmc_result(net, (uint32_t)b, out));
     BANN_CHECK(check_error_flag(net));
     return 0;
@@ -1446,13 +1754,88 @@ int bann_net_lpd_terms(bann_net* net, float* wrt_rss_and_error_precision, float*
 int bann_sweep(bann_net* net, const bann_mcmc_cfg* cfg, const uint64_t* branch_order, uint64_t num, uint32_t group_size,
                uint64_t seed, bann_sweep_stats* out) {
     if (!net || !cfg || !branch_order) BANN_FAIL("NULL argument");
-    if (group_size != 1) BANN_FAIL("bann_sweep supports group_size 1 (sequential-exact); use bann_grouped_* for G = B");
-    for (uint64_t i = 0; i < num; ++i) {
-        if (branch_order[i] >= net->B) BANN_FAIL("branch index out of range");
-        BANN_CHECK(visit_async(net, (uint32_t)branch_order[i], cfg, nullptr, seed));
+    if (group_size == 0) BANN_FAIL("group_size must be >= 1");
+    if (group_size == 1) {          // sequential-exact schedule: the reference's Gauss-Seidel order
+        for (uint64_t i = 0; i < num; ++i) {
+            if (branch_order[i] >= net->B) BANN_FAIL("branch index out of range");
+            BANN_CHECK(visit_async(net, (uint32_t)branch_order[i], cfg, nullptr, seed));
+        }
+    } else {                        // block-Jacobi: consecutive groups of the order advance concurrently
+        {
+            std::vector<uint8_t> seen(net->B, 0);
+            for (uint64_t i = 0; i < num; ++i) {
+                if (branch_order[i] >= net->B) BANN_FAIL("branch index out of range");
+                // a branch twice in one group would race on its own state; twice in a sweep is fine across groups
+                if (i % group_size == 0) std::fill(seen.begin(), seen.end(), 0);
+                if (seen[branch_order[i]]) BANN_FAIL("a branch appears twice in one group");
+                seen[branch_order[i]] = 1;
+            }
+        }
+        BANN_CHECK(upload_order(net, branch_order, num));
+        for (uint64_t i = 0; i < num; i += group_size) {
+            const uint32_t cnt = (uint32_t)std::min<uint64_t>(group_size, num - i);
+            if (cnt == 1) BANN_CHECK(visit_async(net, (uint32_t)branch_order[i], cfg, nullptr, seed));
+            else BANN_CHECK(visit_group_async(net, net->d_order + i, cnt, cfg, seed, nullptr));
+        }
     }
     BANN_CHECK(check_error_flag(net));
     if (out) BANN_CHECK(bann_net_stats(net, out));
+    return 0;
+}
+
+int bann_visit_group(bann_net* net, const uint64_t* members, uint64_t num, const bann_mcmc_cfg* cfg, const bann_rng_inject* inj,
+                     uint64_t seed, bann_hmc_result* out) {
+    if (!net || !members || !cfg || num == 0) BANN_FAIL("NULL / empty argument");
+    cudaStream_t st = net->ctx->stream;
+    {
+        std::vector<uint8_t> seen(net->B, 0);
+        for (uint64_t i = 0; i < num; ++i) {
+            if (members[i] >= net->B) BANN_FAIL("branch index out of range");
+            if (seen[members[i]]) BANN_FAIL("a branch appears twice in one group");
+            seen[members[i]] = 1;
+        }
+    }
+    BANN_CHECK(upload_order(net, members, num));
+    GroupInject gi;
+    if (inj) {
+        // staging: [momenta arena | step-uniform arena | u per entry | gammas per entry x stride]
+        uint32_t stride = 0;
+        for (uint64_t i = 0; i < num; ++i) stride = std::max(stride, inj[i].num_std_gammas);
+        stride = std::max(stride, 1u);
+        const size_t need = 2 * (size_t)net->total_params + num + (size_t)num * stride;
+        if (net->inj_grp_stride < need) {      // (re)allocate: inj_grp_stride doubles as the capacity in floats
+            if (net->d_inj_grp) cudaFree(net->d_inj_grp);
+            net->d_inj_grp = nullptr;
+            net->inj_grp_stride = 0;
+            BANN_CUDA(cudaMalloc(&net->d_inj_grp, need * sizeof(float)));
+            net->inj_grp_stride = (uint32_t)need;
+        }
+        std::vector<float> h(need, 0.f);
+        float* mom = h.data();
+        float* su = mom + net->total_params;
+        float* u = su + net->total_params;
+        float* gam = u + num;
+        bool any_mom = false, any_su = false, any_u = false, any_gam = false;
+        for (uint64_t i = 0; i < num; ++i) {
+            const BranchDesc& d = net->descs[members[i]];
+            if (inj[i].momenta) { memcpy(mom + d.param_off, inj[i].momenta, d.P * sizeof(float)); any_mom = true; }
+            if (inj[i].step_uniforms) { memcpy(su + d.param_off, inj[i].step_uniforms, d.P * sizeof(float)); any_su = true; }
+            if (inj[i].accept_uniform) { u[i] = *inj[i].accept_uniform; any_u = true; }
+            if (inj[i].std_gammas) { memcpy(gam + i * stride, inj[i].std_gammas, inj[i].num_std_gammas * sizeof(float)); any_gam = true; }
+        }
+        BANN_CUDA(cudaMemcpyAsync(net->d_inj_grp, h.data(), need * sizeof(float), cudaMemcpyHostToDevice, st));
+        BANN_CUDA(cudaStreamSynchronize(st));
+        float* base = net->d_inj_grp;
+        if (any_mom) gi.mom = base;
+        if (any_su) gi.su = base + net->total_params;
+        if (any_u) gi.u = base + 2 * (size_t)net->total_params;
+        if (any_gam) { gi.gam = base + 2 * (size_t)net->total_params + num; gi.n_gam = stride; gi.gam_stride = stride; }
+    }
+    if (num == 1 && !inj) BANN_CHECK(visit_async(net, (uint32_t)members[0], cfg, nullptr, seed));
+    else BANN_CHECK(visit_group_async(net, net->d_order, (uint32_t)num, cfg, seed, inj ? &gi : nullptr));
+    BANN_CHECK(check_error_flag(net));
+    if (out)
+        for (uint64_t i = 0; i < num; ++i) BANN_CHECK(read_hmc_result(net, (uint32_t)members[i], &out[i]));
     return 0;
 }
 
@@ -1597,18 +1980,24 @@ int bann_net_gradient_begin(bann_net* net, const float* param_vecs, const float*
     // Pinned (page-locked / registered) caller buffers are copied by DMA directly; pageable ones go through one pinned
     // staging buffer with a single memcpy, so that the copies stay asynchronous either way.
     if (!net->d_dense_in) {
-        BANN_CUDA(cudaMalloc(&net->d_dense_in, std::max<uint64_t>(net->sum_params, 1) * sizeof(float)));
-        BANN_CUDA(cudaMalloc(&net->d_dense_out, (net->sum_params + net->B) * sizeof(float)));
+        BANN_CUDA(cudaMalloc(&net->d_dense_in, (std::max<uint64_t>(net->sum_params, 1) + 4) * sizeof(float)));
+        BANN_CUDA(cudaMalloc(&net->d_dense_out, (net->sum_params + net->B + 4) * sizeof(float)));
     }
     if (!net->h_pin_a && ((param_vecs && !host_pinned(param_vecs)) || (y && !host_pinned(y))))
         BANN_CUDA(cudaMallocHost(&net->h_pin_a, (net->sum_params + net->n) * sizeof(float)));
     if (param_vecs) {
-        const float* src = param_vecs;
+        // Sharded rows with the bulk exchange connected: the parameters are replicated, so every rank uploads only its
+        // 1 / world slice of the vector and the ranks all-gather on the device over NVLink (host traffic / world).
+        uint64_t lo = 0, hi = net->sum_params;
+        const bool sliced = sharded(net) && net->xg_connected;
+        if (sliced) xg_slice(net, net->sum_params, &lo, &hi);
+        const float* src = param_vecs + lo;
         if (!host_pinned(param_vecs)) {
-            memcpy(net->h_pin_a, param_vecs, net->sum_params * sizeof(float));
-            src = net->h_pin_a;
+            memcpy(net->h_pin_a + lo, param_vecs + lo, (hi - lo) * sizeof(float));
+            src = net->h_pin_a + lo;
         }
-        BANN_CUDA(cudaMemcpyAsync(net->d_dense_in, src, net->sum_params * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (hi > lo) BANN_CUDA(cudaMemcpyAsync(net->d_dense_in + lo, src, (hi - lo) * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (sliced) BANN_CHECK(xg_allgather_slices(net, net->d_dense_in, net->sum_params));
         k_dense_to_arena<<<(unsigned)net->B, 128, 0, st>>>(net->d_descs, net->d_dense_in, net->d_theta);
         BANN_LAUNCHED();
     }
@@ -1627,6 +2016,7 @@ int bann_net_gradient_begin(bann_net* net, const float* param_vecs, const float*
     k.nlist = (uint32_t)net->B;
     k.target_mode = TGT_SHARED;
     k.tgt = tgt;
+    k.xg = sharded(net) && net->xg_connected;
     return launch_k1(net, k, true);
 }
 
@@ -1639,24 +2029,84 @@ int bann_net_gradient_end(bann_net* net, float* grads, float* rss) {
     BANN_LAUNCHED();
     const bool pin_g = !grads || host_pinned(grads), pin_r = !rss || host_pinned(rss);
     if (!net->h_pin_b && !(pin_g && pin_r)) BANN_CUDA(cudaMallocHost(&net->h_pin_b, (net->sum_params + net->B) * sizeof(float)));
+    // sharded rows + bulk exchange: every rank holds the full result on the device and writes only its 1 / world slice of
+    // [grads | rss] to the host (bann_net_gradient_slice tells the caller which)
+    uint64_t lo = 0, hi = net->sum_params + net->B;
+    if (sharded(net) && net->xg_connected) xg_slice(net, net->sum_params + net->B, &lo, &hi);
+    const uint64_t glo = std::min(lo, net->sum_params), ghi = std::min(hi, net->sum_params);
+    const uint64_t rlo = std::max(lo, net->sum_params) - net->sum_params, rhi = std::max(hi, net->sum_params) - net->sum_params;
     if (grads) {
         k_arena_to_dense<<<(unsigned)net->B, 128, 0, st>>>(net->d_descs, net->d_grad, net->d_dense_out);
         BANN_LAUNCHED();
-        BANN_CUDA(cudaMemcpyAsync(pin_g ? grads : net->h_pin_b, net->d_dense_out, net->sum_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (ghi > glo)
+            BANN_CUDA(cudaMemcpyAsync((pin_g ? grads : net->h_pin_b) + glo, net->d_dense_out + glo, (ghi - glo) * sizeof(float),
+                                      cudaMemcpyDeviceToHost, st));
     }
     if (rss) {
         k_gather_rss<<<((unsigned)net->B + 255) / 256, 256, 0, st>>>(net->d_gsum, net->pstride, net->d_descs, (uint32_t)net->B,
                                                                      net->d_dense_out + net->sum_params);
         BANN_LAUNCHED();
-        BANN_CUDA(cudaMemcpyAsync(pin_r ? rss : net->h_pin_b + net->sum_params, net->d_dense_out + net->sum_params,
-                                  net->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (rhi > rlo)
+            BANN_CUDA(cudaMemcpyAsync((pin_r ? rss : net->h_pin_b + net->sum_params) + rlo, net->d_dense_out + net->sum_params + rlo,
+                                      (rhi - rlo) * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     BANN_CUDA(cudaGetLastError());
     BANN_CUDA(cudaStreamSynchronize(st));
-    if (grads && !pin_g) memcpy(grads, net->h_pin_b, net->sum_params * sizeof(float));
-    if (rss && !pin_r) memcpy(rss, net->h_pin_b + net->sum_params, net->B * sizeof(float));
+    if (grads && !pin_g && ghi > glo) memcpy(grads + glo, net->h_pin_b + glo, (ghi - glo) * sizeof(float));
+    if (rss && !pin_r && rhi > rlo) memcpy(rss + rlo, net->h_pin_b + net->sum_params + rlo, (rhi - rlo) * sizeof(float));
     return 0;
 }
+
+int bann_net_gradient_slice(bann_net* net, uint64_t* param_lo, uint64_t* param_hi, uint64_t* out_lo, uint64_t* out_hi) {
+    if (!net) BANN_FAIL("NULL net");
+    uint64_t a = 0, b = net->sum_params, c = 0, d = net->sum_params + net->B;
+    if (sharded(net) && net->xg_connected) {
+        xg_slice(net, net->sum_params, &a, &b);
+        xg_slice(net, net->sum_params + net->B, &c, &d);
+    }
+    if (param_lo) *param_lo = a;
+    if (param_hi) *param_hi = b;
+    if (out_lo) *out_lo = c;
+    if (out_hi) *out_hi = d;
+    return 0;
+}
+
+// ---- bulk exchange region of a net (comm.cuh: XgComm); the host layer all-gathers the handles once after bann_net_create
+int bann_net_comm_handle(bann_net* net, uint8_t* out) {
+    if (!net || !out) BANN_FAIL("NULL argument");
+    if (net->ctx->world > kXrMaxWorld) BANN_FAIL("peer-memory exchange supports at most 8 ranks");
+    BANN_CUDA(cudaSetDevice(net->ctx->device));
+    uint8_t*& mine = net->xg_region[net->ctx->rank];
+    if (!mine) {
+        net->xg_cap = ((std::max<uint64_t>((uint64_t)net->B * net->pstride, net->sum_params + net->B) + 3) & ~3ull) + 4;
+        BANN_CUDA(cudaMalloc(&mine, xg_region_bytes(net->xg_cap)));
+        BANN_CUDA(cudaMemset(mine, 0, xg_region_bytes(net->xg_cap)));   // flags 0 = "nothing yet"
+        BANN_CUDA(cudaMalloc(&net->d_xg_counter, sizeof(unsigned int)));
+        BANN_CUDA(cudaMemset(net->d_xg_counter, 0, sizeof(unsigned int)));
+        BANN_CHECK(ensure_cap(&net->d_gsum, &net->gsum_cap, (size_t)net->B * net->pstride + 4));
+        BANN_CUDA(cudaDeviceSynchronize());
+    }
+    return comm_export(mine, net->ctx->device, out);
+}
+
+int bann_net_comm_connect(bann_net* net, const uint8_t* handles) {
+    if (!net || !handles) BANN_FAIL("NULL argument");
+    if (!net->xg_region[net->ctx->rank]) BANN_FAIL("bann_net_comm_connect before bann_net_comm_handle");
+    BANN_CUDA(cudaSetDevice(net->ctx->device));
+    for (int r = 0; r < net->ctx->world; ++r) {
+        if (r == net->ctx->rank) continue;
+        void* p = nullptr;
+        bool ipc = false;
+        BANN_CHECK(comm_import(net->ctx, handles + (size_t)r * BANN_COMM_HANDLE_BYTES, &p, &ipc));
+        net->xg_region[r] = reinterpret_cast<uint8_t*>(p);
+        net->xg_ipc[r] = ipc;
+    }
+    net->xg_connected = true;
+    net->xg_epoch = 0;
+    return 0;
+}
+
+int bann_net_comm_connected(bann_net* net) { return net && net->xg_connected ? 1 : 0; }
 
 int bann_pinned_alloc(uint64_t bytes, void** out) {
     if (!out) BANN_FAIL("NULL argument");
@@ -1669,7 +2119,8 @@ void bann_pinned_free(void* p) {
 
 int bann_net_gradient(bann_net* net, const float* param_vecs, const float* y, float* grads, float* rss) {
     if (!net) BANN_FAIL("NULL net");
-    if (net->ctx->world > 1) BANN_FAIL("with sharded rows call bann_net_gradient_begin, all-reduce, bann_net_gradient_end");
+    if (net->ctx->world > 1 && !net->xg_connected)
+        BANN_FAIL("sharded rows: connect the bulk exchange (bann_net_comm_connect), or call bann_net_gradient_begin, all-reduce, bann_net_gradient_end");
     BANN_CHECK(bann_net_gradient_begin(net, param_vecs, y));
     return bann_net_gradient_end(net, grads, rss);
 }
@@ -1687,12 +2138,13 @@ static HmcRun grouped_run(bann_net* net) {
     return R;
 }
 
-static int grouped_k1(bann_net* net, int first) {
+static int grouped_k1(bann_net* net, int first, bool exchange) {
     HmcRun R = grouped_run(net);
     K1Launch k;
     k.list = nullptr;
     k.nlist = (uint32_t)net->B;
     k.states = net->d_states;
+    k.xg = exchange && sharded(net) && net->xg_connected;   // in-library all-reduce of the sums (bann_net_comm_connect)
     if (first && net->grouped_per_branch) {
         k.target_mode = TGT_RESID_PLUS_PRED;
         k.resid = net->d_r;
@@ -1712,8 +2164,8 @@ int bann_grouped_begin(bann_net* net, const bann_mcmc_cfg* cfg, uint64_t seed, i
     if (per_branch_targets && !net->d_T) BANN_CUDA(cudaMalloc(&net->d_T, (size_t)net->B * net->n * sizeof(float)));
     HmcRun R = grouped_run(net);
     BANN_CHECK(hmc_init_and_first_eval(net, cfg, R, 0));
-    BANN_CHECK(grouped_k1(net, 1));
-    if (net->ctx->world > 1) return 0;   // caller all-reduces, then bann_grouped_phase_b(is_init = 1)
+    BANN_CHECK(grouped_k1(net, 1, true));
+    if (net->ctx->world > 1 && !net->xg_connected) return 0;   // caller all-reduces, then bann_grouped_phase_b(is_init = 1)
     K2Args a = make_k2(net, cfg, R, 1, 0);
     BANN_CUDA(launch_pdl(k2_step, dim3(R.nlist), dim3(256), 0, net->ctx->stream, a));
     BANN_LAUNCHED();
@@ -1723,8 +2175,16 @@ int bann_grouped_begin(bann_net* net, const bann_mcmc_cfg* cfg, uint64_t seed, i
 
 int bann_grouped_phase_a(bann_net* net) {
     if (!net) BANN_FAIL("NULL net");
-    return grouped_k1(net, 0);
+    return grouped_k1(net, 0, false);   // the caller sums over ranks: bann_grouped_allreduce, or its own collective
 }
+
+int bann_grouped_allreduce(bann_net* net) {
+    if (!net) BANN_FAIL("NULL net");
+    if (!sharded(net)) return 0;
+    return xg_allreduce(net, net->d_gsum, (uint64_t)net->B * net->pstride);
+}
+
+const char* bann_net_last_k1_kernel(bann_net* net) { return net ? net->last_k1 : "none"; }
 
 int bann_grouped_phase_b(bann_net* net, const bann_mcmc_cfg* cfg, int is_init, int is_last) {
     if (!net || !cfg) BANN_FAIL("NULL argument");
@@ -1738,9 +2198,10 @@ int bann_grouped_phase_b(bann_net* net, const bann_mcmc_cfg* cfg, int is_init, i
 
 int bann_grouped_leapfrog(bann_net* net, const bann_mcmc_cfg* cfg, uint32_t num_steps, int finalize) {
     if (!net || !cfg) BANN_FAIL("NULL argument");
-    if (net->ctx->world > 1) BANN_FAIL("multi-GPU runs drive bann_grouped_phase_a / _b with an all-reduce in between");
+    if (net->ctx->world > 1 && !net->xg_connected)
+        BANN_FAIL("sharded rows: connect the bulk exchange (bann_net_comm_connect) or drive bann_grouped_phase_a / _b with your own all-reduce in between");
     for (uint32_t s = 0; s < num_steps; ++s) {
-        BANN_CHECK(grouped_k1(net, 0));
+        BANN_CHECK(grouped_k1(net, 0, true));
         BANN_CHECK(bann_grouped_phase_b(net, cfg, 0, (finalize && s + 1 == num_steps) ? 1 : 0));
     }
     return 0;

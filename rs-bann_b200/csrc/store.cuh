@@ -25,6 +25,9 @@ namespace bann {
 // the descriptor of the NEXT exchange (advances the epoch); single-rank contexts get world = 1
 XrComm xr_next(bann_ctx* ctx, int* error_flag);
 void xr_release(bann_ctx* ctx);
+// peer-memory plumbing shared by the context's inbox and a net's bulk exchange region (comm.cu)
+int comm_export(void* dptr, int device, uint8_t* out /* BANN_COMM_HANDLE_BYTES */);
+int comm_import(bann_ctx* ctx, const uint8_t* blob, void** out, bool* opened_ipc);
 }  // namespace bann
 
 struct bann_genotypes {

@@ -2,7 +2,8 @@
 for the plumbing.  Individuals (rows) are sharded on 128-row tile boundaries; parameters,
 momenta and precisions are replicated; the only data-path collectives are
   * an all-reduce(sum) of the per-column genotype counts at load (global column statistics),
-  * an all-reduce(sum) of the per-step [gW | gb | rss] sums between K1 and K2.
+  * an all-reduce(sum) of the per-step [gW | gb | rss] sums between K1 and K2 -- inside the library over
+    NVLink peer memory once `connect_net` has wired the ranks' exchange regions (csrc/comm.cuh: XgComm).
 Every replica then applies the identical update (same Philox keys), so nothing is broadcast.
 The sequential-exact schedule (branch visits of Net::train) sums over ranks INSIDE the library's
 reduction kernels through peer-mapped inboxes (csrc/comm.cuh); `connect_ranks` wires them up."""
@@ -19,6 +20,10 @@ def row_shard(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     tpr = (tiles + world - 1) // world
     r0 = min(n_total, rank * tpr * TILE_ROWS)
     r1 = min(n_total, (rank + 1) * tpr * TILE_ROWS)
+    if r1 <= r0:
+        # an empty shard would mean zero-block kernel launches and zero-sized stores in the library: refuse up front
+        raise ValueError(f"rank {rank} of {world} would hold no individuals: {n_total} individuals are {tiles} row tile(s) of "
+                         f"{TILE_ROWS}, which fill only {(tiles + tpr - 1) // tpr} rank(s); use fewer ranks")
     return r0, r1
 
 
@@ -40,6 +45,24 @@ def global_col_stats(local_counts: np.ndarray, n_total: int, allreduce_sum: Opti
     if allreduce_sum is not None:
         counts = allreduce_sum(counts)
     return stats_from_counts(counts, n_total)
+
+
+def _gather_handles(world: int, mine: bytes, all_gather_bytes: Optional[Callable]):
+    if all_gather_bytes is None:
+        import torch.distributed as dist
+        out = [None] * world
+        dist.all_gather_object(out, mine)
+        return [bytes(h) for h in out]
+    return [bytes(h) for h in all_gather_bytes(mine)]
+
+
+def connect_net(net, all_gather_bytes: Optional[Callable] = None):
+    """Bulk peer-memory exchange of a net (grouped schedule: all-reduce of [gW | gb | rss] inside the library, parameter
+    all-gather of Net.gradient): all-gather every rank's region handle and map the peers.  No-op on one rank."""
+    world = net.ctx.world
+    if world == 1:
+        return
+    net.comm_connect(_gather_handles(world, net.comm_handle(), all_gather_bytes))
 
 
 def connect_ranks(ctx, all_gather_bytes: Optional[Callable] = None):

@@ -3,8 +3,8 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
       tests/multirank_worker.py [--rate]
 
-Check: every rank runs the same sweeps on its row shard; rank 0 also runs the unsharded chain on its own GPU and
-compares (same bar as tests/test_gpu_sharded_chain.py).  --rate: visits / s of the sharded chain at 100k rows.
+Check: every rank runs the same sweeps on its row shard -- sequential (also with early rejections) and block-Jacobi
+groups -- and Net.gradient with 1 / world host slices; rank 0 also runs the unsharded chain on its own GPU and compares.  --rate: visits / s of the sharded chain at 100k rows.
 Prints one line starting with MULTIRANK_OK or MULTIRANK_FAIL (rank 0)."""
 import os
 import sys
@@ -30,16 +30,35 @@ def main():
     ctx = rb.Context(local, rank=rank, world=world)
     rb.connect_ranks(ctx)
     ok, msgs = True, []
-    for model in ("ridge_ard", "lasso_base"):
+    # (model, sweep kwargs): sequential-exact sweeps (push exchange inside KR), the same with a tight Hamiltonian-error bound so
+    # that trajectories are rejected EARLY (every epoch the host hands out must still be exchanged, comm.cuh), and block-Jacobi
+    # sweeps in groups of 3 (bulk exchange: reduce-scatter + all-gather over peer memory)
+    cases = [("ridge_ard", dict()), ("lasso_base", dict()),
+             ("ridge_ard", dict(max_h_err=0.05, factor=1.5)),
+             ("ridge_ard", dict(group_size=3)), ("std_normal", dict(group_size=4))]
+    for model, kw in cases:
         P = build_problem(model, 3000, [20, 50, 9, 33], 5, 5, seed=11)
         B = len(P["groups"])
         r0, r1 = rb.row_shard(P["n"], rank, world)
         gen, net = make_net(rb, ctx, P, r0, r1)
-        out = run_chain(net, rb, P["y"][r0:r1], B, sweeps=2, L=8)
+        rb.connect_net(net)
+        out = run_chain(net, rb, P["y"][r0:r1], B, sweeps=2, L=8, **kw)
+        # Net.gradient on sharded rows: every rank passes only its 1 / world slice of the parameters and receives its slice
+        pv_all = out["pv"].copy()
+        plo, phi, olo, ohi = net.gradient_slice()
+        pv_in = np.full_like(pv_all, np.nan)
+        pv_in[plo:phi] = pv_all[plo:phi]                 # everything outside the slice is never read
+        grads = np.full(net.num_params(), np.nan, dtype=np.float32)
+        rss = np.full(B, np.nan, dtype=np.float32)
+        net.gradient(pv_in, P["y"][r0:r1], out=(grads, rss))
+        gr = np.concatenate([grads, rss])
+        gparts = [None] * world
+        dist.all_gather_object(gparts, (olo, ohi, gr[olo:ohi].copy(), bool(np.all(np.isnan(np.delete(gr, np.s_[olo:ohi]))))))
         net.close(); gen.close()
         # replicas identical: compare a digest over ranks
         dig = torch.tensor([float(np.sum(out["pv"].astype(np.float64))), float(np.sum(out["qv"].astype(np.float64))),
-                            out["stats"]["num_accepted"], out["globals"]["output_bias"]], dtype=torch.float64, device="cuda")
+                            out["stats"]["num_accepted"], out["stats"]["num_early_rejected"], out["globals"]["output_bias"]],
+                           dtype=torch.float64, device="cuda")
         lo, hi = dig.clone(), dig.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -49,18 +68,26 @@ def main():
         if rank == 0:
             c1 = rb.Context(local)
             g1, n1 = make_net(rb, c1, P, 0, P["n"])
-            ref = run_chain(n1, rb, P["y"], B, sweeps=2, L=8)
+            ref = run_chain(n1, rb, P["y"], B, sweeps=2, L=8, **kw)
+            g_ref, rss_ref = n1.gradient(pv_all, P["y"])
             n1.close(); g1.close(); c1.close()
             s, s1 = out["stats"], ref["stats"]
+            gfull = np.concatenate([p[2] for p in sorted(gparts, key=lambda p: p[0])])
+            gexp = np.concatenate([g_ref, rss_ref])
+            grad_ok = (gfull.size == gexp.size and all(p[3] for p in gparts)
+                       and np.allclose(gfull, gexp, rtol=2e-4, atol=2e-4 * float(np.max(np.abs(gexp)))))
             good = (same and s["num_accepted"] == s1["num_accepted"] and s["num_early_rejected"] == s1["num_early_rejected"]
                     and np.allclose(out["pv"], ref["pv"], rtol=2e-4, atol=2e-5)
                     and np.allclose(out["qv"], ref["qv"], rtol=2e-4, atol=2e-5)
                     and np.allclose(np.concatenate(resid), ref["resid"], rtol=0, atol=5e-4)
-                    and abs(s["lpd"] - s1["lpd"]) < 5e-4 * abs(s1["lpd"]))
+                    and abs(s["lpd"] - s1["lpd"]) < 5e-4 * abs(s1["lpd"]) and grad_ok)
+            if "max_h_err" in kw:
+                good = good and s["num_early_rejected"] > 0        # the case exists to exercise early rejections
             ok = ok and good
-            msgs.append(f"{model}: replicas_identical={same} accepted {s['num_accepted']}/{s['num_samples']} (single rank "
-                        f"{s1['num_accepted']}) max|dtheta|={np.max(np.abs(out['pv'] - ref['pv'])):.2e} "
-                        f"lpd {s['lpd']:.4f} vs {s1['lpd']:.4f}")
+            msgs.append(f"{model} {kw}: replicas_identical={same} accepted {s['num_accepted']}/{s['num_samples']} early "
+                        f"{s['num_early_rejected']} (single rank {s1['num_accepted']}, {s1['num_early_rejected']}) "
+                        f"max|dtheta|={np.max(np.abs(out['pv'] - ref['pv'])):.2e} lpd {s['lpd']:.4f} vs {s1['lpd']:.4f} "
+                        f"sliced_gradient_ok={grad_ok}")
     if "--rate" in sys.argv:
         from bench import default_params
         n, B, per, L = 100000, 64, 50, 100

@@ -79,9 +79,16 @@ def test_row_shards_cover_all_rows():
     import rs_bann_b200 as rb
     for n in (1, 127, 128, 129, 1000, 100000):
         for world in (1, 2, 4, 8):
+            tiles = (n + 127) // 128
+            tpr = (tiles + world - 1) // world
+            filled = (tiles + tpr - 1) // tpr
             prev = 0
             for r in range(world):
+                if r >= filled:            # an empty shard is refused with a clear message (not a zero-block launch later)
+                    with pytest.raises(ValueError):
+                        rb.row_shard(n, r, world)
+                    continue
                 r0, r1 = rb.row_shard(n, r, world)
-                assert r0 == prev and r0 % 128 == 0 or r0 == n
+                assert r0 == prev and r0 % 128 == 0 and r1 > r0
                 prev = r1
             assert prev == n

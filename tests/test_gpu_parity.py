@@ -294,6 +294,53 @@ def test_fwd_bwd_activations(rb, ctx, act, shape):
         P.close()
 
 
+@pytest.mark.parametrize("model", ["ridge_ard", "lasso_base", "std_normal"])
+def test_numerical_ldg(rb, ctx, model):
+    """numerical_ldg (branch_sampler.rs:480-504): forward differences with delta = 0.001.  In f32 a difference quotient of a
+    log density of size |ld| carries ~|ld| * 2^-23 / delta of rounding noise, in the reference as much as here: the bar is the
+    f64 oracle within that noise (plus the usual mimic-vs-truth term); the analytical gradient must lie inside the same band
+    plus the O(delta) truncation error."""
+    P = Problem(rb, ctx, model, 400, [12, 9], 4, 3, seed=17)
+    try:
+        for b in range(2):
+            got = P.net.branch_numerical_ldg(b)
+            pv_after, _ = P.net.get_branch(b)
+            assert np.array_equal(pv_after, P.cfgs[b].param_vec())                 # parameters reloaded (:502)
+            x64 = P.x(b, np.float64)
+            br64 = Branch(P.cfgs[b], np.float64)
+            ld = abs(float(br64.log_density(br64.rss(x64, P.y.astype(np.float64)))))
+            t64 = br64.numerical_ldg(x64, P.y.astype(np.float64))
+            t32 = Branch(P.cfgs[b], np.float32).numerical_ldg(P.x(b, np.float32), P.y)
+            noise = 8 * ld * 2.0 ** -23 / 1e-3
+            assert np.all(np.abs(got - t64) <= 8 * np.abs(t32 - t64) + noise + 2e-5 * np.max(np.abs(t64))), \
+                (np.max(np.abs(got - t64)), noise)
+            ana = P.net.branch_fwd_bwd(b)["ldg"]
+            assert np.max(np.abs(ana - got)) <= noise + 0.02 * np.max(np.abs(ana)) + 0.5
+    finally:
+        P.close()
+
+
+def test_num_grad_transition_follows_the_analytical_one(rb, ctx):
+    """hmc_step with mcmc_cfg.num_grad (branch_sampler.rs:1232-1247): same momenta, numerical instead of analytical gradients --
+    the trajectory stays close to the analytical one (short trajectory, small steps) and the decision is the same."""
+    P = Problem(rb, ctx, "ridge_base", 300, [10], 3, 2, seed=23)
+    try:
+        rng = np.random.default_rng(3)
+        mom = rng.standard_normal(P.cfgs[0].num_params).astype(np.float32)
+        outs = []
+        for ng in (False, True):
+            P.net.set_branch(0, P.cfgs[0].param_vec(), P.cfgs[0].precision_vec())
+            cfg = rb.MCMCCfg(hmc_step_size_factor=0.05, hmc_integration_length=4, num_grad=ng)
+            res = P.net.hmc_step(0, cfg, momenta=mom, u=0.0)
+            outs.append((res, P.net.get_branch(0)[0].copy()))
+        assert outs[0][0].status == outs[1][0].status == rb.HMC_ACCEPTED
+        assert abs(outs[0][0].neg_h_final - outs[1][0].neg_h_final) < 2e-2 * abs(outs[0][0].neg_h_final) + 0.5
+        assert np.allclose(outs[0][1], outs[1][1], rtol=0, atol=5e-3)
+        assert not np.array_equal(outs[0][1], outs[1][1])      # the numerical gradient really was used
+    finally:
+        P.close()
+
+
 def test_fixture_branch_golden_values(rb, ctx):
     """The reference's micro-fixture through the CUDA path: raw X is not
     expressible as packed genotypes unless means=0/stds=1, which is exactly the fixture."""
