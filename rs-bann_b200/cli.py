@@ -190,7 +190,7 @@ def _bcast_int(v: int, world: int) -> int:
 
 
 def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
-    """Net::train (net/net.rs:201-358) with the sequential-exact schedule on the device."""
+    """Net::train (net/net.rs:201-358) on the device: the reference's sequential order, or block-Jacobi groups (--group-size)."""
     ctx, rank, world = a._dist if getattr(a, "_dist", None) else _dist_context(a.device)
     gen, y = _load_data(ctx, a.bfile_train, a.groups, a.p_train, shard=True)
     test = None
@@ -199,6 +199,9 @@ def run_chain(a, model: str, nf: files.NetFile, outdir: str, args_json: dict):
     lead = rank == 0              # replicas hold identical state; rank 0 writes the files
     burn_in = a.burn_in if a.burn_in is not None else a.chain_length - 1          # mcmc_cfg.rs:152-156
     net = net_to_device(ctx, gen, model, nf)
+    if world > 1:                 # block-Jacobi groups on sharded rows sum over ranks through the net's bulk exchange region
+        from .dist import connect_net
+        connect_net(net)
     if lead:
         os.makedirs(outdir, exist_ok=True)
         with open(os.path.join(outdir, "args.json"), "w") as f:

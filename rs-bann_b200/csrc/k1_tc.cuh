@@ -404,6 +404,18 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
         if (warp == 0) umma::tmem_dealloc(*tmem_slot, C::TMEM_COLS);
         return;
     }
+    // the packed words of the CTA's first super-tile: requested NOW, so that the HBM round trip runs under the parameter
+    // staging below instead of after it (at 8 GPUs a CTA covers only 49 super-tiles and its fixed cost is ~6 % of its time)
+    const uint32_t t_begin = chunk * a.st_per_chunk;
+    const uint32_t t_end = min(a.nst, t_begin + a.st_per_chunk);
+    const uint32_t nit = t_end > t_begin ? t_end - t_begin : 0;
+    const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
+    umma::fence_async_smem();              // the zero fill above (generic proxy) precedes the bulk copy (async proxy) into the same buffer
+    __syncthreads();                       // ... in every thread; and the barrier initialisation is visible to warp 1
+    if (warp == 1 && nit > 0) {
+        if (umma::elect_one()) umma::bulk_load(sG, gwords + (size_t)t_begin * NC * 128, NC * 512u, &mbar[4]);
+        __syncwarp();
+    }
     // tail parameters; what feeds an activated layer >= 1 (its weights and biases) carries the activation's pre-scale
     using TT = TcTail<H, S, D, ACT>;
     constexpr float cA = TT::cA;
@@ -455,14 +467,10 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
 
     const size_t eoff = a.out_per_entry ? (size_t)li * a.n : 0;
     const size_t toff = (a.target_mode == TGT_PER_ENTRY) ? (size_t)li * a.n : 0;
-    const uint32_t t_begin = chunk * a.st_per_chunk;
-    const uint32_t t_end = min(a.nst, t_begin + a.st_per_chunk);
-    const uint32_t nit = t_end > t_begin ? t_end - t_begin : 0;
     const float* tsrc = (!LEAN && a.target_mode == TGT_RESID_PLUS_PRED) ? a.resid : (a.tgt ? a.tgt + toff : nullptr);
     const bool bwd = LEAN || !a.fwd_only;
 
     // packed words of super-tile `st` -> shared memory, one bulk copy (the branch's super-tiles are contiguous: [st][NC][128] u32)
-    const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
     auto issue_load = [&](uint32_t st) {        // whole issuer warp enters
         if (umma::elect_one()) umma::bulk_load(sG, gwords + (size_t)st * NC * 128, NC * 512u, &mbar[4]);
         __syncwarp();
@@ -523,8 +531,7 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     };
     f2 tg_next = load_targets(t_begin);
     if (nit > 0) {
-        if (warp == 1) issue_load(t_begin);
-        umma::mbar_wait(&mbar[4], 0);
+        umma::mbar_wait(&mbar[4], 0);          // requested at the top of the kernel
         expand(0);
         umma::fence_async_smem();
         __syncthreads();

@@ -1,0 +1,429 @@
+// Persistent per-branch HMC transition for the sequential-exact schedule (VERDICT r1 "next" #3).
+//
+// `bann_visit_branch` runs L leapfrog steps of ONE branch; with separate launches every step is K1 (fused forward + backward
+// over ~300 CTAs) -> KR (chunk reduction) -> K2 (update), three dependent launches, and every K1 launch re-does what does not
+// change during a trajectory: tensor-memory allocation, barrier set-up, the bulk copy of the branch's packed genotypes from
+// HBM and their expansion into tcgen05 operands (84 instructions per thread and super-tile).  19.2 us per leapfrog at
+// N = 100k, against 0.25 us of roofline time.
+//
+// Here the whole transition is ONE cooperative launch.  Every CTA owns one or two 256-row super-tiles of the branch for the
+// whole trajectory: the packed words are loaded and expanded ONCE -- the forward A operand stays in tensor memory, the
+// backward A operand in shared memory -- and the targets stay in registers.  Per leapfrog step a CTA stages the three bf16 pieces
+// of W' = W0 / sd from ITS OWN copy of the parameters, issues the forward MMAs, runs the FP32 tail (TcTail, k1_tc.cuh), issues
+// the backward MMAs, writes its partial sums; a grid barrier; every CTA reduces a slice of the P + 1 values over all partials in
+// a fixed order; a second grid barrier; every CTA applies the SAME parameter / momentum update (gradient under the prior,
+// half steps, position step, Hamiltonian, early-reject and U-turn checks: k2_step's arithmetic) to its own copy -- replicated,
+// deterministic, nothing is broadcast.  CTA 0 writes the branch state and the final parameters.
+//
+// The grid barrier is a monotonic counter (atomicAdd + ld.acquire.gpu spin) and relies on the co-residency a cooperative launch
+// guarantees; a wall-clock limit turns a lost CTA into an error flag instead of a hang.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "k1_tc.cuh"
+
+namespace bann {
+
+constexpr int kTcpMaxTiles = 2;        // super-tiles a CTA keeps resident
+constexpr unsigned long long kTcpBarrierTimeoutNs = 2ull * 1000ull * 1000ull * 1000ull;
+
+struct TcpArgs {
+    const uint32_t* store_tc;
+    const BranchDesc* descs;
+    uint32_t b;
+    const float* mu;
+    const float* sd;
+    uint32_t n, nst, ncb;
+    uint32_t L;                // leapfrog steps
+    // HMC state (arenas, as K2Args)
+    BranchState* state;
+    float* theta;
+    const float* theta0;
+    float* mom;
+    float* grad;
+    const float* eps;
+    const float* prec;
+    int model;
+    float max_h_err;
+    // targets: t = resid + own prediction at the first evaluation (net.rs:279-280) when resid != NULL, else the shared target tgt
+    const float* resid;
+    const float* tgt;
+    float* tgt_out;            // t (resid mode), may be NULL
+    float* prev_out;           // own prediction at the first evaluation, may be NULL
+    float* ynew_out;           // own prediction at the last evaluation, may be NULL
+    // scratch
+    float* part;               // [gridDim.x][pstride]
+    float* gsum;               // [pstride]: the reduced sums of the last evaluation (rss at [P])
+    uint32_t pstride;
+    unsigned int* bar;         // grid barrier counter, zero at launch
+    int* error_flag;
+};
+
+template <int H, int S, int D>
+struct TcpShape {
+    using T = TailShape<H, S, D>;
+    using C = TcShape<H, S, D>;
+    // [expanded genotypes: kTcpMaxTiles images][weight pieces][packed words][delta pieces][tail params + b0p][theta, mom, eps, theta0,
+    //  grad (maxP each)][reduced sums][reduction scratch][barriers]
+    static size_t smem(uint32_t ncb, uint32_t P) {
+        const size_t img = (size_t)ncb * kTcChunkStride;
+        size_t used = (size_t)kTcpMaxTiles * img + C::SW + (size_t)ncb * 512 + C::SD + C::MISC + (size_t)(6 * ((P + 4) & ~3u)) * 4 + 512;
+        const size_t need = (size_t)(ncb + 8) * kTcChunkStride + img;     // the M = 64 backward operand reads 8 chunks of the LAST image
+        return (used > need ? used : need) + 256;
+    }
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all CTAs of the (cooperative) grid; `target` is the count this barrier completes at.  false: timed out / error flagged
+__device__ __forceinline__ bool tcp_grid_sync(unsigned int* bar, unsigned int target, int* error_flag) {
+    __shared__ int ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        int good = 1;
+        const unsigned long long t0 = xr_now();
+        while ((int)(ld_acquire_gpu(bar) - target) < 0) {
+            if (xr_now() - t0 > kTcpBarrierTimeoutNs) { atomicExch(error_flag, 3); good = 0; break; }
+        }
+        ok = good;
+    }
+    __syncthreads();
+    return ok != 0;
+}
+
+template <int H, int S, int D, int ACT>
+__global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
+    using T = TailShape<H, S, D>;
+    using C = TcShape<H, S, D>;
+    using TT = TcTail<H, S, D, ACT>;
+    constexpr int W0 = T::W0, W0P = T::W0P, NN = C::NN, NTACC = T::NTACC;
+    constexpr float cA = TT::cA;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t cta = blockIdx.x, ncta = gridDim.x;
+    const BranchDesc& d = a.descs[a.b];
+    const uint32_t m = d.m, NC = d.nc, NKS = (NC + 1) >> 1, NCB = a.ncb, P = d.P;
+    const uint32_t Pp = (P + 4) & ~3u;
+    // ---- shared memory carve-up
+    uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);
+    const uint32_t sa_bytes = NCB * kTcChunkStride;
+    uint8_t* sW = sA + (size_t)kTcpMaxTiles * sa_bytes;
+    uint32_t* sG = reinterpret_cast<uint32_t*>(sW + C::SW);
+    uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + (size_t)NCB * 512;
+    float* wp = reinterpret_cast<float*>(__builtin_assume_aligned(sD + C::SD, 16));
+    float* b0p = wp + ((T::n_tail() + 3) & ~3);
+    float* red = b0p + ((T::n_tail() + 3) & ~3) + 2 * W0P;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);     // [0] forward MMAs done, [1] backward MMAs done, [4] words landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 6);
+    float* s_th = reinterpret_cast<float*>(tmem_slot + 4);           // this CTA's copy of the branch's parameters ...
+    float* s_p = s_th + Pp;                                          // ... momenta
+    float* s_eps = s_p + Pp;
+    float* s_th0 = s_eps + Pp;
+    float* s_g = s_th0 + Pp;                                         // gradient under the prior
+    float* s_sum = s_g + Pp;                                         // reduced raw sums [P + 1]
+
+    const float* mu = a.mu + d.col_off;
+    const float* sd = a.sd + d.col_off;
+    const float* pr = a.prec + d.prec_off;
+    const uint32_t tpc = (a.nst + ncta - 1) / ncta;                  // <= kTcpMaxTiles (host)
+    const uint32_t t_begin = min(a.nst, cta * tpc);
+    const uint32_t t_end = min(a.nst, t_begin + tpc);
+    const uint32_t ntile = t_end - t_begin;                          // 0 .. kTcpMaxTiles (the host guarantees the bound)
+
+    // ---- one-time setup
+    {
+        const uint32_t nz = (uint32_t)((sD + C::SD - sA) / 16);
+        for (uint32_t k = tid; k < nz; k += 128) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        umma::mbar_init(&mbar[0], 1);
+        umma::mbar_init(&mbar[1], 1);
+        umma::mbar_init(&mbar[4], 1);
+        umma::fence_mbar_init();
+    }
+    constexpr uint32_t kTmemCols = 256;     // per tile: 2 x NN forward accumulators + 64 columns forward A operand; + NN backward accumulator
+    if (warp == 0) umma::tmem_alloc(tmem_slot, kTmemCols);
+    for (uint32_t k = tid; k < P; k += 128) {
+        s_th[k] = a.theta[d.param_off + k];
+        s_p[k] = a.mom[d.param_off + k];
+        s_eps[k] = a.eps[d.param_off + k];
+        s_th0[k] = a.theta0[d.param_off + k];
+    }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((warp * 32u) << 16);
+    // tensor-memory columns: tile k: forward accumulators [96 k, 96 k + 32), forward A operand [96 k + 32, 96 k + 96); backward acc [192, 208)
+    auto tD = [&](uint32_t k) { return 96u * k; };
+    auto tA = [&](uint32_t k) { return 96u * k + 32u; };
+    constexpr uint32_t tB = 192u;
+    const uint32_t sA_u = umma::smem_u32(sA), sD_u = umma::smem_u32(sD), sW_u = umma::smem_u32(sW);
+    constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
+    constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
+    const uint64_t dW_f = umma::make_desc(sW_u, NN * 16, 128);
+    const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
+
+    // ---- the CTA's super-tiles: packed words -> operands, once for the whole trajectory
+    const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
+    for (uint32_t k = 0; k < ntile; ++k) {
+        if (warp == 0) {
+            if (umma::elect_one()) umma::bulk_load(sG, gwords + (size_t)(t_begin + k) * NC * 128, NC * 512u, &mbar[4]);
+            __syncwarp();
+        }
+        umma::mbar_wait(&mbar[4], k & 1u);
+        uint8_t* rowA = sA + k * sa_bytes + tid * 16;
+        const uint32_t ta = tlane + tA(k);
+        for (uint32_t c = 0; c < 64; c += 4) umma::tmem_st4(ta + c, 0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if ((uint32_t)i < NC) {
+                const uint32_t x = sG[i * 128 + tid], y = x >> 8;
+                const uint4 oa = make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
+                const uint4 ob = make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
+                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) = oa;
+                *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride + 128 * 16) = ob;
+                umma::tmem_st4(ta + 4 * i, oa.x, oa.y, oa.z, oa.w);
+                umma::tmem_st4(ta + 32 + 4 * i, ob.x, ob.y, ob.z, ob.w);
+            }
+        umma::tmem_st_wait();
+        __syncthreads();                     // every thread has read the staged words before the next copy overwrites them
+    }
+    // targets of the CTA's rows, in registers for the whole trajectory
+    const f2 zero2 = dup2(0.f);
+    f2 tg[kTcpMaxTiles], valid[kTcpMaxTiles];
+    const float* tsrc = a.resid ? a.resid : a.tgt;
+#pragma unroll
+    for (int k = 0; k < kTcpMaxTiles; ++k) {
+        const uint32_t rA = (t_begin + k) * kTcRows + tid, rB = rA + 128;
+        const bool vA = (uint32_t)k < ntile && rA < a.n, vB = (uint32_t)k < ntile && rB < a.n;
+        valid[k] = mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f);
+        tg[k] = mk2(vA ? tsrc[rA] : 0.f, vB ? tsrc[rB] : 0.f);
+    }
+
+    float* pp = a.part + (size_t)cta * a.pstride;
+    const float lam_e = pr[d.ep_off];
+    const bool lasso = (a.model == BANN_LASSO_BASE || a.model == BANN_LASSO_ARD);
+    unsigned int bar_target = 0;
+    uint32_t nbwd = 0;                                 // backward commits of this CTA so far (phase parity of mbar[1])
+    __shared__ float s_gb0[W0];
+    __shared__ float s_red3[3][4];
+    __shared__ int s_status;
+    int steps_done = 0, u_turn_step = -1;
+    float neg_h_init = 0.f;
+
+    for (uint32_t ev = 0; ev <= a.L; ++ev) {          // evaluation ev at the current parameters: ev = 0 is the initial one
+        // ---- stage the tail parameters and W' = W0 / sd (three bf16 pieces) from this CTA's copy of the parameters
+        TT::stage_tail(s_th + m * W0, wp, tid, 128);
+        float* wtmp = reinterpret_cast<float*>(sD);
+        for (uint32_t k = tid; k < m * W0; k += 128) {
+            const uint32_t j = k / W0, c = k % W0;
+            const float w = __fdiv_rn(s_th[c * m + j], sd[j]);
+            wtmp[k] = w;
+            const float v = w * pow2f(100 - 2 * (int)((j & 7u) >> 1));
+            const float p0 = bf16_round(v), r1 = v - p0, p1 = bf16_round(r1), p2 = bf16_round(r1 - p1);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sW + (j >> 3) * (NN * 16) + (j & 7u) * 2);
+            dst[(0 * W0 + c) * 8] = __float2bfloat16_rn(p0);
+            dst[(1 * W0 + c) * 8] = __float2bfloat16_rn(p1);
+            dst[(2 * W0 + c) * 8] = __float2bfloat16_rn(p2);
+        }
+        __syncthreads();
+        if (tid < W0P) {
+            float acc = 0.f;
+            if (tid < W0) {
+                for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], wtmp[j * W0 + tid], acc);
+                acc = (s_th[m * W0 + T::b_off(0) + tid] - acc) * cA;
+            }
+            b0p[tid] = acc;
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < m * W0; k += 128) wtmp[k] = 0.f;     // the pad columns of the delta operand must stay zero
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- forward contractions of the CTA's tiles (A operand resident in tensor memory)
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                for (uint32_t k = 0; k < ntile; ++k)
+#pragma unroll
+                    for (uint32_t h = 0; h < 2; ++h)
+#pragma unroll
+                        for (uint32_t ks = 0; ks < 4; ++ks)
+                            if (ks < NKS)
+                                umma::mma_f16_ts(tmem + tD(k) + h * NN, tmem + tA(k) + h * 32 + ks * 8, dW_f + ((ks * 2u * (NN * 16)) >> 4),
+                                                 idesc_f, ks > 0);
+                umma::commit(&mbar[0]);
+            }
+            __syncwarp();
+        }
+        umma::mbar_wait(&mbar[0], ev & 1u);
+        umma::fence_after_sync();
+        // ---- tail per tile; the backward contractions accumulate over the CTA's tiles
+        typename TT::Acc A;
+        A.clear();
+        for (uint32_t k = 0; k < ntile; ++k) {
+            float accA[16], accB[16];
+            umma::tmem_ld16x2(tlane + tD(k), tlane + tD(k) + NN, accA, accB);
+            umma::fence_before_sync();
+            f2 yh, sg0[W0], ef0;
+            f2 t = tg[k];
+            TT::part1(accA, accB, wp, b0p, t, a.resid != nullptr && ev == 0, valid[k], true, A, yh, sg0, ef0);
+            const uint32_t rA = (t_begin + k) * kTcRows + tid, rB = rA + 128;
+            if (ev == 0) {
+                tg[k] = t;                              // t = resid + own prediction, fixed for the trajectory (net.rs:280)
+                if (a.resid && a.tgt_out) { if (rA < a.n) a.tgt_out[rA] = lo2(t); if (rB < a.n) a.tgt_out[rB] = hi2(t); }
+                if (a.prev_out) { if (rA < a.n) a.prev_out[rA] = lo2(yh); if (rB < a.n) a.prev_out[rB] = hi2(yh); }
+            }
+            if (a.ynew_out) { if (rA < a.n) a.ynew_out[rA] = lo2(yh); if (rB < a.n) a.ynew_out[rB] = hi2(yh); }
+            {
+                f2 v[W0];
+                TT::delta0(sg0, ef0, A, v);
+                TT::store_pieces(v, sD + tid * 16);
+            }
+            umma::fence_async_smem();
+            __syncthreads();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    const uint64_t base = dA_b + ((k * sa_bytes) >> 4);
+#pragma unroll
+                    for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
+                        umma::mma_f16(tmem + tB, base + ks * 16u, dD_b + ks * 16u, idesc_b, (k | ks) != 0);
+                    umma::commit(&mbar[1]);
+                }
+                __syncwarp();
+            }
+            // the delta buffer is reused by the next tile: wait for this tile's backward MMAs
+            umma::mbar_wait(&mbar[1], nbwd & 1u);
+            ++nbwd;
+            umma::fence_after_sync();
+        }
+        // ---- partial sums of this CTA
+        float sacc[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sacc[q] = 0.f;
+        if (ntile > 0) umma::tmem_ld16(tlane + tB, sacc);
+        umma::fence_before_sync();
+        TT::reduce_and_store(A, red, warp, lane, tid, pp, m, P, s_gb0);
+        if (lane < 16) {
+            const uint32_t j = warp * 16 + lane;
+            if (j < m) {
+                const float unscale = pow2f(33 - 2 * (int)((j & 7u) >> 1));
+#pragma unroll
+                for (int c = 0; c < W0; ++c) {
+                    const float s = (sacc[c] + (sacc[W0 + c] + sacc[2 * W0 + c])) * unscale;
+                    pp[c * m + j] = __fdiv_rn(s - mu[j] * s_gb0[c], sd[j]);
+                }
+            }
+        }
+        // ---- all partials written -> every CTA reduces a slice in a fixed order -> all slices written
+        bar_target += ncta;
+        if (!tcp_grid_sync(a.bar, bar_target, a.error_flag)) break;
+        for (uint32_t k = cta; k <= P; k += ncta) {
+            double s = 0.0;
+            for (uint32_t c = tid; c < ncta; c += 128) s += (double)__ldcg(a.part + (size_t)c * a.pstride + k);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            __shared__ double s_w[4];
+            if (lane == 0) s_w[warp] = s;
+            __syncthreads();
+            if (tid == 0) a.gsum[k] = (float)((s_w[0] + s_w[1]) + (s_w[2] + s_w[3]));
+            __syncthreads();
+        }
+        bar_target += ncta;
+        if (!tcp_grid_sync(a.bar, bar_target, a.error_flag)) break;
+        for (uint32_t k = tid; k <= P; k += 128) s_sum[k] = __ldcg(a.gsum + k);
+        __syncthreads();
+        // ---- the update, replicated in every CTA (k2_step's arithmetic; branch_sampler.rs:1239-1284)
+        const bool is_init = ev == 0, is_last = ev == a.L;
+        float kin = 0.f, prior = 0.f, uturn = 0.f;
+        for (uint32_t k = tid; k < P; k += 128) {
+            int l; uint32_t row, col; bool isb;
+            locate_param(d, k, l, row, col, isb);
+            const float w = s_th[k];
+            float g;
+            if (isb) {
+                g = -(lam_e * s_sum[k]);
+                if (a.model == BANN_STD_NORMAL) prior -= 0.5f * w * w;
+            } else {
+                const float lam = param_prior_precision(d, pr, a.model, l, row, false);
+                if (a.model == BANN_STD_NORMAL) { g = -(lam_e * s_sum[k] + w); prior -= 0.5f * w * w; }
+                else if (lasso) {
+                    const float sg = (w > 0.f) ? 1.f : (w < 0.f ? -1.f : 0.f);
+                    g = -(lam_e * s_sum[k] + lam * sg);
+                    prior -= lam * fabsf(w);
+                } else { g = -(lam_e * s_sum[k] + lam * w); prior -= 0.5f * lam * w * w; }
+            }
+            s_g[k] = g;
+            float pk = s_p[k];
+            if (!is_init) { pk = pk + (0.5f * s_eps[k]) * g; s_p[k] = pk; }
+            kin = fmaf(pk, pk, kin);
+            uturn = fmaf(w - s_th0[k], pk, uturn);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            kin += __shfl_xor_sync(0xffffffffu, kin, o);
+            prior += __shfl_xor_sync(0xffffffffu, prior, o);
+            uturn += __shfl_xor_sync(0xffffffffu, uturn, o);
+        }
+        if (lane == 0) { s_red3[0][warp] = kin; s_red3[1][warp] = prior; s_red3[2][warp] = uturn; }
+        __syncthreads();
+        if (tid == 0) {
+            kin = (s_red3[0][0] + s_red3[0][1]) + (s_red3[0][2] + s_red3[0][3]);
+            prior = (s_red3[1][0] + s_red3[1][1]) + (s_red3[1][2] + s_red3[1][3]);
+            uturn = (s_red3[2][0] + s_red3[2][1]) + (s_red3[2][2] + s_red3[2][3]);
+            const float rss = s_sum[P];
+            const float ld = prior + (-1.0f * lam_e * (rss / 2.0f));
+            const float negh = ld - 0.5f * kin;
+            int status = ST_RUNNING;
+            if (is_init) neg_h_init = negh;
+            else {
+                const int step = steps_done;
+                steps_done = step + 1;
+                if (fabsf(negh - neg_h_init) > a.max_h_err) status = ST_REJECTED_EARLY;
+                else if (u_turn_step < 0 && uturn < 0.f) u_turn_step = step;
+            }
+            s_status = status;
+            if (cta == 0) {
+                BranchState& st = *a.state;
+                st.rss = rss;
+                st.log_density = ld;
+                st.neg_h_cur = negh;
+                if (is_init) st.neg_h_init = negh;
+                st.steps_done = steps_done;
+                st.u_turn_step = u_turn_step;
+                st.status = status;
+            }
+        }
+        __syncthreads();
+        if (s_status == ST_REJECTED_EARLY) {
+            if (cta == 0)
+                for (uint32_t k = tid; k < P; k += 128) { a.theta[d.param_off + k] = s_th0[k]; a.grad[d.param_off + k] = s_g[k]; a.mom[d.param_off + k] = s_p[k]; }
+            break;
+        }
+        if (is_last) {
+            if (cta == 0)
+                for (uint32_t k = tid; k < P; k += 128) { a.theta[d.param_off + k] = s_th[k]; a.grad[d.param_off + k] = s_g[k]; a.mom[d.param_off + k] = s_p[k]; }
+            break;
+        }
+        for (uint32_t k = tid; k < P; k += 128) {
+            const float e = s_eps[k];
+            const float pk = s_p[k] + (0.5f * e) * s_g[k];
+            s_p[k] = pk;
+            s_th[k] = s_th[k] + e * pk;
+        }
+        __syncthreads();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace bann

@@ -109,10 +109,10 @@ __device__ __forceinline__ void locate_param(const BranchDesc& d, uint32_t k, in
     row = r % d.in_dim[l];
 }
 
-#ifdef BANN_NET_TU   // non-template kernels: defined once, in net.cu's translation unit
 // Generic (any depth / widths / activation) fused forward+backward.  128 threads, one row per
 // thread in the forward phase, one parameter per thread in the accumulation phase.  Slow but
 // shape-agnostic; k1_small<> below is the tuned path for narrow branches.
+#ifdef BANN_NET_TU   // non-template kernel: defined once, in net.cu's translation unit
 __global__ void __launch_bounds__(128) k1_generic(K1Args a) {
     extern __shared__ float smf[];
     const uint32_t tid = threadIdx.x;
@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(128) k1_generic(K1Args a) {
         pp[d.w_off[0] + k] = __fdiv_rn(pp[d.w_off[0] + k] - mu[j] * pp[d.b_off[0] + c], sd[j]);
     }
 }
+#endif
 
 inline size_t k1_generic_smem(const BranchDesc& d) {
     size_t SW = d.sumw | 1u;
@@ -272,6 +273,7 @@ inline size_t k1_generic_smem(const BranchDesc& d) {
 // sums, coalesced 128-byte loads), then the eight warp sums are added in ascending order.  Fixed order => deterministic;
 // enough blocks and loads in flight that a single-branch launch with hundreds of chunks reduces in a few microseconds
 // (a thread-per-entry loop over 391 chunks took 60 us: one L2 round trip per chunk).
+#ifdef BANN_NET_TU   // non-template kernel: defined once, in net.cu's translation unit
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ part, float* __restrict__ gsum, uint32_t nchunk,
                                                          uint32_t pstride, const uint32_t* __restrict__ list,
                                                          const BranchDesc* __restrict__ descs,
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
         gsum[(size_t)li * pstride + k] = xr_sum(xc, li * pstride + k, (float)s);
     }
 }
+#endif
 
 // ------------------------------------------------------------------ prior helpers
 __device__ __forceinline__ float param_prior_precision(const BranchDesc& d, const float* prec, int model, int layer,
@@ -344,6 +347,7 @@ struct K2Args {
 //   p += e/2 g; theta += e p; g = grad(theta); p += e/2 g; H check; U-turn
 // This kernel runs [g = grad; p += e/2 g; H check; U-turn; p += e/2 g; theta += e p], i.e. the
 // same sequence cut after the position update, so that K1 is the only pass over the data.
+#ifdef BANN_NET_TU   // non-template kernel: defined once, in net.cu's translation unit
 __global__ void __launch_bounds__(256) k2_step(K2Args a) {
     __shared__ float red[8];
     __shared__ int s_status;
@@ -449,6 +453,7 @@ __global__ void __launch_bounds__(256) k2_step(K2Args a) {
         }
     }
 }
+#endif
 
 // ------------------------------------------------------------------ HMC init / accept
 struct InitArgs {
@@ -518,6 +523,7 @@ __device__ float step_size_for(const InitArgs& a, const BranchDesc& d, const flo
     return __fdiv_rn(__fmul_rn(f, PI), den);                                           // ridge_base.rs:87-94
 }
 
+#ifdef BANN_NET_TU   // non-template kernel: defined once, in net.cu's translation unit
 __global__ void __launch_bounds__(256) k_hmc_init(InitArgs a) {
     const uint32_t li = blockIdx.x, tid = threadIdx.x;
     const uint32_t b = a.list ? a.list[li] : li;
@@ -569,9 +575,11 @@ __global__ void __launch_bounds__(256) k_hmc_init(InitArgs a) {
         st.neg_h_init = st.neg_h_cur = st.log_density = st.rss = st.log_acc = 0.f;
     }
 }
+#endif
 
 // accept_or_reject_hmc_state (branch_sampler.rs:928-962) on the Hamiltonian of the last step
 // (the reference recomputes the forward pass; the value is the same, Q13).
+#ifdef BANN_NET_TU   // non-template kernel: defined once, in net.cu's translation unit
 __global__ void __launch_bounds__(256) k_accept(const BranchDesc* descs, const uint32_t* list, BranchState* states,
                                                 float* theta, const float* theta0, const float* inj_u, uint64_t seed,
                                                 uint64_t stream_base) {
@@ -602,7 +610,6 @@ __global__ void __launch_bounds__(256) k_accept(const BranchDesc* descs, const u
         for (uint32_t k = tid; k < d.P; k += 256) theta[d.param_off + k] = theta0[d.param_off + k];  // :1293-1296
     }
 }
-
-#endif  // BANN_NET_TU
+#endif
 
 }  // namespace bann

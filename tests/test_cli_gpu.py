@@ -148,3 +148,44 @@ def test_train_new_trajectories_file(rb, tmp_path):
     tj = [json.loads(l) for l in open(os.path.join(out_j, "traj"))]
     Q = 3 + 2 + 1
     assert len(tj) == 9 and all(len(r) == Q for t in tj for r in t["precisions"]) and all(len(r) == P + Q for t in tj for r in t["ldg"])
+
+
+def test_train_new_group_size(rb, tmp_path):
+    """`train-new --group-size G` (extension): block-Jacobi groups through bann_sweep; --group-size 1 is the default chain bit for
+    bit, the grouped chains write the same files, visit every branch once per iteration and fit the data."""
+    sim = run(["simulate-xy", "-o", str(tmp_path), "--seed", "6", "ridge-ard", "tanh", "15", "6", "1500", "3", "1", "0.6"]).strip()
+    tr = os.path.join(sim, "train")
+    common = [tr, tr + ".phen", tr + ".groups", "25", "15", "ridge-ard", "tanh", "1", "--fixed-hidden-layer-width", "3",
+              "--burn-in", "24", "--step-size", "0.3", "--seed", "9"]
+    outs = {}
+    for tag, extra in (("default", []), ("g1", ["--group-size", "1"]), ("g4", ["--group-size", "4"]), ("all", ["--group-size", "0"])):
+        out = run(["train-new"] + common + ["-o", str(tmp_path / tag)] + extra).strip()
+        outs[tag] = json.load(open(os.path.join(out, "training_stats")))
+        assert outs[tag]["num_samples"] == 25 * 6 and len(outs[tag]["mse_train"]) == 26
+        assert len(glob.glob(os.path.join(out, "models", "*.bin"))) == 2
+    assert outs["default"] == outs["g1"]
+    for tag in ("g4", "all"):
+        assert np.all(np.isfinite(outs[tag]["mse_train"])) and outs[tag]["num_accepted"] > 0.3 * outs[tag]["num_samples"]
+        assert outs[tag]["mse_train"][-1] < 0.9 * outs[tag]["mse_train"][0]
+    with pytest.raises(SystemExit):
+        run(["train-new"] + common + ["-o", str(tmp_path / "bad"), "--group-size", "3", "--joint-hmc"])
+
+
+def test_train_new_numerical_gradient_trajectories(rb, tmp_path):
+    """--trajectories --num-grad-traj (branch_sampler.rs:1259-1261): every recorded step carries numerical_ldg next to the
+    analytical gradient; --num-grad integrates with it (:1232-1247) and the chain still fits."""
+    sim = run(["simulate-xy", "-o", str(tmp_path), "--seed", "8", "ridge-base", "tanh", "6", "2", "400", "2", "1", "0.5"]).strip()
+    tr = os.path.join(sim, "train")
+    common = [tr, tr + ".phen", tr + ".groups", "2", "4", "ridge-base", "tanh", "1", "--fixed-hidden-layer-width", "2",
+              "--burn-in", "0", "--step-size", "0.2", "--seed", "13"]
+    out = run(["train-new"] + common + ["-o", str(tmp_path / "a"), "--trajectories", "--num-grad-traj"]).strip()
+    lines = [json.loads(l) for l in open(os.path.join(out, "traj"))]
+    assert len(lines) == 2 * 2
+    for t in lines:
+        n = len(t["params"])
+        assert len(t["num_ldg"]) == n and all(len(r) == len(t["ldg"][0]) for r in t["num_ldg"])
+        a, b = np.array(t["ldg"]), np.array(t["num_ldg"])
+        assert np.max(np.abs(a - b)) < 0.05 * np.max(np.abs(a)) + 1.0        # forward differences in f32: noisy, but the same gradient
+    out2 = run(["train-new"] + common + ["-o", str(tmp_path / "b"), "--num-grad"]).strip()
+    ts = json.load(open(os.path.join(out2, "training_stats")))
+    assert ts["num_samples"] == 4 and np.all(np.isfinite(ts["mse_train"]))

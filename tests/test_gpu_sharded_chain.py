@@ -143,7 +143,9 @@ def test_train_new_cli_under_torchrun_matches_single_gpu(tmp_path):
     b = json.load(open(os.path.join(two_dir, "training_stats")))
     assert (a["num_samples"], a["num_accepted"], a["num_early_rejected"]) == (b["num_samples"], b["num_accepted"], b["num_early_rejected"])
     assert np.allclose(a["mse_train"], b["mse_train"], rtol=1e-4) and np.allclose(a["mse_test"], b["mse_test"], rtol=1e-4)
-    assert np.allclose(a["lpd"][1:], b["lpd"][1:], rtol=1e-3, equal_nan=True)   # NaN while a never-accepted branch keeps its infinite ML bias precision (Q7)
+    # null (serde_json's spelling of a non-finite f32) while a never-accepted branch keeps its infinite ML bias precision (Q7)
+    la, lb = (np.array([np.nan if v is None else v for v in x["lpd"][1:]], dtype=np.float64) for x in (a, b))
+    assert np.allclose(la, lb, rtol=1e-3, equal_nan=True)
     ma, mb = files.read_net(os.path.join(one, "models", "6.bin")), files.read_net(os.path.join(two_dir, "models", "6.bin"))
     for ca, cb in zip(ma.branch_cfgs, mb.branch_cfgs):
         assert np.allclose(ca.param_vec(), cb.param_vec(), rtol=2e-3, atol=2e-4)
