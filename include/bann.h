@@ -342,6 +342,14 @@ int  bann_net_force_generic(bann_net*, int on);
  * to 16 and up to 2048 markers), then the FFMA kernel, then the shape-agnostic one. */
 enum { BANN_K1_AUTO = 0, BANN_K1_TENSOR = 1, BANN_K1_FFMA = 2, BANN_K1_GENERIC = 3 };
 int  bann_net_select_k1(bann_net*, int which);
+/* test / profiling hook: how a per-branch HMC transition (bann_hmc_step, bann_visit_branch, bann_sweep with group_size 1) runs.
+ * AUTO: the persistent cooperative kernel (the whole L-step trajectory of BranchSampler::hmc_step, branch_sampler.rs:1239-1284,
+ * in ONE launch, the branch's operands resident on chip) where the branch is eligible, else three launches per leapfrog step;
+ * LAUNCHES: always the launch-per-step path; PERSISTENT: fail loudly when the branch is not eligible. */
+enum { BANN_HMC_AUTO = 0, BANN_HMC_LAUNCHES = 1, BANN_HMC_PERSISTENT = 2 };
+int  bann_net_select_hmc_path(bann_net*, int which);
+/* how many transitions ran through the persistent kernel so far */
+uint64_t bann_net_persistent_launches(bann_net*);
 
 /* counters for bench.py: kernels launched by this library since the last reset */
 uint64_t bann_launch_count(int reset);

@@ -127,6 +127,8 @@ PROTOTYPES = {
     "bann_net_comm_connect": (C.c_int, [_vp, _vp]),
     "bann_net_comm_connected": (C.c_int, [_vp]),
     "bann_grouped_allreduce": (C.c_int, [_vp]),
+    "bann_net_select_hmc_path": (C.c_int, [_vp, C.c_int]),
+    "bann_net_persistent_launches": (C.c_uint64, [_vp]),
     "bann_net_last_k1_kernel": (C.c_char_p, [_vp]),
     "bann_pinned_alloc": (C.c_int, [_u64, C.POINTER(_vp)]),
     "bann_pinned_free": (None, [_vp]),

@@ -673,6 +673,15 @@ class Net:
 
     K1_AUTO, K1_TENSOR, K1_FFMA, K1_GENERIC = 0, 1, 2, 3
 
+    HMC_AUTO, HMC_LAUNCHES, HMC_PERSISTENT = 0, 1, 2
+
+    def select_hmc_path(self, which: int):
+        """Per-branch transitions: persistent cooperative kernel where eligible (AUTO) / launch per step / persistent or fail."""
+        check(lib.bann_net_select_hmc_path(self.h, which))
+
+    def persistent_launches(self) -> int:
+        return int(lib.bann_net_persistent_launches(self.h))
+
     def select_k1(self, which: int):
         """Which fused forward+backward kernel may run: auto / tensor-core / FFMA / shape-agnostic."""
         check(lib.bann_net_select_k1(self.h, int(which)))

@@ -6,7 +6,7 @@
 // HBM and their expansion into tcgen05 operands (84 instructions per thread and super-tile).  19.2 us per leapfrog at
 // N = 100k, against 0.25 us of roofline time.
 //
-// Here the whole transition is ONE cooperative launch.  Every CTA owns one or two 256-row super-tiles of the branch for the
+// Here the whole transition is ONE cooperative launch.  Every CTA owns one to four 256-row super-tiles of the branch for the
 // whole trajectory: the packed words are loaded and expanded ONCE -- the forward A operand stays in tensor memory, the
 // backward A operand in shared memory -- and the targets stay in registers.  Per leapfrog step a CTA stages the three bf16 pieces
 // of W' = W0 / sd from ITS OWN copy of the parameters, issues the forward MMAs, runs the FP32 tail (TcTail, k1_tc.cuh), issues
@@ -24,7 +24,11 @@
 
 namespace bann {
 
-constexpr int kTcpMaxTiles = 2;        // super-tiles a CTA keeps resident
+// super-tiles a CTA keeps resident.  The co-residency a cooperative launch is granted for a kernel that allocates tensor
+// memory is ONE CTA per SM on this driver (the runtime cannot know how many columns tcgen05.alloc will ask for; ncu reports
+// a theoretical occupancy of 3 for the same kernel) -- so the grid is at most the SM count and a CTA takes up to four super-tiles:
+// 148 x 4 x 256 = 151k rows per GPU.
+constexpr int kTcpMaxTiles = 4;
 constexpr unsigned long long kTcpBarrierTimeoutNs = 2ull * 1000ull * 1000ull * 1000ull;
 
 struct TcpArgs {
@@ -34,6 +38,7 @@ struct TcpArgs {
     const float* mu;
     const float* sd;
     uint32_t n, nst, ncb;
+    uint32_t tpc;              // super-tiles per CTA (1 .. kTcpMaxTiles): sizes the resident operand images and the tensor-memory allocation
     uint32_t L;                // leapfrog steps
     // HMC state (arenas, as K2Args)
     BranchState* state;
@@ -57,6 +62,7 @@ struct TcpArgs {
     uint32_t pstride;
     unsigned int* bar;         // grid barrier counter, zero at launch
     int* error_flag;
+    unsigned long long* timing;   // NULL, or 8 phase accumulators (clock64 ticks of CTA 0, BANN_DEBUG_TCP)
 };
 
 template <int H, int S, int D>
@@ -65,10 +71,10 @@ struct TcpShape {
     using C = TcShape<H, S, D>;
     // [expanded genotypes: kTcpMaxTiles images][weight pieces][packed words][delta pieces][tail params + b0p][theta, mom, eps, theta0,
     //  grad (maxP each)][reduced sums][reduction scratch][barriers]
-    static size_t smem(uint32_t ncb, uint32_t P) {
+    static size_t smem(uint32_t ncb, uint32_t P, uint32_t tpc) {
         const size_t img = (size_t)ncb * kTcChunkStride;
-        size_t used = (size_t)kTcpMaxTiles * img + C::SW + (size_t)ncb * 512 + C::SD + C::MISC + (size_t)(6 * ((P + 4) & ~3u)) * 4 + 512;
-        const size_t need = (size_t)(ncb + 8) * kTcChunkStride + img;     // the M = 64 backward operand reads 8 chunks of the LAST image
+        size_t used = (size_t)tpc * img + C::SW + (size_t)ncb * 512 + C::SD + C::MISC + (size_t)(7 * ((P + 4) & ~3u)) * 4 + 512;
+        const size_t need = (size_t)(ncb + 8) * kTcChunkStride + (tpc - 1) * img;     // the M = 64 backward operand reads 8 chunks of the LAST image
         return (used > need ? used : need) + 256;
     }
 };
@@ -97,11 +103,11 @@ __device__ __forceinline__ bool tcp_grid_sync(unsigned int* bar, unsigned int ta
 }
 
 template <int H, int S, int D, int ACT>
-__global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
+__global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
     using TT = TcTail<H, S, D, ACT>;
-    constexpr int W0 = T::W0, W0P = T::W0P, NN = C::NN, NTACC = T::NTACC;
+    constexpr int W0 = T::W0, W0P = T::W0P, NN = C::NN;
     constexpr float cA = TT::cA;
     extern __shared__ __align__(16) uint8_t smraw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
     // ---- shared memory carve-up
     uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);
     const uint32_t sa_bytes = NCB * kTcChunkStride;
-    uint8_t* sW = sA + (size_t)kTcpMaxTiles * sa_bytes;
+    uint8_t* sW = sA + (size_t)a.tpc * sa_bytes;
     uint32_t* sG = reinterpret_cast<uint32_t*>(sW + C::SW);
     uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + (size_t)NCB * 512;
     float* wp = reinterpret_cast<float*>(__builtin_assume_aligned(sD + C::SD, 16));
@@ -126,11 +132,12 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
     float* s_th0 = s_eps + Pp;
     float* s_g = s_th0 + Pp;                                         // gradient under the prior
     float* s_sum = s_g + Pp;                                         // reduced raw sums [P + 1]
+    float* s_lam = s_sum + Pp;                                       // prior precision of each parameter (constant over the trajectory); < 0: a bias
 
     const float* mu = a.mu + d.col_off;
     const float* sd = a.sd + d.col_off;
     const float* pr = a.prec + d.prec_off;
-    const uint32_t tpc = (a.nst + ncta - 1) / ncta;                  // <= kTcpMaxTiles (host)
+    const uint32_t tpc = a.tpc;                                      // 1 .. kTcpMaxTiles (host)
     const uint32_t t_begin = min(a.nst, cta * tpc);
     const uint32_t t_end = min(a.nst, t_begin + tpc);
     const uint32_t ntile = t_end - t_begin;                          // 0 .. kTcpMaxTiles (the host guarantees the bound)
@@ -146,13 +153,17 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
         umma::mbar_init(&mbar[4], 1);
         umma::fence_mbar_init();
     }
-    constexpr uint32_t kTmemCols = 256;     // per tile: 2 x NN forward accumulators + 64 columns forward A operand; + NN backward accumulator
+    // per tile: 2 x NN forward accumulators + 64 columns forward A operand; + NN backward accumulator: 96 tpc + 16 columns
+    const uint32_t kTmemCols = tpc == 1 ? 128u : (tpc == 2 ? 256u : 512u);
     if (warp == 0) umma::tmem_alloc(tmem_slot, kTmemCols);
     for (uint32_t k = tid; k < P; k += 128) {
         s_th[k] = a.theta[d.param_off + k];
         s_p[k] = a.mom[d.param_off + k];
         s_eps[k] = a.eps[d.param_off + k];
         s_th0[k] = a.theta0[d.param_off + k];
+        int l; uint32_t row, col; bool isb;
+        locate_param(d, k, l, row, col, isb);
+        s_lam[k] = isb ? -1.f : param_prior_precision(d, pr, a.model, l, row, false);
     }
     umma::fence_async_smem();
     umma::fence_before_sync();
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
     // tensor-memory columns: tile k: forward accumulators [96 k, 96 k + 32), forward A operand [96 k + 32, 96 k + 96); backward acc [192, 208)
     auto tD = [&](uint32_t k) { return 96u * k; };
     auto tA = [&](uint32_t k) { return 96u * k + 32u; };
-    constexpr uint32_t tB = 192u;
+    const uint32_t tB = 96u * tpc;
     const uint32_t sA_u = umma::smem_u32(sA), sD_u = umma::smem_u32(sD), sW_u = umma::smem_u32(sW);
     constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
     constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
@@ -218,7 +229,16 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
     int steps_done = 0, u_turn_step = -1;
     float neg_h_init = 0.f;
 
+    long long tick = clock64();
+    auto lap = [&](int phase) {                        // debug timing: CTA 0, thread 0 only
+        if (a.timing && cta == 0 && tid == 0) {
+            const long long now = clock64();
+            a.timing[phase] += (unsigned long long)(now - tick);
+            tick = now;
+        }
+    };
     for (uint32_t ev = 0; ev <= a.L; ++ev) {          // evaluation ev at the current parameters: ev = 0 is the initial one
+        lap(7);
         // ---- stage the tail parameters and W' = W0 / sd (three bf16 pieces) from this CTA's copy of the parameters
         TT::stage_tail(s_th + m * W0, wp, tid, 128);
         float* wtmp = reinterpret_cast<float*>(sD);
@@ -234,19 +254,21 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
             dst[(2 * W0 + c) * 8] = __float2bfloat16_rn(p2);
         }
         __syncthreads();
-        if (tid < W0P) {
+        // mean fold b0' = b0 - sum_j mu_j W'_j: warp c sums unit c (and c + 4) over the markers, lanes in a fixed tree
+        for (uint32_t c = warp; c < (uint32_t)W0P; c += 4) {
             float acc = 0.f;
-            if (tid < W0) {
-                for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], wtmp[j * W0 + tid], acc);
-                acc = (s_th[m * W0 + T::b_off(0) + tid] - acc) * cA;
-            }
-            b0p[tid] = acc;
+            if (c < (uint32_t)W0)
+                for (uint32_t j = lane; j < m; j += 32) acc = fmaf(mu[j], wtmp[j * W0 + c], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) b0p[c] = c < (uint32_t)W0 ? (s_th[m * W0 + T::b_off(0) + c] - acc) * cA : 0.f;
         }
         __syncthreads();
         for (uint32_t k = tid; k < m * W0; k += 128) wtmp[k] = 0.f;     // the pad columns of the delta operand must stay zero
         umma::fence_async_smem();
         umma::fence_before_sync();
         __syncthreads();
+        lap(0);      // staging
         // ---- forward contractions of the CTA's tiles (A operand resident in tensor memory)
         if (warp == 0) {
             umma::fence_after_sync();
@@ -265,6 +287,7 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
         }
         umma::mbar_wait(&mbar[0], ev & 1u);
         umma::fence_after_sync();
+        lap(1);      // forward MMAs
         // ---- tail per tile; the backward contractions accumulate over the CTA's tiles
         typename TT::Acc A;
         A.clear();
@@ -305,6 +328,7 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
             ++nbwd;
             umma::fence_after_sync();
         }
+        lap(2);      // tails + backward MMAs
         // ---- partial sums of this CTA
         float sacc[16];
 #pragma unroll
@@ -323,44 +347,40 @@ __global__ void __launch_bounds__(128, 2) k_hmc_persistent(TcpArgs a) {
                 }
             }
         }
+        lap(3);      // partial sums
         // ---- all partials written -> every CTA reduces a slice in a fixed order -> all slices written
         bar_target += ncta;
         if (!tcp_grid_sync(a.bar, bar_target, a.error_flag)) break;
-        for (uint32_t k = cta; k <= P; k += ncta) {
+        lap(4);      // barrier A
+        // values cta, cta + ncta, ...: one warp per value, lanes stride over the CTAs' partials, fixed shuffle tree (deterministic)
+        for (uint32_t k = cta + warp * ncta; k <= P; k += 4 * ncta) {
             double s = 0.0;
-            for (uint32_t c = tid; c < ncta; c += 128) s += (double)__ldcg(a.part + (size_t)c * a.pstride + k);
+            for (uint32_t c = lane; c < ncta; c += 32) s += (double)__ldcg(a.part + (size_t)c * a.pstride + k);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            __shared__ double s_w[4];
-            if (lane == 0) s_w[warp] = s;
-            __syncthreads();
-            if (tid == 0) a.gsum[k] = (float)((s_w[0] + s_w[1]) + (s_w[2] + s_w[3]));
-            __syncthreads();
+            if (lane == 0) a.gsum[k] = (float)s;
         }
+        lap(5);      // slice reduction
         bar_target += ncta;
         if (!tcp_grid_sync(a.bar, bar_target, a.error_flag)) break;
+        lap(6);      // barrier B
         for (uint32_t k = tid; k <= P; k += 128) s_sum[k] = __ldcg(a.gsum + k);
         __syncthreads();
         // ---- the update, replicated in every CTA (k2_step's arithmetic; branch_sampler.rs:1239-1284)
         const bool is_init = ev == 0, is_last = ev == a.L;
         float kin = 0.f, prior = 0.f, uturn = 0.f;
         for (uint32_t k = tid; k < P; k += 128) {
-            int l; uint32_t row, col; bool isb;
-            locate_param(d, k, l, row, col, isb);
-            const float w = s_th[k];
+            const float w = s_th[k], lam = s_lam[k];
             float g;
-            if (isb) {
+            if (lam < 0.f) {                                          // a bias (branch_sampler.rs:322-331)
                 g = -(lam_e * s_sum[k]);
                 if (a.model == BANN_STD_NORMAL) prior -= 0.5f * w * w;
-            } else {
-                const float lam = param_prior_precision(d, pr, a.model, l, row, false);
-                if (a.model == BANN_STD_NORMAL) { g = -(lam_e * s_sum[k] + w); prior -= 0.5f * w * w; }
-                else if (lasso) {
-                    const float sg = (w > 0.f) ? 1.f : (w < 0.f ? -1.f : 0.f);
-                    g = -(lam_e * s_sum[k] + lam * sg);
-                    prior -= lam * fabsf(w);
-                } else { g = -(lam_e * s_sum[k] + lam * w); prior -= 0.5f * lam * w * w; }
-            }
+            } else if (a.model == BANN_STD_NORMAL) { g = -(lam_e * s_sum[k] + w); prior -= 0.5f * w * w; }
+            else if (lasso) {
+                const float sg = (w > 0.f) ? 1.f : (w < 0.f ? -1.f : 0.f);
+                g = -(lam_e * s_sum[k] + lam * sg);
+                prior -= lam * fabsf(w);
+            } else { g = -(lam_e * s_sum[k] + lam * w); prior -= 0.5f * lam * w * w; }
             s_g[k] = g;
             float pk = s_p[k];
             if (!is_init) { pk = pk + (0.5f * s_eps[k]) * g; s_p[k] = pk; }

@@ -1,4 +1,7 @@
 // Translation unit of the persistent per-branch HMC kernel (k1_tcp.cuh): instantiations + the cooperative launch.
+#include <cstdio>
+#include <cstdlib>
+
 #include "k1_tcp.cuh"
 
 namespace bann {
@@ -7,27 +10,49 @@ template <int H, int S, int D, int ACT>
 static int launch_tcp_one(const TcpArgs& a, uint32_t P, int num_sms, cudaStream_t st, bool* launched, float** part_io, bann_net* net) {
     using TS = TcpShape<H, S, D>;
     auto kern = k_hmc_persistent<H, S, D, ACT>;
-    const size_t smem = TS::smem(a.ncb, P);
-    static bool configured = false;
-    static int per_sm = 0;
-    if (!configured) {
-        BANN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::smem(8, 4096)));
-        configured = true;
+    const bool dbg = getenv("BANN_DEBUG_TCP") != nullptr;
+    // One CTA per SM is what a cooperative launch of a tensor-memory kernel is granted (k1_tcp.cuh): as few super-tiles per CTA
+    // as make the grid fit the SM count; more than kTcpMaxTiles would not stay resident -> launch-per-step path.
+    cudaError_t err = cudaErrorCooperativeLaunchTooLarge;
+    for (uint32_t tpc = 1; tpc <= (uint32_t)kTcpMaxTiles && err == cudaErrorCooperativeLaunchTooLarge; ++tpc) {
+        const uint32_t grid = (a.nst + tpc - 1) / tpc;
+        if (grid > (uint32_t)num_sms) continue;
+        const size_t smem = std::max<size_t>(TS::smem(a.ncb, P, tpc), 120 * 1024);   // one CTA per SM, whatever the driver would allow
+        BANN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        float* part = bann_net_partials(net, (size_t)grid * a.pstride);
+        if (!part) return -2;
+        *part_io = part;
+        TcpArgs args = a;
+        args.part = part;
+        args.tpc = tpc;
+        static unsigned long long* d_timing = nullptr;
+        if (dbg) {
+            if (!d_timing) { cudaMalloc(&d_timing, 8 * sizeof(unsigned long long)); }
+            cudaMemsetAsync(d_timing, 0, 8 * sizeof(unsigned long long), st);
+            args.timing = d_timing;
+        }
+        void* params[] = {&args};
+        BANN_CUDA(cudaMemsetAsync(args.bar, 0, sizeof(unsigned int), st));
+        err = cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(128), params, smem, st);
+        if (dbg) {
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+            fprintf(stderr, "[tcp] cooperative launch grid %u (tiles per CTA %u, %zu B shared memory, occupancy %d): %s\n", grid, tpc, smem,
+                    per_sm, cudaGetErrorString(err));
+        }
+        if (dbg && err == cudaSuccess) {
+            unsigned long long h[8];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, d_timing, sizeof(h), cudaMemcpyDeviceToHost);
+            const double per = 1.0 / ((a.L + 1) * 1.965e3);      // us per evaluation at 1965 MHz
+            fprintf(stderr, "[tcp] us per evaluation (CTA 0): staging %.2f  forward MMAs %.2f  tails + backward MMAs %.2f  partial sums %.2f  "
+                            "barrier A %.2f  slice reduction %.2f  barrier B %.2f  update %.2f\n",
+                    h[0] * per, h[1] * per, h[2] * per, h[3] * per, h[4] * per, h[5] * per, h[6] * per, h[7] * per);
+        }
+        if (err == cudaErrorCooperativeLaunchTooLarge) cudaGetLastError();      // clear, try more tiles per CTA
     }
-    BANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-    const uint32_t maxcoop = (uint32_t)std::max(0, per_sm) * (uint32_t)num_sms;
-    if (maxcoop == 0) return 0;
-    const uint32_t tpc = (a.nst + maxcoop - 1) / maxcoop;
-    if (tpc == 0 || tpc > (uint32_t)kTcpMaxTiles) return 0;          // too many rows to keep resident: the launch-per-step path runs
-    const uint32_t grid = (a.nst + tpc - 1) / tpc;
-    float* part = bann_net_partials(net, (size_t)grid * a.pstride);
-    if (!part) return -2;
-    *part_io = part;
-    TcpArgs args = a;
-    args.part = part;
-    void* params[] = {&args};
-    BANN_CUDA(cudaMemsetAsync(args.bar, 0, sizeof(unsigned int), st));
-    BANN_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(128), params, smem, st));
+    if (err == cudaErrorCooperativeLaunchTooLarge) return 0;
+    BANN_CUDA(err);
     BANN_LAUNCHED();
     BANN_CUDA(cudaGetLastError());
     *launched = true;

@@ -488,7 +488,7 @@ __device__ __forceinline__ void philox_normal_pair(Philox& ph, float& a, float& 
     b = rad * s;
 }
 
-__device__ float step_size_for(const InitArgs& a, const BranchDesc& d, const float* pr, int l, uint32_t row, bool isb,
+__device__ __forceinline__ float step_size_for(const InitArgs& a, const BranchDesc& d, const float* pr, int l, uint32_t row, bool isb,
                                float u) {
     const float PI = 3.14159265358979323846f;  // std::f32::consts::PI
     const float f = a.factor, L = a.L;

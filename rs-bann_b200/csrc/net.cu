@@ -12,6 +12,7 @@
 #include "k1_tc.cuh"
 #include "k1_tc_wide.cuh"
 #include "k1_tcx.cuh"
+#include "k1_tcp.cuh"
 #include "store.cuh"
 
 using namespace bann;
@@ -64,6 +65,9 @@ struct bann_net {
     uint64_t visit_seq = 0;
     int k1_mode = BANN_K1_AUTO;   // which K1 kernel launch_k1 may pick (bann_net_select_k1)
     const char* last_k1 = "none"; // kernel family the last fused forward+backward launch used (bann_net_last_k1_kernel)
+    int hmc_path = BANN_HMC_AUTO; // per-branch transitions: persistent cooperative kernel where eligible / launch per step (bann_net_select_hmc_path)
+    unsigned int* d_tcp_bar = nullptr;   // grid-barrier counter of the persistent kernel
+    uint64_t persistent_launches = 0;
     float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient (callers with pageable buffers)
     float *d_dense_in = nullptr, *d_dense_out = nullptr;   // dense host-facing layouts of the parameters / gradients + rss
     uint64_t sum_params = 0;
@@ -90,6 +94,10 @@ static int ensure_cap(float** p, size_t* cap, size_t need) {
     BANN_CUDA(cudaMalloc(p, need * sizeof(float)));
     *cap = need;
     return 0;
+}
+
+namespace bann {
+int launch_hmc_persistent(const BranchDesc& d0, int act, TcpArgs& a, int num_sms, cudaStream_t st, bool* launched, bann_net* net);
 }
 
 // ------------------------------------------------------------------ K1 launch
@@ -517,6 +525,54 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
     cudaStream_t st = net->ctx->stream;
     BANN_CHECK(hmc_init_and_first_eval(net, cfg, R, 0));
     const uint32_t Lsteps = cfg->hmc_integration_length;
+    // ---- one branch, one GPU, no per-step recording: the whole trajectory in ONE cooperative launch (k1_tcp.cuh) where the
+    //      branch is eligible; otherwise (and for A/B tests: bann_net_select_hmc_path) three launches per leapfrog step
+    if (R.nlist == 1 && R.single_branch >= 0 && !sharded(net) && !R.traj_params && !R.traj_h && !cfg->num_grad && !cfg->num_grad_traj
+        && net->hmc_path != BANN_HMC_LAUNCHES && net->k1_mode == BANN_K1_AUTO
+        && (R.first_mode == TGT_RESID_PLUS_PRED || R.first_mode == TGT_SHARED)) {
+        const uint32_t b = (uint32_t)R.single_branch;
+        if (!net->d_tcp_bar) BANN_CUDA(cudaMalloc(&net->d_tcp_bar, sizeof(unsigned int)));
+        BANN_CHECK(ensure_cap(&net->d_gsum, &net->gsum_cap, (size_t)net->pstride));
+        TcpArgs t;
+        memset(&t, 0, sizeof(t));
+        t.store_tc = net->gen->d_store_tc;
+        t.descs = net->d_descs;
+        t.b = b;
+        t.mu = net->gen->d_mu;
+        t.sd = net->gen->d_sd;
+        t.n = (uint32_t)net->gen->n;
+        t.nst = net->gen->nst;
+        t.L = Lsteps;
+        t.state = net->d_states + b;
+        t.theta = net->d_theta;
+        t.theta0 = net->d_theta0;
+        t.mom = net->d_mom;
+        t.grad = net->d_grad;
+        t.eps = net->d_eps;
+        t.prec = net->d_prec;
+        t.model = net->model;
+        t.max_h_err = cfg->hmc_max_hamiltonian_error;
+        if (R.first_mode == TGT_RESID_PLUS_PRED) { t.resid = resid; t.tgt_out = tgt_out; t.prev_out = prev_out; }
+        else t.tgt = R.tgt;
+        t.ynew_out = ynew_out;
+        t.gsum = net->d_gsum;
+        t.pstride = net->pstride;
+        t.bar = net->d_tcp_bar;
+        t.error_flag = net->d_errflag;
+        bool launched = false;
+        BANN_CHECK(launch_hmc_persistent(net->descs[b], net->act, t, net->ctx->num_sms, st, &launched, net));
+        if (launched) {
+            net->persistent_launches += 1;
+            net->last_k1 = "k_hmc_persistent<H,S,D,ACT> (whole trajectory, operands resident in tensor / shared memory)";
+            k_accept<<<R.nlist, 256, 0, st>>>(net->d_descs, R.list, net->d_states, net->d_theta, net->d_theta0, R.inj_u, R.seed,
+                                              R.stream_base);
+            BANN_LAUNCHED();
+            BANN_CUDA(cudaGetLastError());
+            return 0;
+        }
+        if (net->hmc_path == BANN_HMC_PERSISTENT)
+            BANN_FAIL("persistent HMC kernel requested but the branch is not eligible (tanh, <= 64 markers, an instantiated architecture, <= 4 super-tiles per SM: ~150k rows)");
+    }
     K1Launch k;
     k.list = R.list;
     k.nlist = R.nlist;
@@ -885,6 +941,7 @@ static int check_error_flag(bann_net* net) {
     BANN_CUDA(cudaMemcpyAsync(&flag, net->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, net->ctx->stream));
     BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
     if (flag == 2) BANN_FAIL("peer-memory exchange timed out: a rank did not issue the matching call");
+    if (flag == 3) BANN_FAIL("persistent HMC kernel: grid barrier timed out");
     if (flag) BANN_FAIL("Invalid output weight summary statistic (negative or NaN), params.rs:49-54");
     return 0;
 }
@@ -1258,7 +1315,7 @@ void bann_net_destroy(bann_net* net) {
     cudaFree(net->d_ynew); cudaFree(net->d_part); cudaFree(net->d_gsum); cudaFree(net->d_rpart);
     cudaFree(net->d_ow_others); cudaFree(net->d_order); cudaFree(net->d_Tg); cudaFree(net->d_Yg); cudaFree(net->d_inj_grp); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
     cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj); cudaFree(net->d_numgrad);
-    cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
+    cudaFree(net->d_tcp_bar); cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
     for (int i = 0; i < 3; ++i) cudaFree(net->d_tcx[i]);
     if (net->h_pin_a) cudaFreeHost(net->h_pin_a);
     if (net->h_pin_b) cudaFreeHost(net->h_pin_b);
@@ -2265,6 +2322,15 @@ int bann_net_force_generic(bann_net* net, int on) {
     net->k1_mode = on ? BANN_K1_GENERIC : BANN_K1_AUTO;
     return 0;
 }
+
+int bann_net_select_hmc_path(bann_net* net, int which) {
+    if (!net) BANN_FAIL("NULL net");
+    if (which < BANN_HMC_AUTO || which > BANN_HMC_PERSISTENT) BANN_FAIL("unknown HMC path selector");
+    net->hmc_path = which;
+    return 0;
+}
+
+uint64_t bann_net_persistent_launches(bann_net* net) { return net ? net->persistent_launches : 0; }
 
 int bann_net_select_k1(bann_net* net, int which) {
     if (!net) BANN_FAIL("NULL net");

@@ -25,6 +25,8 @@ net.init_residual()
 import os
 if os.environ.get('K1'):
     net.select_k1(int(os.environ['K1']))
+if os.environ.get('HMC_PATH'):          # 0 auto (persistent kernel where eligible), 1 launch per step, 2 persistent or fail
+    net.select_hmc_path(int(os.environ['HMC_PATH']))
 cfg = rb.MCMCCfg(hmc_step_size_factor=0.1, hmc_integration_length=L, hmc_max_hamiltonian_error=1e30)
 net.sweep(cfg, np.arange(B), seed=1)
 ctx.sync()
@@ -34,4 +36,5 @@ st = net.sweep(cfg, np.random.default_rng(2).permutation(B), seed=2)
 ctx.sync()
 dt = time.perf_counter() - t0
 print(f"n={n} B={B} m_b={per} L={L}: {B / dt:.1f} visits/s, {B * L / dt:.0f} branch-leapfrogs/s, {dt / B / L * 1e6:.1f} us per leapfrog, "
-      f"{rb.launch_count() / B:.0f} launches per visit, accepted {st['num_accepted']}/{st['num_samples']}")
+      f"{rb.launch_count() / B:.0f} launches per visit, accepted {st['num_accepted']}/{st['num_samples']}, "
+      f"transitions through the persistent kernel: {net.persistent_launches()}, last kernel: {net.last_k1_kernel()}")
