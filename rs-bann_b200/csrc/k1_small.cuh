@@ -44,6 +44,30 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return ax < 0.25f ? small : big;
 }
 
+// activation_functions.rs:23-45 on one value; `aux` = what the derivative needs besides the activation (SiLU: the sigmoid)
+template <int ACT>
+__device__ __forceinline__ float act_s(float z, float& aux) {
+    if constexpr (ACT == BANN_TANH) { aux = 0.f; return fast_tanh(z); }
+    else if constexpr (ACT == BANN_RELU) { aux = 0.f; return fmaxf(z, 0.f); }
+    else if constexpr (ACT == BANN_LEAKY_RELU) { aux = 0.f; return fmaxf(z, 0.01f * z); }   // x > 0: x, x < 0: 0.01 x, 0 at 0
+    else if constexpr (ACT == BANN_SILU) {
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+        aux = r;
+        return z * r;
+    } else { aux = 0.f; return z; }
+}
+// derivative at the pre-activation, from the activation (a > 0 <=> x > 0 for the rectifiers)
+template <int ACT>
+__device__ __forceinline__ float dact_s(float a, float aux) {
+    if constexpr (ACT == BANN_TANH) return 1.f - a * a;
+    else if constexpr (ACT == BANN_RELU) return a > 0.f ? 1.f : 0.f;
+    else if constexpr (ACT == BANN_LEAKY_RELU) return a > 0.f ? 1.f : (a < 0.f ? 0.01f : 0.f);
+    else if constexpr (ACT == BANN_SILU) return a + aux * (1.f - a);
+    else return 1.f;
+}
+
 // packed FP32 FMA (Blackwell FFMA2): {d0,d1} += {a0,a1} * {b0,b1} in one issue slot
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
     unsigned long long ra, rb, rc;
@@ -87,7 +111,7 @@ struct TailShape {
     static constexpr int NTACC = 1 + S + W0 + (NLA > 1 ? (NLA - 1) * (MW * MW + MW) : 0);
 };
 
-template <int H, int S, int D, int NP, int NW>
+template <int H, int S, int D, int NP, int NW, int ACT>
 __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a, int nstage) {
     using T = TailShape<H, S, D>;
     constexpr int NLA = T::NLA, W0 = T::W0, W0P = T::W0P, W2P = T::W2P, MW = T::MW, NTACC = T::NTACC;
@@ -235,9 +259,9 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
         for (int r = 0; r < 4; ++r) {
             const bool valid = row0 + r < a.n;
             const float unscale = 1.f / (float)(1 << (2 * r));
-            float act[NLA][MW];
+            float act[NLA][MW], aux[NLA][MW];
 #pragma unroll
-            for (int c = 0; c < W0; ++c) act[0][c] = fast_tanh(fmaf(z[r][c], unscale, b0p[c]));
+            for (int c = 0; c < W0; ++c) act[0][c] = act_s<ACT>(fmaf(z[r][c], unscale, b0p[c]), aux[0][c]);
 #pragma unroll
             for (int l = 1; l < NLA; ++l) {
 #pragma unroll
@@ -247,7 +271,7 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
 #pragma unroll
                         for (int i = 0; i < MW; ++i)
                             if (i < T::in_w(l)) zz = fmaf(act[l - 1][i], sp[T::w_off(l) + c * T::in_w(l) + i], zz);
-                        act[l][c] = fast_tanh(zz);
+                        act[l][c] = act_s<ACT>(zz, aux[l][c]);
                     }
                 }
             }
@@ -263,7 +287,7 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
 #pragma unroll
             for (int i = 0; i < S; ++i) {
                 gWo[i] = fmaf(act[NLA - 1][i], e, gWo[i]);
-                delta[i] = (1.f - act[NLA - 1][i] * act[NLA - 1][i]) * (e * sp[T::w_off(NLA) + i]);
+                delta[i] = dact_s<ACT>(act[NLA - 1][i], aux[NLA - 1][i]) * (e * sp[T::w_off(NLA) + i]);
             }
 #pragma unroll
             for (int l = NLA - 1; l >= 1; --l) {
@@ -284,7 +308,7 @@ __global__ void __launch_bounds__(NW * 32, (NP <= 4 ? 2 : 1)) k1_small(K1Args a,
                 }
 #pragma unroll
                 for (int i = 0; i < MW; ++i)
-                    if (i < T::in_w(l)) delta[i] = (1.f - act[l - 1][i] * act[l - 1][i]) * nd[i];
+                    if (i < T::in_w(l)) delta[i] = dact_s<ACT>(act[l - 1][i], aux[l - 1][i]) * nd[i];
             }
 #pragma unroll
             for (int c = 0; c < W0; ++c) {
@@ -439,12 +463,12 @@ size_t k1_small_smem(uint32_t mp, int nstage) {
     return (fl + redn + (size_t)NW * perw) * 4 + 16;
 }
 
-template <int H, int S, int D, int NP, int NW>
-int launch_one_small(K1Args& a, uint32_t nlist, uint32_t mp, cudaStream_t st) {
+template <int H, int S, int D, int NP, int NW, int ACT>
+int launch_one_small_act(K1Args& a, uint32_t nlist, uint32_t mp, cudaStream_t st) {
     int nstage = 2;
     size_t smem = k1_small_smem<H, S, D, NP, NW>(mp, 2);
     if (smem > 100 * 1024) { nstage = 1; smem = k1_small_smem<H, S, D, NP, NW>(mp, 1); }
-    auto kern = k1_small<H, S, D, NP, NW>;
+    auto kern = k1_small<H, S, D, NP, NW, ACT>;
     static size_t configured = 0;
     if (smem > configured) {
         BANN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -457,13 +481,23 @@ int launch_one_small(K1Args& a, uint32_t nlist, uint32_t mp, cudaStream_t st) {
     return 0;
 }
 
+template <int H, int S, int D, int NP, int NW>
+int launch_one_small(K1Args& a, uint32_t nlist, uint32_t mp, cudaStream_t st) {
+    switch (a.act) {
+        case BANN_TANH: return launch_one_small_act<H, S, D, NP, NW, BANN_TANH>(a, nlist, mp, st);
+        case BANN_RELU: return launch_one_small_act<H, S, D, NP, NW, BANN_RELU>(a, nlist, mp, st);
+        case BANN_LEAKY_RELU: return launch_one_small_act<H, S, D, NP, NW, BANN_LEAKY_RELU>(a, nlist, mp, st);
+        case BANN_SILU: return launch_one_small_act<H, S, D, NP, NW, BANN_SILU>(a, nlist, mp, st);
+        default: return launch_one_small_act<H, S, D, NP, NW, BANN_IDENTITY>(a, nlist, mp, st);
+    }
+}
+
 // picks an instantiation for a homogeneous launch (all listed branches share the architecture and
-// fit the marker bound, activation tanh); otherwise leaves *launched = false and the generic kernel runs.
+// fit the marker bound); otherwise leaves *launched = false and the generic kernel runs.
 #ifdef BANN_K1_SMALL_IMPL
 int launch_k1_small(const std::vector<BranchDesc>& descs, int single_branch, K1Args& a, uint32_t nlist, int num_sms,
                            cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
-    if (a.act != BANN_TANH) return 0;
     const BranchDesc& d0 = descs[single_branch >= 0 ? single_branch : 0];
     uint32_t max_m = d0.m, max_mp = d0.m_pad4;
     if (single_branch < 0) {

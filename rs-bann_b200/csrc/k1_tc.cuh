@@ -149,6 +149,25 @@ struct TcShape {
 //   Signs alternate -- sg_l = (-1)^(NLA-l) cA^(NLA-1-l) rho_l -- so that tanh's a^2 - 1 is one instruction and the pre-scaled
 //   weights are used as they are; the factor is undone on the error, one multiplication per layer.
 // part2: delta_0 = sg_0 * (signed, unscaled error) -> three bf16 pieces per unit by truncation (exact: 3 x 8 significand bits).
+// recursive-halving warp reduction of CNT values per lane (TcTail::reduce_and_store<true>): after the steps 16, 8, 4, 2, 1 every lane
+// holds halved_count(CNT, 5) fully reduced values
+__host__ __device__ constexpr int halved_count(int cnt, int steps) { return steps == 0 ? cnt : halved_count((cnt + 1) / 2, steps - 1); }
+template <int CNT, int O, int N>
+__device__ __forceinline__ void halve_step(float (&v)[N], uint32_t lane) {
+    if constexpr (O >= 1) {
+        constexpr int HALF = (CNT + 1) / 2;
+        const bool up = (lane & (uint32_t)O) != 0;
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            const float hi = 2 * i + 1 < CNT ? v[2 * i + 1] : 0.f;
+            const float send = up ? v[2 * i] : hi;
+            const float keep = up ? hi : v[2 * i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+        }
+        halve_step<HALF, O / 2>(v, lane);
+    }
+}
+
 template <int H, int S, int D, int ACT>
 struct TcTail {
     using T = TailShape<H, S, D>;
@@ -286,12 +305,48 @@ struct TcTail {
             wp[k] = scaled ? w * cA : w;
         }
     }
-    // CTA epilogue, first half: fixed-order reduction of the cross-row sums over row pairs, lanes and the four compute warps,
+    // CTA epilogue, first half: fixed-order reduction of the cross-row sums over row pairs, lanes and the NW compute warps,
     // written to the partial slot `pp` in param_vec order (rss at [P]); gb0 also to s_gb0 for the standardisation unfold
+    // HALVING: the warp stage as a recursive-halving exchange -- at every step a lane hands one element of each pair to its
+    // partner and keeps (and sums) the other, so NTACC values cost ~NTACC shuffles instead of 5 x NTACC (the stage is bound by the
+    // SM's shuffle throughput); a fixed tree as well, in another order.  Used where the epilogue runs once per leapfrog step.
+    template <bool HALVING = false, int NW = 4>
     __device__ __forceinline__ static void reduce_and_store(const Acc& A, float* red, uint32_t warp, uint32_t lane, uint32_t tid, float* pp,
                                                             uint32_t m, uint32_t P, float* s_gb0) {
         constexpr int NTACC = T::NTACC;
-        if (warp < 4) {
+        if constexpr (HALVING) {
+            if (warp < (uint32_t)NW) {
+                float v[NTACC];
+                int idx = 0;
+                auto put = [&](f2 v2) { v[idx++] = lo2(v2) + hi2(v2); };
+                put(A.rss);
+#pragma unroll
+                for (int c = 0; c < S; ++c) put(A.gWo[c]);
+#pragma unroll
+                for (int c = 0; c < W0; ++c) put(A.gb0[c]);
+#pragma unroll
+                for (int l = 1; l < NLA; ++l) {
+#pragma unroll
+                    for (int c = 0; c < MW; ++c) put(A.gbt[l - 1][c]);
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+#pragma unroll
+                        for (int c = 0; c < MW; ++c) put(A.gWt[l - 1][i][c]);
+                }
+                halve_step<NTACC, 16>(v, lane);
+                constexpr int cnt = halved_count(NTACC, 5);
+                // element j of this lane is the sum of original value ((((2 j + b1) 2 + b2) 2 + b4) 2 + b8) 2 + b16
+                float* rw = red + warp * NTACC;
+#pragma unroll
+                for (int j = 0; j < cnt; ++j) {
+                    uint32_t k = (uint32_t)j;
+#pragma unroll
+                    for (int o = 1; o <= 16; o <<= 1) k = 2 * k + ((lane & (uint32_t)o) ? 1u : 0u);
+                    if (k < (uint32_t)NTACC) rw[k] = v[j];
+                }
+            }
+        } else
+        if (warp < (uint32_t)NW) {
             float* rw = red + warp * NTACC;
             int idx = 0;
             auto put = [&](f2 v2) {
@@ -320,7 +375,7 @@ struct TcTail {
         if (tid < NTACC) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) s += red[w * NTACC + tid];
+            for (int w = 0; w < NW; ++w) s += red[w * NTACC + tid];
             int idx = tid;
             if (idx == 0) pp[P] = s;
             else if (idx < 1 + S) pp[m * W0 + T::w_off(NLA) + (idx - 1)] = s;                       // output weights

@@ -10,13 +10,18 @@
 // whole trajectory: the packed words are loaded and expanded ONCE -- the forward A operand stays in tensor memory, the
 // backward A operand in shared memory -- and the targets stay in registers.  Per leapfrog step a CTA stages the three bf16 pieces
 // of W' = W0 / sd from ITS OWN copy of the parameters, issues the forward MMAs, runs the FP32 tail (TcTail, k1_tc.cuh), issues
-// the backward MMAs, writes its partial sums; a grid barrier; every CTA reduces a slice of the P + 1 values over all partials in
-// a fixed order; a second grid barrier; every CTA applies the SAME parameter / momentum update (gradient under the prior,
-// half steps, position step, Hamiltonian, early-reject and U-turn checks: k2_step's arithmetic) to its own copy -- replicated,
+// the backward MMAs, publishes its partial sums; every CTA reduces a slice of the P + 1 values over all partials in a fixed
+// order and publishes the sums; every CTA applies the SAME parameter / momentum update (gradient under the prior, half steps,
+// position step, Hamiltonian, early-reject and U-turn checks: k2_step's arithmetic) to its own copy -- replicated,
 // deterministic, nothing is broadcast.  CTA 0 writes the branch state and the final parameters.
 //
-// The grid barrier is a monotonic counter (atomicAdd + ld.acquire.gpu spin) and relies on the co-residency a cooperative launch
-// guarantees; a wall-clock limit turns a lost CTA into an error flag instead of a hang.
+// There is no grid barrier.  Every published value travels as ONE 64-bit word {float bits, tag}, tag = launch base + evaluation
+// index + 1 (st / ld.relaxed.gpu.b64: single-copy atomic), in a buffer double-buffered by the evaluation's parity; a reader
+// spins on the words it needs until their tag is this evaluation's.  A slot of evaluation e is overwritten at e + 2, which a
+// CTA reaches only after it has read every sum of e + 1, i.e. after every reducer has finished reading the partials of e + 1
+// (and of e before that) -- so no reader can still need the old word.  The all-reduce costs two L2 round trips per evaluation
+// instead of two grid barriers plus two read passes (measured 5.2 -> see profiles/r2_seq_rate.log).  Spinning relies on
+// the co-residency a cooperative launch guarantees; a wall-clock limit turns a lost CTA into an error flag instead of a hang.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -29,7 +34,7 @@ namespace bann {
 // a theoretical occupancy of 3 for the same kernel) -- so the grid is at most the SM count and a CTA takes up to four super-tiles:
 // 148 x 4 x 256 = 151k rows per GPU.
 constexpr int kTcpMaxTiles = 4;
-constexpr unsigned long long kTcpBarrierTimeoutNs = 2ull * 1000ull * 1000ull * 1000ull;
+constexpr long long kTcpTimeoutClk = 6ll * 1000ll * 1000ll * 1000ll;      // ~3 s of SM clock (clock64: reading %globaltimer inside the poll loop costs more than the poll)
 
 struct TcpArgs {
     const uint32_t* store_tc;
@@ -57,60 +62,92 @@ struct TcpArgs {
     float* prev_out;           // own prediction at the first evaluation, may be NULL
     float* ynew_out;           // own prediction at the last evaluation, may be NULL
     // scratch
-    float* part;               // [gridDim.x][pstride]
-    float* gsum;               // [pstride]: the reduced sums of the last evaluation (rss at [P])
+    uint2* part;               // [2][gridDim.x][pstride] tagged partial sums {float bits, tag}
+    uint2* sums;               // [2][kTcpSumCopies][pstride] tagged reduced sums (copies: a CTA polls copy blockIdx.x % kTcpSumCopies)
+    uint32_t tag_base;         // tags of this launch are tag_base + 1 .. tag_base + L + 1; every older tag in the buffers is smaller
+    float* gsum;               // [pstride]: the reduced sums of the last evaluation (rss at [P]), written by CTA 0 at the end
     uint32_t pstride;
-    unsigned int* bar;         // grid barrier counter, zero at launch
     int* error_flag;
-    unsigned long long* timing;   // NULL, or 8 phase accumulators (clock64 ticks of CTA 0, BANN_DEBUG_TCP)
+    unsigned long long* timing;   // NULL, or 8 phase accumulators (clock64 ticks of CTA timing_cta, BANN_DEBUG_TCP)
+    uint32_t timing_cta;
+    uint32_t poll_sleep_ns;       // back-off between poll rounds
 };
 
 template <int H, int S, int D>
 struct TcpShape {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
-    // [expanded genotypes: kTcpMaxTiles images][weight pieces][packed words][delta pieces][tail params + b0p][theta, mom, eps, theta0,
-    //  grad (maxP each)][reduced sums][reduction scratch][barriers]
+    // [expanded genotypes: tpc images][weight pieces][packed words x 2][delta pieces x 2][tail params + b0p][reduction scratch][barriers][theta, mom, eps, theta0,
+    //  grad (maxP each)][reduced sums][prior precisions][this CTA's partial sums]
     static size_t smem(uint32_t ncb, uint32_t P, uint32_t tpc) {
         const size_t img = (size_t)ncb * kTcChunkStride;
-        size_t used = (size_t)tpc * img + C::SW + (size_t)ncb * 512 + C::SD + C::MISC + (size_t)(7 * ((P + 4) & ~3u)) * 4 + 512;
+        const size_t misc = (size_t)(2 * ((T::n_tail() + 3) & ~3) + 2 * T::W0P + ((8 * T::NTACC + 3) & ~3) + 16) * 4 + 64;
+        size_t used = (size_t)tpc * img + C::SW + (size_t)2 * ncb * 512 + 2 * C::SD + misc + (size_t)(8 * ((P + 4) & ~3u)) * 4 + 512;
         const size_t need = (size_t)(ncb + 8) * kTcChunkStride + (tpc - 1) * img;     // the M = 64 backward operand reads 8 chunks of the LAST image
         return (used > need ? used : need) + 256;
     }
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+constexpr int kTcpSumCopies = 8;          // every sum is published kTcpSumCopies times so that <= ~19 CTAs spin on one line
+constexpr int kTcpMaxGrid = 160;          // lanes of a reducer warp take <= 5 partials each
+constexpr int kTcpMaxValues = 512;        // a thread gathers <= 2 reduced sums
+
+__device__ __forceinline__ void tg_store(uint2* p, float v, uint32_t tag) {
+    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)tag << 32);
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-// all CTAs of the (cooperative) grid; `target` is the count this barrier completes at.  false: timed out / error flagged
-__device__ __forceinline__ bool tcp_grid_sync(unsigned int* bar, unsigned int target, int* error_flag) {
-    __shared__ int ok;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        int good = 1;
-        const unsigned long long t0 = xr_now();
-        while ((int)(ld_acquire_gpu(bar) - target) < 0) {
-            if (xr_now() - t0 > kTcpBarrierTimeoutNs) { atomicExch(error_flag, 3); good = 0; break; }
+__device__ __forceinline__ uint2 tg_load(const uint2* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+}
+// NV words p[i * stride] (i < NV, i-th word wanted iff bit i of `want`), each awaited until its tag is `tag`.  All loads are in
+// flight together; only late words are re-read.  false: timed out (error flag 3)
+template <int NV>
+__device__ __forceinline__ bool tg_await(const uint2* p, size_t stride, uint32_t want, uint32_t tag, uint2 (&v)[NV], int* error_flag, uint32_t sleep_ns) {
+    uint32_t pending = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = make_uint2(0u, tag);
+        if (want >> i & 1u) {
+            v[i] = tg_load(p + i * stride);
+            if (v[i].y != tag) pending |= 1u << i;
         }
-        ok = good;
     }
-    __syncthreads();
-    return ok != 0;
+    if (pending) {
+        const long long t0 = clock64();
+        while (pending) {
+            if (sleep_ns) __nanosleep(sleep_ns);
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (pending >> i & 1u) {
+                    v[i] = tg_load(p + i * stride);
+                    if (v[i].y == tag) pending &= ~(1u << i);
+                }
+            if (pending && clock64() - t0 > kTcpTimeoutClk) {
+                atomicExch(error_flag, 3);
+                return false;
+            }
+        }
+    }
+    return true;
 }
 
+constexpr int kTcpThreads = 256;          // two warpgroups: group g owns the CTA's tiles g, g + 2 and runs their tails concurrently with the other's
+
+__device__ __forceinline__ void group_sync(uint32_t grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1u) : "memory"); }
+
 template <int H, int S, int D, int ACT>
-__global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
+__global__ void __launch_bounds__(kTcpThreads, 1) k_hmc_persistent(TcpArgs a) {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
     using TT = TcTail<H, S, D, ACT>;
-    constexpr int W0 = T::W0, W0P = T::W0P, NN = C::NN;
+    constexpr int W0 = T::W0, W0P = T::W0P, NN = C::NN, NT = kTcpThreads, NTACC = T::NTACC;
+    constexpr int kGroupTiles = kTcpMaxTiles / 2;
     constexpr float cA = TT::cA;
     extern __shared__ __align__(16) uint8_t smraw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t grp = warp >> 2, wq = warp & 3u, gt = tid & 127u;       // warpgroup, warp within it (= its tensor-memory lane quarter), thread within it
     const uint32_t cta = blockIdx.x, ncta = gridDim.x;
     const BranchDesc& d = a.descs[a.b];
     const uint32_t m = d.m, NC = d.nc, NKS = (NC + 1) >> 1, NCB = a.ncb, P = d.P;
@@ -119,12 +156,12 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
     uint8_t* sA = smraw + ((128u - (umma::smem_u32(smraw) & 127u)) & 127u);
     const uint32_t sa_bytes = NCB * kTcChunkStride;
     uint8_t* sW = sA + (size_t)a.tpc * sa_bytes;
-    uint32_t* sG = reinterpret_cast<uint32_t*>(sW + C::SW);
-    uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + (size_t)NCB * 512;
-    float* wp = reinterpret_cast<float*>(__builtin_assume_aligned(sD + C::SD, 16));
+    uint32_t* sG = reinterpret_cast<uint32_t*>(sW + C::SW);                  // packed words being expanded: one buffer per group
+    uint8_t* sD = reinterpret_cast<uint8_t*>(sG) + (size_t)2 * NCB * 512;    // delta pieces: one buffer per group
+    float* wp = reinterpret_cast<float*>(__builtin_assume_aligned(sD + 2 * C::SD, 16));
     float* b0p = wp + ((T::n_tail() + 3) & ~3);
-    float* red = b0p + ((T::n_tail() + 3) & ~3) + 2 * W0P;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + C::NRED);     // [0] forward MMAs done, [1] backward MMAs done, [4] words landed
+    float* red = b0p + ((T::n_tail() + 3) & ~3) + 2 * W0P;                   // [8 warps][NTACC]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + ((8 * NTACC + 3) & ~3));   // [0] forward MMAs, [1 + g] backward MMAs of group g, [4 + g] its words landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 6);
     float* s_th = reinterpret_cast<float*>(tmem_slot + 4);           // this CTA's copy of the branch's parameters ...
     float* s_p = s_th + Pp;                                          // ... momenta
@@ -133,6 +170,7 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
     float* s_g = s_th0 + Pp;                                         // gradient under the prior
     float* s_sum = s_g + Pp;                                         // reduced raw sums [P + 1]
     float* s_lam = s_sum + Pp;                                       // prior precision of each parameter (constant over the trajectory); < 0: a bias
+    float* s_part = s_lam + Pp;                                      // this CTA's partial sums [P + 1] before they are published
 
     const float* mu = a.mu + d.col_off;
     const float* sd = a.sd + d.col_off;
@@ -141,22 +179,25 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
     const uint32_t t_begin = min(a.nst, cta * tpc);
     const uint32_t t_end = min(a.nst, t_begin + tpc);
     const uint32_t ntile = t_end - t_begin;                          // 0 .. kTcpMaxTiles (the host guarantees the bound)
+    const uint32_t gtiles = ntile > grp ? (ntile - grp + 1) / 2 : 0; // tiles of this group: local k = 2 kk + grp
 
     // ---- one-time setup
     {
-        const uint32_t nz = (uint32_t)((sD + C::SD - sA) / 16);
-        for (uint32_t k = tid; k < nz; k += 128) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
+        const uint32_t nz = (uint32_t)((sD + 2 * C::SD - sA) / 16);
+        for (uint32_t k = tid; k < nz; k += NT) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
         umma::mbar_init(&mbar[0], 1);
         umma::mbar_init(&mbar[1], 1);
+        umma::mbar_init(&mbar[2], 1);
         umma::mbar_init(&mbar[4], 1);
+        umma::mbar_init(&mbar[5], 1);
         umma::fence_mbar_init();
     }
-    // per tile: 2 x NN forward accumulators + 64 columns forward A operand; + NN backward accumulator: 96 tpc + 16 columns
-    const uint32_t kTmemCols = tpc == 1 ? 128u : (tpc == 2 ? 256u : 512u);
+    // per tile: 2 x NN forward accumulators + 64 columns forward A operand; + 2 x 32 for the groups' backward accumulators
+    const uint32_t kTmemCols = tpc <= 2 ? 256u : 512u;
     if (warp == 0) umma::tmem_alloc(tmem_slot, kTmemCols);
-    for (uint32_t k = tid; k < P; k += 128) {
+    for (uint32_t k = tid; k < P; k += NT) {
         s_th[k] = a.theta[d.param_off + k];
         s_p[k] = a.mom[d.param_off + k];
         s_eps[k] = a.eps[d.param_off + k];
@@ -170,32 +211,36 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tlane = tmem + ((warp * 32u) << 16);
-    // tensor-memory columns: tile k: forward accumulators [96 k, 96 k + 32), forward A operand [96 k + 32, 96 k + 96); backward acc [192, 208)
+    const uint32_t tlane = tmem + ((wq * 32u) << 16);
+    // tensor-memory columns: tile k: forward accumulators [96 k, 96 k + 32), forward A operand [96 k + 32, 96 k + 96);
+    // backward accumulator of group g: [96 tpc + 32 g, + NN)
     auto tD = [&](uint32_t k) { return 96u * k; };
     auto tA = [&](uint32_t k) { return 96u * k + 32u; };
-    const uint32_t tB = 96u * tpc;
-    const uint32_t sA_u = umma::smem_u32(sA), sD_u = umma::smem_u32(sD), sW_u = umma::smem_u32(sW);
+    const uint32_t tB = 96u * tpc + 32u * grp;
+    uint8_t* sDg = sD + grp * C::SD;
+    uint32_t* sGg = sG + grp * NCB * 128;
+    const uint32_t sA_u = umma::smem_u32(sA), sD_u = umma::smem_u32(sDg), sW_u = umma::smem_u32(sW);
     constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
     constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
     const uint64_t dW_f = umma::make_desc(sW_u, NN * 16, 128);
     const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
 
-    // ---- the CTA's super-tiles: packed words -> operands, once for the whole trajectory
+    // ---- the CTA's super-tiles: packed words -> operands, once for the whole trajectory (each group expands its own tiles)
     const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
-    for (uint32_t k = 0; k < ntile; ++k) {
-        if (warp == 0) {
-            if (umma::elect_one()) umma::bulk_load(sG, gwords + (size_t)(t_begin + k) * NC * 128, NC * 512u, &mbar[4]);
+    for (uint32_t kk = 0; kk < gtiles; ++kk) {
+        const uint32_t k = 2 * kk + grp;
+        if (wq == 0) {
+            if (umma::elect_one()) umma::bulk_load(sGg, gwords + (size_t)(t_begin + k) * NC * 128, NC * 512u, &mbar[4 + grp]);
             __syncwarp();
         }
-        umma::mbar_wait(&mbar[4], k & 1u);
-        uint8_t* rowA = sA + k * sa_bytes + tid * 16;
+        umma::mbar_wait(&mbar[4 + grp], kk & 1u);
+        uint8_t* rowA = sA + k * sa_bytes + gt * 16;
         const uint32_t ta = tlane + tA(k);
         for (uint32_t c = 0; c < 64; c += 4) umma::tmem_st4(ta + c, 0u, 0u, 0u, 0u);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             if ((uint32_t)i < NC) {
-                const uint32_t x = sG[i * 128 + tid], y = x >> 8;
+                const uint32_t x = sGg[i * 128 + gt], y = x >> 8;
                 const uint4 oa = make_uint4(x & 0x00030003u, x & 0x000C000Cu, x & 0x00300030u, x & 0x00C000C0u);
                 const uint4 ob = make_uint4(y & 0x00030003u, y & 0x000C000Cu, y & 0x00300030u, y & 0x00C000C0u);
                 *reinterpret_cast<uint4*>(rowA + i * kTcChunkStride) = oa;
@@ -204,34 +249,32 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
                 umma::tmem_st4(ta + 32 + 4 * i, ob.x, ob.y, ob.z, ob.w);
             }
         umma::tmem_st_wait();
-        __syncthreads();                     // every thread has read the staged words before the next copy overwrites them
+        group_sync(grp);                     // every thread of the group has read the staged words before the next copy overwrites them
     }
-    // targets of the CTA's rows, in registers for the whole trajectory
+    // targets of the group's rows, in registers for the whole trajectory
     const f2 zero2 = dup2(0.f);
-    f2 tg[kTcpMaxTiles], valid[kTcpMaxTiles];
+    f2 tg[kGroupTiles], valid[kGroupTiles];
     const float* tsrc = a.resid ? a.resid : a.tgt;
 #pragma unroll
-    for (int k = 0; k < kTcpMaxTiles; ++k) {
-        const uint32_t rA = (t_begin + k) * kTcRows + tid, rB = rA + 128;
-        const bool vA = (uint32_t)k < ntile && rA < a.n, vB = (uint32_t)k < ntile && rB < a.n;
-        valid[k] = mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f);
-        tg[k] = mk2(vA ? tsrc[rA] : 0.f, vB ? tsrc[rB] : 0.f);
+    for (int kk = 0; kk < kGroupTiles; ++kk) {
+        const uint32_t rA = (t_begin + 2 * kk + grp) * kTcRows + gt, rB = rA + 128;
+        const bool vA = (uint32_t)kk < gtiles && rA < a.n, vB = (uint32_t)kk < gtiles && rB < a.n;
+        valid[kk] = mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f);
+        tg[kk] = mk2(vA ? tsrc[rA] : 0.f, vB ? tsrc[rB] : 0.f);
     }
 
-    float* pp = a.part + (size_t)cta * a.pstride;
     const float lam_e = pr[d.ep_off];
     const bool lasso = (a.model == BANN_LASSO_BASE || a.model == BANN_LASSO_ARD);
-    unsigned int bar_target = 0;
-    uint32_t nbwd = 0;                                 // backward commits of this CTA so far (phase parity of mbar[1])
+    uint32_t nbwd = 0;                                 // backward commits of this group so far (phase parity of mbar[1 + grp])
     __shared__ float s_gb0[W0];
-    __shared__ float s_red3[3][4];
+    __shared__ float s_red3[3][8];
     __shared__ int s_status;
     int steps_done = 0, u_turn_step = -1;
     float neg_h_init = 0.f;
 
     long long tick = clock64();
-    auto lap = [&](int phase) {                        // debug timing: CTA 0, thread 0 only
-        if (a.timing && cta == 0 && tid == 0) {
+    auto lap = [&](int phase) {                        // debug timing: one CTA, thread 0 only
+        if (a.timing && cta == a.timing_cta && tid == 0) {
             const long long now = clock64();
             a.timing[phase] += (unsigned long long)(now - tick);
             tick = now;
@@ -240,9 +283,9 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
     for (uint32_t ev = 0; ev <= a.L; ++ev) {          // evaluation ev at the current parameters: ev = 0 is the initial one
         lap(7);
         // ---- stage the tail parameters and W' = W0 / sd (three bf16 pieces) from this CTA's copy of the parameters
-        TT::stage_tail(s_th + m * W0, wp, tid, 128);
-        float* wtmp = reinterpret_cast<float*>(sD);
-        for (uint32_t k = tid; k < m * W0; k += 128) {
+        TT::stage_tail(s_th + m * W0, wp, tid, NT);
+        float* wtmp = s_g;                             // W' in fp32 for the mean fold (the gradient buffer is dead here)
+        for (uint32_t k = tid; k < m * W0; k += NT) {
             const uint32_t j = k / W0, c = k % W0;
             const float w = __fdiv_rn(s_th[c * m + j], sd[j]);
             wtmp[k] = w;
@@ -254,8 +297,8 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
             dst[(2 * W0 + c) * 8] = __float2bfloat16_rn(p2);
         }
         __syncthreads();
-        // mean fold b0' = b0 - sum_j mu_j W'_j: warp c sums unit c (and c + 4) over the markers, lanes in a fixed tree
-        for (uint32_t c = warp; c < (uint32_t)W0P; c += 4) {
+        // mean fold b0' = b0 - sum_j mu_j W'_j: one warp per unit, lanes over the markers in a fixed tree
+        for (uint32_t c = warp; c < (uint32_t)W0P; c += NT / 32) {
             float acc = 0.f;
             if (c < (uint32_t)W0)
                 for (uint32_t j = lane; j < m; j += 32) acc = fmaf(mu[j], wtmp[j * W0 + c], acc);
@@ -263,8 +306,6 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) b0p[c] = c < (uint32_t)W0 ? (s_th[m * W0 + T::b_off(0) + c] - acc) * cA : 0.f;
         }
-        __syncthreads();
-        for (uint32_t k = tid; k < m * W0; k += 128) wtmp[k] = 0.f;     // the pad columns of the delta operand must stay zero
         umma::fence_async_smem();
         umma::fence_before_sync();
         __syncthreads();
@@ -288,88 +329,123 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
         umma::mbar_wait(&mbar[0], ev & 1u);
         umma::fence_after_sync();
         lap(1);      // forward MMAs
-        // ---- tail per tile; the backward contractions accumulate over the CTA's tiles
+        // ---- tail per tile, the two groups side by side; a group's backward contractions accumulate over its tiles
         typename TT::Acc A;
         A.clear();
-        for (uint32_t k = 0; k < ntile; ++k) {
-            float accA[16], accB[16];
-            umma::tmem_ld16x2(tlane + tD(k), tlane + tD(k) + NN, accA, accB);
-            umma::fence_before_sync();
-            f2 yh, sg0[W0], ef0;
-            f2 t = tg[k];
-            TT::part1(accA, accB, wp, b0p, t, a.resid != nullptr && ev == 0, valid[k], true, A, yh, sg0, ef0);
-            const uint32_t rA = (t_begin + k) * kTcRows + tid, rB = rA + 128;
-            if (ev == 0) {
-                tg[k] = t;                              // t = resid + own prediction, fixed for the trajectory (net.rs:280)
-                if (a.resid && a.tgt_out) { if (rA < a.n) a.tgt_out[rA] = lo2(t); if (rB < a.n) a.tgt_out[rB] = hi2(t); }
-                if (a.prev_out) { if (rA < a.n) a.prev_out[rA] = lo2(yh); if (rB < a.n) a.prev_out[rB] = hi2(yh); }
-            }
-            if (a.ynew_out) { if (rA < a.n) a.ynew_out[rA] = lo2(yh); if (rB < a.n) a.ynew_out[rB] = hi2(yh); }
-            {
-                f2 v[W0];
-                TT::delta0(sg0, ef0, A, v);
-                TT::store_pieces(v, sD + tid * 16);
-            }
-            umma::fence_async_smem();
-            __syncthreads();
-            if (warp == 0) {
-                umma::fence_after_sync();
-                if (umma::elect_one()) {
-                    const uint64_t base = dA_b + ((k * sa_bytes) >> 4);
 #pragma unroll
-                    for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
-                        umma::mma_f16(tmem + tB, base + ks * 16u, dD_b + ks * 16u, idesc_b, (k | ks) != 0);
-                    umma::commit(&mbar[1]);
+        for (int kk = 0; kk < kGroupTiles; ++kk) {
+            if ((uint32_t)kk < gtiles) {
+                const uint32_t k = 2 * kk + grp;
+                float accA[16], accB[16];
+                umma::tmem_ld16x2(tlane + tD(k), tlane + tD(k) + NN, accA, accB);
+                umma::fence_before_sync();
+                f2 yh, sg0[W0], ef0;
+                f2 t = tg[kk];
+                TT::part1(accA, accB, wp, b0p, t, a.resid != nullptr && ev == 0, valid[kk], true, A, yh, sg0, ef0);
+                const uint32_t rA = (t_begin + k) * kTcRows + gt, rB = rA + 128;
+                if (ev == 0) {
+                    tg[kk] = t;                         // t = resid + own prediction, fixed for the trajectory (net.rs:280)
+                    if (a.resid && a.tgt_out) { if (rA < a.n) a.tgt_out[rA] = lo2(t); if (rB < a.n) a.tgt_out[rB] = hi2(t); }
+                    if (a.prev_out) { if (rA < a.n) a.prev_out[rA] = lo2(yh); if (rB < a.n) a.prev_out[rB] = hi2(yh); }
                 }
-                __syncwarp();
+                if (a.ynew_out) { if (rA < a.n) a.ynew_out[rA] = lo2(yh); if (rB < a.n) a.ynew_out[rB] = hi2(yh); }
+                {
+                    f2 v[W0];
+                    TT::delta0(sg0, ef0, A, v);
+                    TT::store_pieces(v, sDg + gt * 16);
+                }
+                umma::fence_async_smem();
+                group_sync(grp);
+                if (wq == 0) {
+                    umma::fence_after_sync();
+                    if (umma::elect_one()) {
+                        const uint64_t base = dA_b + ((k * sa_bytes) >> 4);
+#pragma unroll
+                        for (uint32_t ks = 0; ks < kTcRows / 16; ++ks)
+                            umma::mma_f16(tmem + tB, base + ks * 16u, dD_b + ks * 16u, idesc_b, ((uint32_t)kk | ks) != 0);
+                        umma::commit(&mbar[1 + grp]);
+                    }
+                    __syncwarp();
+                }
+                // the group's delta buffer is reused by its next tile: wait for this tile's backward MMAs
+                umma::mbar_wait(&mbar[1 + grp], nbwd & 1u);
+                ++nbwd;
+                umma::fence_after_sync();
             }
-            // the delta buffer is reused by the next tile: wait for this tile's backward MMAs
-            umma::mbar_wait(&mbar[1], nbwd & 1u);
-            ++nbwd;
-            umma::fence_after_sync();
         }
+        umma::fence_before_sync();
         lap(2);      // tails + backward MMAs
         // ---- partial sums of this CTA
-        float sacc[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) sacc[q] = 0.f;
-        if (ntile > 0) umma::tmem_ld16(tlane + tB, sacc);
-        umma::fence_before_sync();
-        TT::reduce_and_store(A, red, warp, lane, tid, pp, m, P, s_gb0);
-        if (lane < 16) {
+        TT::template reduce_and_store<true, NT / 32>(A, red, warp, lane, tid, s_part, m, P, s_gb0);
+        umma::fence_after_sync();
+        if (warp < 4) {                                 // accumulator row j lives in lane j % 16 of warp j / 16 (M = 64 layout); both groups' sums
             const uint32_t j = warp * 16 + lane;
-            if (j < m) {
+            float s0[16], s1[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) s0[q] = s1[q] = 0.f;
+            if (ntile > 0) umma::tmem_ld16(tlane + 96u * tpc, s0);          // warp-wide (.sync.aligned)
+            if (ntile > 1) umma::tmem_ld16(tlane + 96u * tpc + 32u, s1);
+            if (lane < 16 && j < m) {
                 const float unscale = pow2f(33 - 2 * (int)((j & 7u) >> 1));
 #pragma unroll
                 for (int c = 0; c < W0; ++c) {
-                    const float s = (sacc[c] + (sacc[W0 + c] + sacc[2 * W0 + c])) * unscale;
-                    pp[c * m + j] = __fdiv_rn(s - mu[j] * s_gb0[c], sd[j]);
+                    const float s = ((s0[c] + (s0[W0 + c] + s0[2 * W0 + c])) + (s1[c] + (s1[W0 + c] + s1[2 * W0 + c]))) * unscale;
+                    s_part[c * m + j] = __fdiv_rn(s - mu[j] * s_gb0[c], sd[j]);
                 }
             }
         }
-        lap(3);      // partial sums
-        // ---- all partials written -> every CTA reduces a slice in a fixed order -> all slices written
-        bar_target += ncta;
-        if (!tcp_grid_sync(a.bar, bar_target, a.error_flag)) break;
-        lap(4);      // barrier A
-        // values cta, cta + ncta, ...: one warp per value, lanes stride over the CTAs' partials, fixed shuffle tree (deterministic)
-        for (uint32_t k = cta + warp * ncta; k <= P; k += 4 * ncta) {
-            double s = 0.0;
-            for (uint32_t c = lane; c < ncta; c += 32) s += (double)__ldcg(a.part + (size_t)c * a.pstride + k);
+        umma::fence_before_sync();
+        __syncthreads();
+        const uint32_t tag = a.tag_base + ev + 1u, par = ev & 1u;
+        {
+            uint2* mine = a.part + ((size_t)par * ncta + cta) * a.pstride;
+            for (uint32_t k = tid; k <= P; k += NT) tg_store(mine + k, s_part[k], tag);
+        }
+        lap(3);      // partial sums, published
+        // ---- values cta, cta + ncta, ...: one warp per value, lanes stride over the CTAs' partials (awaited by tag), summed in
+        //      double in a fixed order (lane's partials ascending, then a fixed shuffle tree): deterministic
+        bool ok = true;
+        {
+            const uint2* theirs = a.part + (size_t)par * ncta * a.pstride;
+            uint2* out = a.sums + ((size_t)par * kTcpSumCopies + (lane & (kTcpSumCopies - 1))) * a.pstride;
+            uint32_t want = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) a.gsum[k] = (float)s;
+            for (int i = 0; i < kTcpMaxGrid / 32; ++i)
+                if (lane + 32u * i < ncta) want |= 1u << i;
+            for (uint32_t k = cta + warp * ncta; k <= P; k += (NT / 32) * ncta) {
+                uint2 v[kTcpMaxGrid / 32];
+                ok = tg_await(theirs + (size_t)lane * a.pstride + k, (size_t)32 * a.pstride, want, tag, v, a.error_flag, a.poll_sleep_ns) && ok;
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < kTcpMaxGrid / 32; ++i)
+                    if (want >> i & 1u) s += (double)__uint_as_float(v[i].x);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const bool all_ok = __all_sync(0xffffffffu, ok);
+                if (lane < (uint32_t)kTcpSumCopies && all_ok) tg_store(out + k, (float)s, tag);
+            }
         }
         lap(5);      // slice reduction
-        bar_target += ncta;
-        if (!tcp_grid_sync(a.bar, bar_target, a.error_flag)) break;
-        lap(6);      // barrier B
-        for (uint32_t k = tid; k <= P; k += 128) s_sum[k] = __ldcg(a.gsum + k);
-        __syncthreads();
+        // ---- every CTA gathers all the sums
+        {
+            const uint2* in = a.sums + ((size_t)par * kTcpSumCopies + (cta & (kTcpSumCopies - 1))) * a.pstride;
+            constexpr int NG = (kTcpMaxValues + NT - 1) / NT;
+            uint32_t want = 0;
+#pragma unroll
+            for (int i = 0; i < NG; ++i)
+                if (tid + (uint32_t)NT * i <= P) want |= 1u << i;
+            uint2 v[NG];
+            ok = tg_await(in + tid, NT, want, tag, v, a.error_flag, a.poll_sleep_ns) && ok;
+#pragma unroll
+            for (int i = 0; i < NG; ++i)
+                if (want >> i & 1u) s_sum[tid + (uint32_t)NT * i] = __uint_as_float(v[i].x);
+        }
+        if (__syncthreads_or(!ok)) break;
+        lap(6);      // gather
         // ---- the update, replicated in every CTA (k2_step's arithmetic; branch_sampler.rs:1239-1284)
         const bool is_init = ev == 0, is_last = ev == a.L;
         float kin = 0.f, prior = 0.f, uturn = 0.f;
-        for (uint32_t k = tid; k < P; k += 128) {
+        for (uint32_t k = tid; k < P; k += NT) {
             const float w = s_th[k], lam = s_lam[k];
             float g;
             if (lam < 0.f) {                                          // a bias (branch_sampler.rs:322-331)
@@ -396,9 +472,10 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
         if (lane == 0) { s_red3[0][warp] = kin; s_red3[1][warp] = prior; s_red3[2][warp] = uturn; }
         __syncthreads();
         if (tid == 0) {
-            kin = (s_red3[0][0] + s_red3[0][1]) + (s_red3[0][2] + s_red3[0][3]);
-            prior = (s_red3[1][0] + s_red3[1][1]) + (s_red3[1][2] + s_red3[1][3]);
-            uturn = (s_red3[2][0] + s_red3[2][1]) + (s_red3[2][2] + s_red3[2][3]);
+            auto sum8 = [&](const float* r) { return ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7])); };
+            kin = sum8(s_red3[0]);
+            prior = sum8(s_red3[1]);
+            uturn = sum8(s_red3[2]);
             const float rss = s_sum[P];
             const float ld = prior + (-1.0f * lam_e * (rss / 2.0f));
             const float negh = ld - 0.5f * kin;
@@ -423,17 +500,15 @@ __global__ void __launch_bounds__(128, 1) k_hmc_persistent(TcpArgs a) {
             }
         }
         __syncthreads();
-        if (s_status == ST_REJECTED_EARLY) {
-            if (cta == 0)
-                for (uint32_t k = tid; k < P; k += 128) { a.theta[d.param_off + k] = s_th0[k]; a.grad[d.param_off + k] = s_g[k]; a.mom[d.param_off + k] = s_p[k]; }
+        if (s_status == ST_REJECTED_EARLY || is_last) {
+            if (cta == 0) {
+                const float* th_end = s_status == ST_REJECTED_EARLY ? s_th0 : s_th;
+                for (uint32_t k = tid; k < P; k += NT) { a.theta[d.param_off + k] = th_end[k]; a.grad[d.param_off + k] = s_g[k]; a.mom[d.param_off + k] = s_p[k]; }
+                for (uint32_t k = tid; k <= P; k += NT) a.gsum[k] = s_sum[k];
+            }
             break;
         }
-        if (is_last) {
-            if (cta == 0)
-                for (uint32_t k = tid; k < P; k += 128) { a.theta[d.param_off + k] = s_th[k]; a.grad[d.param_off + k] = s_g[k]; a.mom[d.param_off + k] = s_p[k]; }
-            break;
-        }
-        for (uint32_t k = tid; k < P; k += 128) {
+        for (uint32_t k = tid; k < P; k += NT) {
             const float e = s_eps[k];
             const float pk = s_p[k] + (0.5f * e) * s_g[k];
             s_p[k] = pk;

@@ -128,7 +128,9 @@ __device__ __forceinline__ void tcx_expand(const uint32_t* src, uint8_t* rowA, u
 // (packed words | W' pieces) per marker block, 8 slots deep; a slot is reloaded once the MMAs that read its W' pieces are done.
 // Warps 0-3 expand (one row pair per thread) and run the epilogue; warp 4 only requests the ring loads and issues the MMAs, so that
 // the ~40 clk per tcgen05.mma of the issuing lane never sits on the expansion's critical path.
-template <int W0>
+// ACT: the value KT needs per first-layer unit goes to HBM -- the activation, from which the rectifiers', tanh's and the identity's
+// derivatives follow; for SiLU (derivative needs the sigmoid as well) the PRE-activation, and KT evaluates the activation itself.
+template <int W0, int ACT>
 __global__ void __launch_bounds__(160, 2) k_tcx_fwd(TcxArgs a) {
     using X = TcxShape<W0>;
     constexpr int NN = X::NN;
@@ -264,11 +266,18 @@ __global__ void __launch_bounds__(160, 2) k_tcx_fwd(TcxArgs a) {
 #pragma unroll
             for (int c = 0; c < W0; ++c) {
                 const float z = v[c] + (v[W0 + c] + v[2 * W0 + c]);
-                const float t = fmaf(z, 8589934592.f /* 2^33 */, b0s[c]) * 2.8853900817779268f;
-                float e, r;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-                out[c] = fmaf(r, -2.f, 1.f);
+                const float z0 = fmaf(z, 8589934592.f /* 2^33 */, b0s[c]);
+                if constexpr (ACT == BANN_TANH) {
+                    float e, r;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z0 * 2.8853900817779268f));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+                    out[c] = fmaf(r, -2.f, 1.f);
+                } else if constexpr (ACT == BANN_SILU) {
+                    out[c] = z0;
+                } else {
+                    float unused;
+                    out[c] = act_s<ACT>(z0, unused);
+                }
             }
             if (row < a.k.n) {
                 float4* dst = reinterpret_cast<float4*>(a0_g + (size_t)row * W0);
@@ -287,7 +296,15 @@ __global__ void __launch_bounds__(160, 2) k_tcx_fwd(TcxArgs a) {
 // ------------------------------------------------------------------ KT: everything after the first layer, FP32
 // thread t owns rows t and 128 + t of a 256-row super-tile (packed f32x2, as in k1_tc); the cross-row sums of the layers >= 1
 // (up to 16 x 16 per layer) go through a shared-memory staged register-tiled product: 8 row groups x 16 blocks of 4 x 4 entries.
-template <int H, int S, int D>
+// derivative of the activation at the pre-activation, from the activation (and aux); tanh keeps its two-instruction form
+template <int ACT>
+__device__ __forceinline__ f2 dact2(f2 a, f2 aux) {
+    if constexpr (ACT == BANN_TANH) return dtanh2(a);
+    else if constexpr (ACT == BANN_IDENTITY) return dup2(1.f);
+    else return mul2(neg_dact2<ACT>(a, aux), dup2(-1.f));
+}
+
+template <int H, int S, int D, int ACT>
 __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
     using T = TailShape<H, S, D>;
     constexpr int NLA = T::NLA, W0 = T::W0, MW = 16, NQ = TcxShape<W0>::NQ, NN = TcxShape<W0>::NN;
@@ -338,7 +355,7 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
     for (uint32_t st = t_begin; st < t_end; ++st) {
         const uint32_t rowA_g = st * kTcRows + tid, rowB_g = rowA_g + 128;
         const bool vA = rowA_g < k.n, vB = rowB_g < k.n;
-        f2 act[NLA][MW];
+        f2 act[NLA][MW], aux[NLA][MW];
         {
             const float4* pa = reinterpret_cast<const float4*>(a0_g + (size_t)rowA_g * W0);
             const float4* pb = reinterpret_cast<const float4*>(a0_g + (size_t)rowB_g * W0);
@@ -348,6 +365,11 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
                 const float4 xb = vB ? pb[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
                 act[0][c] = mk2(xa.x, xb.x); act[0][c + 1] = mk2(xa.y, xb.y);
                 act[0][c + 2] = mk2(xa.z, xb.z); act[0][c + 3] = mk2(xa.w, xb.w);
+            }
+#pragma unroll
+            for (int c = 0; c < W0; ++c) {
+                if constexpr (ACT == BANN_SILU) act[0][c] = act2<ACT>(act[0][c], aux[0][c]);      // KA stored the pre-activation
+                else aux[0][c] = act[0][c];
             }
         }
         f2 tg = zero2;
@@ -361,7 +383,7 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
 #pragma unroll
                     for (int i = 0; i < MW; ++i)
                         if (i < T::in_w(l)) zz = fma2(act[l - 1][i], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), zz);
-                    act[l][c] = tanh2(zz);
+                    act[l][c] = act2<ACT>(mul2(zz, dup2(act_prescale<ACT>())), aux[l][c]);
                 }
             }
         }
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
         // output layer: gWo_i = sum_rows a_last[i] e ; delta of the summary layer
         f2 delta[MW];
 #pragma unroll
-        for (int i = 0; i < S; ++i) delta[i] = mul2(dtanh2(act[NLA - 1][i]), mul2(e, dup2(wp[T::w_off(NLA) + i])));
+        for (int i = 0; i < S; ++i) delta[i] = mul2(dact2<ACT>(act[NLA - 1][i], aux[NLA - 1][i]), mul2(e, dup2(wp[T::w_off(NLA) + i])));
         __syncthreads();
         Es[tid] = lo2(e); Es[128 + tid] = hi2(e);
 #pragma unroll
@@ -451,7 +473,7 @@ __global__ void __launch_bounds__(128, 2) k_tcx_tail(TcxArgs a) {
                 }
 #pragma unroll
             for (int i = 0; i < MW; ++i)
-                if (i < T::in_w(l)) delta[i] = mul2(dtanh2(act[l - 1][i]), nd[i]);
+                if (i < T::in_w(l)) delta[i] = mul2(dact2<ACT>(act[l - 1][i], aux[l - 1][i]), nd[i]);
         }
         // first layer: bias sums from the staged delta_0; output weights from the staged a_last and the errors
         stage(act[NLA - 1], S, delta, W0);
@@ -695,8 +717,8 @@ __global__ void __launch_bounds__(160, 2) k_tcx_bwd(TcxArgs a) {
 
 float* bann_net_tcx_buffer(bann_net* net, int which, size_t bytes);   // net.cu: grows the three work buffers on demand
 
-template <int H, int S, int D>
-int launch_one_tcx(TcxArgs& a, uint32_t nlist, uint32_t nslab, bool bwd, cudaStream_t st) {
+template <int H, int S, int D, int ACT>
+int launch_one_tcx_act(TcxArgs& a, uint32_t nlist, uint32_t nslab, bool bwd, cudaStream_t st) {
     using T = TailShape<H, S, D>;
     using X = TcxShape<T::W0>;
     constexpr int NLA = T::NLA;
@@ -704,17 +726,17 @@ int launch_one_tcx(TcxArgs& a, uint32_t nlist, uint32_t nslab, bool bwd, cudaStr
     const size_t smem_t = ((size_t)((T::n_tail() + 3) & ~3) + 2 * 256 * 16 + 256 + (size_t)128 * PER) * sizeof(float) + 16;
     static bool configured = false;
     if (!configured) {
-        BANN_CUDA(cudaFuncSetAttribute(k_tcx_fwd<T::W0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X::SMEM_A));
+        BANN_CUDA(cudaFuncSetAttribute(k_tcx_fwd<T::W0, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X::SMEM_A));
         BANN_CUDA(cudaFuncSetAttribute(k_tcx_bwd<T::W0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X::SMEM_B));
-        BANN_CUDA(cudaFuncSetAttribute(k_tcx_tail<H, S, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        BANN_CUDA(cudaFuncSetAttribute(k_tcx_tail<H, S, D, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         configured = true;
     }
     k_tcx_prep<T::W0><<<nlist, 128, 0, st>>>(a);
     BANN_LAUNCHED();
     dim3 grid(a.k.nchunk, nlist);
-    BANN_CUDA(launch_pdl(k_tcx_fwd<T::W0>, grid, dim3(160), X::SMEM_A, st, a));
+    BANN_CUDA(launch_pdl(k_tcx_fwd<T::W0, ACT>, grid, dim3(160), X::SMEM_A, st, a));
     BANN_LAUNCHED();
-    BANN_CUDA(launch_pdl(k_tcx_tail<H, S, D>, grid, dim3(128), smem_t, st, a));
+    BANN_CUDA(launch_pdl(k_tcx_tail<H, S, D, ACT>, grid, dim3(128), smem_t, st, a));
     BANN_LAUNCHED();
     if (bwd) {
         dim3 gridb(a.k.nchunk, nlist, nslab);
@@ -725,12 +747,23 @@ int launch_one_tcx(TcxArgs& a, uint32_t nlist, uint32_t nslab, bool bwd, cudaStr
     return 0;
 }
 
-// Wide-branch tensor-core K1: homogeneous architecture, tanh, tensor-core store present, widths in the instantiated set.
+template <int H, int S, int D>
+int launch_one_tcx(TcxArgs& a, uint32_t nlist, uint32_t nslab, bool bwd, cudaStream_t st) {
+    switch (a.k.act) {
+        case BANN_TANH: return launch_one_tcx_act<H, S, D, BANN_TANH>(a, nlist, nslab, bwd, st);
+        case BANN_RELU: return launch_one_tcx_act<H, S, D, BANN_RELU>(a, nlist, nslab, bwd, st);
+        case BANN_LEAKY_RELU: return launch_one_tcx_act<H, S, D, BANN_LEAKY_RELU>(a, nlist, nslab, bwd, st);
+        case BANN_SILU: return launch_one_tcx_act<H, S, D, BANN_SILU>(a, nlist, nslab, bwd, st);
+        default: return launch_one_tcx_act<H, S, D, BANN_IDENTITY>(a, nlist, nslab, bwd, st);
+    }
+}
+
+// Wide-branch tensor-core K1: homogeneous architecture, tensor-core store present, widths in the instantiated set.
 #ifdef BANN_K1_TCX_IMPL
 int launch_k1_tcx(const std::vector<BranchDesc>& descs, int single_branch, K1Args& k, uint32_t nlist, int num_sms,
                          cudaStream_t st, bool* launched, uint32_t* nchunk_io, float** part_io, bann_net* net) {
     *launched = false;
-    if (k.act != BANN_TANH || !k.store_tc) return 0;
+    if (!k.store_tc) return 0;
     const BranchDesc& d0 = descs[single_branch >= 0 ? single_branch : 0];
     uint32_t max_m = d0.m;
     if (single_branch < 0) {

@@ -66,7 +66,8 @@ struct bann_net {
     int k1_mode = BANN_K1_AUTO;   // which K1 kernel launch_k1 may pick (bann_net_select_k1)
     const char* last_k1 = "none"; // kernel family the last fused forward+backward launch used (bann_net_last_k1_kernel)
     int hmc_path = BANN_HMC_AUTO; // per-branch transitions: persistent cooperative kernel where eligible / launch per step (bann_net_select_hmc_path)
-    unsigned int* d_tcp_bar = nullptr;   // grid-barrier counter of the persistent kernel
+    uint2* d_tcp_words = nullptr;        // tagged exchange words of the persistent kernel: [2][kTcpMaxGrid][pstride] partials, [2][kTcpSumCopies][pstride] sums
+    uint32_t tcp_tag = 0;                // every tag in d_tcp_words is <= tcp_tag
     uint64_t persistent_launches = 0;
     float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient (callers with pageable buffers)
     float *d_dense_in = nullptr, *d_dense_out = nullptr;   // dense host-facing layouts of the parameters / gradients + rss
@@ -97,7 +98,7 @@ static int ensure_cap(float** p, size_t* cap, size_t need) {
 }
 
 namespace bann {
-int launch_hmc_persistent(const BranchDesc& d0, int act, TcpArgs& a, int num_sms, cudaStream_t st, bool* launched, bann_net* net);
+int launch_hmc_persistent(const BranchDesc& d0, int act, TcpArgs& a, int num_sms, cudaStream_t st, bool* launched);
 }
 
 // ------------------------------------------------------------------ K1 launch
@@ -260,13 +261,13 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
             if (launched) net->last_k1 = "k1_tcx: k_tcx_fwd + k_tcx_tail + k_tcx_bwd (tcgen05, three passes, first-layer width <= 16)";
         }
         if (!launched && net->k1_mode == BANN_K1_TENSOR)
-            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (tanh, homogeneous architecture, widths in the instantiated set)");
+            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (homogeneous architecture, widths in the instantiated set)");
     }
     if (!launched && net->k1_mode != BANN_K1_GENERIC) {
         int r = launch_k1_small(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
                                 &nchunk, L.fwd_only ? nullptr : &part, net);
         if (r != 0) return r;
-        if (launched) net->last_k1 = "k1_small<H,S,D> (FFMA)";
+        if (launched) net->last_k1 = "k1_small<H,S,D,NP,NW,ACT> (FFMA)";
     }
     if (!launched) {
         net->last_k1 = "k1_generic (shape-agnostic)";
@@ -531,7 +532,12 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
         && net->hmc_path != BANN_HMC_LAUNCHES && net->k1_mode == BANN_K1_AUTO
         && (R.first_mode == TGT_RESID_PLUS_PRED || R.first_mode == TGT_SHARED)) {
         const uint32_t b = (uint32_t)R.single_branch;
-        if (!net->d_tcp_bar) BANN_CUDA(cudaMalloc(&net->d_tcp_bar, sizeof(unsigned int)));
+        const size_t tcp_words = (size_t)(2 * kTcpMaxGrid + 2 * kTcpSumCopies) * net->pstride;
+        if (!net->d_tcp_words || net->tcp_tag > 0xffffffffu - (Lsteps + 2u)) {      // first use / the 32-bit tags would wrap
+            if (!net->d_tcp_words) BANN_CUDA(cudaMalloc(&net->d_tcp_words, tcp_words * sizeof(uint2)));
+            BANN_CUDA(cudaMemsetAsync(net->d_tcp_words, 0, tcp_words * sizeof(uint2), st));
+            net->tcp_tag = 0;
+        }
         BANN_CHECK(ensure_cap(&net->d_gsum, &net->gsum_cap, (size_t)net->pstride));
         TcpArgs t;
         memset(&t, 0, sizeof(t));
@@ -557,10 +563,13 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
         t.ynew_out = ynew_out;
         t.gsum = net->d_gsum;
         t.pstride = net->pstride;
-        t.bar = net->d_tcp_bar;
+        t.part = net->d_tcp_words;
+        t.sums = net->d_tcp_words + (size_t)2 * kTcpMaxGrid * net->pstride;
+        t.tag_base = net->tcp_tag;
+        net->tcp_tag += Lsteps + 1u;
         t.error_flag = net->d_errflag;
         bool launched = false;
-        BANN_CHECK(launch_hmc_persistent(net->descs[b], net->act, t, net->ctx->num_sms, st, &launched, net));
+        BANN_CHECK(launch_hmc_persistent(net->descs[b], net->act, t, net->ctx->num_sms, st, &launched));
         if (launched) {
             net->persistent_launches += 1;
             net->last_k1 = "k_hmc_persistent<H,S,D,ACT> (whole trajectory, operands resident in tensor / shared memory)";
@@ -941,7 +950,7 @@ static int check_error_flag(bann_net* net) {
     BANN_CUDA(cudaMemcpyAsync(&flag, net->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, net->ctx->stream));
     BANN_CUDA(cudaStreamSynchronize(net->ctx->stream));
     if (flag == 2) BANN_FAIL("peer-memory exchange timed out: a rank did not issue the matching call");
-    if (flag == 3) BANN_FAIL("persistent HMC kernel: grid barrier timed out");
+    if (flag == 3) BANN_FAIL("persistent HMC kernel: a CTA waited too long for the partial sums of the others");
     if (flag) BANN_FAIL("Invalid output weight summary statistic (negative or NaN), params.rs:49-54");
     return 0;
 }
@@ -1315,7 +1324,7 @@ void bann_net_destroy(bann_net* net) {
     cudaFree(net->d_ynew); cudaFree(net->d_part); cudaFree(net->d_gsum); cudaFree(net->d_rpart);
     cudaFree(net->d_ow_others); cudaFree(net->d_order); cudaFree(net->d_Tg); cudaFree(net->d_Yg); cudaFree(net->d_inj_grp); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
     cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj); cudaFree(net->d_numgrad);
-    cudaFree(net->d_tcp_bar); cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
+    cudaFree(net->d_tcp_words); cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
     for (int i = 0; i < 3; ++i) cudaFree(net->d_tcx[i]);
     if (net->h_pin_a) cudaFreeHost(net->h_pin_a);
     if (net->h_pin_b) cudaFreeHost(net->h_pin_b);

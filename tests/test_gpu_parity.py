@@ -274,7 +274,9 @@ def test_tensor_core_kernel_refuses_ineligible_launch(rb, ctx):
 @pytest.mark.parametrize("shape", [(500, [40, 21], 5, 5, 1),        # k1_tc
                                    (300, [20, 64], 5, 3, 2),        # k1_tc, two hidden layers (alternating-sign backward)
                                    (515, [128, 129], 5, 5, 1),      # k1_tcw (65..512 markers)
-                                   (150, [12, 7], 4, 2, 0)])        # summary layer reads the markers
+                                   (150, [12, 7], 4, 2, 0),         # summary layer reads the markers
+                                   (300, [600, 520], 16, 16, 2),    # k1_tcx (three passes; SiLU sends the pre-activation to the tail pass)
+                                   (260, [70, 9], 8, 8, 1)])        # k1_tcx, first-layer width 8
 def test_fwd_bwd_activations(rb, ctx, act, shape):
     """activation_functions.rs:23-45 through the shape-agnostic kernel AND the tensor-core kernels (K1_TENSOR fails loudly
     when a launch is not eligible: no silent fall-back to the slow kernel for ReLU / LeakyReLU / SiLU / identity nets)."""
@@ -290,6 +292,27 @@ def test_fwd_bwd_activations(rb, ctx, act, shape):
                 within(got["rss"], t64["rss"], t32["rss"])
                 within(got["d_rss"], t64["d_rss"], t32["d_rss"])
                 within(got["ldg"], t64["ldg"], t32["ldg"])
+    finally:
+        P.close()
+
+
+@pytest.mark.parametrize("act", ["tanh", "relu", "leaky_relu", "silu", "identity"])
+@pytest.mark.parametrize("shape", [(500, [40, 21], 5, 5, 1), (300, [20, 100], 5, 3, 2), (150, [12, 7], 2, 2, 0)])
+def test_fwd_bwd_activations_ffma(rb, ctx, act, shape):
+    """The FFMA kernel (`k1_small`, the path of byte-tile-only stores and of K1_FFMA) with every activation; the launch
+    must really be k1_small's, not the shape-agnostic kernel's."""
+    n, gs, h, s, d = shape
+    P = Problem(rb, ctx, "ridge_ard", n, gs, h, s, depth=d, act=act, seed=6)
+    try:
+        P.net.select_k1(P.net.K1_FFMA)
+        for b in range(len(gs)):
+            got = P.net.branch_fwd_bwd(b)
+            assert "k1_small" in P.net.last_k1_kernel()
+            t64, t32 = oracle_fwd_bwd(P, b, P.y, np.float64), oracle_fwd_bwd(P, b, P.y, np.float32)
+            within(got["yhat"], t64["yhat"], t32["yhat"])
+            within(got["rss"], t64["rss"], t32["rss"])
+            within(got["d_rss"], t64["d_rss"], t32["d_rss"])
+            within(got["ldg"], t64["ldg"], t32["ldg"])
     finally:
         P.close()
 
