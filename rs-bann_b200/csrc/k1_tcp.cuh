@@ -6,8 +6,8 @@
 // HBM and their expansion into tcgen05 operands (84 instructions per thread and super-tile).  19.2 us per leapfrog at
 // N = 100k, against 0.25 us of roofline time.
 //
-// Here the whole transition is ONE cooperative launch.  Every CTA owns one to four 256-row super-tiles of the branch for the
-// whole trajectory: the packed words are loaded and expanded ONCE -- the forward A operand stays in tensor memory, the
+// Here the whole transition is ONE cooperative launch.  Every CTA (two warpgroups, each running the FP32 tails of its own
+// tiles) owns up to four 256-row super-tiles of the branch for the whole trajectory: the packed words are loaded and expanded ONCE -- the forward A operand stays in tensor memory, the
 // backward A operand in shared memory -- and the targets stay in registers.  Per leapfrog step a CTA stages the three bf16 pieces
 // of W' = W0 / sd from ITS OWN copy of the parameters, issues the forward MMAs, runs the FP32 tail (TcTail, k1_tc.cuh), issues
 // the backward MMAs, publishes its partial sums; every CTA reduces a slice of the P + 1 values over all partials in a fixed
@@ -20,7 +20,7 @@
 // spins on the words it needs until their tag is this evaluation's.  A slot of evaluation e is overwritten at e + 2, which a
 // CTA reaches only after it has read every sum of e + 1, i.e. after every reducer has finished reading the partials of e + 1
 // (and of e before that) -- so no reader can still need the old word.  The all-reduce costs two L2 round trips per evaluation
-// instead of two grid barriers plus two read passes (measured 5.2 -> see profiles/r2_seq_rate.log).  Spinning relies on
+// instead of two grid barriers plus two read passes (profiles/r2_seq_rate.log; sleeping between polls only costs time).  Spinning relies on
 // the co-residency a cooperative launch guarantees; a wall-clock limit turns a lost CTA into an error flag instead of a hang.
 #pragma once
 #include <cooperative_groups.h>
@@ -70,7 +70,6 @@ struct TcpArgs {
     int* error_flag;
     unsigned long long* timing;   // NULL, or 8 phase accumulators (clock64 ticks of CTA timing_cta, BANN_DEBUG_TCP)
     uint32_t timing_cta;
-    uint32_t poll_sleep_ns;       // back-off between poll rounds
 };
 
 template <int H, int S, int D>
@@ -104,7 +103,7 @@ __device__ __forceinline__ uint2 tg_load(const uint2* p) {
 // NV words p[i * stride] (i < NV, i-th word wanted iff bit i of `want`), each awaited until its tag is `tag`.  All loads are in
 // flight together; only late words are re-read.  false: timed out (error flag 3)
 template <int NV>
-__device__ __forceinline__ bool tg_await(const uint2* p, size_t stride, uint32_t want, uint32_t tag, uint2 (&v)[NV], int* error_flag, uint32_t sleep_ns) {
+__device__ __forceinline__ bool tg_await(const uint2* p, size_t stride, uint32_t want, uint32_t tag, uint2 (&v)[NV], int* error_flag) {
     uint32_t pending = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -117,7 +116,6 @@ __device__ __forceinline__ bool tg_await(const uint2* p, size_t stride, uint32_t
     if (pending) {
         const long long t0 = clock64();
         while (pending) {
-            if (sleep_ns) __nanosleep(sleep_ns);
 #pragma unroll
             for (int i = 0; i < NV; ++i)
                 if (pending >> i & 1u) {
@@ -414,7 +412,7 @@ __global__ void __launch_bounds__(kTcpThreads, 1) k_hmc_persistent(TcpArgs a) {
                 if (lane + 32u * i < ncta) want |= 1u << i;
             for (uint32_t k = cta + warp * ncta; k <= P; k += (NT / 32) * ncta) {
                 uint2 v[kTcpMaxGrid / 32];
-                ok = tg_await(theirs + (size_t)lane * a.pstride + k, (size_t)32 * a.pstride, want, tag, v, a.error_flag, a.poll_sleep_ns) && ok;
+                ok = tg_await(theirs + (size_t)lane * a.pstride + k, (size_t)32 * a.pstride, want, tag, v, a.error_flag) && ok;
                 double s = 0.0;
 #pragma unroll
                 for (int i = 0; i < kTcpMaxGrid / 32; ++i)
@@ -435,7 +433,7 @@ __global__ void __launch_bounds__(kTcpThreads, 1) k_hmc_persistent(TcpArgs a) {
             for (int i = 0; i < NG; ++i)
                 if (tid + (uint32_t)NT * i <= P) want |= 1u << i;
             uint2 v[NG];
-            ok = tg_await(in + tid, NT, want, tag, v, a.error_flag, a.poll_sleep_ns) && ok;
+            ok = tg_await(in + tid, NT, want, tag, v, a.error_flag) && ok;
 #pragma unroll
             for (int i = 0; i < NG; ++i)
                 if (want >> i & 1u) s_sum[tid + (uint32_t)NT * i] = __uint_as_float(v[i].x);

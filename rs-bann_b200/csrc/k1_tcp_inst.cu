@@ -10,7 +10,7 @@ template <int H, int S, int D, int ACT>
 static int launch_tcp_one(const TcpArgs& a, uint32_t P, int num_sms, cudaStream_t st, bool* launched) {
     using TS = TcpShape<H, S, D>;
     auto kern = k_hmc_persistent<H, S, D, ACT>;
-    const bool dbg = getenv("BANN_DEBUG_TCP") != nullptr;
+    static const bool dbg = getenv("BANN_DEBUG_TCP") != nullptr;          // debugging aid: per-phase clocks of one CTA, read once
     // One CTA per SM is what a cooperative launch of a tensor-memory kernel is granted (k1_tcp.cuh): as few super-tiles per CTA
     // as make the grid fit the SM count; more than kTcpMaxTiles would not stay resident -> launch-per-step path.
     cudaError_t err = cudaErrorCooperativeLaunchTooLarge;
@@ -21,7 +21,6 @@ static int launch_tcp_one(const TcpArgs& a, uint32_t P, int num_sms, cudaStream_
         BANN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TcpArgs args = a;
         args.tpc = tpc;
-        if (const char* e = getenv("BANN_DEBUG_TCP_SLEEP")) args.poll_sleep_ns = (uint32_t)atoi(e);
         static unsigned long long* d_timing = nullptr;
         if (dbg) {
             if (!d_timing) { cudaMalloc(&d_timing, 8 * sizeof(unsigned long long)); }
