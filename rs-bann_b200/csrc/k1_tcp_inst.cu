@@ -56,11 +56,11 @@ static int launch_tcp_one(const TcpArgs& a, uint32_t P, int num_sms, cudaStream_
 }
 
 // The whole HMC trajectory of one branch in one cooperative launch.  *launched stays false when the branch / net is not
-// eligible (tensor-core store, <= 64 markers, 3 * W0 <= 16, an instantiated tanh architecture, few enough super-tiles to
+// eligible (tensor-core store, <= 64 markers, 3 * W0 <= 16, an instantiated architecture, few enough super-tiles to
 // keep resident); the caller then runs the launch-per-step path.
 int launch_hmc_persistent(const BranchDesc& d0, int act, TcpArgs& a, int num_sms, cudaStream_t st, bool* launched) {
     *launched = false;
-    if (act != BANN_TANH || !a.store_tc || d0.m > (uint32_t)kTcMaxMarkers || a.nst == 0) return 0;
+    if (!a.store_tc || d0.m > (uint32_t)kTcMaxMarkers || a.nst == 0) return 0;
     if (num_sms > kTcpMaxGrid || d0.P + 1 > (uint32_t)kTcpMaxValues) return 0;
     const int D = (int)d0.nl - 2;
     const int S = (int)d0.widths[d0.nl - 2];
@@ -70,7 +70,14 @@ int launch_hmc_persistent(const BranchDesc& d0, int act, TcpArgs& a, int num_sms
     a.ncb = (d0.m + 7) / 8;
 #define BANN_TRY_TCP(HH, SS, DD)                                                                                          \
     if (!*launched && H == HH && S == SS && D == DD) {                                                                   \
-        int rc = launch_tcp_one<HH, SS, DD, BANN_TANH>(a, d0.P, num_sms, st, launched);                      \
+        int rc;                                                                                                          \
+        switch (act) {                                                                                                   \
+            case BANN_TANH: rc = launch_tcp_one<HH, SS, DD, BANN_TANH>(a, d0.P, num_sms, st, launched); break;           \
+            case BANN_RELU: rc = launch_tcp_one<HH, SS, DD, BANN_RELU>(a, d0.P, num_sms, st, launched); break;           \
+            case BANN_LEAKY_RELU: rc = launch_tcp_one<HH, SS, DD, BANN_LEAKY_RELU>(a, d0.P, num_sms, st, launched); break; \
+            case BANN_SILU: rc = launch_tcp_one<HH, SS, DD, BANN_SILU>(a, d0.P, num_sms, st, launched); break;           \
+            default: rc = launch_tcp_one<HH, SS, DD, BANN_IDENTITY>(a, d0.P, num_sms, st, launched); break;              \
+        }                                                                                                                \
         if (rc) return rc;                                                                                               \
     }
     BANN_TRY_TCP(5, 5, 1)
@@ -78,6 +85,10 @@ int launch_hmc_persistent(const BranchDesc& d0, int act, TcpArgs& a, int num_sms
     BANN_TRY_TCP(3, 3, 1)
     BANN_TRY_TCP(4, 3, 1)
     BANN_TRY_TCP(4, 4, 1)
+    BANN_TRY_TCP(4, 3, 2)
+    BANN_TRY_TCP(5, 3, 2)
+    BANN_TRY_TCP(2, 2, 0)
+    BANN_TRY_TCP(5, 5, 2)
 #undef BANN_TRY_TCP
     return 0;
 }

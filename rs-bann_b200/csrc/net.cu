@@ -580,7 +580,7 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
             return 0;
         }
         if (net->hmc_path == BANN_HMC_PERSISTENT)
-            BANN_FAIL("persistent HMC kernel requested but the branch is not eligible (tanh, <= 64 markers, an instantiated architecture, <= 4 super-tiles per SM: ~150k rows)");
+            BANN_FAIL("persistent HMC kernel requested but the branch is not eligible (<= 64 markers, an instantiated architecture, <= 4 super-tiles per SM: ~150k rows)");
     }
     K1Launch k;
     k.list = R.list;

@@ -36,16 +36,32 @@ SHAPES = [  # n, group sizes, hidden, summary  (architectures the persistent ker
 ]
 
 
+MODES = (("izmailov", 1.0, 12), ("uniform", 0.002, 10), ("random", 0.01, 8))
+
+
 @pytest.mark.parametrize("model", MODELS)
 @pytest.mark.parametrize("shape", SHAPES)
 def test_persistent_transition_matches_oracle_and_launch_path(rb, ctx, model, shape):
     n, gs, h, s = shape
     P = Problem(rb, ctx, model, n, gs, h, s, seed=(sum(map(ord, model)) + n) % 997)
+    _compare_paths(rb, P, gs, MODES)
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky_relu", "silu", "identity"])
+@pytest.mark.parametrize("shape", [(600, [30, 11], 5, 5, 1), (515, [8, 40], 5, 3, 2), (300, [12, 7], 2, 2, 0), (400, [20], 5, 5, 2)])
+def test_persistent_other_activations_and_depths(rb, ctx, act, shape):
+    """activation_functions.rs:23-45 and the depth-0 / depth-2 architectures through the persistent kernel."""
+    n, gs, h, s, d = shape
+    P = Problem(rb, ctx, "ridge_ard", n, gs, h, s, depth=d, act=act, seed=n % 97)
+    _compare_paths(rb, P, gs, (("izmailov", 0.05, 8), ("uniform", 0.001, 10)))      # mild steps: identity / ReLU nets are unbounded
+
+
+def _compare_paths(rb, P, gs, modes):
     near_ties = 0
     try:
         rng = np.random.default_rng(5)
         for b in range(len(gs)):
-            for mode, factor, L in (("izmailov", 1.0, 12), ("uniform", 0.002, 10), ("random", 0.01, 8)):
+            for mode, factor, L in modes:
                 cfg = rb.MCMCCfg(hmc_step_size_factor=factor, hmc_integration_length=L, hmc_step_size_mode=mode)
                 ocfg = OCfg(hmc_step_size_factor=factor, hmc_integration_length=L, hmc_step_size_mode=mode)
                 Pn = P.cfgs[b].num_params
