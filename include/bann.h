@@ -184,6 +184,11 @@ int  bann_genotypes_decode_branch(bann_genotypes*, uint64_t b, int standardized,
 /* the same, decoded from the tensor-core store (bf16-subnormal layout, every branch <= 512 markers) */
 int  bann_genotypes_decode_branch_tc(bann_genotypes*, uint64_t b, int standardized, float* out);
 int  bann_genotypes_has_tc_store(bann_genotypes*);
+int  bann_genotypes_has_byte_store(bann_genotypes*);
+/* Frees the byte-tile store (the copy the FFMA / shape-agnostic kernels, the probe kernels and bann_genotypes_decode_branch
+ * read) when the tensor-core store exists; later calls that need it fail with a message.  No reference counterpart: the
+ * reference keeps one copy of the genotypes (io/bed.rs:431-446). */
+int  bann_genotypes_release_byte_store(bann_genotypes*);
 
 /* ---- model state: replaces Vec<BranchCfg> + from_cfg/to_cfg round trips
  * (net/net.rs:76-85, net/branch/branch_struct.rs:12-29, net/branch/branch_sampler.rs:155-171).

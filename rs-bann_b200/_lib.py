@@ -85,6 +85,8 @@ PROTOTYPES = {
     "bann_genotypes_decode_branch": (C.c_int, [_vp, _u64, C.c_int, _fp]),
     "bann_genotypes_decode_branch_tc": (C.c_int, [_vp, _u64, C.c_int, _fp]),
     "bann_genotypes_has_tc_store": (C.c_int, [_vp]),
+    "bann_genotypes_has_byte_store": (C.c_int, [_vp]),
+    "bann_genotypes_release_byte_store": (C.c_int, [_vp]),
     "bann_net_create": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(BranchLayout), _fp, C.POINTER(_vp)]),
     "bann_net_destroy": (None, [_vp]),
     "bann_net_branch_sizes": (C.c_int, [_vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),

@@ -240,6 +240,13 @@ class Genotypes:
     def has_tc_store(self) -> bool:
         return bool(lib.bann_genotypes_has_tc_store(self.h))
 
+    def has_byte_store(self) -> bool:
+        return bool(lib.bann_genotypes_has_byte_store(self.h))
+
+    def release_byte_store(self) -> None:
+        """Give back the byte-tile copy of the genotypes (read only by the FFMA / shape-agnostic / probe kernels)."""
+        check(lib.bann_genotypes_release_byte_store(self.h))
+
     def close(self):
         if self.h:
             lib.bann_genotypes_destroy(self.h)

@@ -476,6 +476,7 @@ int bann_genotypes_decode_branch(bann_genotypes* g, uint64_t b, int standardized
     d.m_pad4 = g->m_pad4[b];
     d.tile_off = g->tile_off[b];
     d.col_off = g->col_off[b];
+    if (!g->d_store) BANN_FAIL("the byte-tile store was released (bann_genotypes_release_byte_store): use bann_genotypes_decode_branch_tc");
     uint64_t total = g->n * d.m;
     float* dout = nullptr;
     BANN_CUDA(cudaMalloc(&dout, total * sizeof(float)));
@@ -515,5 +516,18 @@ int bann_genotypes_decode_branch_tc(bann_genotypes* g, uint64_t b, int standardi
 }
 
 int bann_genotypes_has_tc_store(bann_genotypes* g) { return g && g->d_store_tc ? 1 : 0; }
+int bann_genotypes_has_byte_store(bann_genotypes* g) { return g && g->d_store ? 1 : 0; }
+
+// The byte-tile store is read by the FFMA / shape-agnostic kernels, the probe kernels (activations, effect sizes) and
+// bann_genotypes_decode_branch only; where the tensor-core store exists a caller that runs the tensor-core kernels can give its
+// memory back (13 GB of 27 at BASELINE configs[2]).  Anything that still needs it afterwards fails with a message.
+int bann_genotypes_release_byte_store(bann_genotypes* g) {
+    if (!g) BANN_FAIL("NULL argument");
+    if (!g->d_store_tc) BANN_FAIL("no tensor-core store (a branch has more than 2048 markers): the byte-tile store is the only copy of the genotypes");
+    BANN_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    BANN_CUDA(cudaFree(g->d_store));
+    g->d_store = nullptr;
+    return 0;
+}
 
 }  // extern "C"

@@ -263,6 +263,8 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
         if (!launched && net->k1_mode == BANN_K1_TENSOR)
             BANN_FAIL("tensor-core K1 requested but the launch is not eligible (homogeneous architecture, widths in the instantiated set)");
     }
+    if (!launched && !g->d_store)
+        BANN_FAIL("the byte-tile store was released (bann_genotypes_release_byte_store) and no tensor-core kernel is eligible for this launch");
     if (!launched && net->k1_mode != BANN_K1_GENERIC) {
         int r = launch_k1_small(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
                                 &nchunk, L.fwd_only ? nullptr : &part, net);
@@ -1959,6 +1961,7 @@ static int run_probe(bann_net* net, uint64_t b, bann_genotypes* other, float* ac
     cudaStream_t st = net->ctx->stream;
     bann_genotypes* g = other ? other : net->gen;
     if (g->num_branches != net->B || g->m_b[b] != net->descs[b].m) BANN_FAIL("genotypes do not match the net's grouping");
+    if (!g->d_store) BANN_FAIL("the byte-tile store was released (bann_genotypes_release_byte_store): the diagnostic kernels read it");
     if (pop_host && sharded(net)) BANN_FAIL("population effect sizes on sharded rows: sum the per-rank effect sizes on the host");
     BranchDesc d = net->descs[b];
     d.tile_off = g->tile_off[b];

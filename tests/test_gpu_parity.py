@@ -270,6 +270,32 @@ def test_tensor_core_kernel_refuses_ineligible_launch(rb, ctx):
         P.close()
 
 
+def test_release_byte_store(rb, ctx):
+    """The byte-tile copy of the genotypes can be given back where the tensor-core store exists: the tensor-core kernels keep
+    producing the same numbers, everything that reads the released copy fails with a message (no silent fallback)."""
+    P = Problem(rb, ctx, "ridge_ard", 700, [40, 21], 5, 5, seed=4)
+    try:
+        assert P.gen.has_tc_store() and P.gen.has_byte_store()
+        before = [P.net.branch_fwd_bwd(b) for b in range(2)]
+        P.gen.release_byte_store()
+        assert not P.gen.has_byte_store()
+        for b in range(2):
+            got = P.net.branch_fwd_bwd(b)
+            assert np.array_equal(got["ldg"], before[b]["ldg"]) and np.array_equal(got["yhat"], before[b]["yhat"])
+            assert "k1_tc" in P.net.last_k1_kernel()
+        assert np.array_equal(P.gen.x_group_tc(0, standardized=False), obed.decode_columns(P.payload, P.n, P.groups[0]))
+        with pytest.raises(RuntimeError, match="released"):
+            P.gen.x_group(0, standardized=False)
+        P.net.select_k1(P.net.K1_GENERIC)
+        with pytest.raises(RuntimeError, match="released"):
+            P.net.branch_fwd_bwd(0)
+        P.net.select_k1(P.net.K1_AUTO)
+        with pytest.raises(RuntimeError, match="released"):
+            P.net.branch_activations(0)
+    finally:
+        P.close()
+
+
 @pytest.mark.parametrize("act", ["relu", "leaky_relu", "silu", "identity"])
 @pytest.mark.parametrize("shape", [(500, [40, 21], 5, 5, 1),        # k1_tc
                                    (300, [20, 64], 5, 3, 2),        # k1_tc, two hidden layers (alternating-sign backward)
