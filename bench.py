@@ -154,7 +154,7 @@ def cpu_sample_branches(wl):
     return int(min(256, max(4, round(6.4e8 / (wl["n"] * wl["per"])))))
 
 
-def cpu_reference_rate(wl, leapfrogs=4):
+def cpu_reference_rate(wl, leapfrogs=12):
     """Times the oracle's C restatement of the reference's op sequence (host decode + dense f32 + 2 forwards and 1 backward
     per leapfrog) on a FIXED sample: all N rows, cpu_sample_branches(wl) branches, `leapfrogs` leapfrog steps each, every
     allowed host thread (pinned explicitly).  The same sample serves `cpu_baseline` and `--impl reference`; the full-network
@@ -175,7 +175,7 @@ def cpu_reference_rate(wl, leapfrogs=4):
     ins = [m] + widths[:-1]
     P = sum(i * o for i, o in zip(ins, widths)) + sum(widths[:-1])
     L_ref = 100.0                       # decode happens once per visit of L = 100 leapfrogs (mcmc_cfg.rs:38)
-    t_decode, t_leap = 0.0, 0.0
+    t_decode, t_leap, t_wall = 0.0, 0.0, 0.0
     for nbr in range(K + 1):            # branch 0 = warm-up (thread pool, page faults), not timed
         cols = np.arange((nbr % 4) * m, (nbr % 4 + 1) * m)
         theta = rng.normal(0, np.sqrt(1.0 / m), size=P).astype(np.float32)
@@ -188,6 +188,7 @@ def cpu_reference_rate(wl, leapfrogs=4):
         cp.leapfrog(X, y, n, m, widths, "tanh", False, wl["model"] == "std_normal", theta, mom, eps, lam, 2.0, leapfrogs)
         t2 = time.perf_counter()
         if nbr > 0:
+            t_wall += t2 - t0
             t_decode += t1 - t0
             t_leap += (t2 - t1) / (leapfrogs + 0.5)   # + initial gradient evaluation (half a leapfrog)
     per_branch_leapfrog = t_leap / K + (t_decode / K) / L_ref
@@ -196,7 +197,7 @@ def cpu_reference_rate(wl, leapfrogs=4):
               f"{cp.threads} OpenMP threads (nproc {os.cpu_count()}); host decode per visit amortised over L=100; "
               f"extrapolated x{B / K:.1f} to B={B} branches")
     return dict(value=steps_per_s, unit=UNIT, cores=cp.threads, kind="port", sample=sample,
-                sample_branches=K, extrapolation_factor=B / K, sample_seconds=t_leap + t_decode), per_branch_leapfrog
+                sample_branches=K, extrapolation_factor=B / K, sample_seconds=t_wall), per_branch_leapfrog
 
 
 def run_reference(args, wl):
