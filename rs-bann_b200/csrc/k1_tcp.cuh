@@ -16,12 +16,19 @@
 // deterministic, nothing is broadcast.  CTA 0 writes the branch state and the final parameters.
 //
 // There is no grid barrier.  Every published value travels as ONE 64-bit word {float bits, tag}, tag = launch base + evaluation
-// index + 1 (st / ld.relaxed.gpu.b64: single-copy atomic), in a buffer double-buffered by the evaluation's parity; a reader
-// spins on the words it needs until their tag is this evaluation's.  A slot of evaluation e is overwritten at e + 2, which a
-// CTA reaches only after it has read every sum of e + 1, i.e. after every reducer has finished reading the partials of e + 1
-// (and of e before that) -- so no reader can still need the old word.  The all-reduce costs two L2 round trips per evaluation
-// instead of two grid barriers plus two read passes (profiles/r2_seq_rate.log; sleeping between polls only costs time).  Spinning relies on
-// the co-residency a cooperative launch guarantees; a wall-clock limit turns a lost CTA into an error flag instead of a hang.
+// index + 1 (st / ld.relaxed b64: single-copy atomic), in a buffer of four slots (parity of the launch count x parity of the
+// evaluation); a reader spins on the words it needs until their tag is this evaluation's.  A slot of evaluation e is
+// overwritten at e + 2, which a CTA reaches only after it has read every sum of e + 1, i.e. after every reducer has finished
+// reading the partials of e + 1 (and of e before that) -- so no reader can still need the old word; the launch parity keeps a
+// rank that already runs the next transition from touching what a slower peer still reads of this one.  The all-reduce costs
+// two L2 round trips per evaluation instead of two grid barriers plus two read passes (profiles/r2_seq_rate.log; sleeping
+// between polls only costs time).
+// With the rows sharded over GPUs the same kernel runs on every rank: the reducers push the rank-level sums as tagged words
+// into every peer's table over NVLink, the gather adds the world entries in rank order -- compute and collective in one kernel,
+// no host, no separate exchange launch; every rank takes the same decisions because every rank adds the same numbers in
+// the same order.
+// Spinning relies on the co-residency a cooperative launch guarantees; a clock limit turns a lost CTA or rank into an error
+// flag instead of a hang.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -62,9 +69,14 @@ struct TcpArgs {
     float* prev_out;           // own prediction at the first evaluation, may be NULL
     float* ynew_out;           // own prediction at the last evaluation, may be NULL
     // scratch
-    uint2* part;               // [2][gridDim.x][pstride] tagged partial sums {float bits, tag}
-    uint2* sums;               // [2][kTcpSumCopies][pstride] tagged reduced sums (copies: a CTA polls copy blockIdx.x % kTcpSumCopies)
+    uint2* part;               // [4][gridDim.x][pstride] tagged partial sums {float bits, tag}
+    uint2* sums;               // [4][kTcpSumCopies][pstride] tagged reduced sums (copies: a CTA polls copy blockIdx.x % kTcpSumCopies)
+    uint32_t launch_par;       // parity of the launch count (slot = 2 launch_par + evaluation parity)
     uint32_t tag_base;         // tags of this launch are tag_base + 1 .. tag_base + L + 1; every older tag in the buffers is smaller
+    // rows sharded over ranks (world > 1): the rank-level sums go to EVERY rank's [4][8][pstride] table over NVLink peer memory
+    // (slot [parity][source rank]), each rank adds the world entries in rank order -- bit-identical everywhere
+    uint32_t world, rank;
+    uint2* rank_sums[8];
     float* gsum;               // [pstride]: the reduced sums of the last evaluation (rss at [P]), written by CTA 0 at the end
     uint32_t pstride;
     int* error_flag;
@@ -100,16 +112,26 @@ __device__ __forceinline__ uint2 tg_load(const uint2* p) {
     asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
 }
+// the same across GPUs: the word is written by a peer over NVLink into this GPU's memory
+__device__ __forceinline__ void tg_store_sys(uint2* p, float v, uint32_t tag) {
+    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)tag << 32);
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ uint2 tg_load_sys(const uint2* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+}
 // NV words p[i * stride] (i < NV, i-th word wanted iff bit i of `want`), each awaited until its tag is `tag`.  All loads are in
 // flight together; only late words are re-read.  false: timed out (error flag 3)
-template <int NV>
+template <int NV, bool SYS = false>
 __device__ __forceinline__ bool tg_await(const uint2* p, size_t stride, uint32_t want, uint32_t tag, uint2 (&v)[NV], int* error_flag) {
     uint32_t pending = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         v[i] = make_uint2(0u, tag);
         if (want >> i & 1u) {
-            v[i] = tg_load(p + i * stride);
+            v[i] = SYS ? tg_load_sys(p + i * stride) : tg_load(p + i * stride);
             if (v[i].y != tag) pending |= 1u << i;
         }
     }
@@ -119,7 +141,7 @@ __device__ __forceinline__ bool tg_await(const uint2* p, size_t stride, uint32_t
 #pragma unroll
             for (int i = 0; i < NV; ++i)
                 if (pending >> i & 1u) {
-                    v[i] = tg_load(p + i * stride);
+                    v[i] = SYS ? tg_load_sys(p + i * stride) : tg_load(p + i * stride);
                     if (v[i].y == tag) pending &= ~(1u << i);
                 }
             if (pending && clock64() - t0 > kTcpTimeoutClk) {
@@ -394,7 +416,7 @@ __global__ void __launch_bounds__(kTcpThreads, 1) k_hmc_persistent(TcpArgs a) {
         }
         umma::fence_before_sync();
         __syncthreads();
-        const uint32_t tag = a.tag_base + ev + 1u, par = ev & 1u;
+        const uint32_t tag = a.tag_base + ev + 1u, par = (a.launch_par << 1) | (ev & 1u);   // four slots: a rank that is already in the next transition cannot overwrite what a slower peer still reads
         {
             uint2* mine = a.part + ((size_t)par * ncta + cta) * a.pstride;
             for (uint32_t k = tid; k <= P; k += NT) tg_store(mine + k, s_part[k], tag);
@@ -420,12 +442,27 @@ __global__ void __launch_bounds__(kTcpThreads, 1) k_hmc_persistent(TcpArgs a) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 const bool all_ok = __all_sync(0xffffffffu, ok);
-                if (lane < (uint32_t)kTcpSumCopies && all_ok) tg_store(out + k, (float)s, tag);
+                if (a.world > 1) {          // this rank's sum -> slot [par][rank] of every rank's table (its own included)
+                    if (lane < a.world && all_ok) tg_store_sys(a.rank_sums[lane] + ((size_t)par * 8 + a.rank) * a.pstride + k, (float)s, tag);
+                } else if (lane < (uint32_t)kTcpSumCopies && all_ok) tg_store(out + k, (float)s, tag);
             }
         }
         lap(5);      // slice reduction
         // ---- every CTA gathers all the sums
-        {
+        if (a.world > 1) {
+            // the world rank-level sums of every value, from this rank's own table, added in rank order
+            const uint2* in = a.rank_sums[a.rank] + (size_t)par * 8 * a.pstride;
+            const uint32_t want = (1u << a.world) - 1u;
+            for (uint32_t k = tid; k <= P; k += NT) {
+                uint2 v[8];
+                ok = tg_await<8, true>(in + k, a.pstride, want, tag, v, a.error_flag) && ok;
+                float s = __uint_as_float(v[0].x);
+#pragma unroll
+                for (int r = 1; r < 8; ++r)
+                    if ((uint32_t)r < a.world) s += __uint_as_float(v[r].x);
+                s_sum[k] = s;
+            }
+        } else {
             const uint2* in = a.sums + ((size_t)par * kTcpSumCopies + (cta & (kTcpSumCopies - 1))) * a.pstride;
             constexpr int NG = (kTcpMaxValues + NT - 1) / NT;
             uint32_t want = 0;

@@ -66,8 +66,9 @@ struct bann_net {
     int k1_mode = BANN_K1_AUTO;   // which K1 kernel launch_k1 may pick (bann_net_select_k1)
     const char* last_k1 = "none"; // kernel family the last fused forward+backward launch used (bann_net_last_k1_kernel)
     int hmc_path = BANN_HMC_AUTO; // per-branch transitions: persistent cooperative kernel where eligible / launch per step (bann_net_select_hmc_path)
-    uint2* d_tcp_words = nullptr;        // tagged exchange words of the persistent kernel: [2][kTcpMaxGrid][pstride] partials, [2][kTcpSumCopies][pstride] sums
-    uint32_t tcp_tag = 0;                // every tag in d_tcp_words is <= tcp_tag
+    uint2* d_tcp_words = nullptr;        // tagged exchange words of the persistent kernel: [4][kTcpMaxGrid][pstride] partials, [4][kTcpSumCopies][pstride] sums
+    uint32_t tcp_tag = 0;                // every tag in d_tcp_words (and in the ranks' tables behind the bulk-exchange region) is <= tcp_tag
+    uint32_t tcp_launches = 0;           // persistent launches so far (its parity selects the slot pair)
     uint64_t persistent_launches = 0;
     float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient (callers with pageable buffers)
     float *d_dense_in = nullptr, *d_dense_out = nullptr;   // dense host-facing layouts of the parameters / gradients + rss
@@ -138,7 +139,9 @@ static int need_comm(bann_net* net) {
 static bool sharded(const bann_net* net) { return net->ctx->world > 1; }
 
 // ---- bulk exchange (comm.cuh): descriptor of the NEXT exchange, all-reduce(sum) in place, all-gather of 1/world slices
-static size_t xg_region_bytes(uint64_t cap) { return 256 + (size_t)4 * cap * sizeof(float); }
+// [flags | in[2][cap] | out[2][cap]] floats, then the rank-level sums table of the persistent HMC kernel: [4][8][pstride] tagged words
+static size_t xg_table_offset(uint64_t cap) { return 256 + (size_t)4 * cap * sizeof(float); }
+static size_t xg_region_bytes(uint64_t cap, uint32_t pstride) { return xg_table_offset(cap) + (size_t)4 * 8 * pstride * sizeof(uint2); }
 static XgComm xg_next(bann_net* net) {
     XgComm c;
     memset(&c, 0, sizeof(c));
@@ -528,13 +531,18 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
     cudaStream_t st = net->ctx->stream;
     BANN_CHECK(hmc_init_and_first_eval(net, cfg, R, 0));
     const uint32_t Lsteps = cfg->hmc_integration_length;
-    // ---- one branch, one GPU, no per-step recording: the whole trajectory in ONE cooperative launch (k1_tcp.cuh) where the
-    //      branch is eligible; otherwise (and for A/B tests: bann_net_select_hmc_path) three launches per leapfrog step
-    if (R.nlist == 1 && R.single_branch >= 0 && !sharded(net) && !R.traj_params && !R.traj_h && !cfg->num_grad && !cfg->num_grad_traj
+    // ---- one branch, no per-step recording: the whole trajectory in ONE cooperative launch (k1_tcp.cuh) where the branch is
+    //      eligible; otherwise (and for A/B tests: bann_net_select_hmc_path) three launches per leapfrog step.  On sharded rows
+    //      every rank runs the kernel on its shard and the cross-rank sums travel inside it (eligibility must not depend on the
+    //      rank: it is decided on the largest shard)
+    const uint64_t max_shard = (net->gen->n_total + net->ctx->world - 1) / net->ctx->world;
+    if (R.nlist == 1 && R.single_branch >= 0 && (!sharded(net) || net->xg_connected)
+        && (max_shard + kTcRows - 1) / kTcRows <= (uint64_t)net->ctx->num_sms * kTcpMaxTiles && !R.traj_params && !R.traj_h && !cfg->num_grad && !cfg->num_grad_traj
         && net->hmc_path != BANN_HMC_LAUNCHES && net->k1_mode == BANN_K1_AUTO
         && (R.first_mode == TGT_RESID_PLUS_PRED || R.first_mode == TGT_SHARED)) {
         const uint32_t b = (uint32_t)R.single_branch;
-        const size_t tcp_words = (size_t)(2 * kTcpMaxGrid + 2 * kTcpSumCopies) * net->pstride;
+        const size_t tcp_words = (size_t)(4 * kTcpMaxGrid + 4 * kTcpSumCopies) * net->pstride;
+        if (sharded(net) && net->tcp_tag > 0xffffffffu - (Lsteps + 2u)) BANN_FAIL("persistent HMC kernel on sharded rows: 2^32 evaluations reached, re-create the net");
         if (!net->d_tcp_words || net->tcp_tag > 0xffffffffu - (Lsteps + 2u)) {      // first use / the 32-bit tags would wrap
             if (!net->d_tcp_words) BANN_CUDA(cudaMalloc(&net->d_tcp_words, tcp_words * sizeof(uint2)));
             BANN_CUDA(cudaMemsetAsync(net->d_tcp_words, 0, tcp_words * sizeof(uint2), st));
@@ -566,13 +574,20 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
         t.gsum = net->d_gsum;
         t.pstride = net->pstride;
         t.part = net->d_tcp_words;
-        t.sums = net->d_tcp_words + (size_t)2 * kTcpMaxGrid * net->pstride;
+        t.sums = net->d_tcp_words + (size_t)4 * kTcpMaxGrid * net->pstride;
         t.tag_base = net->tcp_tag;
-        net->tcp_tag += Lsteps + 1u;
+        t.launch_par = net->tcp_launches & 1u;
+        t.world = (uint32_t)net->ctx->world;
+        t.rank = (uint32_t)net->ctx->rank;
+        if (sharded(net))
+            for (int r = 0; r < net->ctx->world; ++r)
+                t.rank_sums[r] = reinterpret_cast<uint2*>(net->xg_region[r] + xg_table_offset(net->xg_cap));
         t.error_flag = net->d_errflag;
         bool launched = false;
         BANN_CHECK(launch_hmc_persistent(net->descs[b], net->act, t, net->ctx->num_sms, st, &launched));
         if (launched) {
+            net->tcp_tag += Lsteps + 1u;              // (same sequence on every rank: the tags must agree)
+            net->tcp_launches += 1;
             net->persistent_launches += 1;
             net->last_k1 = "k_hmc_persistent<H,S,D,ACT> (whole trajectory, operands resident in tensor / shared memory)";
             k_accept<<<R.nlist, 256, 0, st>>>(net->d_descs, R.list, net->d_states, net->d_theta, net->d_theta0, R.inj_u, R.seed,
@@ -2148,8 +2163,8 @@ int bann_net_comm_handle(bann_net* net, uint8_t* out) {
     uint8_t*& mine = net->xg_region[net->ctx->rank];
     if (!mine) {
         net->xg_cap = ((std::max<uint64_t>((uint64_t)net->B * net->pstride, net->sum_params + net->B) + 3) & ~3ull) + 4;
-        BANN_CUDA(cudaMalloc(&mine, xg_region_bytes(net->xg_cap)));
-        BANN_CUDA(cudaMemset(mine, 0, xg_region_bytes(net->xg_cap)));   // flags 0 = "nothing yet"
+        BANN_CUDA(cudaMalloc(&mine, xg_region_bytes(net->xg_cap, net->pstride)));
+        BANN_CUDA(cudaMemset(mine, 0, xg_region_bytes(net->xg_cap, net->pstride)));   // flags / tags 0 = "nothing yet"
         BANN_CUDA(cudaMalloc(&net->d_xg_counter, sizeof(unsigned int)));
         BANN_CUDA(cudaMemset(net->d_xg_counter, 0, sizeof(unsigned int)));
         BANN_CHECK(ensure_cap(&net->d_gsum, &net->gsum_cap, (size_t)net->B * net->pstride + 4));

@@ -1,0 +1,6 @@
+set -u
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29641 tests/multirank_worker.py --rate > gpurun_out/r2c13_worker.log 2>&1
+echo "worker exit $?" >> gpurun_out/r2c13_worker.log
+grep -E "MULTIRANK|exit|Error|error" gpurun_out/r2c13_worker.log | cut -c1-3000 | tr '|' '\n'

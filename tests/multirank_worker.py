@@ -33,16 +33,21 @@ def main():
     # (model, sweep kwargs): sequential-exact sweeps (push exchange inside KR), the same with a tight Hamiltonian-error bound so
     # that trajectories are rejected EARLY (every epoch the host hands out must still be exchanged, comm.cuh), and block-Jacobi
     # sweeps in groups of 3 (bulk exchange: reduce-scatter + all-gather over peer memory)
+    # hmc_path: 0 = the persistent per-branch kernel where eligible (its cross-rank sums travel inside the kernel), 1 = a launch per step
     cases = [("ridge_ard", dict()), ("lasso_base", dict()),
              ("ridge_ard", dict(max_h_err=0.05, factor=1.5)),
+             ("ridge_ard", dict(hmc_path=1)), ("ridge_ard", dict(hmc_path=1, max_h_err=0.05, factor=1.5)),
              ("ridge_ard", dict(group_size=3)), ("std_normal", dict(group_size=4))]
-    for model, kw in cases:
+    for model, kw_all in cases:
+        kw = {k: v for k, v in kw_all.items() if k != "hmc_path"}
         P = build_problem(model, 3000, [20, 50, 9, 33], 5, 5, seed=11)
         B = len(P["groups"])
         r0, r1 = rb.row_shard(P["n"], rank, world)
         gen, net = make_net(rb, ctx, P, r0, r1)
         rb.connect_net(net)
+        net.select_hmc_path(kw_all.get("hmc_path", 0))
         out = run_chain(net, rb, P["y"][r0:r1], B, sweeps=2, L=8, **kw)
+        n_persistent = net.persistent_launches()
         # Net.gradient on sharded rows: every rank passes only its 1 / world slice of the parameters and receives its slice
         pv_all = out["pv"].copy()
         plo, phi, olo, ohi = net.gradient_slice()
@@ -83,8 +88,10 @@ def main():
                     and abs(s["lpd"] - s1["lpd"]) < 5e-4 * abs(s1["lpd"]) and grad_ok)
             if "max_h_err" in kw:
                 good = good and s["num_early_rejected"] > 0        # the case exists to exercise early rejections
+            if kw.get("group_size", 1) == 1:                       # sequential sweeps: every visit through the path asked for
+                good = good and n_persistent == (0 if kw_all.get("hmc_path", 0) == 1 else 2 * B)
             ok = ok and good
-            msgs.append(f"{model} {kw}: replicas_identical={same} accepted {s['num_accepted']}/{s['num_samples']} early "
+            msgs.append(f"{model} {kw_all}: persistent launches {n_persistent}, replicas_identical={same} accepted {s['num_accepted']}/{s['num_samples']} early "
                         f"{s['num_early_rejected']} (single rank {s1['num_accepted']}, {s1['num_early_rejected']}) "
                         f"max|dtheta|={np.max(np.abs(out['pv'] - ref['pv'])):.2e} lpd {s['lpd']:.4f} vs {s1['lpd']:.4f} "
                         f"sliced_gradient_ok={grad_ok}")
@@ -109,19 +116,24 @@ def main():
         net.set_globals(2.0, 0.05, float(np.sum(w_out ** 2)), B * 5)
         net.set_targets(np.random.default_rng(1).normal(size=n).astype(np.float32)[r0:r1])
         net.init_residual()
+        rb.connect_net(net)
         cfg = rb.MCMCCfg(hmc_step_size_factor=0.1, hmc_integration_length=L, hmc_max_hamiltonian_error=1e30)
-        net.sweep(cfg, np.arange(B), seed=1)
-        ctx.sync()
-        dist.barrier()
-        t0 = time.perf_counter()
-        st = net.sweep(cfg, np.random.default_rng(2).permutation(B), seed=2)
-        ctx.sync()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dt = float(dt[0])
-        if rank == 0:
-            msgs.append(f"rate: world={world} n={n} B={B} m_b={per} L={L}: {B / dt:.1f} visits/s, "
-                        f"{dt / B / L * 1e6:.1f} us per leapfrog, accepted {st['num_accepted']}/{st['num_samples']}")
+        for path, name in ((1, "launch per step"), (0, "persistent kernel")):
+            net.select_hmc_path(path)
+            net.sweep(cfg, np.arange(B), seed=1)
+            ctx.sync()
+            dist.barrier()
+            before = net.persistent_launches()
+            t0 = time.perf_counter()
+            st = net.sweep(cfg, np.random.default_rng(2).permutation(B), seed=2)
+            ctx.sync()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt[0])
+            if rank == 0:
+                msgs.append(f"rate ({name}, {net.persistent_launches() - before} persistent launches): world={world} n={n} B={B} "
+                            f"m_b={per} L={L}: {B / dt:.1f} visits/s, {dt / B / L * 1e6:.1f} us per leapfrog, "
+                            f"accepted {st['num_accepted']}/{st['num_samples']}")
         net.close(); gen.close()
     ctx.close()
     if rank == 0:
