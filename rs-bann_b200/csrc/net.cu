@@ -604,8 +604,10 @@ static int run_hmc(bann_net* net, const bann_mcmc_cfg* cfg, const HmcRun& R, flo
     k.nlist = R.nlist;
     k.single_branch = R.single_branch;
     k.states = net->d_states;
-    k.xr = sharded(net) && R.nlist == 1 && R.list != nullptr;   // sequential schedule: latency-critical push exchange inside KR
-    k.xg = sharded(net) && !k.xr && R.xg;                        // launches over many branches: bulk exchange after KR
+    // sequential schedule and small groups (up to kXrCap values per step: 112 branches of [5,5,1] x 50 markers): the latency-critical
+    // push exchange inside KR; launches over more branches: the bulk exchange (three kernels) after KR
+    k.xr = sharded(net) && R.list != nullptr && (R.nlist == 1 || (R.xg && (size_t)R.nlist * net->pstride <= kXrCap));
+    k.xg = sharded(net) && !k.xr && R.xg;
     k.target_mode = R.first_mode;
     k.tgt = R.tgt;
     k.resid = resid;
