@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sequential", action="store_true", help="skip the informational timing of the sequential schedule")
     ap.add_argument("--generic", action="store_true", help="force the shape-agnostic kernel (debug)")
     ap.add_argument("--k1", default="auto", choices=["auto", "tensor", "ffma", "generic"],
                     help="which fused forward+backward kernel may run (auto: tensor-core where eligible)")
@@ -387,6 +388,39 @@ def main():
     k1_name = net.last_k1_kernel()
     traffic = NCU_TRAFFIC.get(args.workload) if (world == 1 and k1_name.startswith("k1_tc<")) else None
 
+    # ---- informational: the reference's own schedule (Net::train, net.rs:258-334: one branch at a time, Gibbs draws + one HMC
+    #      transition of L = 100 leapfrog steps per visit) on the same net, 64 visits after 64 warm-up visits
+    seq = None
+    if not args.no_sequential:
+        if world > 1:
+            rb.connect_ranks(ctx)
+        pv0, qv0 = default_params(wl)
+        net.set_all_params(pv0, qv0)
+        ins = [per] + widths[:-1]
+        nw = sum(i * o for i, o in zip(ins, widths))
+        w_out = pv0.reshape(B, -1)[:, nw - widths[-2]:nw]
+        net.set_globals(2.0, 0.05, float(np.sum(w_out.astype(np.float64) ** 2)), B * widths[-2])   # architectures.rs:209-235
+        net.set_targets(y_local)
+        net.init_residual()
+        nv = min(B, 64)
+        scfg = rb.MCMCCfg(hmc_step_size_factor=0.1, hmc_integration_length=100, hmc_max_hamiltonian_error=1e30)
+        net.sweep(scfg, np.arange(nv), seed=1)
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        before = net.persistent_launches()
+        t0 = time.perf_counter()
+        sst = net.sweep(scfg, np.random.default_rng(2).permutation(nv), seed=2)
+        ctx.sync()
+        ts = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ts = float(ts[0])
+        seq = dict(visits_per_s=nv / ts, us_per_leapfrog=ts / nv / 100 * 1e6, branch_leapfrogs_per_s=nv * 100 / ts, visits=nv,
+                   integration_length=100, transitions_through_persistent_kernel=int(net.persistent_launches() - before),
+                   accepted=int(sst["num_accepted"]), kernel=net.last_k1_kernel(),
+                   note="sequential-exact schedule (bann_sweep, group size 1), wall clock around the sweep, not part of `value`")
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -399,7 +433,7 @@ def main():
                                 l2="working set (packed genotypes + per-branch targets) >> 126 MB L2, no flush needed",
                                 init="reference default init, seed 42; bias precisions 1.0",
                                 branch_leapfrogs_per_step=B, active_branches=active, byte_tile_store_released=byte_store_released),
-                    k1_ms=k1_ms, wall_s=t_wall, gpu_launches=int(launches) * world,
+                    k1_ms=k1_ms, wall_s=t_wall, gpu_launches=int(launches) * world, sequential_schedule=seq,
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                                   traffic=traffic["bytes"] if traffic else None,
                                   traffic_source=traffic["source"] if traffic else None,
