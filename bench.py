@@ -42,6 +42,8 @@ WORKLOADS = {
                    n=12544, B=10000, per=50, widths=[5, 5, 1], model="ridge_ard"),
     "cfg3s": dict(desc="configs[2] at 1/10 of the branches (smoke size)", n=100000, B=1000, per=50, widths=[5, 5, 1],
                   model="ridge_ard"),
+    "cfg3s_321": dict(desc="cfg3s with widths [3,2,1]: no kernel is instantiated for it, runs zero-padded on the [5,5,1] kernel",
+                      n=100000, B=1000, per=50, widths=[3, 2, 1], model="ridge_ard"),
 }
 METRIC = "full_network_hmc_leapfrog_steps_per_sec"
 UNIT = "steps/s"

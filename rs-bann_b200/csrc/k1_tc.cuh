@@ -791,6 +791,7 @@ int launch_k1_tc(const std::vector<BranchDesc>& descs, int single_branch, K1Args
     BANN_TRY_TC(3, 3, 1)
     BANN_TRY_TC(4, 4, 1)
     BANN_TRY_TC(5, 5, 2)
+    BANN_TRY_TC(5, 5, 0)
 #undef BANN_TRY_TC
     return 0;
 }

@@ -69,6 +69,17 @@ struct bann_net {
     uint2* d_tcp_words = nullptr;        // tagged exchange words of the persistent kernel: [4][kTcpMaxGrid][pstride] partials, [4][kTcpSumCopies][pstride] sums
     uint32_t tcp_tag = 0;                // every tag in d_tcp_words (and in the ranks' tables behind the bulk-exchange region) is <= tcp_tag
     uint32_t tcp_launches = 0;           // persistent launches so far (its parity selects the slot pair)
+    // zero-padded architectures: widths no tensor-core kernel is instantiated for run through the next larger instantiated
+    // architecture on a padded copy of the parameters (padded units have zero weights and biases: activation 0, delta 0)
+    bool pad_built = false, pad_active = false;
+    std::vector<BranchDesc> pad_descs;   // per branch: the padded description, or the real one when there is no target
+    std::vector<uint8_t> pad_ok;
+    BranchDesc* d_pad_descs = nullptr;
+    float* d_pad_theta = nullptr;
+    uint32_t pad_pstride = 0;
+    float* d_pad_gsum = nullptr; size_t pad_gsum_cap = 0;
+    float* d_pad_part = nullptr; size_t pad_part_cap = 0;
+    uint64_t padded_launches = 0;
     uint64_t persistent_launches = 0;
     float *h_pin_a = nullptr, *h_pin_b = nullptr;  // pinned staging for bann_net_gradient (callers with pageable buffers)
     float *d_dense_in = nullptr, *d_dense_out = nullptr;   // dense host-facing layouts of the parameters / gradients + rss
@@ -194,6 +205,84 @@ static void xg_slice(const bann_net* net, uint64_t count, uint64_t* lo, uint64_t
     *hi = std::min<uint64_t>(count, 4 * per4 * (net->ctx->rank + 1));
 }
 
+// ------------------------------------------------------------------ zero-padded architectures
+// index of real parameter k of `dr` inside the padded layout `dp` (same depth, widths >= the real ones)
+__device__ __forceinline__ uint32_t padded_index(const BranchDesc& dr, const BranchDesc& dp, uint32_t k) {
+    int l; uint32_t row, col; bool isb;
+    locate_param(dr, k, l, row, col, isb);
+    return isb ? dp.b_off[l] + col : dp.w_off[l] + col * dp.in_dim[l] + row;
+}
+__global__ void __launch_bounds__(256) k_pad_params(const BranchDesc* __restrict__ real, const BranchDesc* __restrict__ pad,
+                                                    const uint32_t* __restrict__ list, const float* __restrict__ theta,
+                                                    float* __restrict__ theta_pad) {
+    const uint32_t b = list ? list[blockIdx.x] : blockIdx.x;
+    const BranchDesc& dr = real[b];
+    const BranchDesc& dp = pad[b];
+    for (uint32_t k = threadIdx.x; k < dr.P; k += 256) theta_pad[dp.param_off + padded_index(dr, dp, k)] = theta[dr.param_off + k];
+}
+__global__ void __launch_bounds__(256) k_unpad_sums(const BranchDesc* __restrict__ real, const BranchDesc* __restrict__ pad,
+                                                    const uint32_t* __restrict__ list, const float* __restrict__ gsum_pad,
+                                                    uint32_t pstride_pad, float* __restrict__ gsum, uint32_t pstride) {
+    const uint32_t li = blockIdx.x, b = list ? list[li] : li;
+    const BranchDesc& dr = real[b];
+    const BranchDesc& dp = pad[b];
+    const float* src = gsum_pad + (size_t)li * pstride_pad;
+    float* dst = gsum + (size_t)li * pstride;
+    for (uint32_t k = threadIdx.x; k < dr.P; k += 256) dst[k] = src[padded_index(dr, dp, k)];
+    if (threadIdx.x == 0) dst[dr.P] = src[dp.P];     // rss
+}
+
+// the padded description of every branch: hidden / summary widths raised to the next instantiated pair, same depth
+static int build_padded(bann_net* net) {
+    if (net->pad_built) return 0;
+    net->pad_descs = net->descs;
+    net->pad_ok.assign(net->B, 0);
+    uint64_t poff = 0;
+    uint32_t maxP = 0;
+    for (uint64_t b = 0; b < net->B; ++b) {
+        BranchDesc& d = net->pad_descs[b];
+        const int D = (int)d.nl - 2;
+        const uint32_t S = d.widths[d.nl - 2];
+        uint32_t H = D > 0 ? d.widths[0] : S;
+        bool homogeneous = true;
+        for (int l = 0; l < D; ++l) homogeneous = homogeneous && d.widths[l] == H;
+        const uint32_t mx = std::max(H, S);
+        uint32_t target = 0;
+        if (homogeneous && D >= 0 && D <= 2) {
+            if (mx <= 5 && d.m <= 512 && (D > 0 || d.m <= 64)) target = 5;          // k1_tc / k1_tcw: (5,5,0|1|2)
+            else if (D >= 1 && mx <= 8) target = 8;                                  // k1_tcx: (8,8,1|2), (12,12,1|2), (16,16,1|2)
+            else if (D >= 1 && mx <= 12) target = 12;
+            else if (D >= 1 && mx <= 16) target = 16;
+        }
+        if (target) {
+            net->pad_ok[b] = 1;
+            for (uint32_t l = 0; l + 1 < d.nl; ++l) d.widths[l] = target;
+            uint32_t prev = d.m, off = 0, aoff = 0;
+            for (uint32_t l = 0; l < d.nl; ++l) {
+                d.in_dim[l] = prev;
+                d.w_off[l] = off;
+                off += prev * d.widths[l];
+                if (l + 1 < d.nl) { d.a_off[l] = aoff; aoff += d.widths[l]; }
+                prev = d.widths[l];
+            }
+            d.sumw = aoff;
+            for (uint32_t l = 0; l + 1 < d.nl; ++l) { d.b_off[l] = off; off += d.widths[l]; }
+            d.P = off;
+        }
+        d.param_off = poff;
+        poff += (d.P + 3) & ~3u;
+        maxP = std::max(maxP, d.P);
+    }
+    net->pad_pstride = (maxP + 1 + 3) & ~3u;
+    BANN_CUDA(cudaMalloc(&net->d_pad_descs, net->B * sizeof(BranchDesc)));
+    BANN_CUDA(cudaMemcpy(net->d_pad_descs, net->pad_descs.data(), net->B * sizeof(BranchDesc), cudaMemcpyHostToDevice));
+    BANN_CUDA(cudaMalloc(&net->d_pad_theta, (poff + 4) * sizeof(float)));
+    BANN_CUDA(cudaMemset(net->d_pad_theta, 0, (poff + 4) * sizeof(float)));          // the padded slots stay zero for good
+    BANN_CHECK(ensure_cap(&net->d_pad_gsum, &net->pad_gsum_cap, (size_t)net->B * net->pad_pstride));
+    net->pad_built = true;
+    return 0;
+}
+
 static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
     const bann_genotypes* g = L.store ? L.store : net->gen;
     cudaStream_t st = net->ctx->stream;
@@ -263,8 +352,55 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
             if (r != 0) return r;
             if (launched) net->last_k1 = "k1_tcx: k_tcx_fwd + k_tcx_tail + k_tcx_bwd (tcgen05, three passes, first-layer width <= 16)";
         }
+        // widths outside the instantiated set: the next larger instantiated architecture on a zero-padded copy of the parameters
+        if (!launched && !L.descs_dev && !L.store) {
+            BANN_CHECK(build_padded(net));
+            bool all_ok = true;
+            if (L.single_branch >= 0) all_ok = net->pad_ok[L.single_branch] != 0;
+            else for (uint64_t b = 0; b < net->B && all_ok; ++b) all_ok = net->pad_ok[b] != 0;
+            if (all_ok) {
+                k_pad_params<<<L.nlist, 256, 0, st>>>(net->d_descs, net->d_pad_descs, L.list, net->d_theta, net->d_pad_theta);
+                BANN_LAUNCHED();
+                BANN_CHECK(ensure_cap(&net->d_pad_gsum, &net->pad_gsum_cap, (size_t)L.nlist * net->pad_pstride));
+                K1Args ap = a;
+                ap.descs = net->d_pad_descs;
+                ap.theta = net->d_pad_theta;
+                ap.pstride = net->pad_pstride;
+                float* ppart = nullptr;
+                uint32_t pchunk = nchunk;
+                net->pad_active = true;        // the kernels' buffer hooks (partials, sums, stride) now answer for the padded layout
+                int r = launch_k1_tc(net->pad_descs, L.single_branch, ap, L.nlist, net->ctx->num_sms, st, &launched, &pchunk,
+                                     L.fwd_only ? nullptr : &ppart, net);
+                if (r == 0 && !launched)
+                    r = launch_k1_tcw(net->pad_descs, L.single_branch, ap, L.nlist, net->ctx->num_sms, st, &launched, &pchunk,
+                                      L.fwd_only ? nullptr : &ppart, net);
+                if (r == 0 && !launched)
+                    r = launch_k1_tcx(net->pad_descs, L.single_branch, ap, L.nlist, net->ctx->num_sms, st, &launched, &pchunk,
+                                      L.fwd_only ? nullptr : &ppart, net);
+                net->pad_active = false;
+                if (r != 0) return r;
+                if (launched) {
+                    net->padded_launches += 1;
+                    net->last_k1 = "tensor-core kernel of the next larger instantiated architecture on zero-padded parameters";
+                    if (!L.fwd_only) {
+                        if (ppart != net->d_pad_gsum) {
+                            dim3 grid((net->pad_pstride + 31) / 32, L.nlist);
+                            BANN_CUDA(launch_pdl(k_reduce_partials, grid, dim3(256), 0, st, (const float*)ppart, net->d_pad_gsum, pchunk,
+                                                 net->pad_pstride, L.list, (const BranchDesc*)net->d_pad_descs, L.states, xr_none()));
+                            BANN_LAUNCHED();
+                        }
+                        k_unpad_sums<<<L.nlist, 256, 0, st>>>(net->d_descs, net->d_pad_descs, L.list, net->d_pad_gsum, net->pad_pstride,
+                                                              net->d_gsum, net->pstride);
+                        BANN_LAUNCHED();
+                        BANN_CUDA(cudaGetLastError());
+                        part = net->d_gsum;      // the sums are complete and in place: what follows is the cross-rank exchange only
+                        nchunk = 1;
+                    }
+                }
+            }
+        }
         if (!launched && net->k1_mode == BANN_K1_TENSOR)
-            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (homogeneous architecture, widths in the instantiated set)");
+            BANN_FAIL("tensor-core K1 requested but the launch is not eligible (homogeneous architecture, widths up to 16, depth up to 2)");
     }
     if (!launched && !g->d_store)
         BANN_FAIL("the byte-tile store was released (bann_genotypes_release_byte_store) and no tensor-core kernel is eligible for this launch");
@@ -295,10 +431,14 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
 
 // hooks used by k1_small.cuh to size its partial buffers
 float* bann_net_partials(bann_net* net, size_t need) {
+    if (net->pad_active) {
+        if (ensure_cap(&net->d_pad_part, &net->pad_part_cap, need) != 0) return nullptr;
+        return net->d_pad_part;
+    }
     if (ensure_cap(&net->d_part, &net->part_cap, need) != 0) return nullptr;
     return net->d_part;
 }
-float* bann_net_gsum(bann_net* net) { return net->d_gsum; }
+float* bann_net_gsum(bann_net* net) { return net->pad_active ? net->d_pad_gsum : net->d_gsum; }
 // work buffers of the three-pass wide kernel (k1_tcx.cuh): 0 = W' pieces, 1 = first-layer activations, 2 = delta pieces
 namespace bann {
 float* bann_net_tcx_buffer(bann_net* net, int which, size_t bytes) {
@@ -306,7 +446,7 @@ float* bann_net_tcx_buffer(bann_net* net, int which, size_t bytes) {
     return net->d_tcx[which];
 }
 }  // namespace bann
-uint32_t bann_net_pstride(bann_net* net) { return net->pstride; }
+uint32_t bann_net_pstride(bann_net* net) { return net->pad_active ? net->pad_pstride : net->pstride; }
 
 // gradient under the prior without touching the HMC state (log_density_gradient, a8)
 __global__ void __launch_bounds__(256) k_grad_only(const BranchDesc* descs, const uint32_t* list, const float* theta,
@@ -1343,7 +1483,7 @@ void bann_net_destroy(bann_net* net) {
     cudaFree(net->d_ynew); cudaFree(net->d_part); cudaFree(net->d_gsum); cudaFree(net->d_rpart);
     cudaFree(net->d_ow_others); cudaFree(net->d_order); cudaFree(net->d_Tg); cudaFree(net->d_Yg); cudaFree(net->d_inj_grp); cudaFree(net->d_bias2); cudaFree(net->d_lpd_local); cudaFree(net->d_errflag);
     cudaFree(net->d_list_all); cudaFree(net->d_inj); cudaFree(net->d_T); cudaFree(net->d_traj); cudaFree(net->d_numgrad);
-    cudaFree(net->d_tcp_words); cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
+    cudaFree(net->d_tcp_words); cudaFree(net->d_pad_descs); cudaFree(net->d_pad_theta); cudaFree(net->d_pad_gsum); cudaFree(net->d_pad_part); cudaFree(net->d_scratchB); cudaFree(net->d_jws); cudaFree(net->d_dense_in); cudaFree(net->d_dense_out);
     for (int i = 0; i < 3; ++i) cudaFree(net->d_tcx[i]);
     if (net->h_pin_a) cudaFreeHost(net->h_pin_a);
     if (net->h_pin_b) cudaFreeHost(net->h_pin_b);

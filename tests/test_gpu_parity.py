@@ -270,6 +270,58 @@ def test_tensor_core_kernel_refuses_ineligible_launch(rb, ctx):
         P.close()
 
 
+@pytest.mark.parametrize("act", ["tanh", "silu"])
+@pytest.mark.parametrize("shape", [(400, [30, 11], 3, 2, 1),        # -> k1_tc on (5,5,1)
+                                   (300, [20, 64], 4, 2, 2),        # -> k1_tc on (5,5,2)
+                                   (350, [12, 7], 1, 1, 1),         # single units
+                                   (300, [40, 9], 5, 4, 0),         # no hidden layer: the summary layer reads the markers, (5,5,0)
+                                   (515, [100, 70], 4, 2, 1),       # 65..512 markers -> k1_tcw on (5,5,1)
+                                   (300, [600, 90], 10, 6, 1),      # -> k1_tcx on (12,12,1)
+                                   (260, [80, 33], 7, 7, 2)])       # -> k1_tcx on (8,8,2)
+def test_fwd_bwd_zero_padded_architectures(rb, ctx, act, shape):
+    """Widths no tensor-core kernel is instantiated for run through the next larger instantiated architecture on a
+    zero-padded copy of the parameters (padded units: zero weights and biases, activation 0, delta 0) -- K1_TENSOR fails
+    loudly instead of falling back, so passing means the padded launch really ran."""
+    n, gs, h, s, d = shape
+    P = Problem(rb, ctx, "ridge_ard", n, gs, h, s, depth=d, act=act, seed=8)
+    try:
+        P.net.select_k1(P.net.K1_TENSOR)
+        for b in range(len(gs)):
+            got = P.net.branch_fwd_bwd(b)
+            assert "zero-padded" in P.net.last_k1_kernel()
+            t64, t32 = oracle_fwd_bwd(P, b, P.y, np.float64), oracle_fwd_bwd(P, b, P.y, np.float32)
+            within(got["yhat"], t64["yhat"], t32["yhat"])
+            within(got["rss"], t64["rss"], t32["rss"])
+            within(got["d_rss"], t64["d_rss"], t32["d_rss"])
+            within(got["ldg"], t64["ldg"], t32["ldg"])
+    finally:
+        P.close()
+
+
+def test_chain_on_zero_padded_architecture_matches_generic_kernel(rb, ctx):
+    """Three sweeps of Net::train visits on a [3,2,1] net: the padded tensor-core path against the shape-agnostic kernel
+    (same seeds): identical decisions, parameters within the FP32 reduction-order tolerance."""
+    res = {}
+    for mode in ("auto", "generic"):
+        P = Problem(rb, ctx, "ridge_ard", 600, [30, 11, 25], 3, 2, seed=9)
+        try:
+            P.net.select_k1(P.net.K1_AUTO if mode == "auto" else P.net.K1_GENERIC)
+            onet_ = mirror_net(P)
+            P.net.set_globals(2.0, 0.05, onet_.g_ow_reg_sum, onet_.g_ow_num_params, 0.0)
+            P.net.init_residual()
+            cfg = rb.MCMCCfg(hmc_step_size_factor=0.3, hmc_integration_length=10)
+            st = None
+            for it in range(3):
+                st = P.net.sweep(cfg, np.arange(3), seed=100 + it)
+            res[mode] = (P.net.get_all_params()[0], st, P.net.last_k1_kernel())
+        finally:
+            P.close()
+    assert "zero-padded" in res["auto"][2] and "generic" in res["generic"][2]
+    assert res["auto"][1]["num_accepted"] == res["generic"][1]["num_accepted"]
+    assert res["auto"][1]["num_early_rejected"] == res["generic"][1]["num_early_rejected"]
+    assert np.allclose(res["auto"][0], res["generic"][0], rtol=5e-4, atol=5e-5)
+
+
 def test_release_byte_store(rb, ctx):
     """The byte-tile copy of the genotypes can be given back where the tensor-core store exists: the tensor-core kernels keep
     producing the same numbers, everything that reads the released copy fails with a message (no silent fallback)."""
