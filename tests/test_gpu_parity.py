@@ -260,12 +260,16 @@ def test_tensor_core_fwd_bwd_parity(rb, ctx, model, shape):
 
 
 def test_tensor_core_kernel_refuses_ineligible_launch(rb, ctx):
-    P = Problem(rb, ctx, "ridge_ard", 300, [600], 5, 5, seed=3)        # 600 markers x widths [5,5,1]: no tensor-core kernel instantiated
+    P = Problem(rb, ctx, "ridge_ard", 300, [40], 5, 5, depth=3, seed=3)     # three hidden layers: no tensor-core kernel, not even zero-padded
     try:
-        assert P.gen.has_tc_store()                                    # (the store itself exists up to 2048 markers per branch)
+        assert P.gen.has_tc_store()
         P.net.select_k1(P.net.K1_TENSOR)
         with pytest.raises(RuntimeError):
             P.net.branch_fwd_bwd(0)
+        P.net.select_k1(P.net.K1_AUTO)
+        got = P.net.branch_fwd_bwd(0)                                       # AUTO: the shape-agnostic kernel
+        t64, t32 = oracle_fwd_bwd(P, 0, P.y, np.float64), oracle_fwd_bwd(P, 0, P.y, np.float32)
+        within(got["ldg"], t64["ldg"], t32["ldg"])
     finally:
         P.close()
 
@@ -277,6 +281,7 @@ def test_tensor_core_kernel_refuses_ineligible_launch(rb, ctx):
                                    (300, [40, 9], 5, 4, 0),         # no hidden layer: the summary layer reads the markers, (5,5,0)
                                    (515, [100, 70], 4, 2, 1),       # 65..512 markers -> k1_tcw on (5,5,1)
                                    (300, [600, 90], 10, 6, 1),      # -> k1_tcx on (12,12,1)
+                                   (300, [600], 5, 5, 1),           # [5,5,1] with more than 512 markers -> k1_tcx on (8,8,1)
                                    (260, [80, 33], 7, 7, 2)])       # -> k1_tcx on (8,8,2)
 def test_fwd_bwd_zero_padded_architectures(rb, ctx, act, shape):
     """Widths no tensor-core kernel is instantiated for run through the next larger instantiated architecture on a
