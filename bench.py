@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--generic", action="store_true", help="force the shape-agnostic kernel (debug)")
     ap.add_argument("--k1", default="auto", choices=["auto", "tensor", "ffma", "generic"],
                     help="which fused forward+backward kernel may run (auto: tensor-core where eligible)")
+    ap.add_argument("--k1-tc-variant", default="default", choices=["default", "four", "five"],
+                    help="<= 64-marker tensor-core kernel: k1_tc (compute warps issue the MMAs) or k1_tc5 (dedicated issuing warp)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -289,6 +291,8 @@ def main():
         net.force_generic(True)
     elif args.k1 != "auto":
         net.select_k1(dict(tensor=net.K1_TENSOR, ffma=net.K1_FFMA, generic=net.K1_GENERIC)[args.k1])
+    if args.k1_tc_variant != "default":
+        net.select_k1_tc_variant(dict(four=net.TC_FOUR_WARPS, five=net.TC_FIVE_WARPS)[args.k1_tc_variant])
     # cross-rank sums: INSIDE the library over NVLink peer memory (bann_net_comm_connect: reduce-scatter + all-gather kernels
     # on the same stream, csrc/comm.cuh).  torch.distributed only carries the 128-byte region handles once.
     rb.connect_net(net)

@@ -347,6 +347,12 @@ int  bann_net_force_generic(bann_net*, int on);
  * to 16 and up to 2048 markers), then the FFMA kernel, then the shape-agnostic one. */
 enum { BANN_K1_AUTO = 0, BANN_K1_TENSOR = 1, BANN_K1_FFMA = 2, BANN_K1_GENERIC = 3 };
 int  bann_net_select_k1(bann_net*, int which);
+/* test / profiling hook: which variant of the <= 64-marker tensor-core kernel a gradient / leapfrog launch uses.
+ * FOUR_WARPS: k1_tc, the four compute warps issue the tcgen05.mma themselves; FIVE_WARPS: k1_tc5, a dedicated issuing warp
+ * (instantiated for the benchmarked architecture [5,5,1]; other architectures keep k1_tc).  Same arithmetic per row; the
+ * cross-row sums are taken in a different (fixed) order, so results agree to FP32 rounding, not bit for bit. */
+enum { BANN_TC_FOUR_WARPS = 0, BANN_TC_FIVE_WARPS = 1 };
+int  bann_net_select_k1_tc_variant(bann_net*, int which);
 /* test / profiling hook: how a per-branch HMC transition (bann_hmc_step, bann_visit_branch, bann_sweep with group_size 1) runs.
  * AUTO: the persistent cooperative kernel (the whole L-step trajectory of BranchSampler::hmc_step, branch_sampler.rs:1239-1284,
  * in ONE launch, the branch's operands resident on chip) where the branch is eligible, else three launches per leapfrog step;

@@ -146,6 +146,7 @@ PROTOTYPES = {
     "bann_net_force_generic": (C.c_int, [_vp, C.c_int]),
     "bann_net_lpd_terms": (C.c_int, [_vp, _fp, _fp, _fp]),
     "bann_net_select_k1": (C.c_int, [_vp, C.c_int]),
+    "bann_net_select_k1_tc_variant": (C.c_int, [_vp, C.c_int]),
     "bann_launch_count": (_u64, [C.c_int]),
     "bann_net_algorithmic_bytes": (C.c_int, [_vp, C.POINTER(_u64)]),
 }

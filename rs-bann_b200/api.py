@@ -693,6 +693,12 @@ class Net:
         """Which fused forward+backward kernel may run: auto / tensor-core / FFMA / shape-agnostic."""
         check(lib.bann_net_select_k1(self.h, int(which)))
 
+    TC_FOUR_WARPS, TC_FIVE_WARPS = 0, 1
+
+    def select_k1_tc_variant(self, which: int):
+        """Variant of the <= 64-marker tensor-core kernel: k1_tc (compute warps issue the MMAs) / k1_tc5 (dedicated issuing warp)."""
+        check(lib.bann_net_select_k1_tc_variant(self.h, int(which)))
+
     def algorithmic_bytes(self) -> int:
         v = C.c_uint64()
         check(lib.bann_net_algorithmic_bytes(self.h, C.byref(v)))

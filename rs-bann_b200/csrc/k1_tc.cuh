@@ -168,16 +168,32 @@ __device__ __forceinline__ void halve_step(float (&v)[N], uint32_t lane) {
     }
 }
 
-template <int H, int S, int D, int ACT>
+// SACC: the cross-row sums as ONE float per value (row t and row 128 + t summed as they arrive: two FFMA instead of one FFMA2,
+// the same FMA-pipe cycles, one more issue slot) instead of a packed pair -- half the accumulator registers (41 instead of 82 for
+// [5,5,1]), which is what lets k1_tc5's fifth (issuing) warp fit three CTAs per SM (k1_tc5.cuh).
+template <bool SACC> struct TcAccElem { using type = f2; };
+template <> struct TcAccElem<true> { using type = float; };
+template <bool SACC> __device__ __forceinline__ typename TcAccElem<SACC>::type acc_zero() {
+    if constexpr (SACC) return 0.f; else return dup2(0.f);
+}
+__device__ __forceinline__ void acc_fma(f2& d, f2 a, f2 b) { d = fma2(a, b, d); }
+__device__ __forceinline__ void acc_fma(float& d, f2 a, f2 b) { d = fmaf(hi2(a), hi2(b), fmaf(lo2(a), lo2(b), d)); }
+__device__ __forceinline__ void acc_add(f2& d, f2 a) { d = add2(d, a); }
+__device__ __forceinline__ void acc_add(float& d, f2 a) { d = (d + lo2(a)) + hi2(a); }
+__device__ __forceinline__ float acc_total(f2 v) { return lo2(v) + hi2(v); }
+__device__ __forceinline__ float acc_total(float v) { return v; }
+
+template <int H, int S, int D, int ACT, bool SACC = false>
 struct TcTail {
     using T = TailShape<H, S, D>;
     static constexpr int NLA = T::NLA, W0 = T::W0, MW = T::MW, NN = 16;
     static constexpr int NL1 = NLA > 1 ? NLA - 1 : 1;
     static constexpr float cA = act_prescale<ACT>();
+    using AE = typename TcAccElem<SACC>::type;
     struct Acc {                          // cross-row sums, persistent over the super-tiles of a CTA
-        f2 gb0[W0], gWo[S], rss, gWt[NL1][MW][MW], gbt[NL1][MW];
+        AE gb0[W0], gWo[S], rss, gWt[NL1][MW][MW], gbt[NL1][MW];
         __device__ __forceinline__ void clear() {
-            const f2 z = dup2(0.f);
+            const AE z = acc_zero<SACC>();
             rss = z;
 #pragma unroll
             for (int c = 0; c < W0; ++c) gb0[c] = z;
@@ -228,9 +244,9 @@ struct TcTail {
         f2 sg[MW];
 #pragma unroll
         for (int i = 0; i < S; ++i) sg[i] = mul2(neg_dact2<ACT>(act[NLA - 1][i], aux[NLA - 1][i]), dup2(wp[T::w_off(NLA) + i]));
-        A.rss = fma2(e, e, A.rss);
+        acc_fma(A.rss, e, e);
 #pragma unroll
-        for (int i = 0; i < S; ++i) A.gWo[i] = fma2(act[NLA - 1][i], e, A.gWo[i]);
+        for (int i = 0; i < S; ++i) acc_fma(A.gWo[i], act[NLA - 1][i], e);
         float fac = -1.f;                  // (-1)^(NLA-l) cA^-(NLA-1-l) at l = NLA - 1
 #pragma unroll
         for (int l = NLA - 1; l >= 1; --l) {
@@ -249,10 +265,10 @@ struct TcTail {
             for (int c = 0; c < MW; ++c)
                 if (c < T::width(l)) {
                     const f2 dl = mul2(sg[c], ef);
-                    A.gbt[l - 1][c] = add2(A.gbt[l - 1][c], dl);
+                    acc_add(A.gbt[l - 1][c], dl);
 #pragma unroll
                     for (int i = 0; i < MW; ++i)
-                        if (i < T::in_w(l)) A.gWt[l - 1][i][c] = fma2(act[l - 1][i], dl, A.gWt[l - 1][i][c]);
+                        if (i < T::in_w(l)) acc_fma(A.gWt[l - 1][i][c], act[l - 1][i], dl);
                 }
 #pragma unroll
             for (int i = 0; i < MW; ++i)
@@ -268,7 +284,7 @@ struct TcTail {
 #pragma unroll
         for (int c = 0; c < W0; ++c) {
             const f2 d0 = mul2(sg0[c], ef0);
-            A.gb0[c] = add2(A.gb0[c], d0);
+            acc_add(A.gb0[c], d0);
             v[c] = mul2(d0, dup2(1.2676506002282294e30f));
         }
     }
@@ -318,7 +334,7 @@ struct TcTail {
             if (warp < (uint32_t)NW) {
                 float v[NTACC];
                 int idx = 0;
-                auto put = [&](f2 v2) { v[idx++] = lo2(v2) + hi2(v2); };
+                auto put = [&](AE v2) { v[idx++] = acc_total(v2); };
                 put(A.rss);
 #pragma unroll
                 for (int c = 0; c < S; ++c) put(A.gWo[c]);
@@ -349,8 +365,8 @@ struct TcTail {
         if (warp < (uint32_t)NW) {
             float* rw = red + warp * NTACC;
             int idx = 0;
-            auto put = [&](f2 v2) {
-                float v = lo2(v2) + hi2(v2);
+            auto put = [&](AE v2) {
+                float v = acc_total(v2);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0) rw[idx] = v;
@@ -696,6 +712,9 @@ __global__ void __launch_bounds__(128, 3) k1_tc(K1Args a) {
     }
 }
 
+// k1_tc5_inst.cu: launches k1_tc5<H,S,D,ACT,true,*> when that tuple is instantiated (*launched), else leaves the launch to k1_tc
+int launch_one_tc5(int H, int S, int D, int act, K1Args& a, uint32_t nlist, size_t smem, cudaStream_t st, bool* launched);
+
 template <int H, int S, int D, int ACT>
 int launch_one_tc_act(K1Args& a, uint32_t nlist, cudaStream_t st) {
     using C = TcShape<H, S, D>;
@@ -710,6 +729,12 @@ int launch_one_tc_act(K1Args& a, uint32_t nlist, cudaStream_t st) {
     const size_t smem = C::smem(a.ncb);
     dim3 grid(a.nchunk, nlist);
     const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
+    if (lean && a.tc_variant == 1) {           // the five-warp kernel (k1_tc5.cuh) where it is instantiated
+        bool done = false;
+        int rc = launch_one_tc5(H, S, D, ACT, a, nlist, smem, st, &done);
+        if (rc) return rc;
+        if (done) { a.tc_variant = 101; return 0; }   // tells launch_k1 which family ran (bann_net_last_k1_kernel)
+    }
     if (lean && kNct7 && a.nc_uniform == 7) BANN_CUDA(launch_pdl(k1_tc<H, S, D, ACT, true, kNct7 ? 7 : 0>, grid, dim3(128), smem, st, a));   // 49..56 markers in every listed branch
     else if (lean) BANN_CUDA(launch_pdl(k1_tc<H, S, D, ACT, true, 0>, grid, dim3(128), smem, st, a));
     else BANN_CUDA(launch_pdl(k1_tc<H, S, D, ACT, false, 0>, grid, dim3(128), smem, st, a));

@@ -15,7 +15,12 @@
 #include "k1_tcp.cuh"
 #include "store.cuh"
 
-using namespace bann;
+using // which <= 64-marker tensor-core kernel gradient / leapfrog launches use unless bann_net_select_k1_tc_variant says otherwise
+#ifndef BANN_TC_DEFAULT_VARIANT
+#define BANN_TC_DEFAULT_VARIANT BANN_TC_FOUR_WARPS
+#endif
+
+namespace bann;
 
 struct bann_net {
     bann_ctx* ctx = nullptr;
@@ -64,6 +69,7 @@ struct bann_net {
     float* d_scratchB = nullptr;  // [3*B] gather buffer
     uint64_t visit_seq = 0;
     int k1_mode = BANN_K1_AUTO;   // which K1 kernel launch_k1 may pick (bann_net_select_k1)
+    int tc_variant = BANN_TC_DEFAULT_VARIANT;   // k1_tc (four warps) or k1_tc5 (dedicated issuing warp) (bann_net_select_k1_tc_variant)
     const char* last_k1 = "none"; // kernel family the last fused forward+backward launch used (bann_net_last_k1_kernel)
     int hmc_path = BANN_HMC_AUTO; // per-branch transitions: persistent cooperative kernel where eligible / launch per step (bann_net_select_hmc_path)
     uint2* d_tcp_words = nullptr;        // tagged exchange words of the persistent kernel: [4][kTcpMaxGrid][pstride] partials, [4][kTcpSumCopies][pstride] sums
@@ -333,13 +339,16 @@ static int launch_k1(bann_net* net, const K1Launch& L, bool reduce) {
     a.st_per_chunk = 0;
     a.ncb = 8;
     a.nc_uniform = 0;
+    a.tc_variant = net->tc_variant;
 
     bool launched = false;
     if (net->k1_mode == BANN_K1_AUTO || net->k1_mode == BANN_K1_TENSOR) {
         int r = launch_k1_tc(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched,
                              &nchunk, L.fwd_only ? nullptr : &part, net);
         if (r != 0) return r;
-        if (launched) net->last_k1 = "k1_tc<H,S,D,ACT> (tcgen05 + tensor memory, <= 64 markers per branch)";
+        if (launched)
+            net->last_k1 = a.tc_variant == 101 ? "k1_tc5<H,S,D,ACT> (tcgen05 + tensor memory, dedicated issuing warp, <= 64 markers per branch)"
+                                               : "k1_tc<H,S,D,ACT> (tcgen05 + tensor memory, <= 64 markers per branch)";
         if (!launched) {   // 65..512 markers per branch: the K-blocked variant
             r = launch_k1_tcw(net->descs, L.single_branch, a, L.nlist, net->ctx->num_sms, st, &launched, &nchunk,
                               L.fwd_only ? nullptr : &part, net);
@@ -2500,6 +2509,13 @@ int bann_net_select_hmc_path(bann_net* net, int which) {
 }
 
 uint64_t bann_net_persistent_launches(bann_net* net) { return net ? net->persistent_launches : 0; }
+
+int bann_net_select_k1_tc_variant(bann_net* net, int which) {
+    if (!net) BANN_FAIL("NULL net");
+    if (which < BANN_TC_FOUR_WARPS || which > BANN_TC_FIVE_WARPS) BANN_FAIL("unknown k1_tc variant");
+    net->tc_variant = which;
+    return 0;
+}
 
 int bann_net_select_k1(bann_net* net, int which) {
     if (!net) BANN_FAIL("NULL net");

@@ -96,6 +96,40 @@ def test_tensor_core_and_ffma_kernels_agree_on_every_branch(full):
     assert abs(r_tc.astype(np.float64).sum() - r_ff.astype(np.float64).sum()) < 1e-6 * r_ff.astype(np.float64).sum()
 
 
+def test_five_warp_kernel_matches_the_oracle_and_k1_tc(full):
+    """k1_tc5 (dedicated issuing warp, csrc/k1_tc5.cuh) at full size: sampled branches against the oracle on all rows, every
+    branch against k1_tc, run-to-run identical."""
+    f = full
+    f.net.select_k1(f.net.K1_TENSOR)
+    f.net.select_k1_tc_variant(f.net.TC_FIVE_WARPS)
+    try:
+        g5, r5 = f.net.gradient(y=f.y)
+        assert "k1_tc5" in f.net.last_k1_kernel()
+        g5b, r5b = f.net.gradient(y=f.y)
+        assert np.array_equal(g5, g5b) and np.array_equal(r5, r5b)
+    finally:
+        f.net.select_k1_tc_variant(f.net.TC_FOUR_WARPS)
+    g4, r4 = f.net.gradient(y=f.y)
+    f.net.select_k1(f.net.K1_AUTO)
+    assert np.allclose(r5, r4, rtol=2e-5, atol=0)
+    a, b = g5.reshape(B, f.P), g4.reshape(B, f.P)
+    scale = np.max(np.abs(b), axis=1, keepdims=True)
+    assert np.max(np.abs(a - b) / scale) < 1e-4
+    for br_ix in (17, 7777):
+        x = f.gen.x_group(br_ix, standardized=True).astype(np.float64)
+        cfg = make_cfg("ridge_ard", PER, [5], 5)
+        cfg.load_param_vec(f.pv.reshape(B, f.P)[br_ix])
+        cfg.load_precision_vec(f.qv.reshape(B, f.qv.size // B)[br_ix])
+        o = {}
+        for dt in (np.float32, np.float64):
+            r, lw, lb = Branch(cfg, dt).log_density_gradient(x.astype(dt), f.y.astype(dt))
+            o[dt] = (float(r), Branch.join_vec(lw, lb).astype(np.float64))
+        t, m = o[np.float64], o[np.float32]
+        assert abs(r5[br_ix] - t[0]) <= 8 * abs(m[0] - t[0]) + 2e-5 * t[0]
+        tol = 8 * np.abs(m[1] - t[1]) + 2e-5 * np.max(np.abs(t[1]))
+        assert np.all(np.abs(a[br_ix] - t[1]) <= tol), np.max(np.abs(a[br_ix] - t[1]) / tol)
+
+
 def test_raw_sums_are_affine_in_the_targets(full):
     f = full
     rng = np.random.default_rng(11)
