@@ -238,7 +238,7 @@ def main():
     ap.add_argument("--generic", action="store_true", help="force the shape-agnostic kernel (debug)")
     ap.add_argument("--k1", default="auto", choices=["auto", "tensor", "ffma", "generic"],
                     help="which fused forward+backward kernel may run (auto: tensor-core where eligible)")
-    ap.add_argument("--k1-tc-variant", default="default", choices=["default", "four", "five"],
+    ap.add_argument("--k1-tc-variant", default="default", choices=["default", "four", "five", "five-plain"],
                     help="<= 64-marker tensor-core kernel: k1_tc (compute warps issue the MMAs) or k1_tc5 (dedicated issuing warp)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -292,7 +292,8 @@ def main():
     elif args.k1 != "auto":
         net.select_k1(dict(tensor=net.K1_TENSOR, ffma=net.K1_FFMA, generic=net.K1_GENERIC)[args.k1])
     if args.k1_tc_variant != "default":
-        net.select_k1_tc_variant(dict(four=net.TC_FOUR_WARPS, five=net.TC_FIVE_WARPS)[args.k1_tc_variant])
+        net.select_k1_tc_variant({"four": net.TC_FOUR_WARPS, "five": net.TC_FIVE_WARPS,
+                                  "five-plain": net.TC_FIVE_WARPS_PLAIN}[args.k1_tc_variant])
     # cross-rank sums: INSIDE the library over NVLink peer memory (bann_net_comm_connect: reduce-scatter + all-gather kernels
     # on the same stream, csrc/comm.cuh).  torch.distributed only carries the 128-byte region handles once.
     rb.connect_net(net)
@@ -392,7 +393,7 @@ def main():
         dist.all_reduce(hb)
     h2d, d2h = int(hb[0]), int(hb[1])
     k1_name = net.last_k1_kernel()
-    traffic = NCU_TRAFFIC.get(args.workload) if (world == 1 and k1_name.startswith("k1_tc<")) else None
+    traffic = NCU_TRAFFIC.get(args.workload) if (world == 1 and k1_name.startswith(("k1_tc<", "k1_tc5<"))) else None
 
     # ---- informational: the reference's own schedule (Net::train, net.rs:258-334: one branch at a time, Gibbs draws + one HMC
     #      transition of L = 100 leapfrog steps per visit) on the same net, 64 visits after 64 warm-up visits

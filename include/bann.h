@@ -348,10 +348,12 @@ int  bann_net_force_generic(bann_net*, int on);
 enum { BANN_K1_AUTO = 0, BANN_K1_TENSOR = 1, BANN_K1_FFMA = 2, BANN_K1_GENERIC = 3 };
 int  bann_net_select_k1(bann_net*, int which);
 /* test / profiling hook: which variant of the <= 64-marker tensor-core kernel a gradient / leapfrog launch uses.
- * FOUR_WARPS: k1_tc, the four compute warps issue the tcgen05.mma themselves; FIVE_WARPS: k1_tc5, a dedicated issuing warp
- * (instantiated for the benchmarked architecture [5,5,1]; other architectures keep k1_tc).  Same arithmetic per row; the
- * cross-row sums are taken in a different (fixed) order, so results agree to FP32 rounding, not bit for bit. */
-enum { BANN_TC_FOUR_WARPS = 0, BANN_TC_FIVE_WARPS = 1 };
+ * FOUR_WARPS: k1_tc, the four compute warps issue the tcgen05.mma themselves; FIVE_WARPS (the default): k1_tc5, a dedicated
+ * issuing warp, the cross-row sums of a super-tile taken under the next super-tile's MUFU phase (architectures with at most
+ * one hidden layer; the others keep k1_tc); FIVE_WARPS_PLAIN: k1_tc5 with the sums where k1_tc takes them ([5,5,1] only, A/B).
+ * Same arithmetic per row; the cross-row sums are taken in a different (fixed) order, so the variants agree to FP32
+ * rounding, not bit for bit. */
+enum { BANN_TC_FOUR_WARPS = 0, BANN_TC_FIVE_WARPS = 1, BANN_TC_FIVE_WARPS_PLAIN = 2 };
 int  bann_net_select_k1_tc_variant(bann_net*, int which);
 /* test / profiling hook: how a per-branch HMC transition (bann_hmc_step, bann_visit_branch, bann_sweep with group_size 1) runs.
  * AUTO: the persistent cooperative kernel (the whole L-step trajectory of BranchSampler::hmc_step, branch_sampler.rs:1239-1284,

@@ -693,10 +693,11 @@ class Net:
         """Which fused forward+backward kernel may run: auto / tensor-core / FFMA / shape-agnostic."""
         check(lib.bann_net_select_k1(self.h, int(which)))
 
-    TC_FOUR_WARPS, TC_FIVE_WARPS = 0, 1
+    TC_FOUR_WARPS, TC_FIVE_WARPS, TC_FIVE_WARPS_PLAIN = 0, 1, 2
 
     def select_k1_tc_variant(self, which: int):
-        """Variant of the <= 64-marker tensor-core kernel: k1_tc (compute warps issue the MMAs) / k1_tc5 (dedicated issuing warp)."""
+        """Variant of the <= 64-marker tensor-core kernel: k1_tc (compute warps issue the MMAs) / k1_tc5 (dedicated issuing warp,
+        cross-row sums deferred under the next super-tile's MUFU phase; the default) / k1_tc5 without the deferral."""
         check(lib.bann_net_select_k1_tc_variant(self.h, int(which)))
 
     def algorithmic_bytes(self) -> int:

@@ -279,6 +279,99 @@ struct TcTail {
         for (int c = 0; c < W0; ++c) sg0[c] = sg[c];
         ef0 = mul2(e, dup2(fac));
     }
+    // ---- part1 without the cross-row sums (k1_tc5): those need nothing but registers and nobody waits for them, so the caller
+    // takes them later, in slices (`accumulate_slice`) placed by hand where a warp would otherwise only wait for one pipe --
+    // ptxas keeps blocks of different kinds of work apart even inside one basic block, hand placement is what interleaves them.
+    // Mid: what the sums need.  part1x calls between(c) behind unit c of the first layer (ex2 / rcp on the MUFU pipe) and
+    // after() behind the whole layer; both run BEFORE any field of M other than act[0] is written, so the caller may keep the
+    // previous super-tile's terms in the same M (and a copy of its act[0]).
+    struct Mid { f2 act[NLA][MW], sgl[NL1][MW], e; };
+    template <class Between, class After>
+    __device__ __forceinline__ static void part1x(const float* accA, const float* accB, const float* wp, const float* b0p, f2& tg,
+                                                  bool add_pred_to_target, f2 valid, bool bwd, Mid& M, f2& yh, f2 (&sg0)[W0], f2& ef0,
+                                                  Between between, After after) {
+        const f2 zero2 = dup2(0.f);
+        f2 aux[NLA][MW];
+#pragma unroll
+        for (int c = 0; c < W0; ++c) {
+            const f2 z = mk2(accA[c] + (accA[W0 + c] + accA[2 * W0 + c]), accB[c] + (accB[W0 + c] + accB[2 * W0 + c]));
+            M.act[0][c] = act2<ACT>(fma2(z, dup2(8589934592.f /* 2^33 */ * cA), dup2(b0p[c])), aux[0][c]);
+            between(c);
+        }
+        after();
+#pragma unroll
+        for (int l = 1; l < NLA; ++l) {
+#pragma unroll
+            for (int c = 0; c < MW; ++c) {
+                if (c < T::width(l)) {
+                    f2 zz = dup2(wp[T::b_off(l) + c]);
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) zz = fma2(M.act[l - 1][i], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), zz);
+                    M.act[l][c] = act2<ACT>(zz, aux[l][c]);
+                }
+            }
+        }
+        yh = zero2;
+#pragma unroll
+        for (int i = 0; i < S; ++i) yh = fma2(M.act[NLA - 1][i], dup2(wp[T::w_off(NLA) + i]), yh);
+        if (add_pred_to_target) tg = add2(tg, yh);                         // net.rs:280
+        M.e = mul2(fma2(tg, dup2(-1.f), yh), valid);                       // branch_sampler.rs:821
+        ef0 = zero2;
+#pragma unroll
+        for (int c = 0; c < W0; ++c) sg0[c] = zero2;
+        if (!bwd) return;
+        f2 sg[MW];
+#pragma unroll
+        for (int i = 0; i < S; ++i) sg[i] = mul2(neg_dact2<ACT>(M.act[NLA - 1][i], aux[NLA - 1][i]), dup2(wp[T::w_off(NLA) + i]));
+        float fac = -1.f;
+#pragma unroll
+        for (int l = NLA - 1; l >= 1; --l) {
+            f2 nd[MW];
+#pragma unroll
+            for (int i = 0; i < MW; ++i) nd[i] = zero2;
+#pragma unroll
+            for (int c = 0; c < MW; ++c)
+                if (c < T::width(l)) {
+                    M.sgl[l - 1][c] = sg[c];
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) nd[i] = fma2(sg[c], dup2(wp[T::w_off(l) + c * T::in_w(l) + i]), nd[i]);
+                }
+#pragma unroll
+            for (int i = 0; i < MW; ++i)
+                if (i < T::in_w(l)) sg[i] = mul2(neg_dact2<ACT>(M.act[l - 1][i], aux[l - 1][i]), nd[i]);
+            fac = -fac / cA;
+        }
+#pragma unroll
+        for (int c = 0; c < W0; ++c) sg0[c] = sg[c];
+        ef0 = mul2(M.e, dup2(fac));
+    }
+    // the cross-row sums of the layers >= 1, the output layer and rss (same terms per accumulator as part1) in NSLICE slices:
+    // slice 0 = rss + output layer, slice 1 + (NLA-1-l) MW + c = unit c of layer l.  a0: the first layer's activations (M.act[0],
+    // or the caller's copy of them)
+    static constexpr int NSLICE = 1 + (NLA - 1) * MW;
+    __device__ __forceinline__ static void accumulate_slice(const Mid& M, const f2 (&a0)[MW], Acc& A, int k) {
+        if (k == 0) {
+            acc_fma(A.rss, M.e, M.e);
+#pragma unroll
+            for (int i = 0; i < S; ++i) acc_fma(A.gWo[i], NLA == 1 ? a0[i] : M.act[NLA - 1][i], M.e);
+        }
+        float fac = -1.f;
+#pragma unroll
+        for (int l = NLA - 1; l >= 1; --l) {
+#pragma unroll
+            for (int c = 0; c < MW; ++c)
+                if (c < T::width(l) && k == 1 + (NLA - 1 - l) * MW + c) {
+                    const f2 dl = mul2(M.sgl[l - 1][c], mul2(M.e, dup2(fac)));
+                    acc_add(A.gbt[l - 1][c], dl);
+#pragma unroll
+                    for (int i = 0; i < MW; ++i)
+                        if (i < T::in_w(l)) acc_fma(A.gWt[l - 1][i][c], l == 1 ? a0[i] : M.act[l - 1][i], dl);
+                }
+            fac = -fac / cA;
+        }
+    }
     // delta_0 of the pair, accumulated into gb0 and lifted by 2^100 (exact) for the piece split
     __device__ __forceinline__ static void delta0(const f2 (&sg0)[W0], f2 ef0, Acc& A, f2 (&v)[W0]) {
 #pragma unroll
@@ -297,9 +390,13 @@ struct TcTail {
         for (int c = 0; c < W0; ++c) {
 #pragma unroll
             for (int piece = 0; piece < 3; ++piece) {
-                const uint32_t ua = __float_as_uint(lo2(v[c])) & 0xFFFF0000u, ub = __float_as_uint(hi2(v[c])) & 0xFFFF0000u;
-                pa[piece * W0 + c] = ua; pb[piece * W0 + c] = ub;
-                if (piece < 2) v[c] = add2(v[c], mk2(-__uint_as_float(ua), -__uint_as_float(ub)));
+                if (piece < 2) {
+                    const uint32_t ua = __float_as_uint(lo2(v[c])) & 0xFFFF0000u, ub = __float_as_uint(hi2(v[c])) & 0xFFFF0000u;
+                    pa[piece * W0 + c] = ua; pb[piece * W0 + c] = ub;
+                    v[c] = add2(v[c], mk2(-__uint_as_float(ua), -__uint_as_float(ub)));
+                } else {      // the last piece needs no mask: the byte permutation below takes the upper halves only
+                    pa[piece * W0 + c] = __float_as_uint(lo2(v[c])); pb[piece * W0 + c] = __float_as_uint(hi2(v[c]));
+                }
             }
         }
 #pragma unroll
@@ -729,7 +826,7 @@ int launch_one_tc_act(K1Args& a, uint32_t nlist, cudaStream_t st) {
     const size_t smem = C::smem(a.ncb);
     dim3 grid(a.nchunk, nlist);
     const bool lean = !a.fwd_only && !a.yhat_out && a.target_mode != TGT_RESID_PLUS_PRED && a.tgt;
-    if (lean && a.tc_variant == 1) {           // the five-warp kernel (k1_tc5.cuh) where it is instantiated
+    if (lean && a.tc_variant >= 1) {           // the five-warp kernel (k1_tc5.cuh) where it is instantiated
         bool done = false;
         int rc = launch_one_tc5(H, S, D, ACT, a, nlist, smem, st, &done);
         if (rc) return rc;

@@ -16,7 +16,16 @@ namespace bann {
 
 constexpr int kTc5Threads = 160;
 
-template <int H, int S, int D, int ACT, bool LEAN, int NCT>
+// DEFER: where the cross-row sums of a super-tile (layers >= 1, output layer, rss: ~85 FMA-pipe instructions that nothing waits
+// for) are taken.  false: inside part 1, as k1_tc.  true: one super-tile later, placed by hand between the first layer's
+// activations of the NEXT super-tile, where the warp otherwise only waits for the MUFU pipe (ex2 / rcp, 8 clk per warp
+// instruction); the terms they need (activations, rho of the layers >= 1, error: `Mid`) stay in registers until then.
+// Measured on cfg3s (100k x 1000 branches x 50 markers, one B200, profiles/r2_k1_tc5_ab.md): k1_tc 1.641 ms, five warps 1.446,
+// five warps + deferred sums 1.387.  Tried and rejected on the way: the sums behind the expansion of the next super-tile (1.395)
+// or behind the delta pieces (1.429); the expansion moved up between the units of layer 1 or between the steps of the rho chain
+// (1.61 / 1.65: the earlier the wait for the previous backward contraction sits, the less skew between the four compute warps
+// of a CTA is tolerated); the loop unrolled twice to save the register copies of the deferred terms (spills, 2.16).
+template <int H, int S, int D, int ACT, bool LEAN, int NCT, bool DEFER = true>
 __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
     using T = TailShape<H, S, D>;
     using C = TcShape<H, S, D>;
@@ -192,6 +201,22 @@ __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
         return mk2(rA < a.n ? __ldg(tsrc + rA) : 0.f, rB < a.n ? __ldg(tsrc + rB) : 0.f);
     };
     f2 tg_next = load_targets(t_begin);
+    // DEFER: the previous super-tile's terms.  One `Mid` serves both super-tiles: the fields of the layers >= 1 and the error are
+    // read by the deferred sums BEFORE this super-tile's forward pass overwrites them; only the first layer's activations
+    // overlap (written while the sums still run) and keep a copy, a0p.  All zero at the start: the first sums add nothing.
+    typename TT::Mid M;
+    f2 a0p[TT::MW];
+    if constexpr (DEFER) {
+#pragma unroll
+        for (int i = 0; i < TT::MW; ++i) {
+            a0p[i] = zero2;
+#pragma unroll
+            for (int l = 0; l < TT::NLA; ++l) M.act[l][i] = zero2;
+#pragma unroll
+            for (int l = 0; l < TT::NL1; ++l) M.sgl[l][i] = zero2;
+        }
+        M.e = zero2;
+    }
     if (nit > 0) {
         umma::mbar_wait(&mbar[4], 0);
         expand(0);
@@ -211,8 +236,19 @@ __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
         umma::fence_before_sync();      // these reads precede the next forward MMA (ordered by the "expanded" barrier below)
 
         f2 yh, sg0[W0], ef0;
-        TT::part1(accA, accB, wp, b0p, tg, !LEAN && a.target_mode == TGT_RESID_PLUS_PRED, mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f), bwd, A,
-                  yh, sg0, ef0);
+        if constexpr (DEFER) {
+            TT::part1x(accA, accB, wp, b0p, tg, !LEAN && a.target_mode == TGT_RESID_PLUS_PRED, mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f), bwd, M,
+                       yh, sg0, ef0, [&](int c) { if (bwd) TT::accumulate_slice(M, a0p, A, c); },
+                       [&]() {
+                           if (bwd) {
+#pragma unroll
+                               for (int k = W0; k < TT::NSLICE; ++k) TT::accumulate_slice(M, a0p, A, k);
+                           }
+                       });
+        } else {
+            TT::part1(accA, accB, wp, b0p, tg, !LEAN && a.target_mode == TGT_RESID_PLUS_PRED, mk2(vA ? 1.f : 0.f, vB ? 1.f : 0.f), bwd, A,
+                      yh, sg0, ef0);
+        }
         if (!LEAN) {
             auto put = [&](float* dst, uint32_t row, float v, int accumulate) {
                 if (!dst || row >= a.n) return;
@@ -244,6 +280,16 @@ __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
         }
         umma::fence_async_smem();
         umma::mbar_arrive(&mbar[3]);          // phase it
+        if constexpr (DEFER) {
+#pragma unroll
+            for (int i = 0; i < TT::MW; ++i) a0p[i] = M.act[0][i];
+        }
+    }
+    if constexpr (DEFER) {                     // the last super-tile's sums
+        if (bwd) {
+#pragma unroll
+            for (int k = 0; k < TT::NSLICE; ++k) TT::accumulate_slice(M, a0p, A, k);
+        }
     }
     const bool has_bwd = epilogue && nit > 0;
     float sacc[16];

@@ -17,7 +17,7 @@
 
 using // which <= 64-marker tensor-core kernel gradient / leapfrog launches use unless bann_net_select_k1_tc_variant says otherwise
 #ifndef BANN_TC_DEFAULT_VARIANT
-#define BANN_TC_DEFAULT_VARIANT BANN_TC_FOUR_WARPS
+#define BANN_TC_DEFAULT_VARIANT BANN_TC_FIVE_WARPS
 #endif
 
 namespace bann;
@@ -2512,7 +2512,7 @@ uint64_t bann_net_persistent_launches(bann_net* net) { return net ? net->persist
 
 int bann_net_select_k1_tc_variant(bann_net* net, int which) {
     if (!net) BANN_FAIL("NULL net");
-    if (which < BANN_TC_FOUR_WARPS || which > BANN_TC_FIVE_WARPS) BANN_FAIL("unknown k1_tc variant");
+    if (which < BANN_TC_FOUR_WARPS || which > BANN_TC_FIVE_WARPS_PLAIN) BANN_FAIL("unknown k1_tc variant");
     net->tc_variant = which;
     return 0;
 }

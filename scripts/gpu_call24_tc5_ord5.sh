@@ -1,0 +1,16 @@
+# round 2, k1_tc5 variant 6 (ORD 5: expansion between the steps of the rho chain): parity + A/B on one box, ncu of variant 4 (ORD 3)
+set -u
+cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_tc5.py -x -q > gpurun_out/r2c24_tests.log 2>&1; echo "tc5 tests exit $?"; tail -3 gpurun_out/r2c24_tests.log
+rm -f gpurun_out/r2c24_ab_cfg3s.jsonl
+for v in 4 6 4 6; do
+  timeout 300 python bench.py --workload cfg3s --k1-tc-variant $v --no-cpu-baseline --no-sequential >> gpurun_out/r2c24_ab_cfg3s.jsonl 2> gpurun_out/r2c24_ab.err; echo "cfg3s $v exit $?"
+done
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2c24_ab_cfg3s.jsonl'):
+    d = json.loads(l); print(d['roofline']['kernel'][:8], 'k1_ms', round(d['k1_ms'],4), 'value', round(d['value'],1), 'frac', round(d['roofline']['frac'],4))
+PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_tc5 -s 4 -c 1 -o gpurun_out/r2c24_k1_tc5_v4 \
+  python bench.py --workload cfg3s --k1-tc-variant 4 --steps 3 --warmup 3 --no-cpu-baseline --no-sequential > gpurun_out/r2c24_ncu.log 2>&1
+echo "ncu exit $?"

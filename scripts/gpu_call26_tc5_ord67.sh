@@ -1,0 +1,13 @@
+# round 2, k1_tc5 variants 7 (first slices of the sums before the proxy fence) and 8 (loop unrolled twice)
+set -u
+cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_tc5.py -x -q > gpurun_out/r2c26_tests.log 2>&1; echo "tc5 tests exit $?"; tail -3 gpurun_out/r2c26_tests.log
+rm -f gpurun_out/r2c26_ab_cfg3s.jsonl
+for v in 4 7 8 4 7 8; do
+  timeout 300 python bench.py --workload cfg3s --k1-tc-variant $v --no-cpu-baseline --no-sequential >> gpurun_out/r2c26_ab_cfg3s.jsonl 2> gpurun_out/r2c26_ab.err; echo "cfg3s $v exit $?"
+done
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2c26_ab_cfg3s.jsonl'):
+    d = json.loads(l); print(d['roofline']['kernel'][:8], 'k1_ms', round(d['k1_ms'],4), 'value', round(d['value'],1), 'frac', round(d['roofline']['frac'],4))
+PY

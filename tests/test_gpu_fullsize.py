@@ -97,8 +97,8 @@ def test_tensor_core_and_ffma_kernels_agree_on_every_branch(full):
 
 
 def test_five_warp_kernel_matches_the_oracle_and_k1_tc(full):
-    """k1_tc5 (dedicated issuing warp, csrc/k1_tc5.cuh) at full size: sampled branches against the oracle on all rows, every
-    branch against k1_tc, run-to-run identical."""
+    """k1_tc5 (dedicated issuing warp, deferred cross-row sums: csrc/k1_tc5.cuh, the default) at full size: sampled branches
+    against the oracle on all rows, every branch against k1_tc, run-to-run identical."""
     f = full
     f.net.select_k1(f.net.K1_TENSOR)
     f.net.select_k1_tc_variant(f.net.TC_FIVE_WARPS)
@@ -107,9 +107,11 @@ def test_five_warp_kernel_matches_the_oracle_and_k1_tc(full):
         assert "k1_tc5" in f.net.last_k1_kernel()
         g5b, r5b = f.net.gradient(y=f.y)
         assert np.array_equal(g5, g5b) and np.array_equal(r5, r5b)
-    finally:
         f.net.select_k1_tc_variant(f.net.TC_FOUR_WARPS)
-    g4, r4 = f.net.gradient(y=f.y)
+        g4, r4 = f.net.gradient(y=f.y)
+        assert "k1_tc<" in f.net.last_k1_kernel()
+    finally:
+        f.net.select_k1_tc_variant(f.net.TC_FIVE_WARPS)
     f.net.select_k1(f.net.K1_AUTO)
     assert np.allclose(r5, r4, rtol=2e-5, atol=0)
     a, b = g5.reshape(B, f.P), g4.reshape(B, f.P)

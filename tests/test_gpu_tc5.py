@@ -37,15 +37,19 @@ SHAPES = [
 ]
 
 
+VARIANTS = [1, 2]       # bann_net_select_k1_tc_variant: TC_FIVE_WARPS (cross-row sums deferred, the default), TC_FIVE_WARPS_PLAIN
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("model", ["ridge_ard", "std_normal", "lasso_base"])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_tc5_gradient_matches_oracle_and_k1_tc(rb, ctx, model, shape):
+def test_tc5_gradient_matches_oracle_and_k1_tc(rb, ctx, model, shape, variant):
     n, gs = shape
     P = Problem(rb, ctx, model, n, gs, 5, 5, seed=(sum(map(ord, model)) + 3 * n) % 1000, overlap=len(gs) > 1)
     try:
         net = P.net
         net.select_k1(net.K1_TENSOR)
-        net.select_k1_tc_variant(net.TC_FIVE_WARPS)
+        net.select_k1_tc_variant(variant)
         g5, r5 = net.gradient(y=P.y)
         assert "k1_tc5" in net.last_k1_kernel(), net.last_k1_kernel()
         g5b, r5b = net.gradient(y=P.y)
@@ -87,14 +91,51 @@ def test_tc5_other_activations(rb, ctx, act):
         P.close()
 
 
-def test_tc5_other_architectures_keep_k1_tc(rb, ctx):
-    P = Problem(rb, ctx, "ridge_ard", 515, [20, 33], 4, 3, seed=5)
+# the other architectures k1_tc5 is instantiated for (at most one hidden layer): n, group sizes, hidden, summary, depth
+ARCHS = [
+    (515, [20, 33], 4, 3, 1),
+    (700, [40, 24, 7], 2, 2, 1),
+    (600, [20, 64], 3, 3, 1),
+    (300, [33, 8], 4, 4, 1),
+    (150, [12, 7], 2, 2, 0),          # no hidden layer: the summary layer reads the markers
+    (900, [50, 56], 5, 5, 0),
+]
+
+
+@pytest.mark.parametrize("act", ["tanh", "silu"])
+@pytest.mark.parametrize("arch", ARCHS)
+def test_tc5_other_architectures(rb, ctx, arch, act):
+    n, gs, h, s_, d = arch
+    P = Problem(rb, ctx, "ridge_ard", n, gs, h, s_, depth=d, act=act, seed=n % 89, overlap=True)
+    try:
+        net = P.net
+        net.select_k1(net.K1_TENSOR)
+        net.select_k1_tc_variant(net.TC_FIVE_WARPS)
+        g5, r5 = net.gradient(y=P.y)
+        assert "k1_tc5" in net.last_k1_kernel(), net.last_k1_kernel()
+        net.select_k1_tc_variant(net.TC_FOUR_WARPS)
+        g4, r4 = net.gradient(y=P.y)
+        off = 0
+        for b in range(len(gs)):
+            Pn = P.cfgs[b].num_params
+            t64, t32 = oracle_fwd_bwd(P, b, P.y, np.float64), oracle_fwd_bwd(P, b, P.y, np.float32)
+            within(g5[off:off + Pn], t64["ldg"], t32["ldg"])
+            within(r5[b], t64["rss"], t32["rss"])
+            sc = np.max(np.abs(t64["ldg"]))
+            assert np.max(np.abs(g5[off:off + Pn].astype(np.float64) - g4[off:off + Pn])) <= 4e-5 * sc
+            off += Pn
+    finally:
+        P.close()
+
+
+def test_tc5_two_hidden_layers_keep_k1_tc(rb, ctx):
+    P = Problem(rb, ctx, "ridge_ard", 515, [50, 64], 5, 5, depth=2, seed=5)
     try:
         net = P.net
         net.select_k1(net.K1_TENSOR)
         net.select_k1_tc_variant(net.TC_FIVE_WARPS)
         g, r = net.gradient(y=P.y)
-        assert "k1_tc<" in net.last_k1_kernel()         # [4,3,1]: not instantiated for five warps, the four-warp kernel runs
+        assert "k1_tc<" in net.last_k1_kernel()         # [5,5,5,1]: not instantiated for five warps, the four-warp kernel runs
         t64, t32 = oracle_fwd_bwd(P, 0, P.y, np.float64), oracle_fwd_bwd(P, 0, P.y, np.float32)
         within(g[:P.cfgs[0].num_params], t64["ldg"], t32["ldg"])
     finally:
