@@ -50,8 +50,8 @@ UNIT = "steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures
 # (NOT measured in this run -- a bench run is never profiled); None where no capture exists for the workload
 NCU_TRAFFIC = {
-    "cfg3s": dict(bytes=1.8099e9, source="profiles/r2_k1_tc_ncu_summary.md (ncu, not this run)"),
-    "cfg3": dict(bytes=1.8099e10, source="profiles/r2_k1_tc_ncu_summary.md: cfg3s capture x 10 branches (ncu, not this run)"),
+    "cfg3s": dict(bytes=1.8090e9, source="profiles/r2_k1_tc5_ncu_summary.md (ncu, not this run)"),
+    "cfg3": dict(bytes=1.8090e10, source="profiles/r2_k1_tc5_ncu_summary.md: cfg3s capture x 10 branches (ncu, not this run)"),
 }
 
 
