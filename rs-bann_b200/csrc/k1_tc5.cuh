@@ -56,10 +56,13 @@ __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
     const float* mu = a.mu + d.col_off;
     const float* sd = a.sd + d.col_off;
 
-    {
-        const uint32_t nz = (uint32_t)((sD + C::SD - sA) / 16);
-        for (uint32_t k = tid; k < nz; k += kTc5Threads) reinterpret_cast<uint4*>(sA)[k] = make_uint4(0, 0, 0, 0);
-    }
+    // ---- prologue.  At 8 GPUs a CTA covers only 49 super-tiles, so what happens before the first one counts (measured on the
+    // 8-GPU shard shape, bench.py --workload cfg3r8: ~10 % of K1): every global load of the staging is issued up front (one
+    // memory round trip instead of four dependent ones), the first packed words are requested before the staging, the mean fold
+    // of the first-layer bias is a warp reduction per unit instead of one thread walking the markers, and only what is read
+    // before it is written gets zeroed (the weight pieces of the k-chunks >= nc; the operand images and the delta pieces are
+    // rewritten for every super-tile, rows of the backward accumulator beyond m are never read).
+    for (uint32_t k = tid; k < (uint32_t)(C::SW / 16); k += kTc5Threads) reinterpret_cast<uint4*>(sW)[k] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         umma::mbar_init(&mbar[0], 1);
         umma::mbar_init(&mbar[1], 1);
@@ -78,31 +81,63 @@ __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
         if (warp == 0) umma::tmem_dealloc(*tmem_slot, C::TMEM_COLS);
         return;
     }
-    TT::stage_tail(th + m * W0, wp, tid, kTc5Threads);
-    __syncthreads();
-    float* wtmp = reinterpret_cast<float*>(sD);                // [m][W0], transient
-    for (uint32_t k = tid; k < m * W0; k += kTc5Threads) {
-        const uint32_t j = k / W0, c = k % W0;
-        const float w = __fdiv_rn(th[c * m + j], sd[j]);       // bed.rs:354 folded into the first layer
-        wtmp[k] = w;
-        const float v = w * pow2f(100 - 2 * (int)((j & 7u) >> 1));
-        const float p0 = bf16_round(v), r1 = v - p0, p1 = bf16_round(r1), p2 = bf16_round(r1 - p1);
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sW + (j >> 3) * (NN * 16) + (j & 7u) * 2);
-        dst[(0 * W0 + c) * 8] = __float2bfloat16_rn(p0);
-        dst[(1 * W0 + c) * 8] = __float2bfloat16_rn(p1);
-        dst[(2 * W0 + c) * 8] = __float2bfloat16_rn(p2);
+    const uint32_t t_begin = chunk * a.st_per_chunk;
+    const uint32_t t_end = min(a.nst, t_begin + a.st_per_chunk);
+    const uint32_t nit = t_end > t_begin ? t_end - t_begin : 0;
+    const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
+    // all global loads of the staging, before anything waits
+    const float* th_tail = th + m * W0;
+    const uint32_t mw = m * W0;
+    constexpr uint32_t NQ = (kTcMaxMarkers * 5 + kTc5Threads - 1) / kTc5Threads;       // W0 <= 5
+    float g_th[NQ], g_sd[NQ], g_mu[NQ];
+#pragma unroll
+    for (uint32_t q = 0; q < NQ; ++q) {
+        const uint32_t k = tid + q * kTc5Threads;
+        const bool in = k < mw;
+        const uint32_t j = in ? k / W0 : 0, c = in ? k % W0 : 0;
+        g_th[q] = in ? th[c * m + j] : 0.f;
+        g_sd[q] = in ? sd[j] : 1.f;
+        g_mu[q] = in ? mu[j] : 0.f;
     }
-    __syncthreads();
-    if (tid < W0P) {
-        float acc = 0.f;
-        if (tid < W0) {
-            for (uint32_t j = 0; j < m; ++j) acc = fmaf(mu[j], wtmp[j * W0 + tid], acc);
-            acc = (th[m * W0 + T::b_off(0) + tid] - acc) * cA;
+    const float g_tail = tid < (uint32_t)T::n_tail() ? th_tail[tid] : 0.f;
+    const float g_b0 = (lane == 0 && warp < (uint32_t)W0) ? th_tail[T::b_off(0) + warp] : 0.f;
+    __syncthreads();                       // barrier initialisation visible to the issuing warp
+    if (warp == 4 && nit > 0) {            // the first packed words: their HBM round trip runs under the staging
+        if (umma::elect_one()) umma::bulk_load(sG, gwords + (size_t)t_begin * NC * 128, NC * 512u, &mbar[4]);
+        __syncwarp();
+    }
+    {   // tail parameters; what feeds an activated layer >= 1 carries the activation's pre-scale (TcTail::stage_tail)
+        auto put_tail = [&](uint32_t k, float w) {
+            const bool scaled = TT::NLA > 1 && ((int)k < T::w_off(TT::NLA) || (int)k >= T::b_off(TT::NLA > 1 ? 1 : 0));
+            wp[k] = scaled ? w * cA : w;
+        };
+        if (tid < (uint32_t)T::n_tail()) put_tail(tid, g_tail);
+        for (uint32_t k = tid + kTc5Threads; k < (uint32_t)T::n_tail(); k += kTc5Threads) put_tail(k, th_tail[k]);
+    }
+    float* prod = reinterpret_cast<float*>(sD);                // [W0][64] products mu_j * W'_jc, transient
+#pragma unroll
+    for (uint32_t q = 0; q < NQ; ++q) {
+        const uint32_t k = tid + q * kTc5Threads;
+        if (k < mw) {
+            const uint32_t j = k / W0, c = k % W0;
+            const float w = __fdiv_rn(g_th[q], g_sd[q]);       // bed.rs:354 folded into the first layer
+            prod[c * kTcMaxMarkers + j] = g_mu[q] * w;
+            const float v = w * pow2f(100 - 2 * (int)((j & 7u) >> 1));
+            const float p0 = bf16_round(v), r1 = v - p0, p1 = bf16_round(r1), p2 = bf16_round(r1 - p1);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sW + (j >> 3) * (NN * 16) + (j & 7u) * 2);
+            dst[(0 * W0 + c) * 8] = __float2bfloat16_rn(p0);
+            dst[(1 * W0 + c) * 8] = __float2bfloat16_rn(p1);
+            dst[(2 * W0 + c) * 8] = __float2bfloat16_rn(p2);
         }
-        b0p[tid] = acc;
     }
+    if (tid < (uint32_t)W0P) b0p[tid] = 0.f;
     __syncthreads();
-    for (uint32_t k = tid; k < m * W0; k += kTc5Threads) wtmp[k] = 0.f;   // the pad columns of the delta operand must stay zero
+    if (warp < (uint32_t)W0) {             // b0' = (b0 - sum_j mu_j W'_jc) * cA: lanes over the markers, fixed shuffle tree
+        float sacc0 = (lane < m ? prod[warp * kTcMaxMarkers + lane] : 0.f) + (lane + 32 < m ? prod[warp * kTcMaxMarkers + lane + 32] : 0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc0 += __shfl_xor_sync(0xffffffffu, sacc0, o);
+        if (lane == 0) b0p[warp] = (g_b0 - sacc0) * cA;
+    }
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
@@ -112,15 +147,11 @@ __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
     constexpr uint32_t idesc_f = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 0, 0, 128, NN);
     constexpr uint32_t idesc_b = umma::make_idesc(umma::FMT_BF16, umma::FMT_BF16, 1, 1, 64, NN);
 
-    const uint32_t t_begin = chunk * a.st_per_chunk;
-    const uint32_t t_end = min(a.nst, t_begin + a.st_per_chunk);
-    const uint32_t nit = t_end > t_begin ? t_end - t_begin : 0;
     const bool bwd = LEAN || !a.fwd_only;
     const bool epilogue = bwd && a.part;
 
     if (warp == 4) {
         // ================================================================ issuing warp
-        const uint32_t* gwords = a.store_tc + (d.tc_off >> 2);
         const uint64_t dW_f = umma::make_desc(sW_u, NN * 16, 128);
         const uint64_t dA_b = umma::make_desc(sA_u, 128, kTcChunkStride), dD_b = umma::make_desc(sD_u, 128, kTcChunkStride);
         auto issue_bwd = [&](uint32_t e) {      // backward contraction of super-tile e: 16 K steps of 16 rows into ONE accumulator
@@ -135,11 +166,7 @@ __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
             }
             __syncwarp();
         };
-        if (nit > 0) {
-            if (umma::elect_one()) umma::bulk_load(sG, gwords + (size_t)t_begin * NC * 128, NC * 512u, &mbar[4]);
-            __syncwarp();
-        }
-        for (uint32_t e = 0; e < nit; ++e) {
+        for (uint32_t e = 0; e < nit; ++e) {      // (the words of the first super-tile were requested in the prologue)
             umma::mbar_wait(&mbar[2], e & 1u);          // super-tile e expanded by all 128 compute threads (and z0 of e - 1 read)
             umma::fence_after_sync();
             if (umma::elect_one()) {
@@ -305,7 +332,7 @@ __global__ void __launch_bounds__(kTc5Threads, 3) k1_tc5(K1Args a) {
 
     float* pp = a.part + ((size_t)li * a.nchunk + chunk) * a.pstride;
     __shared__ float s_gb0[W0];
-    TT::reduce_and_store(A, red, warp, lane, tid, pp, m, d.P, s_gb0);
+    TT::template reduce_and_store<true>(A, red, warp, lane, tid, pp, m, d.P, s_gb0);   // recursive halving: ~41 shuffles instead of 205
     if (lane < 16) {
         const uint32_t j = warp * 16 + lane;      // M = 64 accumulator: row j in lane j % 16 of warp j / 16
         if (j < m) {
