@@ -41,3 +41,15 @@ def test_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_selector_constants_match_the_header():
+    """The Python mirror of the test / profiling selectors (Net.K1_*, Net.HMC_*, Net.TC_*) carries the header's enum values."""
+    import rs_bann_b200 as rb
+    src = open(os.path.join(ROOT, "include", "bann.h")).read()
+    enums = dict((k, int(v)) for k, v in re.findall(r"\b(BANN_[A-Z0-9_]+)\s*=\s*(\d+)", src))
+    for py, c in (("K1_AUTO", "BANN_K1_AUTO"), ("K1_TENSOR", "BANN_K1_TENSOR"), ("K1_FFMA", "BANN_K1_FFMA"), ("K1_GENERIC", "BANN_K1_GENERIC"),
+                  ("HMC_AUTO", "BANN_HMC_AUTO"), ("HMC_LAUNCHES", "BANN_HMC_LAUNCHES"), ("HMC_PERSISTENT", "BANN_HMC_PERSISTENT"),
+                  ("TC_FOUR_WARPS", "BANN_TC_FOUR_WARPS"), ("TC_FIVE_WARPS", "BANN_TC_FIVE_WARPS"),
+                  ("TC_FIVE_WARPS_PLAIN", "BANN_TC_FIVE_WARPS_PLAIN")):
+        assert getattr(rb.Net, py) == enums[c], (py, c)
