@@ -87,7 +87,7 @@ struct K1Args {
     uint32_t st_per_chunk;
     uint32_t ncb;              // 8-marker chunks per expanded-genotype buffer (max over the listed branches)
     uint32_t nc_uniform;       // chunks per row when every listed branch has the same count, else 0
-    int tc_variant;            // k1_tc launches: 0 = four compute warps issue the MMAs themselves, 1 = k1_tc5 (dedicated issuing warp)
+    int tc_variant;            // k1_tc launches: BANN_TC_FOUR_WARPS / FIVE_WARPS / FIVE_WARPS_PLAIN (bann.h); set to 101 by the launcher when k1_tc5 ran
 };
 
 __device__ __forceinline__ void locate_param(const BranchDesc& d, uint32_t k, int& layer, uint32_t& row,

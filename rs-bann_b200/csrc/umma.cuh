@@ -93,16 +93,6 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// the same without the compiler-level memory clobber, and a 16-byte shared-memory store in the same style: for operand images
-// written BETWEEN arithmetic that reads other shared memory (weights) -- with the clobber (or a C++ store through a char
-// pointer) the compiler keeps every such load behind the store, each with its latency exposed.  Volatile asm statements keep
-// their order among themselves, so the waits / fences / arrivals around the image still order it.
-__device__ __forceinline__ void tmem_st4_nc(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d));
-}
-__device__ __forceinline__ void st_shared_v4_nc(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d));
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // all MMAs issued so far by this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void commit(uint64_t* mbar) {
