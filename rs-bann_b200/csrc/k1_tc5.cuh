@@ -6,7 +6,7 @@
 // its slowest warp.  Here warp 4 does nothing but wait on the two 128-arrival barriers, issue the 8 + 16 MMAs of a super-tile and
 // request the packed words; the compute warps never leave the FP32 tail, and the backward contraction accumulates in ONE
 // tensor-memory accumulator (one issuer, one fixed order).
-// Registers: 160 threads x 3 CTAs per SM leave 136 per thread.  setmaxnreg cannot help (it dead-locks with a lone fifth warp,
+// Registers: 160 threads x 3 CTAs per SM leave 128 per thread (136 by division, 128 by the allocation granularity).  setmaxnreg cannot help (it dead-locks with a lone fifth warp,
 // tests/probe/probe_setmaxnreg.cu); instead the cross-row sums are kept as ONE float per value (TcTail<..., SACC = true>: 41
 // registers instead of 82 for [5,5,1]), which brings the compute warps under the limit without spills.
 #pragma once
@@ -20,7 +20,7 @@ constexpr int kTc5Threads = 160;
 // for) are taken.  false: inside part 1, as k1_tc.  true: one super-tile later, placed by hand between the first layer's
 // activations of the NEXT super-tile, where the warp otherwise only waits for the MUFU pipe (ex2 / rcp, 8 clk per warp
 // instruction); the terms they need (activations, rho of the layers >= 1, error: `Mid`) stay in registers until then.
-// Measured on cfg3s (100k x 1000 branches x 50 markers, one B200, profiles/r2_k1_tc5_ab.md): k1_tc 1.641 ms, five warps 1.446,
+// Measured on cfg3s (100k x 1000 branches x 50 markers, one B200, profiles/r2_k1_tc5_ncu_summary.md): k1_tc 1.641 ms, five warps 1.446,
 // five warps + deferred sums 1.387.  Tried and rejected on the way: the sums behind the expansion of the next super-tile (1.395)
 // or behind the delta pieces (1.429); the expansion moved up between the units of layer 1 or between the steps of the rho chain
 // (1.61 / 1.65: the earlier the wait for the previous backward contraction sits, the less skew between the four compute warps
