@@ -1,12 +1,15 @@
 """Static look at a kernel's SASS: per instruction the control fields (stall count, yield, scoreboard set / wait), so that the
 issue cycles a single warp needs for a stretch of code can be added up without a GPU.
-usage: cuobjdump -sass -fun <mangled> obj.o > k.sass; python scripts/sass_stalls.py k.sass [lo_addr hi_addr]"""
+usage: cuobjdump -sass -fun <mangled> obj.o > k.sass; python scripts/sass_stalls.py k.sass|- [lo_addr hi_addr [-v]]"""
 import re
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # quiet under `| head`
 from collections import Counter
 
 ins = []
-lines = open(sys.argv[1]).read().splitlines()
+lines = (sys.stdin if sys.argv[1] == "-" else open(sys.argv[1])).read().splitlines()
 i = 0
 pat = re.compile(r"^\s*/\*([0-9a-f]{4,})\*/\s+(.*?);\s*/\* (0x[0-9a-f]{16}) \*/")
 while i < len(lines):
